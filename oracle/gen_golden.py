@@ -1,0 +1,173 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference on CPU (build container only).
+
+    python oracle/gen_golden.py            # needs /root/reference; writes tests/golden/
+
+Each fixture stores the reference's own state_dict (small configs), the inputs and the reference's
+outputs, so the oracle (tests/test_oracle_golden.py, CPU) and the CUDA path (tests/test_gpu_*.py)
+can both be checked against numbers the reference itself produced.  Inputs that are large are
+regenerated from ``portable_uniform`` (numpy Philox: platform independent, exact arithmetic only).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_harness as rh  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def portable_uniform(seed: int, shape) -> torch.Tensor:
+    """U[0,1) fp32 from numpy Philox -- bit-identical on every platform."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    return torch.from_numpy(rng.random(size=tuple(shape), dtype=np.float32))
+
+
+def sampler_case_inputs(case: int, B=2, K=256, L=265):
+    """(logits (B,K,L), x_t (B,L), t (B,), u (B,K+1,L)) for the posterior/sampler golden cases."""
+    scale = [1.0, 6.0, 40.0, 2.0, 12.0][case % 5]
+    logits = (portable_uniform(100 + case, (B, K, L)) - 0.5) * scale
+    u = portable_uniform(200 + case, (B, K + 1, L))
+    t_pair = [(99, 99), (57, 12), (1, 1), (0, 0), (98, 33)][case % 5]
+    t = torch.tensor([t_pair[i % 2] for i in range(B)], dtype=torch.long)
+    ids = (portable_uniform(300 + case, (B, L)) * K).long().clamp(max=K - 1)
+    masked = portable_uniform(400 + case, (B, L)) < ([1.1, 0.35, 0.05, 0.02, 0.9][case % 5])
+    x_t = torch.where(masked, torch.full_like(ids, K), ids)
+    return logits, x_t, t, u
+
+
+def sd_np(sd, drop=("attn2.mask",)):
+    return {k: v.numpy() for k, v in sd.items() if not any(d in k for d in drop)}
+
+
+def gen_xf_tiny():
+    K, D, NL, NH, CD = 32, 128, 2, 2, 64
+    model, _ = rh.build_dalle(K=K, overrides=dict(n_layer=NL, n_embd=D, n_head=NH, condition_dim=CD, dec_ch=32,
+                                                  dec_ch_mult=[1, 1, 1, 1, 2], dec_z_channels=64, embed_dim=64), seed=0)
+    tr = model.transformer  # DiffusionTransformer
+    g = torch.Generator().manual_seed(7)
+    # the reference zero-inits biases and unit-inits LayerNorm; perturb so that bias/affine paths are pinned too
+    for n, p in tr.named_parameters():
+        if n.endswith("bias") or "ln2.weight" in n or "to_logits.0.weight" in n:
+            p.add_(torch.randn(p.shape, generator=g) * 0.05)
+    B, L = 3, 265
+    cond = torch.randn(B, 77, CD, generator=g)
+    cond = cond / cond.norm(dim=-1, keepdim=True)
+    x_t = torch.randint(0, K + 1, (B, L), generator=g)
+    t = torch.tensor([99, 41, 0])
+    logits = tr.transformer(x_t.clone(), cond, t)
+    log_x = torch.log(torch.nn.functional.one_hot(x_t, K + 1).permute(0, 2, 1).float().clamp(min=1e-30))
+    wrapped = model.predict_start_with_truncation(tr.predict_start, "top0.85r")
+    lp = wrapped(log_x, cond, t)
+    post = tr.q_posterior(lp, log_x, t)
+    # free-running reference sample(): global CPU generator, exactly as generate_content would
+    model.truncation_forward = True
+    tr.predict_start = wrapped
+    out = dict(sd_np(tr.state_dict()))
+    torch.manual_seed(1234)
+    tok = tr.sample(condition_token=None, condition_mask=None, condition_embed=cond, filter_ratio=0, batch_size=B)["content_token"]
+    np.savez_compressed(os.path.join(GOLD, "xf_tiny.npz"), __cfg=np.array([K, D, NL, NH, CD, B, L]),
+                        in_cond=cond.numpy(), in_x_t=x_t.numpy().astype(np.int16), in_t=t.numpy(),
+                        out_logits=logits.numpy(), out_lp=lp.numpy(), out_post=post.numpy(),
+                        out_sample_tokens=tok.numpy().astype(np.int16), **{"sd." + k: v for k, v in out.items()})
+    print("xf_tiny: logits", tuple(logits.shape), "tokens", tok[0, :8].tolist())
+    return model
+
+
+def gen_sampler_cases():
+    """K=256 posterior + nucleus + Gumbel sampler through the reference's own methods."""
+    model, _ = rh.build_dalle(K=256, overrides=dict(n_layer=1, n_embd=64, n_head=1, dec_ch=32, dec_ch_mult=[1, 1, 1, 1, 2]), seed=0)
+    tr = model.transformer
+    K, L = 256, 265
+    res = {}
+    for case in range(5):
+        logits, x_t, t, u = sampler_case_inputs(case)
+        # feed the case logits through the reference's predict_start tail by stubbing the denoiser
+        tr.transformer.forward = lambda *_a, _l=logits, **_k: _l
+        for trunc in ("top0.85r", None):
+            ps = type(tr).predict_start.__get__(tr)
+            if trunc:
+                ps = model.predict_start_with_truncation(ps, trunc)
+            if case == 0:  # the all-[MASK] start state with its -inf carrier (diffusion_transformer.py:633-636)
+                log_x = torch.log(torch.nn.functional.one_hot(x_t, K + 1).permute(0, 2, 1).float())
+            else:
+                log_x = torch.log(torch.nn.functional.one_hot(x_t, K + 1).permute(0, 2, 1).float().clamp(min=1e-30))
+            lp = ps(log_x, None, t)
+            post = tr.q_posterior(lp, log_x, t)
+            g = -torch.log(-torch.log(u + 1e-30) + 1e-30)
+            nxt = (g + post).argmax(1)
+            tag = f"c{case}_{'nuc' if trunc else 'raw'}"
+            res[tag + "_next"] = nxt.numpy().astype(np.int16)
+            res[tag + "_post_head"] = post[:, :, :6].numpy()
+            res[tag + "_lp_head"] = lp[:, :, :6].numpy()
+            top2 = (g + post).topk(2, dim=1).values
+            res[tag + "_margin"] = (top2[:, 0] - top2[:, 1]).numpy()
+    np.savez_compressed(os.path.join(GOLD, "sampler_cases.npz"), **res)
+    print("sampler_cases:", len(res), "arrays")
+
+
+def gen_decoder_tiny():
+    K = 32
+    model, _ = rh.build_dalle(K=K, overrides=dict(n_layer=1, n_embd=64, n_head=1, dec_ch=32, dec_ch_mult=[1, 1, 1, 1, 2],
+                                                  dec_z_channels=64, embed_dim=64, grid=(2, 7)), seed=3)
+    g = torch.Generator().manual_seed(11)
+    cc = model.content_codec
+    cc.quantize.embedding.weight.mul_(K * 0.5)  # U(-1/K,1/K) init is tiny; scale to O(1) like a trained codebook
+    B, H, W = 2, 2, 7
+    ids = torch.randint(0, K, (B, H * W), generator=g)
+    mel = model.decode_to_img(ids, (B, 64, H, W))
+    sd = {k: v for k, v in model.state_dict().items()
+          if k.startswith("content_codec.") and ".encoder." not in k and "quant_conv" not in k.replace("post_quant_conv", "") and ".loss." not in k}
+    np.savez_compressed(os.path.join(GOLD, "decoder_tiny.npz"), in_ids=ids.numpy().astype(np.int16), out_mel=mel.numpy(),
+                        __cfg=np.array([K, 64, 32, H, W]), **{"sd." + k: v.numpy() for k, v in sd.items()})
+    print("decoder_tiny: mel", tuple(mel.shape), float(mel.abs().max()))
+
+
+def gen_melgan():
+    rh.install_shims()
+    from vocoder.modules import Generator
+    torch.manual_seed(5)
+    gen = Generator(80, 4, 3).eval()
+    g = torch.Generator().manual_seed(13)
+    with torch.no_grad():
+        for n, p in gen.named_parameters():  # weights_init gives N(0,0.02) v with g=|v|; make g and bias non-trivial
+            if n.endswith("weight_g"):
+                p.mul_(1 + 0.2 * torch.randn(p.shape, generator=g))
+            if n.endswith("bias"):
+                p.add_(0.05 * torch.randn(p.shape, generator=g))
+        mel = torch.rand(2, 80, 24, generator=g)
+        wav = gen(mel)
+    np.savez_compressed(os.path.join(GOLD, "melgan_tiny.npz"), in_mel=mel.numpy(), out_wav=wav.numpy(),
+                        **{"sd." + k: v.numpy() for k, v in gen.state_dict().items()})
+    # real shipped checkpoint: only input/output are committed; the weights travel in oracle/_ref/
+    real = rh.build_vocoder(real_weights=True)
+    mel = torch.rand(1, 80, 40, generator=g)
+    with torch.no_grad():
+        wav = real(mel)
+    np.savez_compressed(os.path.join(GOLD, "melgan_real_io.npz"), in_mel=mel.numpy(), out_wav=wav.numpy())
+    print("melgan: tiny wav", tuple(gen(torch.rand(1, 80, 8)).shape), "real wav absmax", float(wav.abs().max()))
+
+
+def gen_schedule():
+    model, _ = rh.build_dalle(K=256, overrides=dict(n_layer=1, n_embd=64, n_head=1, dec_ch=32, dec_ch_mult=[1, 1, 1, 1, 2]), seed=0)
+    tr = model.transformer
+    names = ["log_at", "log_bt", "log_ct", "log_cumprod_at", "log_cumprod_bt", "log_cumprod_ct", "log_1_min_ct", "log_1_min_cumprod_ct"]
+    np.savez_compressed(os.path.join(GOLD, "schedule_k256.npz"), **{n: getattr(tr, n).numpy() for n in names})
+
+
+if __name__ == "__main__":
+    assert rh.available(), "reference tree not found"
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_grad_enabled(False)
+    gen_schedule()
+    gen_xf_tiny()
+    gen_sampler_cases()
+    gen_decoder_tiny()
+    gen_melgan()
+    for f in sorted(os.listdir(GOLD)):
+        print(f, os.path.getsize(os.path.join(GOLD, f)) // 1024, "KB")
