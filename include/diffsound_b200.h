@@ -1,0 +1,128 @@
+/* diffsound_b200.h -- C-ABI of libdiffsound_b200.so (hand-written sm_100a kernels for the Diffsound hot path).
+ *
+ * The reference (yangdongchao/Text-to-sound-Synthesis) is pure PyTorch and has NO native / FFI interface to mirror
+ * (SURVEY.md section 2.1, 8b): the seam it offers is Python classes built by instantiate_from_config
+ * (Diffsound/sound_synthesis/utils/misc.py:125-132).  This header is therefore the boundary a maintainer would bind
+ * with ctypes from those classes; every entry point names the reference code it replaces.  INTEGRATION.md shows the
+ * binding stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless it says "host".
+ *   - the caller (PyTorch) owns all memory; the library never allocates, frees or retains caller pointers.
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on that stream, performs no
+ *     synchronisation and no allocation, and is CUDA-graph capturable.
+ *   - return 0 on success, non-zero on error; dsb_last_error() returns a thread-local message.  No C++ exceptions
+ *     cross this boundary.
+ */
+#ifndef DIFFSOUND_B200_H
+#define DIFFSOUND_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSB_VERSION 100
+
+/* operand types of the tensor-core GEMM */
+#define DSB_DTYPE_TF32 0 /* fp32 containers, tcgen05 kind::tf32 (inputs should be pre-rounded with dsb_round_tf32) */
+#define DSB_DTYPE_BF16 1 /* bf16 containers, tcgen05 kind::f16 */
+
+/* epilogue flags */
+#define DSB_GEMM_GELU2 1      /* x * sigmoid(1.702 x)           (reference transformer_utils.py:111-115) */
+#define DSB_GEMM_ROUND_TF32 2 /* round the fp32 output to tf32 (it feeds another tf32 GEMM) */
+#define DSB_GEMM_OUT_BF16 4   /* store bf16 instead of fp32 */
+
+const char* dsb_last_error(void);
+int dsb_version(void);
+/* host out-params; returns non-zero when no CUDA device is usable */
+int dsb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Tensor-core GEMM (TMA -> smem -> tcgen05.mma -> TMEM -> fused epilogue).
+ *   out[b][m, n] = epi( alpha * sum_{tap, k} A[b][m + tap_shift[tap], k] * W[b?][n, tap*K + k] + bias[n] ) (+ residual[b][m, n])
+ * Replaces torch.nn.Linear / addmm on the hot path (reference transformer_utils.py:45-47,57,95-97,108,248-253,347) and,
+ * with taps on zero-padded channels-last buffers, Conv2d 3x3/1x1 (specvqgan/modules/diffusionmodules/model.py:92-151,174-226)
+ * and Conv1d/ConvTranspose1d (vocoder/modules.py:72-126).
+ * A: (a_rows, K) row-major, leading dimension lda (elements); W: (N, num_taps*K) row-major, ldw.  Rows read outside
+ * [0, a_rows) are zeros (TMA out-of-bounds fill).  16-byte alignment of pointers and leading dimensions is required.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct dsb_gemm_desc {
+  const void* A;
+  const void* W;
+  const float* bias;     /* [N] or NULL */
+  const float* residual; /* fp32 (M, N) with ld_res, or NULL; may alias out */
+  void* out;             /* fp32 or bf16 (M, N) with ldo */
+  int M, N, K;           /* K = reduction length per tap */
+  int batch;             /* >= 1 */
+  long long a_rows;      /* rows of A that exist (0 -> M) */
+  long long lda, ldw, ldo, ld_res;
+  long long a_batch_stride, w_batch_stride /* 0 = shared W */, out_batch_stride, res_batch_stride;
+  int dtype;             /* DSB_DTYPE_* */
+  int flags;             /* DSB_GEMM_* */
+  int num_taps;          /* 1..9 */
+  int tap_shift[9];
+  int geo_P, geo_Wp, geo_y0, geo_y1, geo_x0, geo_x1; /* optional zero-border row mask, geo_P = 0 disables */
+  float alpha;           /* 0 -> 1 */
+  int block_n;           /* 0 = auto, 128, 256 */
+  int max_ctas;          /* 0 = one per SM */
+} dsb_gemm_desc;
+int dsb_gemm_ex(const dsb_gemm_desc* desc, void* stream);
+
+/* Exact fp32 (FFMA) GEMM with the same epilogue: out = epi(A W^T + bias) (+ residual).  Used for set-up time tables and
+ * as the "fp32-exact" mode that proves free-running token parity. */
+int dsb_gemm_f32(const float* A, const float* W, const float* bias, const float* residual, float* out, int M, int N, int K,
+                 long long lda, long long ldw, long long ldo, long long ld_res, int flags, void* stream);
+
+/* elementwise helpers */
+int dsb_round_tf32(const float* in, float* out, long long n, void* stream);
+int dsb_f32_to_bf16(const float* in, void* out_bf16, long long n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Denoiser pieces (reference sound_synthesis/modeling/transformers/transformer_utils.py,
+ *                  sound_synthesis/modeling/embeddings/dalle_mask_image_embedding.py)
+ * ------------------------------------------------------------------------------------------------------------- */
+/* DalleMaskImageEmbedding.forward (dalle_mask_image_embedding.py:36-58): out[b,l,:] = emb[max(ids,0)] + height[l / W] + width[l % W].
+ * Returns an error through *err_flag (device int, may be NULL) if an id >= num_embed. */
+int dsb_embed_tokens(const int64_t* ids, const float* emb, const float* height_emb, const float* width_emb, float* out, int B, int L,
+                     int D, int H, int W, int num_embed, int* err_flag, void* stream);
+
+/* nn.LayerNorm(D) with affine (transformer_utils.py:197 ln2, :345 to_logits.0): out = LN(x) * gamma + beta. flags: DSB_GEMM_ROUND_TF32 | DSB_GEMM_OUT_BF16 */
+int dsb_layernorm(const float* x, void* out, const float* gamma, const float* beta, int rows, int D, float eps, int flags, void* stream);
+
+/* AdaLayerNorm.forward (transformer_utils.py:145-149) with the timestep MLP hoisted into a table:
+ * table[t] = Linear(SiLU(emb[t])) = (scale | shift), shape (T, 2D); out[b,l,:] = LN(x[b,l,:]) * (1 + scale[t[b]]) + shift[t[b]]. */
+int dsb_ada_layernorm(const float* x, void* out, const float* table, const int64_t* t, int B, int L, int D, int T, float eps, int flags,
+                      void* stream);
+
+/* SiLU on a (rows, D) table (set-up of the AdaLN table) */
+int dsb_silu(const float* in, float* out, long long n, void* stream);
+
+/* softmax(Q K^T * scale) V per (batch, head), head_dim 64, no mask, no dropout (FullAttention / CrossAttention,
+ * transformer_utils.py:48-54, :99-105).  q/k/v/o are fp32 with row strides ld* (elements); head h occupies columns
+ * [64h, 64h+64).  Rows of batch b start at b*Lq (q, o) and b*Lk (k, v).  flags: DSB_GEMM_ROUND_TF32 on the output. */
+int dsb_attention(const float* q, long long ldq, const float* k, long long ldk, const float* v, long long ldv, float* o, long long ldo,
+                  int B, int H, int Lq, int Lk, float scale, int flags, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Posterior + truncation + Gumbel-argmax sampler, one kernel (reference diffusion_transformer.py:285-289 predict_start tail,
+ * models/dalle_spec.py:146-174 top-k / nucleus truncation, diffusion_transformer.py:293-339 q_posterior,
+ * :359-368 log_sample_categorical).  ids are carried instead of log-one-hot tensors.
+ *   logits  (B, L, K) fp32  -- denoiser output BEFORE the reference's 'b l c -> b c l' view
+ *   x_t     (B, L) int64, values in [0, K]; K is [MASK]
+ *   t       (B,) int64 timestep fed to the denoiser;  t_post (B,) int64 timestep used by q_posterior (NULL -> t)
+ *   uniform (B, K+1, L) fp32 in [0,1) -- the tensor torch.rand_like(logits) would have produced
+ *   sched   (8, T+1) fp32: rows log_at, log_bt, log_ct, log_1_min_ct (T entries used), log_cumprod_at, log_cumprod_bt,
+ *           log_cumprod_ct, log_1_min_cumprod_ct (T+1 entries)      (diffusion_transformer.py:224-231)
+ *   trunc_mode 0 none, 1 nucleus 'top{r}r' (trunc_r), 2 top-k 'top{k}p' (trunc_k)
+ *   x_next  (B, L) int64;  log_prob_out optional (B, K+1, L) fp32 model_log_prob (NULL to skip)
+ * ------------------------------------------------------------------------------------------------------------- */
+int dsb_posterior_sample(const float* logits, const int64_t* x_t, const int64_t* t, const int64_t* t_post, const float* uniform,
+                         const float* sched, int64_t* x_next, float* log_prob_out, int B, int K, int L, int T, int trunc_mode,
+                         float trunc_r, int trunc_k, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFSOUND_B200_H */

@@ -1,0 +1,104 @@
+"""tcgen05 GEMM parity: TF32 / BF16 operands pre-rounded on the host so the only error left is fp32 accumulation order."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def G():
+    from tests import gpu_common
+    return gpu_common
+
+
+def _ref(a, w, bias=None, res=None, gelu=False, taps=None, out_rows=None):
+    a, w = a.double(), w.double()
+    if taps is None:
+        y = a @ w.T
+    else:
+        K = a.shape[1]
+        M = out_rows or a.shape[0]
+        y = torch.zeros(M, w.shape[0], dtype=torch.float64)
+        for i, s in enumerate(taps):
+            idx = torch.arange(M) + s
+            ok = (idx >= 0) & (idx < a.shape[0])
+            sh = torch.zeros(M, K, dtype=torch.float64)
+            sh[ok] = a[idx[ok]]
+            y += sh @ w[:, i * K:(i + 1) * K].T
+    if bias is not None:
+        y = y + bias.double()
+    if gelu:
+        y = y * torch.sigmoid(1.702 * y)
+    if res is not None:
+        y = y + res.double()
+    return y
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(128, 128, 32, 128), (128, 256, 128, 256), (530, 256, 1024, 0), (4240, 1024, 1024, 0), (1000, 3072, 1024, 256),
+                                      (265, 4096, 1024, 128), (300, 1024, 4096, 0), (77 * 3, 2048, 512, 0), (200, 33, 64, 0), (130, 260, 100, 0)])
+def test_gemm_tf32(G, M, N, K, bn):
+    g = torch.Generator().manual_seed(M + N + K)
+    a = G.tf32_round_ref(torch.randn(M, K, generator=g))
+    w = G.tf32_round_ref(torch.randn(N, K, generator=g) * 0.05)
+    bias = torch.randn(N, generator=g)
+    out = G.ops.gemm(a.cuda(), w.cuda(), bias.cuda(), block_n=bn)
+    torch.cuda.synchronize()
+    assert G.relerr(out, _ref(a, w, bias)) < 2e-5
+
+
+def test_gemm_epilogues_and_persistence(G):
+    g = torch.Generator().manual_seed(1)
+    M, N, K = 2000, 1024, 512
+    a = G.tf32_round_ref(torch.randn(M, K, generator=g))
+    w = G.tf32_round_ref(torch.randn(N, K, generator=g) * 0.05)
+    bias, res = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    ref = _ref(a, w, bias, res, gelu=True)
+    # max_ctas=5 forces many tiles per CTA: exercises the smem ring wrap and both TMEM accumulator stages
+    out = G.ops.gemm(a.cuda(), w.cuda(), bias.cuda(), res.cuda(), gelu=True, max_ctas=5)
+    assert G.relerr(out, ref) < 2e-5
+    # in-place residual (x += proj(y)) and tf32-rounded output
+    x = res.cuda().clone()
+    G.ops.gemm(a.cuda(), w.cuda(), bias.cuda(), x, out=x)
+    assert G.relerr(x, _ref(a, w, bias, res)) < 2e-5
+    out = G.ops.gemm(a.cuda(), w.cuda(), bias.cuda(), round_out=True)
+    assert torch.equal(out.cpu(), G.tf32_round_ref(G.ops.gemm(a.cuda(), w.cuda(), bias.cuda()).cpu()))
+
+
+def test_gemm_bf16(G):
+    g = torch.Generator().manual_seed(2)
+    M, N, K = 777, 512, 1024
+    a = torch.randn(M, K, generator=g).bfloat16()
+    w = (torch.randn(N, K, generator=g) * 0.05).bfloat16()
+    out = G.ops.gemm(a.cuda(), w.cuda(), dtype=G.ops.BF16)
+    assert G.relerr(out, _ref(a.float(), w.float())) < 2e-5
+    outh = G.ops.gemm(a.cuda(), w.cuda(), dtype=G.ops.BF16, out_bf16=True)
+    assert G.relerr(outh.float(), _ref(a.float(), w.float())) < 5e-3
+
+
+def test_gemm_taps_and_row_mask(G):
+    """3 taps with row shifts (-7, 0, +7) and a zero-border mask: the implicit-GEMM form used by the conv layers."""
+    g = torch.Generator().manual_seed(4)
+    rows, C, N = 7 * 30, 64, 96
+    a = G.tf32_round_ref(torch.randn(rows, C, generator=g))
+    w = G.tf32_round_ref(torch.randn(N, 3 * C, generator=g) * 0.1)
+    taps = [-7, 0, 7]
+    ref = _ref(a, w, taps=taps)
+    out = G.ops.gemm(a.cuda(), w.cuda(), taps=taps)
+    assert G.relerr(out, ref) < 2e-5
+    geo = (7 * 10, 7, 1, 9, 1, 6)  # images of 10x7 rows, interior y in [1,9), x in [1,6)
+    out = G.ops.gemm(a.cuda(), w.cuda(), taps=taps, geo=geo).cpu()
+    r = torch.arange(rows)
+    y, x = (r % 70) // 7, r % 7
+    inside = (y >= 1) & (y < 9) & (x >= 1) & (x < 6)
+    assert float(out[~inside].abs().max()) == 0.0
+    assert G.relerr(out[inside], ref[inside]) < 2e-5
+
+
+def test_gemm_batched(G):
+    g = torch.Generator().manual_seed(5)
+    Bt, M, N, K = 3, 265, 265, 512
+    a = G.tf32_round_ref(torch.randn(Bt, M, K, generator=g))
+    w = G.tf32_round_ref(torch.randn(Bt, N, K, generator=g))
+    out = G.ops.gemm(a.cuda(), w.cuda(), alpha=0.5)
+    ref = 0.5 * torch.einsum("bmk,bnk->bmn", a.double(), w.double())
+    assert G.relerr(out, ref) < 2e-5

@@ -1,0 +1,83 @@
+// Error plumbing, device info and elementwise helpers of libdiffsound_b200.so.
+#include "common.cuh"
+#include "diffsound_b200.h"
+#include <cuda_bf16.h>
+#include <cstdarg>
+
+namespace dsb {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+__global__ void round_tf32_kernel(const float* __restrict__ in, float* __restrict__ out, long long n) {
+  long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4;
+  const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  for (; i + 3 < n; i += stride) {
+    float4 v = *reinterpret_cast<const float4*>(in + i);
+    v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+    *reinterpret_cast<float4*>(out + i) = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long j = n & ~3LL; j < n; ++j) out[j] = round_tf32(in[j]);
+}
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = __float2bfloat16(in[i]);
+}
+__global__ void silu_kernel(const float* __restrict__ in, float* __restrict__ out, long long n) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const float x = in[i];
+    out[i] = x / (1.0f + expf(-x));
+  }
+}
+}  // namespace dsb
+using namespace dsb;
+
+extern "C" const char* dsb_last_error(void) { return g_err; }
+extern "C" int dsb_version(void) { return DSB_VERSION; }
+extern "C" int dsb_device_info(int* sms, int* major, int* minor) {
+  int dev = 0;
+  DSB_CHECK_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  DSB_CHECK_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (sms) *sms = prop.multiProcessorCount;
+  if (major) *major = prop.major;
+  if (minor) *minor = prop.minor;
+  return 0;
+}
+static int grid_for(long long n, int per_block) {
+  long long g = (n + per_block - 1) / per_block;
+  const long long cap = (long long)sm_count() * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+extern "C" int dsb_round_tf32(const float* in, float* out, long long n, void* stream) {
+  DSB_REQUIRE(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "dsb_round_tf32: pointers must be 16-byte aligned");
+  round_tf32_kernel<<<grid_for(n, 1024), 256, 0, (cudaStream_t)stream>>>(in, out, n);
+  DSB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int dsb_f32_to_bf16(const float* in, void* out, long long n, void* stream) {
+  f32_to_bf16_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)out, n);
+  DSB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int dsb_silu(const float* in, float* out, long long n, void* stream) {
+  silu_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, out, n);
+  DSB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,356 @@
+// TMA + tcgen05 GEMM for sm_100a:  out[b][M,N] = epilogue( sum_tap A[b][m + shift_tap, :Kc] . W[n, tap*Kc : (tap+1)*Kc]^T )
+//
+// * A and W are K-contiguous ("TN"), i.e. torch.nn.Linear's activation (M,K) and weight (N,K) as they lie in HBM.
+// * operands: TF32 (fp32 containers, kind::tf32) or BF16 (kind::f16); accumulation fp32 in TMEM.
+// * "taps": the K loop runs over (tap, channel-block); each tap reads A rows shifted by shift_tap.  With one tap this is
+//   a plain Linear layer (Text2ImageTransformer, reference transformer_utils.py:45-57,95-108,248-253,345-348); with 9 / 3 / 7
+//   taps on zero-padded channels-last buffers it is the implicit-GEMM form of the SpecVQGAN decoder's 3x3 convs (reference
+//   specvqgan/modules/diffusionmodules/model.py:92-151) and the MelGAN convs (reference vocoder/modules.py:72-126).
+// * warp-specialised persistent kernel: warp0 = TMA producer, warp1 = tcgen05.mma issuer (+TMEM owner), warps2-5 = epilogue
+//   (TMEM -> registers -> bias / GELU2 / residual / tf32-round -> HBM); smem ring of kStages, 2 TMEM accumulator stages.
+#include "common.cuh"
+#include "diffsound_b200.h"
+#include <cuda_bf16.h>
+
+namespace dsb {
+
+constexpr int BLOCK_M = 128;
+constexpr int ROW_BYTES = 128;  // one swizzle-128B row of K per operand row
+constexpr int GEMM_THREADS = 192;
+constexpr int MAX_TAPS = 9;
+
+struct GemmParams {
+  int M, N, batch;
+  int tiles_m, tiles_n;
+  int kb_per_tap;  // ceil(Kc / BLOCK_K)
+  int block_k;     // elements per k-block (32 tf32 / 64 bf16)
+  int num_taps;
+  int tap_shift[MAX_TAPS];
+  int kc;          // channels per tap (B column offset per tap)
+  int b_batched;
+  const float* bias;
+  const float* residual;
+  long long ld_res, res_bstride;
+  void* out;
+  long long ldo, out_bstride;
+  int flags;
+  // optional row mask (padded conv geometry): row r -> p = r % geo_P; y = p / geo_Wp; x = p % geo_Wp;
+  // rows outside [y0,y1) x [x0,x1) are written as zeros.  geo_P == 0 disables.
+  int geo_P, geo_Wp, geo_y0, geo_y1, geo_x0, geo_x1;
+  float alpha;     // scale applied to the accumulator before bias (1.0 for Linear)
+};
+
+template <int BLOCK_N>
+struct GemmSmem {
+  static constexpr int A_BYTES = BLOCK_M * ROW_BYTES;
+  static constexpr int B_BYTES = BLOCK_N * ROW_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BLOCK_N, bool kTf32>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ GemmParams p) {
+  using S = GemmSmem<BLOCK_N>;
+  constexpr int STAGES = S::STAGES;
+  constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;  // 2 accumulator stages; 256 or 512 (power of two)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.tiles_m * p.tiles_n * p.batch;
+  const int num_kb = p.kb_per_tap * p.num_taps;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % p.tiles_m;
+        const int n_blk = (tile / p.tiles_m) % p.tiles_n;
+        const int b = tile / (p.tiles_m * p.tiles_n);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / p.kb_per_tap;
+          const int c0 = (kb - tap * p.kb_per_tap) * p.block_k;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+          uint8_t* sa = smem + stage * S::STAGE_BYTES;
+          tma_load_3d(&tmap_a, &full_bar[stage], sa, c0, m_blk * BLOCK_M + p.tap_shift[tap], b);
+          tma_load_3d(&tmap_b, &full_bar[stage], sa + S::A_BYTES, tap * p.kc + c0, n_blk * BLOCK_N, p.b_batched ? b : 0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kTf32, BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint64_t da = make_sw128_kmajor_desc(sa);
+          const uint64_t db = make_sw128_kmajor_desc(sa + S::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // 4 x 32-byte K slices per 128-byte swizzle row
+            umma<kTf32>(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[as]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps (2..5): TMEM lane quadrant = warp % 4
+    const int q = warp & 3;
+    const bool has_geo = p.geo_P > 0;
+    const bool out_bf16 = (p.flags & DSB_GEMM_OUT_BF16) != 0;
+    const bool do_gelu = (p.flags & DSB_GEMM_GELU2) != 0;
+    const bool do_round = (p.flags & DSB_GEMM_ROUND_TF32) != 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m_blk = tile % p.tiles_m;
+      const int n_blk = (tile / p.tiles_m) % p.tiles_n;
+      const int b = tile / (p.tiles_m * p.tiles_n);
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tmem_full[as], aphase);
+      tc_fence_after();
+      const int row = m_blk * BLOCK_M + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      bool interior = true;
+      if (has_geo) {
+        const int pp = row % p.geo_P;
+        const int y = pp / p.geo_Wp, x = pp - y * p.geo_Wp;
+        interior = (y >= p.geo_y0) && (y < p.geo_y1) && (x >= p.geo_x0) && (x < p.geo_x1);
+      }
+      const float* res_row = p.residual ? p.residual + (long long)b * p.res_bstride + (long long)row * p.ld_res : nullptr;
+      float* out_f = reinterpret_cast<float*>(p.out) + (long long)b * p.out_bstride + (long long)row * p.ldo;
+      __nv_bfloat16* out_h = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)b * p.out_bstride + (long long)row * p.ldo;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        const int col0 = n_blk * BLOCK_N + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld_32x32(t_row + c * 32, v);
+        tmem_ld_wait();
+        if (row_ok) {
+        const bool full_chunk = (col0 + 32 <= p.N) && ((p.N & 3) == 0);
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (full_chunk || col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
+        }
+        if (do_gelu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.0f + __expf(-1.702f * f[j]));
+        }
+        if (res_row) {
+          if (full_chunk) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 r = *reinterpret_cast<const float4*>(res_row + col0 + j);
+              f[j] += r.x; f[j + 1] += r.y; f[j + 2] += r.z; f[j + 3] += r.w;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) f[j] += res_row[col0 + j];
+          }
+        }
+        if (do_round) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = round_tf32(f[j]);
+        }
+        if (!interior) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = 0.0f;
+        }
+        if (!out_bf16) {
+          if (full_chunk) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(out_f + col0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) out_f[col0 + j] = f[j];
+          }
+        } else {
+          if (full_chunk && (p.N & 7) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(f[j], f[j + 1]);
+              __nv_bfloat162 h1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
+              __nv_bfloat162 h3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+              uint4 u;
+              u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+              u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+              *reinterpret_cast<uint4*>(out_h + col0 + j) = u;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) out_h[col0 + j] = __float2bfloat16(f[j]);
+          }
+        }
+        }  // row_ok
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// 3-D map (K, rows, batch) over a K-contiguous matrix; box = (128 bytes of K, box_rows, 1); SWIZZLE_128B; OOB -> 0
+static int make_operand_map(CUtensorMap* map, const void* ptr, bool bf16, long long kdim, long long rows, long long batch,
+                            long long ld_elems, long long bstride_elems, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  DSB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  const int es = bf16 ? 2 : 4;
+  DSB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "GEMM operand pointer must be 16-byte aligned");
+  DSB_REQUIRE((ld_elems * es) % 16 == 0, "GEMM operand leading dimension must be a multiple of 16 bytes (ld=%lld)", ld_elems);
+  DSB_REQUIRE(batch == 1 || (bstride_elems * es) % 16 == 0, "GEMM batch stride must be a multiple of 16 bytes");
+  cuuint64_t gdim[3] = {(cuuint64_t)kdim, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t gstr[2] = {(cuuint64_t)(ld_elems * es), (cuuint64_t)((batch == 1 ? ld_elems * rows : bstride_elems) * es)};
+  cuuint32_t box[3] = {(cuuint32_t)(ROW_BYTES / es), (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), gdim, gstr,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DSB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): k=%lld rows=%lld batch=%lld ld=%lld", (int)r, kdim, rows, batch, ld_elems);
+  return 0;
+}
+
+template <int BLOCK_N, bool kTf32>
+static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int max_ctas, cudaStream_t st) {
+  using S = GemmSmem<BLOCK_N>;
+  auto kern = gemm_tcgen05_kernel<BLOCK_N, kTf32>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    attr_done = true;
+  }
+  const int tiles = p.tiles_m * p.tiles_n * p.batch;
+  int grid = tiles < max_ctas ? tiles : max_ctas;
+  kern<<<grid, GEMM_THREADS, S::TOTAL, st>>>(ma, mb, p);
+  DSB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace dsb
+
+using namespace dsb;
+
+extern "C" int dsb_gemm_ex(const dsb_gemm_desc* d, void* stream) {
+  DSB_REQUIRE(d != nullptr, "dsb_gemm_ex: null descriptor");
+  DSB_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0 && d->batch > 0, "dsb_gemm_ex: bad shape M=%d N=%d K=%d batch=%d", d->M, d->N, d->K, d->batch);
+  DSB_REQUIRE(d->num_taps >= 1 && d->num_taps <= MAX_TAPS, "dsb_gemm_ex: num_taps=%d out of range", d->num_taps);
+  DSB_REQUIRE(d->dtype == DSB_DTYPE_TF32 || d->dtype == DSB_DTYPE_BF16, "dsb_gemm_ex: dtype must be TF32 or BF16 (use dsb_gemm_f32 for exact fp32)");
+  const bool bf16 = d->dtype == DSB_DTYPE_BF16;
+  const int block_k = bf16 ? 64 : 32;
+  GemmParams p{};
+  p.M = d->M; p.N = d->N; p.batch = d->batch;
+  p.tiles_m = (d->M + BLOCK_M - 1) / BLOCK_M;
+  p.kb_per_tap = (d->K + block_k - 1) / block_k;
+  p.block_k = block_k;
+  p.num_taps = d->num_taps;
+  for (int i = 0; i < MAX_TAPS; ++i) p.tap_shift[i] = i < d->num_taps ? d->tap_shift[i] : 0;
+  p.kc = d->K;
+  p.b_batched = d->w_batch_stride != 0;
+  p.bias = d->bias; p.residual = d->residual; p.ld_res = d->ld_res; p.res_bstride = d->res_batch_stride;
+  p.out = d->out; p.ldo = d->ldo; p.out_bstride = d->out_batch_stride;
+  p.flags = d->flags;
+  p.geo_P = d->geo_P; p.geo_Wp = d->geo_Wp; p.geo_y0 = d->geo_y0; p.geo_y1 = d->geo_y1; p.geo_x0 = d->geo_x0; p.geo_x1 = d->geo_x1;
+  p.alpha = d->alpha == 0.0f ? 1.0f : d->alpha;
+
+  // tile-N choice: fewest waves, then the wider tile (less A re-read)
+  const int sms = sm_count();
+  int block_n = d->block_n;
+  if (block_n == 0) {
+    if (d->N <= 128) block_n = 128;
+    else {
+      const long long t256 = (long long)p.tiles_m * ((d->N + 255) / 256) * d->batch;
+      const long long t128 = (long long)p.tiles_m * ((d->N + 127) / 128) * d->batch;
+      const long long cost256 = ((t256 + sms - 1) / sms) * 2, cost128 = ((t128 + sms - 1) / sms);
+      block_n = cost128 < cost256 ? 128 : 256;
+    }
+  }
+  DSB_REQUIRE(block_n == 128 || block_n == 256, "dsb_gemm_ex: block_n must be 0, 128 or 256");
+  p.tiles_n = (d->N + block_n - 1) / block_n;
+
+  CUtensorMap ma, mb;
+  const long long a_rows = d->a_rows > 0 ? d->a_rows : d->M;
+  if (make_operand_map(&ma, d->A, bf16, d->K, a_rows, d->batch, d->lda, d->a_batch_stride, BLOCK_M)) return 3;
+  if (make_operand_map(&mb, d->W, bf16, (long long)d->K * d->num_taps, d->N, p.b_batched ? d->batch : 1, d->ldw, d->w_batch_stride, block_n)) return 3;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int max_ctas = d->max_ctas > 0 ? d->max_ctas : sms;
+  if (block_n == 256) return bf16 ? launch<256, false>(ma, mb, p, max_ctas, st) : launch<256, true>(ma, mb, p, max_ctas, st);
+  return bf16 ? launch<128, false>(ma, mb, p, max_ctas, st) : launch<128, true>(ma, mb, p, max_ctas, st);
+}

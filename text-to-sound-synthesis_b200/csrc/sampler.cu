@@ -1,0 +1,235 @@
+// Fused p_sample tail: fp64 log_softmax + clamp  ->  top-k / nucleus truncation  ->  closed-form q_posterior  ->
+// Gumbel-argmax, one warp per (batch, position) column, token ids in / token ids out.
+//   reference: diffusion_transformer.py:285-289 (predict_start tail), models/dalle_spec.py:146-174 (truncation wrappers),
+//              diffusion_transformer.py:28-30,241-267,293-339 (q_posterior), :359-368 (log_sample_categorical).
+// Numerics follow the reference's CPU path op by op: fp64 exactly where it uses fp64 (log_softmax; torch's CPU cumsum
+// accumulates fp32 in fp64), fp32 expf/logf elsewhere.  Nucleus membership is computed by rank instead of a sort: element
+// k is kept iff the fp64 sum of exp(v_i) over all i ordered before k (v_i > v_k, ties by lower index = stable descending
+// sort) rounds to an fp32 below r -- the same predicate as sort + cumsum + shift-by-one + gather(argsort).
+// HBM-bound: reads K + (K+1) floats and writes one id per column.
+#include "common.cuh"
+#include "diffsound_b200.h"
+
+namespace dsb {
+constexpr int SW = 8;  // warps (= columns) per CTA
+
+__device__ __forceinline__ float lae(float a, float b) {  // log_add_exp, diffusion_transformer.py:28-30
+  const float m = fmaxf(a, b);
+  return m + logf(expf(a - m) + expf(b - m));
+}
+__device__ __forceinline__ float wmaxf(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float wsumf(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double wsumd(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// NJ = ceil((K+1)/32): elements per lane; element index k = lane + 32*j
+template <int NJ>
+__global__ void __launch_bounds__(SW * 32)
+posterior_sample_kernel(const float* __restrict__ logits, const int64_t* __restrict__ x_t, const int64_t* __restrict__ t,
+                        const int64_t* __restrict__ t_post, const float* __restrict__ uniform, const float* __restrict__ sched,
+                        int64_t* __restrict__ x_next, float* __restrict__ log_prob_out, int K, int L, int T, int trunc_mode, float trunc_r,
+                        int trunc_k) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int C = K + 1;
+  float* u_s = reinterpret_cast<float*>(smem_raw);                    // [C][SW]  uniforms, later reused for log_prob_out
+  float* v_s = u_s + C * SW;                                          // [SW][C]  truncation keys (log-probs)
+  double* e_s = reinterpret_cast<double*>(v_s + ((SW * C + 1) & ~1)); // [SW][C]  exp(v) in fp64
+  const int b = blockIdx.y;
+  const int l0 = blockIdx.x * SW;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int l = l0 + warp;
+  const bool active = l < L;
+
+  // stage the (C x SW) tile of uniforms: u[b, k, l0 + j]
+  const float* ub = uniform + (long long)b * C * L;
+  for (int idx = threadIdx.x; idx < C * SW; idx += SW * 32) {
+    const int k = idx / SW, j = idx - k * SW;
+    u_s[idx] = (l0 + j < L) ? ub[(long long)k * L + l0 + j] : 0.5f;
+  }
+  __syncthreads();
+
+  float lp[NJ];
+  int xt = 0;
+  if (active) {
+    const float* row = logits + ((long long)b * L + l) * K;
+    float x[NJ];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int k = lane + 32 * j;
+      x[j] = k < K ? row[k] : -INFINITY;
+      mx = fmaxf(mx, x[j]);
+    }
+    mx = wmaxf(mx);
+    // A.1: log_softmax in fp64, cast to fp32, clamp to [-70, 0]; class K (mask) = -70
+    double se = 0.0;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+      if (lane + 32 * j < K) se += exp((double)x[j] - (double)mx);
+    se = wsumd(se);
+    const double lse = log(se);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int k = lane + 32 * j;
+      float vlp = -70.f;
+      if (k < K) vlp = fminf(fmaxf((float)(((double)x[j] - (double)mx) - lse), -70.f), 0.f);
+      lp[j] = vlp;
+    }
+    // A.2: truncation
+    if (trunc_mode != 0) {
+      float* vw = v_s + warp * C;
+      double* ew = e_s + warp * C;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int k = lane + 32 * j;
+        if (k < C) { vw[k] = lp[j]; ew[k] = (double)expf(lp[j]); }
+      }
+      __syncwarp();
+      double ahead_sum[NJ];
+      int ahead_cnt[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) { ahead_sum[j] = 0.0; ahead_cnt[j] = 0; }
+      for (int i = 0; i < C; ++i) {
+        const float vi = vw[i];
+        const double ei = ew[i];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const int k = lane + 32 * j;
+          const bool ahead = (vi > lp[j]) || (vi == lp[j] && i < k);
+          if (ahead) { ahead_sum[j] += ei; ahead_cnt[j] += 1; }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        bool keep;
+        if (trunc_mode == 1) keep = (ahead_cnt[j] == 0) || ((float)ahead_sum[j] < trunc_r);
+        else keep = ahead_cnt[j] < trunc_k;
+        if (!keep) lp[j] = -70.f;
+      }
+    }
+    // A.3: q_posterior closed form
+    xt = (int)x_t[(long long)b * L + l];
+    const bool masked = (xt == K);
+    long long tp = t_post ? t_post[b] : t[b];
+    tp = tp < 0 ? 0 : (tp >= T ? T - 1 : tp);
+    const int tm1 = (int)((tp - 1 + (T + 1)) % (T + 1));
+    const int S1 = T + 1;
+    const float la = sched[0 * S1 + tp], lb = sched[1 * S1 + tp], lc = sched[2 * S1 + tp];
+    const float cA = sched[4 * S1 + tp], cB = sched[5 * S1 + tp], cC = sched[6 * S1 + tp];
+    const float pA = sched[4 * S1 + tm1], pB = sched[5 * S1 + tm1], pC = sched[6 * S1 + tm1], pC1 = sched[7 * S1 + tm1];
+    const float LOGZ = -69.07755279f;  // log(1e-30) in fp32
+    float qv[NJ], lq1[NJ];
+    float qmax = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int k = lane + 32 * j;
+      float lqt, l1;
+      if (k < K) {
+        if (masked) { lqt = cC; l1 = lc; }
+        else {
+          const float oh = (k == xt) ? 0.f : LOGZ;
+          lqt = lae(oh + cA, cB);
+          l1 = lae(oh + la, lb);
+        }
+      } else {  // k == K (and padding lanes, ignored below)
+        lqt = masked ? 0.f : LOGZ;
+        l1 = lqt;
+      }
+      lq1[j] = l1;
+      qv[j] = (k < C) ? lp[j] - lqt : -INFINITY;
+      qmax = fmaxf(qmax, qv[j]);
+    }
+    qmax = wmaxf(qmax);
+    float ssum = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+      if (lane + 32 * j < C) ssum += expf(qv[j] - qmax);
+    ssum = wsumf(ssum);
+    const float slse = logf(ssum) + qmax;  // torch.logsumexp
+    // A.4: Gumbel-argmax (first index wins ties)
+    float best = -INFINITY;
+    int besti = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int k = lane + 32 * j;
+      if (k < C) {
+        const float qn = qv[j] - slse;
+        const float r = (k < K) ? lae(qn + pA, pB) : lae(qn + pC1, pC);
+        const float outv = fminf(fmaxf(r + lq1[j] + slse, -70.f), 0.f);
+        lp[j] = outv;
+        const float u = u_s[k * SW + warp];
+        const float gmb = -logf(-logf(u + 1e-30f) + 1e-30f);
+        const float val = gmb + outv;
+        if (val > best) { best = val; besti = k; }  // ascending k per lane -> keeps the first maximum
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+      if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+    }
+    if (lane == 0) x_next[(long long)b * L + l] = besti;
+  }
+  if (log_prob_out) {  // optional model_log_prob (B, K+1, L): stage through smem for coalesced rows
+    __syncthreads();
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int k = lane + 32 * j;
+        if (k < C) u_s[k * SW + warp] = lp[j];
+      }
+    }
+    __syncthreads();
+    float* ob = log_prob_out + (long long)b * C * L;
+    for (int idx = threadIdx.x; idx < C * SW; idx += SW * 32) {
+      const int k = idx / SW, j = idx - k * SW;
+      if (l0 + j < L) ob[(long long)k * L + l0 + j] = u_s[idx];
+    }
+  }
+}
+
+template <int NJ>
+static int launch_sampler(const float* logits, const int64_t* x_t, const int64_t* t, const int64_t* t_post, const float* uniform,
+                          const float* sched, int64_t* x_next, float* lpo, int B, int K, int L, int T, int mode, float r, int kk, cudaStream_t st) {
+  const int C = K + 1;
+  const size_t smem = (size_t)C * SW * 4 + (((size_t)SW * C + 1) & ~(size_t)1) * 4 + (size_t)SW * C * 8;
+  auto kern = posterior_sample_kernel<NJ>;
+  if (smem > 48 * 1024) DSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((L + SW - 1) / SW, B);
+  kern<<<grid, SW * 32, smem, st>>>(logits, x_t, t, t_post, uniform, sched, x_next, lpo, K, L, T, mode, r, kk);
+  DSB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+}  // namespace dsb
+using namespace dsb;
+
+extern "C" int dsb_posterior_sample(const float* logits, const int64_t* x_t, const int64_t* t, const int64_t* t_post, const float* uniform,
+                                    const float* sched, int64_t* x_next, float* log_prob_out, int B, int K, int L, int T, int trunc_mode,
+                                    float trunc_r, int trunc_k, void* stream) {
+  DSB_REQUIRE(B > 0 && K > 0 && L > 0 && T > 0, "dsb_posterior_sample: bad shape");
+  DSB_REQUIRE(trunc_mode >= 0 && trunc_mode <= 2, "dsb_posterior_sample: trunc_mode must be 0, 1 or 2");
+  DSB_REQUIRE(K + 1 <= 32 * 33, "dsb_posterior_sample: K=%d too large (max 1055)", K);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nj = (K + 1 + 31) / 32;
+#define DSB_SAMPLER_CASE(N) \
+  if (nj <= N) return launch_sampler<N>(logits, x_t, t, t_post, uniform, sched, x_next, log_prob_out, B, K, L, T, trunc_mode, trunc_r, trunc_k, st)
+  DSB_SAMPLER_CASE(2);
+  DSB_SAMPLER_CASE(5);
+  DSB_SAMPLER_CASE(9);
+  DSB_SAMPLER_CASE(17);
+  DSB_SAMPLER_CASE(33);
+#undef DSB_SAMPLER_CASE
+  return 2;
+}

@@ -1,0 +1,171 @@
+"""torch-tensor front end of the C-ABI kernels: pointer extraction, shape checks, current-stream plumbing.
+
+PyTorch is used here only for device memory and streams; all arithmetic happens in libdiffsound_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+
+TF32, BF16 = 0, 1
+GELU2, ROUND_TF32, OUT_BF16 = 1, 2, 4
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("diffsound_b200 ops need CUDA tensors: this path has no CPU fallback")
+
+
+def device_info():
+    s, a, b = C.c_int(), C.c_int(), C.c_int()
+    _lib.check(_lib.lib().dsb_device_info(C.byref(s), C.byref(a), C.byref(b)), "dsb_device_info")
+    return s.value, a.value, b.value
+
+
+def round_tf32(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(x)
+    x = x.contiguous()
+    out = torch.empty_like(x) if out is None else out
+    _lib.check(_lib.lib().dsb_round_tf32(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "dsb_round_tf32")
+    return out
+
+
+def to_bf16(x: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x)
+    x = x.contiguous()
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.lib().dsb_f32_to_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "dsb_f32_to_bf16")
+    return out
+
+
+def silu(x: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x)
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().dsb_silu(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "dsb_silu")
+    return out
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+         out: Optional[torch.Tensor] = None, *, dtype: int = TF32, gelu: bool = False, round_out: bool = False, out_bf16: bool = False,
+         taps: Optional[Sequence[int]] = None, out_rows: Optional[int] = None, geo: Optional[Sequence[int]] = None, alpha: float = 1.0,
+         block_n: int = 0, max_ctas: int = 0) -> torch.Tensor:
+    """out = epi(alpha * A @ W^T + bias) (+ residual) on tcgen05.  a: (M,K) or (batch,M,K); w: (N, taps*K) or (batch,N,K)."""
+    _need_cuda(a, w, bias, residual, out)
+    batched = a.dim() == 3
+    if a.stride(-1) != 1 or w.stride(-1) != 1:
+        raise RuntimeError("gemm operands must be K-contiguous")
+    ntaps = 1 if taps is None else len(taps)
+    batch = a.shape[0] if batched else 1
+    a_rows, K = a.shape[-2], a.shape[-1]
+    N = w.shape[-2]
+    if w.shape[-1] != K * ntaps:
+        raise RuntimeError(f"gemm: W has {w.shape[-1]} columns, expected {K}*{ntaps}")
+    M = a_rows if out_rows is None else out_rows
+    odt = torch.bfloat16 if out_bf16 else torch.float32
+    if out is None:
+        out = torch.empty((batch, M, N) if batched else (M, N), dtype=odt, device=a.device)
+    d = _lib.GemmDesc()
+    d.A, d.W, d.bias, d.residual, d.out = a.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(residual), out.data_ptr()
+    d.M, d.N, d.K, d.batch = M, N, K, batch
+    d.a_rows = a_rows
+    d.lda, d.ldw, d.ldo = a.stride(-2), w.stride(-2), out.stride(-2)
+    d.ld_res = residual.stride(-2) if residual is not None else 0
+    d.a_batch_stride = a.stride(0) if batched else 0
+    d.w_batch_stride = w.stride(0) if w.dim() == 3 else 0
+    d.out_batch_stride = out.stride(0) if batched else 0
+    d.res_batch_stride = residual.stride(0) if (residual is not None and batched) else 0
+    d.dtype = dtype
+    d.flags = (GELU2 if gelu else 0) | (ROUND_TF32 if round_out else 0) | (OUT_BF16 if out_bf16 else 0)
+    d.num_taps = ntaps
+    for i, s in enumerate(taps or [0]):
+        d.tap_shift[i] = int(s)
+    if geo is not None:
+        d.geo_P, d.geo_Wp, d.geo_y0, d.geo_y1, d.geo_x0, d.geo_x1 = [int(v) for v in geo]
+    d.alpha = alpha
+    d.block_n, d.max_ctas = block_n, max_ctas
+    _lib.check(_lib.lib().dsb_gemm_ex(C.byref(d), _stream()), "dsb_gemm_ex")
+    return out
+
+
+def gemm_f32(a, w, bias=None, residual=None, out=None, *, gelu=False, round_out=False):
+    """Exact fp32 FFMA GEMM (set-up tables, fp32-exact mode)."""
+    _need_cuda(a, w, bias, residual, out)
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty((M, N), dtype=torch.float32, device=a.device) if out is None else out
+    flags = (GELU2 if gelu else 0) | (ROUND_TF32 if round_out else 0)
+    _lib.check(_lib.lib().dsb_gemm_f32(a.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(residual), out.data_ptr(), M, N, K, a.stride(0), w.stride(0),
+                                       out.stride(0), residual.stride(0) if residual is not None else 0, flags, _stream()), "dsb_gemm_f32")
+    return out
+
+
+def embed_tokens(ids, emb, height_emb, width_emb, out=None, err_flag=None):
+    _need_cuda(ids, emb, height_emb, width_emb)
+    B, L = ids.shape
+    D = emb.shape[1]
+    H, W = height_emb.shape[0], width_emb.shape[0]
+    out = torch.empty((B, L, D), dtype=torch.float32, device=ids.device) if out is None else out
+    _lib.check(_lib.lib().dsb_embed_tokens(ids.data_ptr(), emb.data_ptr(), height_emb.data_ptr(), width_emb.data_ptr(), out.data_ptr(), B, L, D, H, W,
+                                           emb.shape[0], _ptr(err_flag), _stream()), "dsb_embed_tokens")
+    return out
+
+
+def layernorm(x, gamma, beta, out=None, *, eps=1e-5, round_out=False, out_bf16=False):
+    _need_cuda(x, gamma, beta)
+    D = x.shape[-1]
+    rows = x.numel() // D
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x.device)
+    flags = (ROUND_TF32 if round_out else 0) | (OUT_BF16 if out_bf16 else 0)
+    _lib.check(_lib.lib().dsb_layernorm(x.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), rows, D, eps, flags, _stream()), "dsb_layernorm")
+    return out
+
+
+def ada_layernorm(x, table, t, out=None, *, eps=1e-5, round_out=False, out_bf16=False):
+    """x (B,L,D), table (T,2D) = Linear(SiLU(emb)) rows, t (B,) int64."""
+    _need_cuda(x, table, t)
+    B, L, D = x.shape
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x.device)
+    flags = (ROUND_TF32 if round_out else 0) | (OUT_BF16 if out_bf16 else 0)
+    _lib.check(_lib.lib().dsb_ada_layernorm(x.data_ptr(), out.data_ptr(), table.data_ptr(), t.data_ptr(), B, L, D, table.shape[0], eps, flags, _stream()),
+               "dsb_ada_layernorm")
+    return out
+
+
+def attention(q, k, v, out, *, B, H, Lq, Lk, scale, round_out=False):
+    """q/out: row-strided views with (B*Lq) rows; k/v: (B*Lk) rows; head h = columns [64h, 64h+64)."""
+    _need_cuda(q, k, v, out)
+    for t_ in (q, k, v, out):
+        if t_.stride(-1) != 1:
+            raise RuntimeError("attention operands must be contiguous in the head dimension")
+    _lib.check(_lib.lib().dsb_attention(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), out.data_ptr(), out.stride(0),
+                                        B, H, Lq, Lk, scale, ROUND_TF32 if round_out else 0, _stream()), "dsb_attention")
+    return out
+
+
+def posterior_sample(logits_blk, x_t, t, uniform, sched, *, T, trunc_mode=1, trunc_r=0.85, trunc_k=0, t_post=None, x_next=None, log_prob_out=None):
+    """logits_blk (B,L,K) fp32 contiguous; x_t (B,L) int64; uniform (B,K+1,L); sched (8,T+1) -> x_next (B,L) int64."""
+    _need_cuda(logits_blk, x_t, t, uniform, sched)
+    B, L, K = logits_blk.shape
+    assert logits_blk.is_contiguous() and uniform.is_contiguous() and x_t.is_contiguous() and sched.is_contiguous()
+    assert uniform.shape == (B, K + 1, L) and sched.shape == (8, T + 1)
+    x_next = torch.empty((B, L), dtype=torch.int64, device=x_t.device) if x_next is None else x_next
+    _lib.check(_lib.lib().dsb_posterior_sample(logits_blk.data_ptr(), x_t.data_ptr(), t.data_ptr(), _ptr(t_post), uniform.data_ptr(), sched.data_ptr(),
+                                               x_next.data_ptr(), _ptr(log_prob_out), B, K, L, T, trunc_mode, trunc_r, trunc_k, _stream()),
+               "dsb_posterior_sample")
+    return x_next
