@@ -116,11 +116,21 @@ int dsb_attention(const float* q, long long ldq, const float* k, long long ldk, 
  *   sched   (8, T+1) fp32: rows log_at, log_bt, log_ct, log_1_min_ct (T entries used), log_cumprod_at, log_cumprod_bt,
  *           log_cumprod_ct, log_1_min_cumprod_ct (T+1 entries)      (diffusion_transformer.py:224-231)
  *   trunc_mode 0 none, 1 nucleus 'top{r}r' (trunc_r), 2 top-k 'top{k}p' (trunc_k)
- *   x_next  (B, L) int64;  log_prob_out optional (B, K+1, L) fp32 model_log_prob (NULL to skip)
+ *   x_next  (B, L) int64;  log_prob_out optional (B, K+1, L) fp32 (NULL to skip): the last stage's log-probabilities
+ *   stage_flags select a sub-range of the pipeline so the reference's separately callable (and monkey-patchable,
+ *   dalle_spec.py:207-210) methods map onto the same kernel:
+ *     predict_start          = 0 | SKIP_POSTERIOR | SKIP_SAMPLE           (log_prob_out = log_pred)
+ *     q_posterior            = INPUT_LOGPROB | SKIP_SAMPLE, trunc_mode 0  (log_prob_out = model_log_prob)
+ *     log_sample_categorical = INPUT_LOGPROB | SKIP_POSTERIOR, trunc_mode 0
+ *     p_sample (fused)       = 0
+ *   With INPUT_LOGPROB, `logits` is a (B, K+1, L) log-probability tensor instead of raw (B, L, K) logits.
  * ------------------------------------------------------------------------------------------------------------- */
+#define DSB_STAGE_INPUT_LOGPROB 1
+#define DSB_STAGE_SKIP_POSTERIOR 2
+#define DSB_STAGE_SKIP_SAMPLE 4
 int dsb_posterior_sample(const float* logits, const int64_t* x_t, const int64_t* t, const int64_t* t_post, const float* uniform,
                          const float* sched, int64_t* x_next, float* log_prob_out, int B, int K, int L, int T, int trunc_mode,
-                         float trunc_r, int trunc_k, void* stream);
+                         float trunc_r, int trunc_k, int stage_flags, void* stream);
 
 #ifdef __cplusplus
 }

@@ -39,7 +39,7 @@ SIGNATURES = {
     "dsb_layernorm": [c_vp] * 4 + [c_i, c_i, c_f, c_i, c_vp],
     "dsb_ada_layernorm": [c_vp] * 4 + [c_i] * 4 + [c_f, c_i, c_vp],
     "dsb_attention": [c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_i, c_i, c_i, c_i, c_f, c_i, c_vp],
-    "dsb_posterior_sample": [c_vp] * 8 + [c_i] * 5 + [c_f, c_i, c_vp],
+    "dsb_posterior_sample": [c_vp] * 8 + [c_i] * 5 + [c_f, c_i, c_i, c_vp],
 }
 
 _lib = None

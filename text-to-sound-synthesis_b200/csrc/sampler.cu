@@ -39,12 +39,16 @@ __global__ void __launch_bounds__(SW * 32)
 posterior_sample_kernel(const float* __restrict__ logits, const int64_t* __restrict__ x_t, const int64_t* __restrict__ t,
                         const int64_t* __restrict__ t_post, const float* __restrict__ uniform, const float* __restrict__ sched,
                         int64_t* __restrict__ x_next, float* __restrict__ log_prob_out, int K, int L, int T, int trunc_mode, float trunc_r,
-                        int trunc_k) {
+                        int trunc_k, int stage) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int C = K + 1;
   float* u_s = reinterpret_cast<float*>(smem_raw);                    // [C][SW]  uniforms, later reused for log_prob_out
   float* v_s = u_s + C * SW;                                          // [SW][C]  truncation keys (log-probs)
   double* e_s = reinterpret_cast<double*>(v_s + ((SW * C + 1) & ~1)); // [SW][C]  exp(v) in fp64
+  float* in_s = reinterpret_cast<float*>(e_s + SW * C);               // [C][SW]  input tile when it arrives as (B, K+1, L) log-probs
+  const bool in_logprob = (stage & DSB_STAGE_INPUT_LOGPROB) != 0;
+  const bool do_post = (stage & DSB_STAGE_SKIP_POSTERIOR) == 0;
+  const bool do_sample = (stage & DSB_STAGE_SKIP_SAMPLE) == 0;
   const int b = blockIdx.y;
   const int l0 = blockIdx.x * SW;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -52,16 +56,32 @@ posterior_sample_kernel(const float* __restrict__ logits, const int64_t* __restr
   const bool active = l < L;
 
   // stage the (C x SW) tile of uniforms: u[b, k, l0 + j]
-  const float* ub = uniform + (long long)b * C * L;
-  for (int idx = threadIdx.x; idx < C * SW; idx += SW * 32) {
-    const int k = idx / SW, j = idx - k * SW;
-    u_s[idx] = (l0 + j < L) ? ub[(long long)k * L + l0 + j] : 0.5f;
+  if (do_sample) {
+    const float* ub = uniform + (long long)b * C * L;
+    for (int idx = threadIdx.x; idx < C * SW; idx += SW * 32) {
+      const int k = idx / SW, j = idx - k * SW;
+      u_s[idx] = (l0 + j < L) ? ub[(long long)k * L + l0 + j] : 0.5f;
+    }
+  }
+  if (in_logprob) {
+    const float* ib = logits + (long long)b * C * L;
+    for (int idx = threadIdx.x; idx < C * SW; idx += SW * 32) {
+      const int k = idx / SW, j = idx - k * SW;
+      in_s[idx] = (l0 + j < L) ? ib[(long long)k * L + l0 + j] : -70.f;
+    }
   }
   __syncthreads();
 
   float lp[NJ];
   int xt = 0;
   if (active) {
+    if (in_logprob) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int k = lane + 32 * j;
+        lp[j] = k < C ? in_s[k * SW + warp] : -70.f;
+      }
+    } else {
     const float* row = logits + ((long long)b * L + l) * K;
     float x[NJ];
     float mx = -INFINITY;
@@ -86,6 +106,7 @@ posterior_sample_kernel(const float* __restrict__ logits, const int64_t* __restr
       if (k < K) vlp = fminf(fmaxf((float)(((double)x[j] - (double)mx) - lse), -70.f), 0.f);
       lp[j] = vlp;
     }
+    }  // !in_logprob
     // A.2: truncation
     if (trunc_mode != 0) {
       float* vw = v_s + warp * C;
@@ -118,45 +139,49 @@ posterior_sample_kernel(const float* __restrict__ logits, const int64_t* __restr
         if (!keep) lp[j] = -70.f;
       }
     }
+    if (do_post || do_sample) {
     // A.3: q_posterior closed form
-    xt = (int)x_t[(long long)b * L + l];
-    const bool masked = (xt == K);
-    long long tp = t_post ? t_post[b] : t[b];
-    tp = tp < 0 ? 0 : (tp >= T ? T - 1 : tp);
-    const int tm1 = (int)((tp - 1 + (T + 1)) % (T + 1));
-    const int S1 = T + 1;
-    const float la = sched[0 * S1 + tp], lb = sched[1 * S1 + tp], lc = sched[2 * S1 + tp];
-    const float cA = sched[4 * S1 + tp], cB = sched[5 * S1 + tp], cC = sched[6 * S1 + tp];
-    const float pA = sched[4 * S1 + tm1], pB = sched[5 * S1 + tm1], pC = sched[6 * S1 + tm1], pC1 = sched[7 * S1 + tm1];
-    const float LOGZ = -69.07755279f;  // log(1e-30) in fp32
     float qv[NJ], lq1[NJ];
-    float qmax = -INFINITY;
+    float slse = 0.f, pA = 0.f, pB = 0.f, pC = 0.f, pC1 = 0.f;
+    if (do_post) {
+      xt = (int)x_t[(long long)b * L + l];
+      const bool masked = (xt == K);
+      long long tp = t_post ? t_post[b] : t[b];
+      tp = tp < 0 ? 0 : (tp >= T ? T - 1 : tp);
+      const int tm1 = (int)((tp - 1 + (T + 1)) % (T + 1));
+      const int S1 = T + 1;
+      const float la = sched[0 * S1 + tp], lb = sched[1 * S1 + tp], lc = sched[2 * S1 + tp];
+      const float cA = sched[4 * S1 + tp], cB = sched[5 * S1 + tp], cC = sched[6 * S1 + tp];
+      pA = sched[4 * S1 + tm1]; pB = sched[5 * S1 + tm1]; pC = sched[6 * S1 + tm1]; pC1 = sched[7 * S1 + tm1];
+      const float LOGZ = -69.07755279f;  // log(1e-30) in fp32
+      float qmax = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      const int k = lane + 32 * j;
-      float lqt, l1;
-      if (k < K) {
-        if (masked) { lqt = cC; l1 = lc; }
-        else {
-          const float oh = (k == xt) ? 0.f : LOGZ;
-          lqt = lae(oh + cA, cB);
-          l1 = lae(oh + la, lb);
+      for (int j = 0; j < NJ; ++j) {
+        const int k = lane + 32 * j;
+        float lqt, l1;
+        if (k < K) {
+          if (masked) { lqt = cC; l1 = lc; }
+          else {
+            const float oh = (k == xt) ? 0.f : LOGZ;
+            lqt = lae(oh + cA, cB);
+            l1 = lae(oh + la, lb);
+          }
+        } else {  // k == K (and padding lanes, ignored below)
+          lqt = masked ? 0.f : LOGZ;
+          l1 = lqt;
         }
-      } else {  // k == K (and padding lanes, ignored below)
-        lqt = masked ? 0.f : LOGZ;
-        l1 = lqt;
+        lq1[j] = l1;
+        qv[j] = (k < C) ? lp[j] - lqt : -INFINITY;
+        qmax = fmaxf(qmax, qv[j]);
       }
-      lq1[j] = l1;
-      qv[j] = (k < C) ? lp[j] - lqt : -INFINITY;
-      qmax = fmaxf(qmax, qv[j]);
-    }
-    qmax = wmaxf(qmax);
-    float ssum = 0.f;
+      qmax = wmaxf(qmax);
+      float ssum = 0.f;
 #pragma unroll
-    for (int j = 0; j < NJ; ++j)
-      if (lane + 32 * j < C) ssum += expf(qv[j] - qmax);
-    ssum = wsumf(ssum);
-    const float slse = logf(ssum) + qmax;  // torch.logsumexp
+      for (int j = 0; j < NJ; ++j)
+        if (lane + 32 * j < C) ssum += expf(qv[j] - qmax);
+      ssum = wsumf(ssum);
+      slse = logf(ssum) + qmax;  // torch.logsumexp
+    }
     // A.4: Gumbel-argmax (first index wins ties)
     float best = -INFINITY;
     int besti = 0x7fffffff;
@@ -164,11 +189,14 @@ posterior_sample_kernel(const float* __restrict__ logits, const int64_t* __restr
     for (int j = 0; j < NJ; ++j) {
       const int k = lane + 32 * j;
       if (k < C) {
-        const float qn = qv[j] - slse;
-        const float r = (k < K) ? lae(qn + pA, pB) : lae(qn + pC1, pC);
-        const float outv = fminf(fmaxf(r + lq1[j] + slse, -70.f), 0.f);
-        lp[j] = outv;
-        const float u = u_s[k * SW + warp];
+        float outv = lp[j];
+        if (do_post) {
+          const float qn = qv[j] - slse;
+          const float r = (k < K) ? lae(qn + pA, pB) : lae(qn + pC1, pC);
+          outv = fminf(fmaxf(r + lq1[j] + slse, -70.f), 0.f);
+          lp[j] = outv;
+        }
+        const float u = do_sample ? u_s[k * SW + warp] : 0.5f;
         const float gmb = -logf(-logf(u + 1e-30f) + 1e-30f);
         const float val = gmb + outv;
         if (val > best) { best = val; besti = k; }  // ascending k per lane -> keeps the first maximum
@@ -180,7 +208,8 @@ posterior_sample_kernel(const float* __restrict__ logits, const int64_t* __restr
       const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
       if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
     }
-    if (lane == 0) x_next[(long long)b * L + l] = besti;
+    if (lane == 0 && do_sample) x_next[(long long)b * L + l] = besti;
+    }  // do_post || do_sample
   }
   if (log_prob_out) {  // optional model_log_prob (B, K+1, L): stage through smem for coalesced rows
     __syncthreads();
@@ -202,13 +231,13 @@ posterior_sample_kernel(const float* __restrict__ logits, const int64_t* __restr
 
 template <int NJ>
 static int launch_sampler(const float* logits, const int64_t* x_t, const int64_t* t, const int64_t* t_post, const float* uniform,
-                          const float* sched, int64_t* x_next, float* lpo, int B, int K, int L, int T, int mode, float r, int kk, cudaStream_t st) {
+                          const float* sched, int64_t* x_next, float* lpo, int B, int K, int L, int T, int mode, float r, int kk, int stage, cudaStream_t st) {
   const int C = K + 1;
-  const size_t smem = (size_t)C * SW * 4 + (((size_t)SW * C + 1) & ~(size_t)1) * 4 + (size_t)SW * C * 8;
+  const size_t smem = (size_t)C * SW * 4 + (((size_t)SW * C + 1) & ~(size_t)1) * 4 + (size_t)SW * C * 8 + (size_t)C * SW * 4;
   auto kern = posterior_sample_kernel<NJ>;
   if (smem > 48 * 1024) DSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((L + SW - 1) / SW, B);
-  kern<<<grid, SW * 32, smem, st>>>(logits, x_t, t, t_post, uniform, sched, x_next, lpo, K, L, T, mode, r, kk);
+  kern<<<grid, SW * 32, smem, st>>>(logits, x_t, t, t_post, uniform, sched, x_next, lpo, K, L, T, mode, r, kk, stage);
   DSB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -217,14 +246,16 @@ using namespace dsb;
 
 extern "C" int dsb_posterior_sample(const float* logits, const int64_t* x_t, const int64_t* t, const int64_t* t_post, const float* uniform,
                                     const float* sched, int64_t* x_next, float* log_prob_out, int B, int K, int L, int T, int trunc_mode,
-                                    float trunc_r, int trunc_k, void* stream) {
+                                    float trunc_r, int trunc_k, int stage_flags, void* stream) {
   DSB_REQUIRE(B > 0 && K > 0 && L > 0 && T > 0, "dsb_posterior_sample: bad shape");
   DSB_REQUIRE(trunc_mode >= 0 && trunc_mode <= 2, "dsb_posterior_sample: trunc_mode must be 0, 1 or 2");
   DSB_REQUIRE(K + 1 <= 32 * 33, "dsb_posterior_sample: K=%d too large (max 1055)", K);
+  DSB_REQUIRE((stage_flags & DSB_STAGE_SKIP_SAMPLE) || (uniform && x_next), "dsb_posterior_sample: sampling needs uniform and x_next");
+  DSB_REQUIRE((stage_flags & DSB_STAGE_SKIP_POSTERIOR) || (x_t && t && sched), "dsb_posterior_sample: the posterior needs x_t, t and sched");
   cudaStream_t st = (cudaStream_t)stream;
   const int nj = (K + 1 + 31) / 32;
 #define DSB_SAMPLER_CASE(N) \
-  if (nj <= N) return launch_sampler<N>(logits, x_t, t, t_post, uniform, sched, x_next, log_prob_out, B, K, L, T, trunc_mode, trunc_r, trunc_k, st)
+  if (nj <= N) return launch_sampler<N>(logits, x_t, t, t_post, uniform, sched, x_next, log_prob_out, B, K, L, T, trunc_mode, trunc_r, trunc_k, stage_flags, st)
   DSB_SAMPLER_CASE(2);
   DSB_SAMPLER_CASE(5);
   DSB_SAMPLER_CASE(9);

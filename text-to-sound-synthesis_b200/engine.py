@@ -1,0 +1,150 @@
+"""Denoiser execution engine: packs a Text2ImageTransformer's parameters for the sm_100a kernels and runs one
+forward pass as a fixed sequence of C-ABI launches (12 per layer), CUDA-graph capturable.
+
+What is hoisted relative to the reference (all algebraically identical):
+  * the AdaLayerNorm timestep MLP  Linear(SiLU(emb[t]))  depends only on t -> a (T, 2D) table per norm, built once
+    (reference recomputes it for every token batch: transformer_utils.py:145-147);
+  * cross-attention K/V projections of cond_emb depend only on the caption -> one GEMM for all layers, once per
+    sample() (reference recomputes them every step in every layer: transformer_utils.py:95,97);
+  * query/key/value of self-attention run as one (3D x D) GEMM (reference: three Linears, :45-47).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+
+
+class DenoiserEngine:
+    def __init__(self, transformer, precision: str = "tf32"):
+        if precision not in ("tf32", "fp32"):
+            raise ValueError("precision must be 'tf32' (tcgen05 tensor cores) or 'fp32' (exact FFMA GEMMs)")
+        self.m = transformer
+        self.precision = precision
+        self.packed = False
+        self._ws: Dict[int, dict] = {}
+        self.launches_per_forward = 0
+
+    # ------------------------------------------------------------------ weights
+    @property
+    def device(self):
+        return self.m.to_logits[1].weight.device
+
+    def _prep(self, w: torch.Tensor) -> torch.Tensor:
+        w = w.detach().float().contiguous()
+        return ops.round_tf32(w) if self.precision == "tf32" else w.clone()
+
+    @torch.no_grad()
+    def repack(self) -> None:
+        """(Re)build packed copies from the module's current parameters.  Call after load_state_dict / EMA swaps."""
+        m = self.m
+        if self.device.type != "cuda":
+            raise RuntimeError("DenoiserEngine needs the module on a CUDA device (no CPU fallback)")
+        self.D = m.n_embd
+        self.H = m.n_head
+        self.n_layer = len(m.blocks)
+        self.T = m.diffusion_step
+        D = self.D
+        if D % 64 or D // self.H != 64:
+            raise RuntimeError(f"kernels are specialised for head_dim 64 (n_embd={D}, n_head={self.H})")
+        f = lambda p: p.detach().float().contiguous()
+        self.layers = []
+        kv_w, kv_b = [], []
+        for blk in m.blocks:
+            a1, a2 = blk.attn1, blk.attn2
+            lay = dict(
+                tab1=self._adaln_table(blk.ln1), tab2=self._adaln_table(blk.ln1_1),
+                wqkv=self._prep(torch.cat([a1.query.weight, a1.key.weight, a1.value.weight], 0)),
+                bqkv=f(torch.cat([a1.query.bias, a1.key.bias, a1.value.bias], 0)),
+                wo1=self._prep(a1.proj.weight), bo1=f(a1.proj.bias),
+                wq2=self._prep(a2.query.weight), bq2=f(a2.query.bias),
+                wo2=self._prep(a2.proj.weight), bo2=f(a2.proj.bias),
+                g2=f(blk.ln2.weight), b2=f(blk.ln2.bias), eps2=blk.ln2.eps,
+                w1=self._prep(blk.mlp[0].weight), b1=f(blk.mlp[0].bias),
+                w2=self._prep(blk.mlp[2].weight), bm2=f(blk.mlp[2].bias),
+            )
+            kv_w += [a2.key.weight, a2.value.weight]
+            kv_b += [a2.key.bias, a2.value.bias]
+            self.layers.append(lay)
+        self.wkv_all = self._prep(torch.cat(kv_w, 0))          # (n_layer*2D, cond_dim)
+        self.bkv_all = f(torch.cat(kv_b, 0))
+        self.gf, self.bf, self.epsf = f(m.to_logits[0].weight), f(m.to_logits[0].bias), m.to_logits[0].eps
+        self.wlog, self.blog = self._prep(m.to_logits[1].weight), f(m.to_logits[1].bias)
+        ce = m.content_emb
+        self.emb, self.hemb, self.wemb = f(ce.emb.weight), f(ce.height_emb.weight), f(ce.width_emb.weight)
+        self.K = self.wlog.shape[0]
+        self.packed = True
+        self._ws.clear()
+
+    def _adaln_table(self, ln) -> torch.Tensor:
+        """(T, 2D) table of Linear(SiLU(emb[t])) in exact fp32 (transformer_utils.py:145-147)."""
+        e = ln.emb.weight.detach().float().contiguous()
+        return ops.gemm_f32(ops.silu(e), ln.linear.weight.detach().float().contiguous(), ln.linear.bias.detach().float().contiguous())
+
+    # ------------------------------------------------------------------ workspaces
+    def workspace(self, B: int, L: int) -> dict:
+        key = (B, L)
+        ws = self._ws.get(key)
+        if ws is None:
+            dev, M, D = self.device, B * L, self.D
+            e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+            ws = dict(x=e(B, L, D), h=e(B, L, D), qkv=e(M, 3 * D), att=e(M, D), q2=e(M, D), hid=e(M, self.layers[0]["w1"].shape[0]),
+                      logits=e(B, L, self.K), err=torch.zeros(1, dtype=torch.int32, device=dev))
+            self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------ compute
+    def _linear(self, a, w, bias, residual=None, out=None, gelu=False, round_out=False):
+        if self.precision == "tf32":
+            return ops.gemm(a, w, bias, residual, out, dtype=ops.TF32, gelu=gelu, round_out=round_out)
+        return ops.gemm_f32(a, w, bias, residual, out, gelu=gelu)
+
+    @torch.no_grad()
+    def encode_condition(self, cond_emb: torch.Tensor) -> torch.Tensor:
+        """cond_emb (B, Lc, cond_dim) -> K/V of every layer's cross-attention, (B*Lc, n_layer*2D)."""
+        if not self.packed:
+            self.repack()
+        B, Lc, Cd = cond_emb.shape
+        c = cond_emb.detach().float().reshape(B * Lc, Cd).contiguous()
+        if self.precision == "tf32":
+            c = ops.round_tf32(c)
+        return self._linear(c, self.wkv_all, self.bkv_all)
+
+    @torch.no_grad()
+    def forward(self, ids: torch.Tensor, kv_all: torch.Tensor, t: torch.Tensor, Lc: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """ids (B,L) int64, kv_all from encode_condition, t (B,) int64 -> logits (B, L, K) fp32 (the reference returns its
+        'b l c -> b c l' view, transformer_utils.py:442; callers permute)."""
+        if not self.packed:
+            self.repack()
+        B, L = ids.shape
+        D, H = self.D, self.H
+        ws = self.workspace(B, L)
+        x, h, qkv, att, q2, hid = ws["x"], ws["h"], ws["qkv"], ws["att"], ws["q2"], ws["hid"]
+        rnd = self.precision == "tf32"
+        x2 = x.view(B * L, D)
+        h2 = h.view(B * L, D)
+        scale = 1.0 / math.sqrt(64)
+        n = 0
+        ops.embed_tokens(ids, self.emb, self.hemb, self.wemb, out=x, err_flag=ws["err"]); n += 1
+        for li, lay in enumerate(self.layers):
+            ops.ada_layernorm(x, lay["tab1"], t, out=h, round_out=rnd)
+            self._linear(h2, lay["wqkv"], lay["bqkv"], out=qkv)
+            ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], att, B=B, H=H, Lq=L, Lk=L, scale=scale, round_out=rnd)
+            self._linear(att, lay["wo1"], lay["bo1"], residual=x2, out=x2)
+            ops.ada_layernorm(x, lay["tab2"], t, out=h, round_out=rnd)
+            self._linear(h2, lay["wq2"], lay["bq2"], out=q2)
+            kv = kv_all[:, li * 2 * D:(li + 1) * 2 * D]
+            ops.attention(q2, kv[:, :D], kv[:, D:], att, B=B, H=H, Lq=L, Lk=Lc, scale=scale, round_out=rnd)
+            self._linear(att, lay["wo2"], lay["bo2"], residual=x2, out=x2)
+            ops.layernorm(x, lay["g2"], lay["b2"], out=h, eps=lay["eps2"], round_out=rnd)
+            self._linear(h2, lay["w1"], lay["b1"], out=hid, gelu=True, round_out=rnd)
+            self._linear(hid, lay["w2"], lay["bm2"], residual=x2, out=x2)
+            n += 11
+        ops.layernorm(x, self.gf, self.bf, out=h, eps=self.epsf, round_out=rnd)
+        logits = ws["logits"] if out is None else out
+        self._linear(h2, self.wlog, self.blog, out=logits.view(B * L, self.K))
+        self.launches_per_forward = n + 2
+        return logits

@@ -158,14 +158,28 @@ def attention(q, k, v, out, *, B, H, Lq, Lk, scale, round_out=False):
     return out
 
 
-def posterior_sample(logits_blk, x_t, t, uniform, sched, *, T, trunc_mode=1, trunc_r=0.85, trunc_k=0, t_post=None, x_next=None, log_prob_out=None):
-    """logits_blk (B,L,K) fp32 contiguous; x_t (B,L) int64; uniform (B,K+1,L); sched (8,T+1) -> x_next (B,L) int64."""
-    _need_cuda(logits_blk, x_t, t, uniform, sched)
-    B, L, K = logits_blk.shape
-    assert logits_blk.is_contiguous() and uniform.is_contiguous() and x_t.is_contiguous() and sched.is_contiguous()
-    assert uniform.shape == (B, K + 1, L) and sched.shape == (8, T + 1)
-    x_next = torch.empty((B, L), dtype=torch.int64, device=x_t.device) if x_next is None else x_next
-    _lib.check(_lib.lib().dsb_posterior_sample(logits_blk.data_ptr(), x_t.data_ptr(), t.data_ptr(), _ptr(t_post), uniform.data_ptr(), sched.data_ptr(),
-                                               x_next.data_ptr(), _ptr(log_prob_out), B, K, L, T, trunc_mode, trunc_r, trunc_k, _stream()),
-               "dsb_posterior_sample")
+STAGE_INPUT_LOGPROB, STAGE_SKIP_POSTERIOR, STAGE_SKIP_SAMPLE = 1, 2, 4
+
+
+def posterior_sample(inp, x_t, t, uniform, sched, *, T, trunc_mode=1, trunc_r=0.85, trunc_k=0, t_post=None, x_next=None, log_prob_out=None,
+                     stage=0):
+    """Fused p_sample tail (see dsb_posterior_sample).  inp: raw logits (B,L,K) fp32, or (B,K+1,L) log-probs with STAGE_INPUT_LOGPROB;
+    x_t (B,L) int64; uniform (B,K+1,L); sched (8,T+1) -> x_next (B,L) int64 (None when sampling is skipped)."""
+    _need_cuda(inp, x_t, t, uniform, sched, log_prob_out)
+    if stage & STAGE_INPUT_LOGPROB:
+        B, C_, L = inp.shape
+        K = C_ - 1
+    else:
+        B, L, K = inp.shape
+    for t_ in (inp, x_t, uniform, sched, log_prob_out, t, t_post):
+        if t_ is not None and not t_.is_contiguous():
+            raise RuntimeError("posterior_sample needs contiguous tensors")
+    if uniform is not None and tuple(uniform.shape) != (B, K + 1, L):
+        raise RuntimeError(f"uniform must be (B,K+1,L)={(B, K + 1, L)}, got {tuple(uniform.shape)}")
+    if sched is not None and tuple(sched.shape) != (8, T + 1):
+        raise RuntimeError("sched must be (8, T+1)")
+    if not (stage & STAGE_SKIP_SAMPLE) and x_next is None:
+        x_next = torch.empty((B, L), dtype=torch.int64, device=inp.device)
+    _lib.check(_lib.lib().dsb_posterior_sample(inp.data_ptr(), _ptr(x_t), _ptr(t), _ptr(t_post), _ptr(uniform), _ptr(sched), _ptr(x_next),
+                                               _ptr(log_prob_out), B, K, L, T, trunc_mode, trunc_r, trunc_k, stage, _stream()), "dsb_posterior_sample")
     return x_next
