@@ -27,6 +27,7 @@ class DenoiserEngine:
         self.packed = False
         self._ws: Dict[int, dict] = {}
         self.launches_per_forward = 0
+        self.generation = 0  # bumped by repack(): captured CUDA graphs that baked old pointers must be rebuilt
 
     # ------------------------------------------------------------------ weights
     @property
@@ -77,6 +78,7 @@ class DenoiserEngine:
         self.emb, self.hemb, self.wemb = f(ce.emb.weight), f(ce.height_emb.weight), f(ce.width_emb.weight)
         self.K = self.wlog.shape[0]
         self.packed = True
+        self.generation += 1
         self._ws.clear()
 
     def _adaln_table(self, ln) -> torch.Tensor:

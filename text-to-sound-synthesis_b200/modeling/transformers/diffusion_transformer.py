@@ -1,0 +1,300 @@
+"""Drop-in for sound_synthesis/modeling/transformers/diffusion_transformer.py::DiffusionTransformer (inference side).
+
+Same constructor arguments, buffers and state_dict keys as the reference (ckpt['ema'] loads unchanged).  The 100-step
+loop carries token ids (not (B,K+1,L) log-one-hot tensors); each step is  denoiser (DenoiserEngine)  ->  one fused
+posterior/truncation/Gumbel kernel, optionally replayed as a CUDA graph.  The reference's separately callable methods
+(`predict_start`, `q_posterior`, `log_sample_categorical`, `p_sample`, `p_pred`) are kept -- and stay re-bindable
+instance attributes, because reference code monkey-patches them (models/dalle_spec.py:207-210) -- each mapped onto the
+same kernel through its stage flags.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+from torch import nn
+
+from ... import ops
+from ...utils.misc import instantiate_from_config
+
+_SCHED_ROWS = ["log_at", "log_bt", "log_ct", "log_1_min_ct", "log_cumprod_at", "log_cumprod_bt", "log_cumprod_ct", "log_1_min_cumprod_ct"]
+
+
+def alpha_schedule(time_step, N=100, att_1=0.99999, att_T=0.000009, ctt_1=0.000009, ctt_T=0.9):
+    """fp64 mask-and-uniform schedule; must stay bit-identical to the reference (diffusion_transformer.py:122-151)."""
+    att = np.arange(0, time_step) / (time_step - 1) * (att_T - att_1) + att_1
+    att = np.concatenate(([1], att))
+    at = att[1:] / att[:-1]
+    ctt = np.arange(0, time_step) / (time_step - 1) * (ctt_T - ctt_1) + ctt_1
+    ctt = np.concatenate(([0], ctt))
+    one_minus_ctt = 1 - ctt
+    one_minus_ct = one_minus_ctt[1:] / one_minus_ctt[:-1]
+    ct = 1 - one_minus_ct
+    bt = (1 - at - ct) / N
+    att = np.concatenate((att[1:], [1]))
+    ctt = np.concatenate((ctt[1:], [0]))
+    btt = (1 - att - ctt) / N
+    return at, bt, ct, att, btt, ctt
+
+
+def parse_truncation(sample_type):
+    """'top0.85r' -> (1, 0.85, 0); 'top20p' -> (2, 0, 20); None/'normal' -> (0, 0, 0)   (dalle_spec.py:146-177)."""
+    if not sample_type:
+        return 0, 0.0, 0
+    head = sample_type.split(",")[0]
+    if head[:3] != "top":
+        return 0, 0.0, 0
+    if head[-1] == "r":
+        return 1, float(head[3:-1]), 0
+    if head[-1] == "p":
+        return 2, 0.0, int(head[3:-1])
+    raise ValueError(f"wrong sample type {sample_type!r}")
+
+
+class DiffusionTransformer(nn.Module):
+    def __init__(self, *, content_emb_config=None, condition_emb_config=None, transformer_config=None, diffusion_step=100,
+                 alpha_init_type="cos", auxiliary_loss_weight=0, adaptive_auxiliary_loss=False, mask_weight=[1, 1]):
+        super().__init__()
+        if condition_emb_config is None:
+            self.condition_emb = None
+        else:
+            self.condition_emb = instantiate_from_config(condition_emb_config)
+            self.condition_dim = self.condition_emb.embed_dim
+        transformer_config["params"]["diffusion_step"] = diffusion_step  # the reference mutates the config the same way (:177-178)
+        transformer_config["params"]["content_emb_config"] = content_emb_config
+        self.transformer = instantiate_from_config(transformer_config)
+        self.content_seq_len = transformer_config["params"]["content_seq_len"]
+        self.amp = False
+        self.num_classes = self.transformer.content_emb.num_embed  # K + 1
+        self.loss_type = "vb_stochastic"
+        self.shape = transformer_config["params"]["content_seq_len"]
+        self.num_timesteps = diffusion_step
+        self.parametrization = "x0"
+        self.auxiliary_loss_weight = auxiliary_loss_weight
+        self.adaptive_auxiliary_loss = adaptive_auxiliary_loss
+        self.mask_weight = mask_weight
+        if alpha_init_type != "alpha1":
+            raise ValueError("alpha_init_type must be 'alpha1' (the reference only prints a warning and then fails, :196-199)")
+        at, bt, ct, att, btt, ctt = alpha_schedule(self.num_timesteps, N=self.num_classes)
+        t64 = lambda a: torch.tensor(a.astype("float64"))
+        log_at, log_bt, log_ct = torch.log(t64(at)), torch.log(t64(bt)), torch.log(t64(ct))
+        log_cumprod_at, log_cumprod_bt, log_cumprod_ct = torch.log(t64(att)), torch.log(t64(btt)), torch.log(t64(ctt))
+        log_1_min_a = lambda a: torch.log(1 - a.exp() + 1e-40)
+        log_1_min_ct = log_1_min_a(log_ct)
+        log_1_min_cumprod_ct = log_1_min_a(log_cumprod_ct)
+        lae = lambda a, b: torch.max(a, b) + torch.log(torch.exp(a - torch.max(a, b)) + torch.exp(b - torch.max(a, b)))
+        assert lae(log_ct, log_1_min_ct).abs().sum().item() < 1.0e-5
+        assert lae(log_cumprod_ct, log_1_min_cumprod_ct).abs().sum().item() < 1.0e-5
+        self.diffusion_acc_list = [0] * self.num_timesteps
+        self.diffusion_keep_list = [0] * self.num_timesteps
+        for name, v in (("log_at", log_at), ("log_bt", log_bt), ("log_ct", log_ct), ("log_cumprod_at", log_cumprod_at),
+                        ("log_cumprod_bt", log_cumprod_bt), ("log_cumprod_ct", log_cumprod_ct), ("log_1_min_ct", log_1_min_ct),
+                        ("log_1_min_cumprod_ct", log_1_min_cumprod_ct)):
+            self.register_buffer(name, v.float())
+        self.register_buffer("Lt_history", torch.zeros(self.num_timesteps))
+        self.register_buffer("Lt_count", torch.zeros(self.num_timesteps))
+        # knobs of the fused path (not in the reference): truncation applied inside the sampler kernel, CUDA-graph replay
+        self.truncation = None
+        self.use_cuda_graph = True
+        self._sched_cache = None
+        self._graphs = {}
+        self.last_gpu_launches = 0
+
+    # ------------------------------------------------------------------ helpers
+    @property
+    def device(self):
+        return self.transformer.to_logits[-1].weight.device
+
+    def _sched(self) -> torch.Tensor:
+        """(8, T+1) fp32 table in the row order dsb_posterior_sample expects, rebuilt if the buffers moved/changed."""
+        key = (self.log_at.data_ptr(), self.log_at.device)
+        if self._sched_cache is None or self._sched_cache[0] != key:
+            T = self.num_timesteps
+            s = torch.zeros(8, T + 1, dtype=torch.float32, device=self.log_at.device)
+            for i, n in enumerate(_SCHED_ROWS):
+                b = getattr(self, n)
+                s[i, : b.numel()] = b
+            self._sched_cache = (key, s)
+        return self._sched_cache[1]
+
+    def _trunc(self):
+        return parse_truncation(self.truncation)
+
+    # ------------------------------------------------------------------ reference-compatible stage methods
+    @torch.no_grad()
+    def predict_start(self, log_x_t, cond_emb, t):
+        """p(x0|xt): (B,K+1,L) log-one-hot -> log_pred (B,K+1,L)  (diffusion_transformer.py:269-291); applies self.truncation if set."""
+        x_t = log_x_t.argmax(1)
+        out = self.transformer(x_t, cond_emb, t)  # (B,K,L) view of the (B,L,K) kernel output
+        assert out.size(0) == x_t.size(0) and out.size(1) == self.num_classes - 1 and out.size()[2:] == x_t.size()[1:]
+        blk = out.permute(0, 2, 1)
+        assert blk.is_contiguous()
+        B, L, K = blk.shape
+        log_pred = torch.empty(B, K + 1, L, dtype=torch.float32, device=blk.device)
+        mode, r, k = self._trunc()
+        ops.posterior_sample(blk, None, None, None, None, T=self.num_timesteps, trunc_mode=mode, trunc_r=r, trunc_k=k, log_prob_out=log_pred,
+                             stage=ops.STAGE_SKIP_POSTERIOR | ops.STAGE_SKIP_SAMPLE)
+        return log_pred
+
+    @torch.no_grad()
+    def q_posterior(self, log_x_start, log_x_t, t):
+        """log p_theta(x_{t-1}|x_t) (diffusion_transformer.py:293-339); log_x_t is a log-one-hot (only its argmax is used)."""
+        assert t.min().item() >= 0 and t.max().item() < self.num_timesteps
+        x_t = log_x_t.argmax(1).contiguous()
+        out = torch.empty_like(log_x_start, memory_format=torch.contiguous_format)
+        ops.posterior_sample(log_x_start.contiguous().float(), x_t, t.contiguous(), None, self._sched(), T=self.num_timesteps, trunc_mode=0,
+                             log_prob_out=out, stage=ops.STAGE_INPUT_LOGPROB | ops.STAGE_SKIP_SAMPLE)
+        return out
+
+    @torch.no_grad()
+    def log_sample_categorical(self, logits, return_index=False):
+        """Gumbel-argmax with torch.rand_like's stream (diffusion_transformer.py:359-368); returns the log-one-hot re-encoding."""
+        uniform = torch.rand_like(logits)
+        ids = ops.posterior_sample(logits.contiguous().float(), None, None, uniform, None, T=self.num_timesteps, trunc_mode=0,
+                                   stage=ops.STAGE_INPUT_LOGPROB | ops.STAGE_SKIP_POSTERIOR)
+        return ids if return_index else index_to_log_onehot(ids, self.num_classes)
+
+    def p_pred(self, log_x, cond_emb, t):
+        log_x_recon = self.predict_start(log_x, cond_emb, t)
+        return self.q_posterior(log_x_start=log_x_recon, log_x_t=log_x, t=t)
+
+    @torch.no_grad()
+    def p_sample(self, log_x, cond_emb, t):
+        return self.log_sample_categorical(self.p_pred(log_x, cond_emb, t))
+
+    def q_pred(self, log_x_start, t):
+        raise NotImplementedError("q_pred is only reached from training / content-conditioned sampling (SURVEY.md section 8 row A13: next)")
+
+    # ------------------------------------------------------------------ fused fast path
+    def _stages_overridden(self) -> bool:
+        """True when a caller re-bound one of the stage methods on the instance (e.g. the reference DALLE's truncation wrapper)."""
+        return any(n in self.__dict__ for n in ("predict_start", "q_posterior", "log_sample_categorical", "p_sample", "p_pred"))
+
+    @torch.no_grad()
+    def _fused_step(self, st):
+        """One p_sample on ids: denoiser -> fused sampler (reads st['x'], st['t'], st['t_post']; writes st['x'])."""
+        eng = self.transformer.engine
+        logits = eng.forward(st["x"], st["kv"], st["t"], st["Lc"])
+        u = torch.rand(st["ushape"], dtype=torch.float32, device=logits.device)  # == torch.rand_like(model_log_prob) in the reference
+        mode, r, k = st["trunc"]
+        ops.posterior_sample(logits, st["x"], st["t"], u, self._sched(), T=self.num_timesteps, trunc_mode=mode, trunc_r=r, trunc_k=k,
+                             t_post=st["t_post"], x_next=st["x_next"])
+        st["x"].copy_(st["x_next"])
+
+    def _run_steps(self, cond_emb, batch_size, steps, post_steps, x_init=None):
+        dev = self.device
+        if dev.type != "cuda":
+            raise RuntimeError("DiffusionTransformer sampling needs a CUDA device (no CPU fallback)")
+        eng = self.transformer.engine
+        K, L, B = self.num_classes - 1, self.shape, batch_size
+        kv = eng.encode_condition(cond_emb)  # (re)packs the weights if they changed
+        key = (B, cond_emb.shape[1], self.truncation)
+        st = self._graphs.get(key) if self.use_cuda_graph else None
+        if st is not None and st["generation"] != eng.generation:
+            st = None  # weights were repacked: the captured graph holds stale pointers
+        if st is None:
+            st = dict(x=torch.empty(B, L, dtype=torch.int64, device=dev), x_next=torch.empty(B, L, dtype=torch.int64, device=dev),
+                      t=torch.zeros(B, dtype=torch.int64, device=dev), t_post=torch.zeros(B, dtype=torch.int64, device=dev),
+                      kv=torch.empty_like(kv), Lc=cond_emb.shape[1], ushape=(B, K + 1, L), trunc=self._trunc(), graph=None, generation=eng.generation)
+        st["kv"].copy_(kv)
+        if x_init is None:
+            st["x"].fill_(K)  # all-[MASK] start state (diffusion_transformer.py:633-636)
+        else:
+            st["x"].copy_(x_init)
+        if self.use_cuda_graph and st["graph"] is None:
+            # warm-up on a side stream (lazy inits: cudaFuncSetAttribute, workspaces), then capture one step.  The warm-up
+            # must not disturb the sampling RNG stream or the token state, so both are restored.
+            rng = torch.cuda.get_rng_state(dev)
+            x_save = st["x"].clone()
+            s = torch.cuda.Stream(device=dev)
+            s.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(s):
+                self._fused_step(st)
+            torch.cuda.current_stream(dev).wait_stream(s)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._fused_step(st)
+            st["graph"] = g
+            st["x"].copy_(x_save)
+            torch.cuda.set_rng_state(rng, dev)
+            self._graphs[key] = st
+        for ti, tp in zip(steps, post_steps):
+            st["t"].fill_(ti)
+            st["t_post"].fill_(tp)
+            if st["graph"] is not None:
+                st["graph"].replay()
+            else:
+                self._fused_step(st)
+        self.last_gpu_launches = len(steps) * (eng.launches_per_forward + 1)
+        return st["x"].clone()
+
+    def _cond(self, condition_token, condition_embed):
+        if self.condition_emb is not None:
+            with torch.no_grad():
+                return self.condition_emb(condition_token).float()
+        return condition_embed.float() if condition_embed is not None else None
+
+    @torch.no_grad()
+    def sample(self, condition_token, condition_mask, condition_embed, content_token=None, filter_ratio=0.5, temperature=1.0,
+               return_att_weight=False, return_logits=False, content_logits=None, print_log=True, **kwargs):
+        """Reference signature (diffusion_transformer.py:587-659).  filter_ratio=0 (the only value the inference script uses,
+        generate_samples_batch.py:164) starts from all-[MASK]."""
+        batch_size = condition_token.shape[0] if condition_token is not None else kwargs["batch_size"]
+        start_step = int(self.num_timesteps * filter_ratio)
+        cond_emb = self._cond(condition_token, condition_embed)
+        if start_step != 0:
+            raise NotImplementedError("content-conditioned sampling (filter_ratio > 0) needs q_sample: SURVEY.md section 8 'next'")
+        steps = list(range(self.num_timesteps - 1, -1, -1))
+        if self._stages_overridden():
+            content_token = self._sample_unfused(cond_emb, batch_size, steps, steps)
+        else:
+            content_token = self._run_steps(cond_emb, batch_size, steps, steps)
+        output = {"content_token": content_token}
+        if return_logits:
+            output["logits"] = torch.exp(index_to_log_onehot(content_token, self.num_classes))
+        return output
+
+    @torch.no_grad()
+    def sample_fast(self, condition_token, condition_mask, condition_embed, content_token=None, filter_ratio=0.5, temperature=1.0,
+                    return_att_weight=False, return_logits=False, content_logits=None, print_log=True, skip_step=1, **kwargs):
+        """Skip-step sampler (diffusion_transformer.py:748-812): the denoiser sees t, q_posterior sees t - skip_step."""
+        batch_size = condition_token.shape[0] if condition_token is not None else kwargs["batch_size"]
+        assert int(self.num_timesteps * filter_ratio) == 0
+        cond_emb = self._cond(condition_token, condition_embed)
+        steps = list(range(self.num_timesteps - 1, -1, -1 - skip_step))
+        if steps[-1] != 0:
+            steps.append(0)
+        post = [s - skip_step if s > skip_step else s for s in steps]
+        if self._stages_overridden():
+            content_token = self._sample_unfused(cond_emb, batch_size, steps, post)
+        else:
+            content_token = self._run_steps(cond_emb, batch_size, steps, post)
+        output = {"content_token": content_token}
+        if return_logits:
+            output["logits"] = torch.exp(index_to_log_onehot(content_token, self.num_classes))
+        return output
+
+    @torch.no_grad()
+    def _sample_unfused(self, cond_emb, batch_size, steps, post_steps):
+        """Stage-by-stage loop through the (possibly re-bound) reference-named methods; every stage is still a CUDA kernel."""
+        dev = self.device
+        K, L = self.num_classes - 1, self.shape
+        log_z = index_to_log_onehot(torch.full((batch_size, L), K, dtype=torch.int64, device=dev), self.num_classes)
+        for ti, tp in zip(steps, post_steps):
+            t = torch.full((batch_size,), ti, device=dev, dtype=torch.long)
+            if ti == tp:
+                log_z = self.p_sample(log_z, cond_emb, t)
+            else:
+                log_x_recon = self.predict_start(log_z, cond_emb, t)
+                log_z = self.log_sample_categorical(self.q_posterior(log_x_start=log_x_recon, log_x_t=log_z,
+                                                                     t=torch.full((batch_size,), tp, device=dev, dtype=torch.long)))
+        return log_z.argmax(1)
+
+    def forward(self, input, return_loss=False, return_logits=True, return_att_weight=False, is_train=True, **kwargs):
+        raise NotImplementedError("training forward/_train_loss (config 4) is SURVEY.md section 8 row A13 -- after the inference path")
+
+
+def index_to_log_onehot(x, num_classes):
+    """log(clamp(one_hot, 1e-30)) carrier (diffusion_transformer.py:45-56); memory-format plumbing only."""
+    out = torch.full((x.shape[0], num_classes, x.shape[1]), float(np.log(np.float32(1e-30))), dtype=torch.float32, device=x.device)
+    out.scatter_(1, x.unsqueeze(1), 0.0)
+    return out

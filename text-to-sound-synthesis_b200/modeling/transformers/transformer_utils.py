@@ -113,4 +113,4 @@ class Text2ImageTransformer(nn.Module):
         """input (B,L) int64 ids, cond_emb (B,Lc,condition_dim) fp32, t (B,) int64 -> logits (B, K, L) (view, as the reference's rearrange)."""
         kv = self.engine.encode_condition(cond_emb)
         logits = self.engine.forward(input.contiguous(), kv, t.to(input.device).contiguous(), cond_emb.shape[1])
-        return logits.permute(0, 2, 1)
+        return logits.clone().permute(0, 2, 1)  # clone: the engine reuses its workspace on the next call
