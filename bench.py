@@ -41,12 +41,12 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.index, self.rows, self._halt = index, [], threading.Event()
 
     def run(self):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
@@ -54,10 +54,10 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=3)
         sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -106,12 +106,12 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def build_model(K, n_layer=19):
+def build_model(K, n_layer=19, precision="f16"):
     import _pkg
     _pkg.load()
     from tests.test_gpu_transformer import build_dt
     torch.manual_seed(0)
-    m = build_dt(K, 1024, n_layer, 16, 512)
+    m = build_dt(K, 1024, n_layer, 16, 512, precision=precision)
     m.truncation = "top0.85r"
     return m
 
@@ -136,12 +136,13 @@ def gemm_roofline(model, B, peaks, peaks_src):
     M = B * L
     st = torch.cuda.current_stream()
     h2, x2 = ws["h"].view(M, D), ws["x"].view(M, D)
-    shapes = [("qkv", lambda l: ops.gemm(h2, l["wqkv"], l["bqkv"], out=ws["qkv"]), 3 * D, D),
-              ("proj1", lambda l: ops.gemm(ws["att"], l["wo1"], l["bo1"], residual=x2, out=x2), D, D),
-              ("q2", lambda l: ops.gemm(h2, l["wq2"], l["bq2"], out=ws["q2"]), D, D),
-              ("proj2", lambda l: ops.gemm(ws["att"], l["wo2"], l["bo2"], residual=x2, out=x2), D, D),
-              ("mlp1", lambda l: ops.gemm(h2, l["w1"], l["b1"], out=ws["hid"], gelu=True, round_out=True), 4 * D, D),
-              ("mlp2", lambda l: ops.gemm(ws["hid"], l["w2"], l["bm2"], residual=x2, out=x2), D, 4 * D)]
+    lin = eng._linear
+    shapes = [("qkv", lambda l: lin(h2, l["wqkv"], l["bqkv"], out=ws["qkv"]), 3 * D, D),
+              ("proj1", lambda l: lin(ws["att"], l["wo1"], l["bo1"], residual=x2, out=x2), D, D),
+              ("q2", lambda l: lin(h2, l["wq2"], l["bq2"], out=ws["q2"]), D, D),
+              ("proj2", lambda l: lin(ws["att"], l["wo2"], l["bo2"], residual=x2, out=x2), D, D),
+              ("mlp1", lambda l: lin(h2, l["w1"], l["b1"], out=ws["hid"], gelu=True, round_out=True), 4 * D, D),
+              ("mlp2", lambda l: lin(ws["hid"], l["w2"], l["bm2"], residual=x2, out=x2), D, 4 * D)]
     ws["x"].normal_(); ws["h"].normal_(); ws["att"].normal_(); ws["hid"].normal_()
     per = {}
     tot_ms, tot_flop, launches = 0.0, 0.0, 0
@@ -159,11 +160,13 @@ def gemm_roofline(model, B, peaks, peaks_src):
         launches += 1
     achieved = tot_flop / (tot_ms * 1e-3) / 1e12
     peak_bf16 = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
-    peak = peak_bf16 / 2.0  # kind::tf32 issues at half the kind::f16 rate
-    return {"bound": "tensor", "kernel": "gemm_tcgen05_kernel<tf32>", "achieved": round(achieved, 1), "peak": round(peak, 1), "unit": "TFLOP/s",
+    tf32 = eng.precision == "tf32"
+    peak = peak_bf16 / 2.0 if tf32 else peak_bf16  # kind::tf32 issues at half the kind::f16 rate; fp16 == bf16 rate
+    return {"bound": "tensor", "kernel": f"gemm_tcgen05_kernel<{eng.precision}>", "achieved": round(achieved, 1), "peak": round(peak, 1), "unit": "TFLOP/s",
             "frac": round(achieved / peak, 4), "traffic": None,
-            "peak_source": f"{peaks_src} MEASURED_PEAKS.json bf16_tflops_sustained={peak_bf16} / 2 (tf32 dense rate is half of bf16)",
-            "frac_of_bf16_peak": round(achieved / peak_bf16, 4), "per_gemm": per,
+            "peak_source": f"{peaks_src} MEASURED_PEAKS.json bf16_tflops_sustained={peak_bf16}" + (" / 2 (tf32 dense rate is half of bf16)" if tf32 else
+                           " (cuBLAS bf16 GEMM inside a long loop; kind::f16 fp16 operands issue at the same rate)"),
+            "per_gemm": per,
             "flop_per_launch_avg": tot_flop / launches, "us_per_launch_avg": round(tot_ms * 1e3 / launches, 2)}
 
 
@@ -178,7 +181,7 @@ def run_gpu_arm(args):
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     B, K = args.batch, args.codebook
-    model = build_model(K, args.layers)
+    model = build_model(K, args.layers, args.precision)
     cond_host = synthetic_cond(B, 1 + rank).pin_memory()
     cond_dev = cond_host.to(dev)
     gathered = [torch.empty(B, 265, dtype=torch.int64, device=dev) for _ in range(world)] if world > 1 else None
@@ -237,7 +240,7 @@ def run_gpu_arm(args):
             cpu = {"value": v, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample}
         line = {"metric": "clips/sec (10s audio, 100 diffusion steps)", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "tf32", "data": "synthetic",
+                "dtype": {"f16": "f16 (fp16 operands, fp32 accumulate)", "tf32": "tf32", "fp32": "f32"}[args.precision], "data": "synthetic",
                 "config": {"workload": f"Diffsound AudioCaps inference: batch {B}/GPU, 100 steps, K={K} codebook, 265-token grid, top0.85r "
                                        f"(BASELINE.json configs[1]); {args.layers}-layer D=1024 denoiser, random-init weights, synthetic caption embeddings",
                            "global_batch": B * world, "parallelism": f"dp{world} (independent captions per rank, all_gather of tokens)",
@@ -260,6 +263,7 @@ def main():
     ap.add_argument("--layers", type=int, default=19)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="f16", choices=["f16", "tf32", "fp32"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -28,11 +28,19 @@ extern "C" {
 /* operand types of the tensor-core GEMM */
 #define DSB_DTYPE_TF32 0 /* fp32 containers, tcgen05 kind::tf32 (inputs should be pre-rounded with dsb_round_tf32) */
 #define DSB_DTYPE_BF16 1 /* bf16 containers, tcgen05 kind::f16 */
+#define DSB_DTYPE_F16 2  /* fp16 containers, tcgen05 kind::f16: same 11-bit significand as TF32 at twice the MMA rate */
 
 /* epilogue flags */
 #define DSB_GEMM_GELU2 1      /* x * sigmoid(1.702 x)           (reference transformer_utils.py:111-115) */
 #define DSB_GEMM_ROUND_TF32 2 /* round the fp32 output to tf32 (it feeds another tf32 GEMM) */
 #define DSB_GEMM_OUT_BF16 4   /* store bf16 instead of fp32 */
+#define DSB_GEMM_LRELU 8      /* LeakyReLU(0.2)                 (reference vocoder/modules.py:76,79) */
+#define DSB_GEMM_TANH 16      /* tanh                           (reference vocoder/modules.py:123) */
+#define DSB_GEMM_OUT_F16 256   /* store fp16 instead of fp32 */
+#define DSB_GEMM_RES_BEFORE_ACT 128 /* add the residual before the activation (default: after) */
+/* GroupNorm-apply flags (share the ROUND_TF32 bit) */
+#define DSB_GN_SWISH 32       /* x * sigmoid(x) after the affine (reference model.py:29-31) */
+#define DSB_GN_COMPACT 64     /* write (B, Lp, C) tokens instead of the zero-padded image */
 
 const char* dsb_last_error(void);
 int dsb_version(void);
@@ -78,6 +86,7 @@ int dsb_gemm_f32(const float* A, const float* W, const float* bias, const float*
 /* elementwise helpers */
 int dsb_round_tf32(const float* in, float* out, long long n, void* stream);
 int dsb_f32_to_bf16(const float* in, void* out_bf16, long long n, void* stream);
+int dsb_f32_to_f16(const float* in, void* out_f16, long long n, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Denoiser pieces (reference sound_synthesis/modeling/transformers/transformer_utils.py,
@@ -131,6 +140,35 @@ int dsb_attention(const float* q, long long ldq, const float* k, long long ldk, 
 int dsb_posterior_sample(const float* logits, const int64_t* x_t, const int64_t* t, const int64_t* t_post, const float* uniform,
                          const float* sched, int64_t* x_next, float* log_prob_out, int B, int K, int L, int T, int trunc_mode,
                          float trunc_r, int trunc_k, int stage_flags, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * SpecVQGAN decoder support (reference Diffsound/specvqgan/modules/diffusionmodules/model.py:570-671 Decoder and its
+ * blocks; sound_synthesis/modeling/models/dalle_spec.py:80-91 decode_to_img).  Activations are fp32 channels-last images
+ * with a one-pixel zero border, (B, H+2, W+2, C); the convolutions themselves are dsb_gemm_ex calls with 9 (3x3) or 1 (1x1)
+ * taps and the geo_* border mask.
+ * ------------------------------------------------------------------------------------------------------------- */
+/* ColumnMajor(reverse=True) + get_codebook_entry (permuter.py:46-49, quantize.py:88-103): ids (B, H*W) int64 in column-major
+ * token order -> padded z (B, H+2, W+2, E). */
+int dsb_codebook_gather_padded(const int64_t* ids, const float* codebook, float* out, int B, int H, int W, int E, int n_codes, int flags,
+                               int* err_flag, void* stream);
+/* GroupNorm statistics: stats (B, groups, 2) fp64 = (sum, sum of squares) over the P = (H+2)(W+2) rows of each image */
+int dsb_groupnorm_stats(const float* x, double* stats, int B, int P, int C, int groups, void* stream);
+/* GroupNorm affine (+swish) from those statistics (model.py:34-35, :29-31); border stays zero.  flags: DSB_GN_SWISH,
+ * DSB_GEMM_ROUND_TF32, DSB_GN_COMPACT (then out is (B, Lp, C) tokens in row-major pixel order, rows >= H*W zero). */
+int dsb_groupnorm_apply(const float* x, const double* stats, const float* gamma, const float* beta, float* out, int B, int H, int W, int C,
+                        int groups, float eps, int flags, int Lp, void* stream);
+/* nearest-neighbour x2 (model.py:48-52): (B, H+2, W+2, C) -> (B, 2H+2, 2W+2, C) */
+int dsb_upsample2x_padded(const float* in, float* out, int B, int H, int W, int C, int flags, void* stream);
+/* AttnBlock plumbing (model.py:202-226): in-place masked row softmax; scatter-add of (B, Lp, C) tokens into the padded image */
+int dsb_softmax_rows(float* x, long long rows, int n_valid, int ld, int flags, void* stream);
+int dsb_tokens_add_to_padded(const float* tok, float* xpad, int B, int H, int W, int C, int Lp, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * MelGAN generator support (reference Diffsound/vocoder/modules.py:72-130): LeakyReLU(slope) + reflection / zero padding
+ * into a channels-last (B, T+2*pad, C) buffer; in_channel_major reads a (B, C, T) input (the mel spectrogram).
+ * ------------------------------------------------------------------------------------------------------------- */
+int dsb_lrelu_pad(const float* in, float* out, int B, int T, int C, int pad, float slope, int reflect, int in_channel_major, int flags,
+                  void* stream);
 
 #ifdef __cplusplus
 }

@@ -75,6 +75,34 @@ def test_gemm_bf16(G):
     assert G.relerr(outh.float(), _ref(a.float(), w.float())) < 5e-3
 
 
+def test_gemm_f16(G):
+    g = torch.Generator().manual_seed(3)
+    M, N, K = 4240, 1024, 1024
+    a = torch.randn(M, K, generator=g).half()
+    w = (torch.randn(N, K, generator=g) * 0.05).half()
+    bias = torch.randn(N, generator=g)
+    ref = _ref(a.float(), w.float(), bias, gelu=True)
+    out = G.ops.gemm(a.cuda(), w.cuda(), bias.cuda(), dtype=G.ops.F16, gelu=True)
+    assert G.relerr(out, ref) < 2e-5
+    outh = G.ops.gemm(a.cuda(), w.cuda(), bias.cuda(), dtype=G.ops.F16, gelu=True, out_f16=True)
+    assert outh.dtype == torch.float16 and G.relerr(outh.float(), ref) < 1e-3
+
+
+def test_gemm_activation_flags(G):
+    g = torch.Generator().manual_seed(6)
+    M, N, K = 300, 64, 96
+    a = G.tf32_round_ref(torch.randn(M, K, generator=g))
+    w = G.tf32_round_ref(torch.randn(N, K, generator=g) * 0.2)
+    bias, res = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    y = a.double() @ w.double().T + bias.double()
+    out = G.ops.gemm(a.cuda(), w.cuda(), bias.cuda(), res.cuda(), lrelu=True)
+    assert G.relerr(out, torch.nn.functional.leaky_relu(y, 0.2) + res.double()) < 2e-5
+    out = G.ops.gemm(a.cuda(), w.cuda(), bias.cuda(), res.cuda(), lrelu=True, res_before_act=True)
+    assert G.relerr(out, torch.nn.functional.leaky_relu(y + res.double(), 0.2)) < 2e-5
+    out = G.ops.gemm(a.cuda(), w.cuda(), bias.cuda(), tanh=True)
+    assert G.relerr(out, torch.tanh(y)) < 2e-5
+
+
 def test_gemm_taps_and_row_mask(G):
     """3 taps with row shifts (-7, 0, +7) and a zero-border mask: the implicit-GEMM form used by the conv layers."""
     g = torch.Generator().manual_seed(4)

@@ -14,7 +14,7 @@ def G():
     return gpu_common
 
 
-def build_dt(K, D, NL, NH, CD, sd=None, spatial=(5, 53), T=100):
+def build_dt(K, D, NL, NH, CD, sd=None, spatial=(5, 53), T=100, precision="f16"):
     from diffsound_b200.modeling.transformers.diffusion_transformer import DiffusionTransformer
     cfg = dict(
         content_emb_config=dict(target="diffsound_b200.modeling.embeddings.dalle_mask_image_embedding.DalleMaskImageEmbedding",
@@ -23,7 +23,7 @@ def build_dt(K, D, NL, NH, CD, sd=None, spatial=(5, 53), T=100):
         transformer_config=dict(target="diffsound_b200.modeling.transformers.transformer_utils.Text2ImageTransformer",
                                 params=dict(attn_type="selfcross", n_layer=NL, condition_seq_len=77, content_seq_len=spatial[0] * spatial[1],
                                             content_spatial_size=list(spatial), n_embd=D, condition_dim=CD, n_head=NH, attn_pdrop=0.0,
-                                            resid_pdrop=0.0, block_activate="GELU2", timestep_type="adalayernorm", mlp_hidden_times=4)),
+                                            resid_pdrop=0.0, block_activate="GELU2", timestep_type="adalayernorm", mlp_hidden_times=4, precision=precision)),
         diffusion_step=T, alpha_init_type="alpha1", auxiliary_loss_weight=5.0e-4, adaptive_auxiliary_loss=True, mask_weight=[1, 1])
     m = DiffusionTransformer(**cfg)
     if sd is not None:
@@ -52,7 +52,7 @@ def test_tiny_denoiser_and_stage_methods_match_reference_golden(G):
     cond, x_t, t = torch.from_numpy(g["in_cond"]).cuda(), torch.from_numpy(g["in_x_t"]).long().cuda(), torch.from_numpy(g["in_t"]).cuda()
     logits = m.transformer(x_t, cond, t)
     assert logits.shape == (B, K, L)
-    assert rel_err(logits.cpu(), torch.from_numpy(g["out_logits"])) < 1e-3
+    assert rel_err(logits.cpu(), torch.from_numpy(g["out_logits"])) < 2e-3  # 11-bit-significand operands, 2 layers
     log_x = O.index_to_log_onehot(x_t.cpu(), K + 1).cuda()
     m.truncation = "top0.85r"
     lp = m.predict_start(log_x, cond, t).cpu()
@@ -90,11 +90,14 @@ def test_fused_graph_and_unfused_paths_agree(G):
     assert torch.equal(again, toks[0])
 
 
-def test_teacher_forced_steps_match_oracle_full_width(G):
-    """D=1024 / 16 heads / K=256 (4 layers to keep the CPU oracle fast): feed the oracle's x_t each step (SURVEY 7.2 ladder ii)."""
+@pytest.mark.parametrize("precision,tol", [("f16", 2e-3), ("tf32", 2e-3), ("fp32", 3e-4)])
+def test_teacher_forced_steps_match_oracle_full_width(G, precision, tol):
+    """D=1024 / 16 heads / K=256 (4 layers to keep the CPU oracle fast): feed the oracle's x_t each step (SURVEY 7.2 ladder ii).
+    Logit tolerance (max|err| / max|ref|): 2e-3 for 11-bit-significand tensor-core operands (f16 / tf32), 3e-4 with exact fp32
+    GEMMs (the attention core keeps TF32 operands); sampled ids must agree on >= 98 % of positions given the same uniforms."""
     K, D, NL, NH, CD, B, L = 256, 1024, 4, 16, 512, 2, 265
     sd = O.make_transformer_state_dict(K=K, D=D, n_layer=NL, n_head=NH, cond_dim=CD, seed=0)
-    m = build_dt(K, D, NL, NH, CD, sd)
+    m = build_dt(K, D, NL, NH, CD, sd, precision=precision)
     g = torch.Generator().manual_seed(5)
     cond = torch.randn(B, 77, CD, generator=g)
     cond = cond / cond.norm(dim=-1, keepdim=True)
@@ -107,7 +110,9 @@ def test_teacher_forced_steps_match_oracle_full_width(G):
         t = torch.full((B,), ti, dtype=torch.long)
         ref_logits = O.transformer_forward(sd, x, cond, t, n_layer=NL, n_head=NH, spatial=(5, 53))
         logits = eng.forward(x.cuda(), kv, t.cuda(), 77)
-        assert rel_err(logits.permute(0, 2, 1).cpu(), ref_logits) < 1e-3, f"t={ti}"
+        err = rel_err(logits.permute(0, 2, 1).cpu(), ref_logits)
+        print(f"[{precision}] t={ti} logits rel err {err:.2e}")
+        assert err < tol, f"t={ti}"
         u = torch.rand(B, K + 1, L, generator=g)
         ref_next, _, _ = O.posterior_sample_step(sched, ref_logits, x, t, u, T=100)
         nxt = G.ops.posterior_sample(logits, x.cuda(), t.cuda(), u.cuda(), m._sched(), T=100).cpu()

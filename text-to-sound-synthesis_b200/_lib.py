@@ -34,11 +34,19 @@ SIGNATURES = {
     "dsb_gemm_f32": [c_vp] * 5 + [c_i] * 3 + [c_ll] * 4 + [c_i, c_vp],
     "dsb_round_tf32": [c_vp, c_vp, c_ll, c_vp],
     "dsb_f32_to_bf16": [c_vp, c_vp, c_ll, c_vp],
+    "dsb_f32_to_f16": [c_vp, c_vp, c_ll, c_vp],
     "dsb_silu": [c_vp, c_vp, c_ll, c_vp],
     "dsb_embed_tokens": [c_vp] * 5 + [c_i] * 6 + [c_vp, c_vp],
     "dsb_layernorm": [c_vp] * 4 + [c_i, c_i, c_f, c_i, c_vp],
     "dsb_ada_layernorm": [c_vp] * 4 + [c_i] * 4 + [c_f, c_i, c_vp],
     "dsb_attention": [c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_i, c_i, c_i, c_i, c_f, c_i, c_vp],
+    "dsb_codebook_gather_padded": [c_vp] * 3 + [c_i] * 6 + [c_vp, c_vp],
+    "dsb_groupnorm_stats": [c_vp, c_vp] + [c_i] * 4 + [c_vp],
+    "dsb_groupnorm_apply": [c_vp] * 5 + [c_i] * 5 + [c_f, c_i, c_i, c_vp],
+    "dsb_upsample2x_padded": [c_vp, c_vp] + [c_i] * 5 + [c_vp],
+    "dsb_softmax_rows": [c_vp, c_ll, c_i, c_i, c_i, c_vp],
+    "dsb_tokens_add_to_padded": [c_vp, c_vp] + [c_i] * 5 + [c_vp],
+    "dsb_lrelu_pad": [c_vp, c_vp] + [c_i] * 4 + [c_f, c_i, c_i, c_i, c_vp],
     "dsb_posterior_sample": [c_vp] * 8 + [c_i] * 5 + [c_f, c_i, c_i, c_vp],
 }
 

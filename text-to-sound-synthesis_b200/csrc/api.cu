@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "diffsound_b200.h"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdarg>
 
 namespace dsb {
@@ -36,6 +37,11 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* 
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) out[i] = __float2bfloat16(in[i]);
+}
+__global__ void f32_to_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, long long n) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = __float2half_rn(in[i]);
 }
 __global__ void silu_kernel(const float* __restrict__ in, float* __restrict__ out, long long n) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -73,6 +79,11 @@ extern "C" int dsb_round_tf32(const float* in, float* out, long long n, void* st
 }
 extern "C" int dsb_f32_to_bf16(const float* in, void* out, long long n, void* stream) {
   f32_to_bf16_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)out, n);
+  DSB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int dsb_f32_to_f16(const float* in, void* out, long long n, void* stream) {
+  f32_to_f16_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, (__half*)out, n);
   DSB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -4,6 +4,7 @@
 // Round-1 implementation: warp-level mma.sync m16n8k8 TF32 (legacy tensor path); a tcgen05/TMEM version is the follow-up.
 #include "common.cuh"
 #include "diffsound_b200.h"
+#include <cuda_fp16.h>
 
 namespace dsb {
 constexpr int HD = 64, QT = 64, KT = 64, KS = 68;  // KS: padded smem row stride (floats) -> conflict-free fragment loads
@@ -116,6 +117,15 @@ attention_kernel(const float* __restrict__ q, long long ldq, const float* __rest
   const bool rnd = (flags & DSB_GEMM_ROUND_TF32) != 0;
   float* ob = o + (long long)b * Lq * ldo + h * HD;
   const int ra = r0 + g, rb = r0 + g + 8;
+  if (flags & DSB_GEMM_OUT_F16) {  // `o` is an fp16 buffer with row stride ldo (elements)
+    __half* oh = reinterpret_cast<__half*>(o) + (long long)b * Lq * ldo + h * HD;
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd) {
+      if (ra < Lq) *reinterpret_cast<__half2*>(oh + (long long)ra * ldo + nd * 8 + 2 * t) = __floats2half2_rn(oacc[nd][0] * i0, oacc[nd][1] * i0);
+      if (rb < Lq) *reinterpret_cast<__half2*>(oh + (long long)rb * ldo + nd * 8 + 2 * t) = __floats2half2_rn(oacc[nd][2] * i1, oacc[nd][3] * i1);
+    }
+    return;
+  }
 #pragma unroll
   for (int nd = 0; nd < 8; ++nd) {
     float2 x = make_float2(oacc[nd][0] * i0, oacc[nd][1] * i0), y = make_float2(oacc[nd][2] * i1, oacc[nd][3] * i1);
@@ -131,7 +141,7 @@ extern "C" int dsb_attention(const float* q, long long ldq, const float* k, long
                              int B, int H, int Lq, int Lk, float scale, int flags, void* stream) {
   DSB_REQUIRE(B > 0 && H > 0 && Lq > 0 && Lk > 0, "dsb_attention: bad shape");
   DSB_REQUIRE(ldk % 4 == 0 && ldv % 4 == 0 && ldo % 2 == 0, "dsb_attention: ldk/ldv must be multiples of 4, ldo of 2");
-  DSB_REQUIRE(((reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) & 15) == 0 && (reinterpret_cast<uintptr_t>(o) & 7) == 0,
+  DSB_REQUIRE(((reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) & 15) == 0 && (reinterpret_cast<uintptr_t>(o) & 3) == 0,
               "dsb_attention: k/v must be 16-byte aligned, o 8-byte aligned");
   dim3 grid((Lq + QT - 1) / QT, H, B);
   attention_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(q, ldq, k, ldk, v, ldv, o, ldo, Lq, Lk, scale * 1.4426950408889634f, flags);

@@ -161,9 +161,10 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
   return d;
 }
 // cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b format @7/@10 (BF16=1, TF32=2), K-major both, N>>3 @17, M>>4 @24
-__host__ __device__ constexpr uint32_t make_idesc(bool tf32, int M, int N) {
-  return (1u << 4) | ((tf32 ? 2u : 1u) << 7) | ((tf32 ? 2u : 1u) << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
-         (static_cast<uint32_t>(M >> 4) << 24);
+// kind: 0 = TF32 (format 2), 1 = BF16 (format 1), 2 = F16 (format 0)   [DSB_DTYPE_*]
+__host__ __device__ constexpr uint32_t make_idesc(int kind, int M, int N) {
+  const uint32_t fmt = kind == 0 ? 2u : (kind == 1 ? 1u : 0u);
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
 }  // namespace dsb

@@ -1,0 +1,235 @@
+// SpecVQGAN decoder support kernels on zero-padded channels-last buffers (B, H+2, W+2, C):
+//   codebook gather + ColumnMajor un-permute (reference dalle_spec.py:80-91, permuter.py:46-49, quantize.py:88-103),
+//   GroupNorm(32, eps 1e-6) statistics / apply (+swish) (model.py:29-35), nearest x2 upsample (model.py:48-52),
+//   AttnBlock plumbing (model.py:202-226): token compaction, masked row softmax, scatter-add back into the padded image.
+// The 3x3 / 1x1 convolutions themselves run on the tcgen05 GEMM with 9 / 1 taps (gemm_tcgen05.cu); a zero border makes a
+// 3x3 tap a pure row shift of the flattened (b, y, x) index.  All kernels here are HBM-bound elementwise/reduction passes.
+#include "common.cuh"
+#include "diffsound_b200.h"
+
+namespace dsb {
+
+__global__ void codebook_gather_padded_kernel(const int64_t* __restrict__ ids, const float* __restrict__ codebook, float* __restrict__ out,
+                                              int B, int H, int W, int E, int n_codes, int flags, int* err_flag) {
+  const int Hp = H + 2, Wp = W + 2;
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= (long long)B * Hp * Wp) return;
+  const int lane = threadIdx.x & 31;
+  const int b = row / (Hp * Wp);
+  const int p = row % (Hp * Wp);
+  const int y = p / Wp - 1, x = p % Wp - 1;
+  float4* o = reinterpret_cast<float4*>(out + row * E);
+  if (y < 0 || y >= H || x < 0 || x >= W) {
+    for (int i = lane; i < E / 4; i += 32) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  // ColumnMajor reverse: row-major position (y, x) holds the token at column-major index x*H + y
+  long long id = ids[(long long)b * H * W + (long long)x * H + y];
+  if (id < 0 || id >= n_codes) {
+    if (lane == 0 && err_flag) atomicExch(err_flag, 1);
+    id = 0;
+  }
+  const float4* c = reinterpret_cast<const float4*>(codebook + id * E);
+  const bool rnd = flags & DSB_GEMM_ROUND_TF32;
+  for (int i = lane; i < E / 4; i += 32) {
+    float4 v = __ldg(c + i);
+    if (rnd) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+    o[i] = v;
+  }
+}
+
+// stats[b][g] = (sum, sumsq) in fp64 over all rows of image b (border rows are exact zeros, so they do not contribute)
+__global__ void __launch_bounds__(256)
+groupnorm_stats_kernel(const float* __restrict__ x, double* __restrict__ stats, int P, int C, int groups, int rows_per_block) {
+  extern __shared__ double sacc[];  // [groups][2]
+  const int b = blockIdx.y;
+  const int c4n = C / 4;
+  const int cg = C / groups;
+  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sacc[i] = 0.0;
+  __syncthreads();
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(P, r0 + rows_per_block);
+  const float* xb = x + (long long)b * P * C;
+  const int tpr = blockDim.x / c4n > 0 ? blockDim.x / c4n : 1;  // threads per row-slot
+  const int c4 = threadIdx.x % c4n;
+  const int rs = threadIdx.x / c4n;
+  if (rs < tpr) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int r = r0 + rs; r < r1; r += tpr) {
+      const float4 v = *reinterpret_cast<const float4*>(xb + (long long)r * C + c4 * 4);
+      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+      q[0] += v.x * v.x; q[1] += v.y * v.y; q[2] += v.z * v.z; q[3] += v.w * v.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int g = (c4 * 4 + j) / cg;
+      atomicAdd(&sacc[g * 2], (double)s[j]);
+      atomicAdd(&sacc[g * 2 + 1], (double)q[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) atomicAdd(&stats[(long long)b * groups * 2 + i], sacc[i]);
+}
+
+// out = [swish]( (x - mean) * rstd * gamma + beta ) on interior pixels, 0 on the border.
+// COMPACT mode writes tokens (B, Lp, C) (row-major pixel order, rows >= H*W zero) instead of the padded image.
+__global__ void groupnorm_apply_kernel(const float* __restrict__ x, const double* __restrict__ stats, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, float* __restrict__ out, int B, int H, int W, int C, int groups, float eps,
+                                       int flags, int Lp) {
+  const int Hp = H + 2, Wp = W + 2, c4n = C / 4;
+  const bool compact = flags & DSB_GN_COMPACT;
+  const long long total = (compact ? (long long)B * Lp : (long long)B * Hp * Wp) * c4n;
+  const int cg = C / groups;
+  const double cnt = (double)H * W * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = i % c4n;
+    const long long orow = i / c4n;
+    int b, y, xx;
+    bool inside;
+    if (compact) {
+      b = orow / Lp;
+      const int tkn = orow % Lp;
+      inside = tkn < H * W;
+      y = tkn / W; xx = tkn % W;
+    } else {
+      b = orow / (Hp * Wp);
+      const int p = orow % (Hp * Wp);
+      y = p / Wp - 1; xx = p % Wp - 1;
+      inside = y >= 0 && y < H && xx >= 0 && xx < W;
+    }
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (inside) {
+      const float4 v = *reinterpret_cast<const float4*>(x + (((long long)b * Hp + y + 1) * Wp + xx + 1) * C + c4 * 4);
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = c4 * 4 + j;
+        const int g = c / cg;
+        const double mean = stats[((long long)b * groups + g) * 2] / cnt;
+        double var = stats[((long long)b * groups + g) * 2 + 1] / cnt - mean * mean;
+        var = var < 0.0 ? 0.0 : var;
+        const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+        float t = (vv[j] - (float)mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+        if (flags & DSB_GN_SWISH) t = t / (1.0f + expf(-t));
+        if (flags & DSB_GEMM_ROUND_TF32) t = round_tf32(t);
+        o[j] = t;
+      }
+      r = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    *reinterpret_cast<float4*>(out + orow * C + c4 * 4) = r;
+  }
+}
+
+__global__ void upsample2x_padded_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C, int flags) {
+  const int Hi = H + 2, Wi = W + 2, Ho = 2 * H + 2, Wo = 2 * W + 2, c4n = C / 4;
+  const long long total = (long long)B * Ho * Wo * c4n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = i % c4n;
+    const long long orow = i / c4n;
+    const int b = orow / (Ho * Wo);
+    const int p = orow % (Ho * Wo);
+    const int y = p / Wo - 1, x = p % Wo - 1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (y >= 0 && y < 2 * H && x >= 0 && x < 2 * W) {
+      v = *reinterpret_cast<const float4*>(in + (((long long)b * Hi + (y >> 1) + 1) * Wi + (x >> 1) + 1) * C + c4 * 4);
+      if (flags & DSB_GEMM_ROUND_TF32) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+    }
+    *reinterpret_cast<float4*>(out + orow * C + c4 * 4) = v;
+  }
+}
+
+// in-place softmax over the first n_valid columns of each row (one warp per row); columns [n_valid, ld) are set to zero
+__global__ void softmax_rows_kernel(float* __restrict__ x, long long rows, int n_valid, int ld, int flags) {
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float* r = x + row * ld;
+  float m = -INFINITY;
+  for (int i = lane; i < n_valid; i += 32) m = fmaxf(m, r[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float s = 0.f;
+  for (int i = lane; i < n_valid; i += 32) s += expf(r[i] - m);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float inv = 1.0f / s;
+  for (int i = lane; i < ld; i += 32) {
+    float v = i < n_valid ? expf(r[i] - m) * inv : 0.f;
+    if (flags & DSB_GEMM_ROUND_TF32) v = round_tf32(v);
+    r[i] = v;
+  }
+}
+
+// x_pad[b, y+1, x+1, :] += tok[b, y*W + x, :]
+__global__ void tokens_add_to_padded_kernel(const float* __restrict__ tok, float* __restrict__ xpad, int B, int H, int W, int C, int Lp) {
+  const int Hp = H + 2, Wp = W + 2, c4n = C / 4;
+  const long long total = (long long)B * H * W * c4n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = i % c4n;
+    const long long t = i / c4n;
+    const int b = t / (H * W);
+    const int p = t % (H * W);
+    const int y = p / W, x = p % W;
+    const float4 a = *reinterpret_cast<const float4*>(tok + ((long long)b * Lp + p) * C + c4 * 4);
+    float4* d = reinterpret_cast<float4*>(xpad + (((long long)b * Hp + y + 1) * Wp + x + 1) * C + c4 * 4);
+    float4 v = *d;
+    v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    *d = v;
+  }
+}
+}  // namespace dsb
+using namespace dsb;
+
+static int ew_grid(long long n) {
+  long long g = (n + 255) / 256;
+  const long long cap = (long long)sm_count() * 8;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+extern "C" int dsb_codebook_gather_padded(const int64_t* ids, const float* codebook, float* out, int B, int H, int W, int E, int n_codes, int flags,
+                                          int* err_flag, void* stream) {
+  DSB_REQUIRE(E % 4 == 0, "dsb_codebook_gather_padded: embed dim must be a multiple of 4");
+  const long long rows = (long long)B * (H + 2) * (W + 2);
+  codebook_gather_padded_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(ids, codebook, out, B, H, W, E, n_codes, flags, err_flag);
+  DSB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int dsb_groupnorm_stats(const float* x, double* stats, int B, int P, int C, int groups, void* stream) {
+  DSB_REQUIRE(C % 4 == 0 && C % groups == 0 && C / 4 <= 256, "dsb_groupnorm_stats: unsupported channel count %d", C);
+  cudaStream_t st = (cudaStream_t)stream;
+  DSB_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * B * groups, st));
+  const int rows_per_block = 256;
+  dim3 grid((P + rows_per_block - 1) / rows_per_block, B);
+  groupnorm_stats_kernel<<<grid, 256, sizeof(double) * 2 * groups, st>>>(x, stats, P, C, groups, rows_per_block);
+  DSB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int dsb_groupnorm_apply(const float* x, const double* stats, const float* gamma, const float* beta, float* out, int B, int H, int W, int C,
+                                   int groups, float eps, int flags, int Lp, void* stream) {
+  DSB_REQUIRE(C % 4 == 0 && C % groups == 0, "dsb_groupnorm_apply: unsupported channel count %d", C);
+  DSB_REQUIRE(!(flags & DSB_GN_COMPACT) || Lp >= H * W, "dsb_groupnorm_apply: Lp too small");
+  const long long total = ((flags & DSB_GN_COMPACT) ? (long long)B * Lp : (long long)B * (H + 2) * (W + 2)) * (C / 4);
+  groupnorm_apply_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(x, stats, gamma, beta, out, B, H, W, C, groups, eps, flags, Lp);
+  DSB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int dsb_upsample2x_padded(const float* in, float* out, int B, int H, int W, int C, int flags, void* stream) {
+  DSB_REQUIRE(C % 4 == 0, "dsb_upsample2x_padded: C must be a multiple of 4");
+  const long long total = (long long)B * (2 * H + 2) * (2 * W + 2) * (C / 4);
+  upsample2x_padded_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(in, out, B, H, W, C, flags);
+  DSB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int dsb_softmax_rows(float* x, long long rows, int n_valid, int ld, int flags, void* stream) {
+  DSB_REQUIRE(n_valid > 0 && n_valid <= ld, "dsb_softmax_rows: bad n_valid");
+  softmax_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, rows, n_valid, ld, flags);
+  DSB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int dsb_tokens_add_to_padded(const float* tok, float* xpad, int B, int H, int W, int C, int Lp, void* stream) {
+  DSB_REQUIRE(C % 4 == 0, "dsb_tokens_add_to_padded: C must be a multiple of 4");
+  tokens_add_to_padded_kernel<<<ew_grid((long long)B * H * W * (C / 4)), 256, 0, (cudaStream_t)stream>>>(tok, xpad, B, H, W, C, Lp);
+  DSB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

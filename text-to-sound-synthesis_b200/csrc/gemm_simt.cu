@@ -48,6 +48,8 @@ gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ W, const 
       float v = acc[i][j];
       if (bias) v += bias[n];
       if (flags & DSB_GEMM_GELU2) v = v / (1.0f + expf(-1.702f * v));
+      if (flags & DSB_GEMM_LRELU) v = v > 0.f ? v : 0.2f * v;
+      if (flags & DSB_GEMM_TANH) v = tanhf(v);
       if (residual) v += residual[(long long)m * ld_res + n];
       if (flags & DSB_GEMM_ROUND_TF32) v = round_tf32(v);
       out[(long long)m * ldo + n] = v;

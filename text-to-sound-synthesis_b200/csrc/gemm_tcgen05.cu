@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "diffsound_b200.h"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace dsb {
 
@@ -49,7 +50,7 @@ struct GemmSmem {
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BLOCK_N, bool kTf32>
+template <int BLOCK_N, int KIND>  // KIND = DSB_DTYPE_*
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ GemmParams p) {
   using S = GemmSmem<BLOCK_N>;
@@ -114,7 +115,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(kTf32, BLOCK_M, BLOCK_N);
+      constexpr uint32_t idesc = make_idesc(KIND, BLOCK_M, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -132,7 +133,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const uint64_t db = make_sw128_kmajor_desc(sa + S::A_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k)  // 4 x 32-byte K slices per 128-byte swizzle row
-            umma<kTf32>(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma<KIND == DSB_DTYPE_TF32>(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -144,8 +145,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int q = warp & 3;
     const bool has_geo = p.geo_P > 0;
     const bool out_bf16 = (p.flags & DSB_GEMM_OUT_BF16) != 0;
+    const bool out_f16 = (p.flags & DSB_GEMM_OUT_F16) != 0;
     const bool do_gelu = (p.flags & DSB_GEMM_GELU2) != 0;
     const bool do_round = (p.flags & DSB_GEMM_ROUND_TF32) != 0;
+    const bool do_lrelu = (p.flags & DSB_GEMM_LRELU) != 0;
+    const bool do_tanh = (p.flags & DSB_GEMM_TANH) != 0;
+    const bool res_first = (p.flags & DSB_GEMM_RES_BEFORE_ACT) != 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile % p.tiles_m;
@@ -185,22 +190,33 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           for (int j = 0; j < 32; ++j)
             if (full_chunk || col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
         }
+#define DSB_ADD_RESIDUAL()                                                                     \
+        if (res_row) {                                                                           \
+          if (full_chunk) {                                                                      \
+            _Pragma("unroll") for (int j = 0; j < 32; j += 4) {                                  \
+              const float4 r = *reinterpret_cast<const float4*>(res_row + col0 + j);             \
+              f[j] += r.x; f[j + 1] += r.y; f[j + 2] += r.z; f[j + 3] += r.w;                    \
+            }                                                                                    \
+          } else {                                                                               \
+            for (int j = 0; j < 32; ++j)                                                         \
+              if (col0 + j < p.N) f[j] += res_row[col0 + j];                                     \
+          }                                                                                      \
+        }
+        if (res_first) { DSB_ADD_RESIDUAL() }
         if (do_gelu) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.0f + __expf(-1.702f * f[j]));
         }
-        if (res_row) {
-          if (full_chunk) {
+        if (do_lrelu) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 r = *reinterpret_cast<const float4*>(res_row + col0 + j);
-              f[j] += r.x; f[j + 1] += r.y; f[j + 2] += r.z; f[j + 3] += r.w;
-            }
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) f[j] += res_row[col0 + j];
-          }
+          for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : 0.2f * f[j];
         }
+        if (do_tanh) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
+        }
+        if (!res_first) { DSB_ADD_RESIDUAL() }
+#undef DSB_ADD_RESIDUAL
         if (do_round) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = round_tf32(f[j]);
@@ -209,7 +225,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = 0.0f;
         }
-        if (!out_bf16) {
+        if (out_f16) {
+          __half* out_hh = reinterpret_cast<__half*>(p.out) + (long long)b * p.out_bstride + (long long)row * p.ldo;
+          if (full_chunk && (p.N & 7) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              __half2 h0 = __floats2half2_rn(f[j], f[j + 1]), h1 = __floats2half2_rn(f[j + 2], f[j + 3]);
+              __half2 h2 = __floats2half2_rn(f[j + 4], f[j + 5]), h3 = __floats2half2_rn(f[j + 6], f[j + 7]);
+              uint4 u;
+              u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+              u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+              *reinterpret_cast<uint4*>(out_hh + col0 + j) = u;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) out_hh[col0 + j] = __float2half_rn(f[j]);
+          }
+        } else if (!out_bf16) {
           if (full_chunk) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
@@ -269,11 +301,11 @@ static PFN_encodeTiled get_encode() {
 }
 
 // 3-D map (K, rows, batch) over a K-contiguous matrix; box = (128 bytes of K, box_rows, 1); SWIZZLE_128B; OOB -> 0
-static int make_operand_map(CUtensorMap* map, const void* ptr, bool bf16, long long kdim, long long rows, long long batch,
+static int make_operand_map(CUtensorMap* map, const void* ptr, int kind, long long kdim, long long rows, long long batch,
                             long long ld_elems, long long bstride_elems, int box_rows) {
   PFN_encodeTiled enc = get_encode();
   DSB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
-  const int es = bf16 ? 2 : 4;
+  const int es = kind == DSB_DTYPE_TF32 ? 4 : 2;
   DSB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "GEMM operand pointer must be 16-byte aligned");
   DSB_REQUIRE((ld_elems * es) % 16 == 0, "GEMM operand leading dimension must be a multiple of 16 bytes (ld=%lld)", ld_elems);
   DSB_REQUIRE(batch == 1 || (bstride_elems * es) % 16 == 0, "GEMM batch stride must be a multiple of 16 bytes");
@@ -281,17 +313,17 @@ static int make_operand_map(CUtensorMap* map, const void* ptr, bool bf16, long l
   cuuint64_t gstr[2] = {(cuuint64_t)(ld_elems * es), (cuuint64_t)((batch == 1 ? ld_elems * rows : bstride_elems) * es)};
   cuuint32_t box[3] = {(cuuint32_t)(ROW_BYTES / es), (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), gdim, gstr,
+  CUresult r = enc(map, kind == DSB_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : (kind == DSB_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32), 3, const_cast<void*>(ptr), gdim, gstr,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DSB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): k=%lld rows=%lld batch=%lld ld=%lld", (int)r, kdim, rows, batch, ld_elems);
   return 0;
 }
 
-template <int BLOCK_N, bool kTf32>
+template <int BLOCK_N, int KIND>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int max_ctas, cudaStream_t st) {
   using S = GemmSmem<BLOCK_N>;
-  auto kern = gemm_tcgen05_kernel<BLOCK_N, kTf32>;
+  auto kern = gemm_tcgen05_kernel<BLOCK_N, KIND>;
   static bool attr_done = false;
   if (!attr_done) {
     DSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
@@ -312,9 +344,10 @@ extern "C" int dsb_gemm_ex(const dsb_gemm_desc* d, void* stream) {
   DSB_REQUIRE(d != nullptr, "dsb_gemm_ex: null descriptor");
   DSB_REQUIRE(d->M > 0 && d->N > 0 && d->K > 0 && d->batch > 0, "dsb_gemm_ex: bad shape M=%d N=%d K=%d batch=%d", d->M, d->N, d->K, d->batch);
   DSB_REQUIRE(d->num_taps >= 1 && d->num_taps <= MAX_TAPS, "dsb_gemm_ex: num_taps=%d out of range", d->num_taps);
-  DSB_REQUIRE(d->dtype == DSB_DTYPE_TF32 || d->dtype == DSB_DTYPE_BF16, "dsb_gemm_ex: dtype must be TF32 or BF16 (use dsb_gemm_f32 for exact fp32)");
-  const bool bf16 = d->dtype == DSB_DTYPE_BF16;
-  const int block_k = bf16 ? 64 : 32;
+  DSB_REQUIRE(d->dtype == DSB_DTYPE_TF32 || d->dtype == DSB_DTYPE_BF16 || d->dtype == DSB_DTYPE_F16,
+              "dsb_gemm_ex: dtype must be TF32, BF16 or F16 (use dsb_gemm_f32 for exact fp32)");
+  const int kind = d->dtype;
+  const int block_k = kind == DSB_DTYPE_TF32 ? 32 : 64;
   GemmParams p{};
   p.M = d->M; p.N = d->N; p.batch = d->batch;
   p.tiles_m = (d->M + BLOCK_M - 1) / BLOCK_M;
@@ -347,10 +380,16 @@ extern "C" int dsb_gemm_ex(const dsb_gemm_desc* d, void* stream) {
 
   CUtensorMap ma, mb;
   const long long a_rows = d->a_rows > 0 ? d->a_rows : d->M;
-  if (make_operand_map(&ma, d->A, bf16, d->K, a_rows, d->batch, d->lda, d->a_batch_stride, BLOCK_M)) return 3;
-  if (make_operand_map(&mb, d->W, bf16, (long long)d->K * d->num_taps, d->N, p.b_batched ? d->batch : 1, d->ldw, d->w_batch_stride, block_n)) return 3;
+  if (make_operand_map(&ma, d->A, kind, d->K, a_rows, d->batch, d->lda, d->a_batch_stride, BLOCK_M)) return 3;
+  if (make_operand_map(&mb, d->W, kind, (long long)d->K * d->num_taps, d->N, p.b_batched ? d->batch : 1, d->ldw, d->w_batch_stride, block_n)) return 3;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int max_ctas = d->max_ctas > 0 ? d->max_ctas : sms;
-  if (block_n == 256) return bf16 ? launch<256, false>(ma, mb, p, max_ctas, st) : launch<256, true>(ma, mb, p, max_ctas, st);
-  return bf16 ? launch<128, false>(ma, mb, p, max_ctas, st) : launch<128, true>(ma, mb, p, max_ctas, st);
+  if (block_n == 256) {
+    if (kind == DSB_DTYPE_TF32) return launch<256, DSB_DTYPE_TF32>(ma, mb, p, max_ctas, st);
+    if (kind == DSB_DTYPE_BF16) return launch<256, DSB_DTYPE_BF16>(ma, mb, p, max_ctas, st);
+    return launch<256, DSB_DTYPE_F16>(ma, mb, p, max_ctas, st);
+  }
+  if (kind == DSB_DTYPE_TF32) return launch<128, DSB_DTYPE_TF32>(ma, mb, p, max_ctas, st);
+  if (kind == DSB_DTYPE_BF16) return launch<128, DSB_DTYPE_BF16>(ma, mb, p, max_ctas, st);
+  return launch<128, DSB_DTYPE_F16>(ma, mb, p, max_ctas, st);
 }

@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "diffsound_b200.h"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace dsb {
 
@@ -73,6 +74,7 @@ __global__ void layernorm_kernel(const float* __restrict__ x, void* __restrict__
   }
   const bool rnd = (flags & DSB_GEMM_ROUND_TF32) != 0;
   const bool obf = (flags & DSB_GEMM_OUT_BF16) != 0;
+  const bool of16 = (flags & DSB_GEMM_OUT_F16) != 0;
   for (int i = lane; i < nv; i += 32) {
     const float4 v = xr[i];
     const float4 g = __ldg(g4 + i), b = __ldg(b4 + i);
@@ -84,7 +86,12 @@ __global__ void layernorm_kernel(const float* __restrict__ x, void* __restrict__
       y.x = (v.x - mean) * rstd * (1.f + g.x) + b.x; y.y = (v.y - mean) * rstd * (1.f + g.y) + b.y;
       y.z = (v.z - mean) * rstd * (1.f + g.z) + b.z; y.w = (v.w - mean) * rstd * (1.f + g.w) + b.w;
     }
-    if (obf) {
+    if (of16) {
+      __half2 h0 = __floats2half2_rn(y.x, y.y), h1 = __floats2half2_rn(y.z, y.w);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+      reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out) + (long long)row * D)[i] = u;
+    } else if (obf) {
       __nv_bfloat162 h0 = __floats2bfloat162_rn(y.x, y.y), h1 = __floats2bfloat162_rn(y.z, y.w);
       uint2 u;
       u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);

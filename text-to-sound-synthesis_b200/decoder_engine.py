@@ -1,0 +1,150 @@
+"""SpecVQGAN decoder on sm_100a: every Conv2d is a tcgen05 implicit GEMM over a zero-padded channels-last image.
+
+Layout: activations are fp32 (B, H+2, W+2, C) with an exact-zero one-pixel border.  Flattening (b, y, x) to a row index makes
+a 3x3 tap (dy, dx) the row shift dy*(W+2)+dx, so conv3x3 = one GEMM with 9 taps, A = the padded image (rows, Cin), W packed
+as (Cout, 9*Cin); the epilogue adds bias (+ residual) and re-zeroes border rows.  GroupNorm needs image-wide statistics, so
+it stays a separate reduction + apply(+swish) pass that also rounds to TF32 for the next GEMM.
+Reference: specvqgan/modules/diffusionmodules/model.py:92-151 (ResnetBlock), :174-226 (AttnBlock), :37-52 (Upsample), :640-671.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+def _pack_conv(conv) -> torch.Tensor:
+    w = conv.weight.detach().float()  # (Cout, Cin, kh, kw) -> (Cout, kh*kw*Cin), tap-major
+    return ops.round_tf32(w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous())
+
+
+class DecoderEngine:
+    def __init__(self, vq):
+        self.vq = vq
+        self.packed = False
+        self.launches = 0
+
+    @torch.no_grad()
+    def repack(self):
+        vq, d = self.vq, self.vq.decoder
+        if vq.post_quant_conv.weight.device.type != "cuda":
+            raise RuntimeError("DecoderEngine needs the module on a CUDA device (no CPU fallback)")
+        f = lambda p: p.detach().float().contiguous()
+        self.w = {}
+
+        def conv(name, m):
+            self.w[name] = (_pack_conv(m), f(m.bias), m.kernel_size[0])
+
+        def gn(name, m):
+            self.w[name] = (f(m.weight), f(m.bias), m.eps)
+
+        def res(name, m):
+            gn(name + ".norm1", m.norm1); conv(name + ".conv1", m.conv1); gn(name + ".norm2", m.norm2); conv(name + ".conv2", m.conv2)
+            if hasattr(m, "nin_shortcut"):
+                conv(name + ".nin", m.nin_shortcut)
+
+        def attn(name, m):
+            gn(name + ".norm", m.norm)
+            for n in ("q", "k", "v", "proj_out"):
+                conv(name + "." + n, getattr(m, n))
+
+        conv("post_quant", vq.post_quant_conv)
+        conv("conv_in", d.conv_in)
+        res("mid.block_1", d.mid.block_1); attn("mid.attn_1", d.mid.attn_1); res("mid.block_2", d.mid.block_2)
+        for lvl, up in enumerate(d.up):
+            for j, blk in enumerate(up.block):
+                res(f"up.{lvl}.block.{j}", blk)
+            for j, a in enumerate(up.attn):
+                attn(f"up.{lvl}.attn.{j}", a)
+            if hasattr(up, "upsample"):
+                conv(f"up.{lvl}.upsample", up.upsample.conv)
+        gn("norm_out", d.norm_out)
+        conv("conv_out", d.conv_out)
+        self.codebook = f(vq.quantize.embedding.weight)
+        self.packed = True
+
+    # ------------------------------------------------------------------ building blocks (all on padded NHWC tensors)
+    def _conv(self, x, name, residual=None, round_out=False):
+        w, b, k = self.w[name]
+        B, Hp, Wp, C = x.shape
+        R = B * Hp * Wp
+        taps = [dy * Wp + dx for dy in (-1, 0, 1) for dx in (-1, 0, 1)] if k == 3 else [0]
+        out = torch.empty(B, Hp, Wp, w.shape[0], dtype=torch.float32, device=x.device)
+        ops.gemm(x.view(R, C), w, b, None if residual is None else residual.view(R, -1), out.view(R, -1), taps=taps,
+                 geo=(Hp * Wp, Wp, 1, Hp - 1, 1, Wp - 1), round_out=round_out)
+        self.launches += 1
+        return out
+
+    def _gn(self, x, name, swish=True, compact_len=0):
+        g, b, eps = self.w[name]
+        st = ops.groupnorm_stats(x)
+        self.launches += 3  # memset + stats + apply
+        return ops.groupnorm_apply(x, st, g, b, eps=eps, swish=swish, round_out=True, compact_len=compact_len)
+
+    def _res(self, x, name):
+        h = self._conv(self._gn(x, name + ".norm1"), name + ".conv1")
+        h = self._gn(h, name + ".norm2")
+        if (name + ".nin") in self.w:
+            self.launches += 1
+            x = self._conv(ops.round_tf32(x), name + ".nin")
+        return self._conv(h, name + ".conv2", residual=x)
+
+    def _attn(self, x, name):
+        """AttnBlock (model.py:202-226): single head over the H*W interior tokens, scale C^-0.5; x is updated in place."""
+        B, Hp, Wp, C = x.shape
+        L = (Hp - 2) * (Wp - 2)
+        Lp = (L + 15) // 16 * 16  # token rows padded so every TMA stride is a multiple of 16 bytes
+        h = self._gn(x, name + ".norm", swish=False, compact_len=Lp).view(B * Lp, C)
+        (wq, bq, _), (wk, bk, _), (wv, bv, _), (wp, bp, _) = (self.w[name + "." + n] for n in ("q", "k", "v", "proj_out"))
+        q = ops.gemm(h, wq, bq, round_out=True).view(B, Lp, C)
+        k = ops.gemm(h, wk, bk, round_out=True).view(B, Lp, C)
+        vT = ops.gemm(wv, h, round_out=True)  # (C, B*Lp) = Wv h^T: V transposed, bias folded in after P V (softmax rows sum to 1)
+        s = ops.gemm(q, k, alpha=float(C) ** -0.5)  # (B, Lp, Lp)
+        ops.softmax_rows_(s, L)
+        o = ops.gemm(s, vT.view(C, B, Lp).permute(1, 0, 2), bv, round_out=True)  # (B, Lp, C)
+        proj = ops.gemm(o.view(B * Lp, C), wp, bp).view(B, Lp, C)
+        ops.tokens_add_to_padded_(proj, x)
+        self.launches += 8
+        return x
+
+    # ------------------------------------------------------------------ entry points
+    @torch.no_grad()
+    def _decode_padded(self, z):
+        d = self.vq.decoder
+        z = self._conv(z, "post_quant", round_out=True)
+        h = self._conv(z, "conv_in")
+        h = self._res(h, "mid.block_1")
+        h = self._attn(h, "mid.attn_1")
+        h = self._res(h, "mid.block_2")
+        for lvl in reversed(range(d.num_resolutions)):
+            for j in range(d.num_res_blocks + 1):
+                h = self._res(h, f"up.{lvl}.block.{j}")
+                if len(d.up[lvl].attn) > 0:
+                    h = self._attn(h, f"up.{lvl}.attn.{j}")
+            if lvl != 0:
+                h = self._conv(ops.upsample2x_padded(h), f"up.{lvl}.upsample")
+                self.launches += 1
+        out = self._conv(self._gn(h, "norm_out"), "conv_out")  # (B, Hp, Wp, out_ch)
+        return out[:, 1:-1, 1:-1, :].permute(0, 3, 1, 2).contiguous()
+
+    @torch.no_grad()
+    def decode_tokens(self, ids, grid):
+        if not self.packed:
+            self.repack()
+        self.launches = 1
+        H, W = grid
+        err = torch.zeros(1, dtype=torch.int32, device=ids.device)
+        z = ops.codebook_gather_padded(ids, self.codebook, H, W, round_out=True, err_flag=err)
+        mel = self._decode_padded(z)
+        if int(err.item()):
+            raise RuntimeError("codebook index out of range")
+        return mel
+
+    @torch.no_grad()
+    def decode_latents(self, quant):
+        """quant (B, E, H, W) NCHW (the reference's VQModel.decode input) -> mel; layout conversion is plain data movement."""
+        if not self.packed:
+            self.repack()
+        self.launches = 1
+        z = torch.nn.functional.pad(quant.detach().float().permute(0, 2, 3, 1), (0, 0, 1, 1, 1, 1)).contiguous()
+        return self._decode_padded(ops.round_tf32(z))

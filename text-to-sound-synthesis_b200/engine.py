@@ -19,9 +19,13 @@ from . import ops
 
 
 class DenoiserEngine:
-    def __init__(self, transformer, precision: str = "tf32"):
-        if precision not in ("tf32", "fp32"):
-            raise ValueError("precision must be 'tf32' (tcgen05 tensor cores) or 'fp32' (exact FFMA GEMMs)")
+    def __init__(self, transformer, precision: str = "f16"):
+        """precision: 'f16'  -- fp16 GEMM operands on tcgen05 kind::f16 (11-bit significand = TF32's, at twice the rate), fp32
+                                accumulation, fp32 residual stream / LayerNorm statistics / softmax / logits;
+                      'tf32' -- fp32 containers rounded to TF32, tcgen05 kind::tf32;
+                      'fp32' -- exact FFMA GEMMs (slow; the fp32-exact mode of SURVEY.md section 7.2)."""
+        if precision not in ("f16", "tf32", "fp32"):
+            raise ValueError("precision must be 'f16', 'tf32' or 'fp32'")
         self.m = transformer
         self.precision = precision
         self.packed = False
@@ -36,6 +40,8 @@ class DenoiserEngine:
 
     def _prep(self, w: torch.Tensor) -> torch.Tensor:
         w = w.detach().float().contiguous()
+        if self.precision == "f16":
+            return ops.to_f16(w)
         return ops.round_tf32(w) if self.precision == "tf32" else w.clone()
 
     @torch.no_grad()
@@ -93,13 +99,16 @@ class DenoiserEngine:
         if ws is None:
             dev, M, D = self.device, B * L, self.D
             e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
-            ws = dict(x=e(B, L, D), h=e(B, L, D), qkv=e(M, 3 * D), att=e(M, D), q2=e(M, D), hid=e(M, self.layers[0]["w1"].shape[0]),
+            a = (lambda *s: torch.empty(*s, dtype=torch.float16, device=dev)) if self.precision == "f16" else e  # GEMM A operands
+            ws = dict(x=e(B, L, D), h=a(B, L, D), qkv=e(M, 3 * D), att=a(M, D), q2=e(M, D), hid=a(M, self.layers[0]["w1"].shape[0]),
                       logits=e(B, L, self.K), err=torch.zeros(1, dtype=torch.int32, device=dev))
             self._ws[key] = ws
         return ws
 
     # ------------------------------------------------------------------ compute
     def _linear(self, a, w, bias, residual=None, out=None, gelu=False, round_out=False):
+        if self.precision == "f16":
+            return ops.gemm(a, w, bias, residual, out, dtype=ops.F16, gelu=gelu)
         if self.precision == "tf32":
             return ops.gemm(a, w, bias, residual, out, dtype=ops.TF32, gelu=gelu, round_out=round_out)
         return ops.gemm_f32(a, w, bias, residual, out, gelu=gelu)
@@ -113,6 +122,8 @@ class DenoiserEngine:
         c = cond_emb.detach().float().reshape(B * Lc, Cd).contiguous()
         if self.precision == "tf32":
             c = ops.round_tf32(c)
+        elif self.precision == "f16":
+            c = ops.to_f16(c)
         return self._linear(c, self.wkv_all, self.bkv_all)
 
     @torch.no_grad()

@@ -70,7 +70,7 @@ class Text2ImageTransformer(nn.Module):
     def __init__(self, condition_seq_len=77, n_layer=14, n_embd=1024, n_head=16, content_seq_len=1024, attn_pdrop=0, resid_pdrop=0,
                  mlp_hidden_times=4, block_activate=None, attn_type="selfcross", content_spatial_size=[32, 32], condition_dim=512,
                  diffusion_step=1000, timestep_type="adalayernorm", content_emb_config=None, mlp_type="fc", checkpoint=False,
-                 precision="tf32"):
+                 precision="f16"):
         super().__init__()
         assert attn_type == "selfcross"
         assert mlp_type == "fc", "conv_mlp is not used by the Diffsound configs"
@@ -91,7 +91,7 @@ class Text2ImageTransformer(nn.Module):
         self.n_embd, self.n_head, self.diffusion_step = n_embd, n_head, diffusion_step
         self.apply(self._init_weights)
         self.engine = DenoiserEngine(self, precision=precision)
-        self._register_load_state_dict_post_hook(lambda module, incompatible: module.engine.__setattr__("packed", False))
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.engine.__setattr__("packed", False))
 
     def _init_weights(self, module):  # same distribution as the reference (:355-363)
         if isinstance(module, (nn.Linear, nn.Embedding)):

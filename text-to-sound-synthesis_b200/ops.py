@@ -11,8 +11,8 @@ import torch
 
 from . import _lib
 
-TF32, BF16 = 0, 1
-GELU2, ROUND_TF32, OUT_BF16 = 1, 2, 4
+TF32, BF16, F16 = 0, 1, 2
+GELU2, ROUND_TF32, OUT_BF16, LRELU, TANH, GN_SWISH, GN_COMPACT, RES_BEFORE_ACT, OUT_F16 = 1, 2, 4, 8, 16, 32, 64, 128, 256
 
 
 def _stream() -> int:
@@ -51,6 +51,14 @@ def to_bf16(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def to_f16(x: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x)
+    x = x.contiguous()
+    out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    _lib.check(_lib.lib().dsb_f32_to_f16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "dsb_f32_to_f16")
+    return out
+
+
 def silu(x: torch.Tensor) -> torch.Tensor:
     _need_cuda(x)
     x = x.contiguous()
@@ -60,8 +68,8 @@ def silu(x: torch.Tensor) -> torch.Tensor:
 
 
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
-         out: Optional[torch.Tensor] = None, *, dtype: int = TF32, gelu: bool = False, round_out: bool = False, out_bf16: bool = False,
-         taps: Optional[Sequence[int]] = None, out_rows: Optional[int] = None, geo: Optional[Sequence[int]] = None, alpha: float = 1.0,
+         out: Optional[torch.Tensor] = None, *, dtype: int = TF32, gelu: bool = False, round_out: bool = False, out_bf16: bool = False, out_f16: bool = False,
+         lrelu: bool = False, tanh: bool = False, res_before_act: bool = False, taps: Optional[Sequence[int]] = None, out_rows: Optional[int] = None, geo: Optional[Sequence[int]] = None, alpha: float = 1.0,
          block_n: int = 0, max_ctas: int = 0) -> torch.Tensor:
     """out = epi(alpha * A @ W^T + bias) (+ residual) on tcgen05.  a: (M,K) or (batch,M,K); w: (N, taps*K) or (batch,N,K)."""
     _need_cuda(a, w, bias, residual, out)
@@ -75,9 +83,11 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     if w.shape[-1] != K * ntaps:
         raise RuntimeError(f"gemm: W has {w.shape[-1]} columns, expected {K}*{ntaps}")
     M = a_rows if out_rows is None else out_rows
-    odt = torch.bfloat16 if out_bf16 else torch.float32
+    odt = torch.bfloat16 if out_bf16 else (torch.float16 if out_f16 else torch.float32)
     if out is None:
         out = torch.empty((batch, M, N) if batched else (M, N), dtype=odt, device=a.device)
+    out_f16 = out.dtype == torch.float16
+    out_bf16 = out.dtype == torch.bfloat16
     d = _lib.GemmDesc()
     d.A, d.W, d.bias, d.residual, d.out = a.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(residual), out.data_ptr()
     d.M, d.N, d.K, d.batch = M, N, K, batch
@@ -89,7 +99,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     d.out_batch_stride = out.stride(0) if batched else 0
     d.res_batch_stride = residual.stride(0) if (residual is not None and batched) else 0
     d.dtype = dtype
-    d.flags = (GELU2 if gelu else 0) | (ROUND_TF32 if round_out else 0) | (OUT_BF16 if out_bf16 else 0)
+    d.flags = (GELU2 if gelu else 0) | (ROUND_TF32 if round_out else 0) | (OUT_BF16 if out_bf16 else 0) | (LRELU if lrelu else 0) | (TANH if tanh else 0) | (RES_BEFORE_ACT if res_before_act else 0) | (OUT_F16 if out_f16 else 0)
     d.num_taps = ntaps
     for i, s in enumerate(taps or [0]):
         d.tap_shift[i] = int(s)
@@ -124,13 +134,21 @@ def embed_tokens(ids, emb, height_emb, width_emb, out=None, err_flag=None):
     return out
 
 
+def _out_flags(out, round_out):
+    if out.dtype == torch.float16:
+        return OUT_F16
+    if out.dtype == torch.bfloat16:
+        return OUT_BF16
+    return ROUND_TF32 if round_out else 0
+
+
 def layernorm(x, gamma, beta, out=None, *, eps=1e-5, round_out=False, out_bf16=False):
     _need_cuda(x, gamma, beta)
     D = x.shape[-1]
     rows = x.numel() // D
     if out is None:
         out = torch.empty(x.shape, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x.device)
-    flags = (ROUND_TF32 if round_out else 0) | (OUT_BF16 if out_bf16 else 0)
+    flags = _out_flags(out, round_out)
     _lib.check(_lib.lib().dsb_layernorm(x.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), rows, D, eps, flags, _stream()), "dsb_layernorm")
     return out
 
@@ -141,7 +159,7 @@ def ada_layernorm(x, table, t, out=None, *, eps=1e-5, round_out=False, out_bf16=
     B, L, D = x.shape
     if out is None:
         out = torch.empty(x.shape, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x.device)
-    flags = (ROUND_TF32 if round_out else 0) | (OUT_BF16 if out_bf16 else 0)
+    flags = _out_flags(out, round_out)
     _lib.check(_lib.lib().dsb_ada_layernorm(x.data_ptr(), out.data_ptr(), table.data_ptr(), t.data_ptr(), B, L, D, table.shape[0], eps, flags, _stream()),
                "dsb_ada_layernorm")
     return out
@@ -154,7 +172,7 @@ def attention(q, k, v, out, *, B, H, Lq, Lk, scale, round_out=False):
         if t_.stride(-1) != 1:
             raise RuntimeError("attention operands must be contiguous in the head dimension")
     _lib.check(_lib.lib().dsb_attention(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), out.data_ptr(), out.stride(0),
-                                        B, H, Lq, Lk, scale, ROUND_TF32 if round_out else 0, _stream()), "dsb_attention")
+                                        B, H, Lq, Lk, scale, _out_flags(out, round_out), _stream()), "dsb_attention")
     return out
 
 
@@ -183,3 +201,75 @@ def posterior_sample(inp, x_t, t, uniform, sched, *, T, trunc_mode=1, trunc_r=0.
     _lib.check(_lib.lib().dsb_posterior_sample(inp.data_ptr(), _ptr(x_t), _ptr(t), _ptr(t_post), _ptr(uniform), _ptr(sched), _ptr(x_next),
                                                _ptr(log_prob_out), B, K, L, T, trunc_mode, trunc_r, trunc_k, stage, _stream()), "dsb_posterior_sample")
     return x_next
+
+
+# ---------------------------------------------------------------------------------------------- decoder / vocoder support
+def codebook_gather_padded(ids, codebook, H, W, *, round_out=True, err_flag=None):
+    _need_cuda(ids, codebook)
+    B = ids.shape[0]
+    E = codebook.shape[1]
+    out = torch.empty(B, H + 2, W + 2, E, dtype=torch.float32, device=ids.device)
+    _lib.check(_lib.lib().dsb_codebook_gather_padded(ids.contiguous().data_ptr(), codebook.data_ptr(), out.data_ptr(), B, H, W, E, codebook.shape[0],
+                                                     ROUND_TF32 if round_out else 0, _ptr(err_flag), _stream()), "dsb_codebook_gather_padded")
+    return out
+
+
+def groupnorm_stats(x_pad, stats=None, groups=32):
+    """x_pad (B, Hp, Wp, C) zero-bordered -> stats (B, groups, 2) fp64 (sum, sumsq)."""
+    _need_cuda(x_pad)
+    B, Hp, Wp, C = x_pad.shape
+    stats = torch.empty(B, groups, 2, dtype=torch.float64, device=x_pad.device) if stats is None else stats
+    _lib.check(_lib.lib().dsb_groupnorm_stats(x_pad.data_ptr(), stats.data_ptr(), B, Hp * Wp, C, groups, _stream()), "dsb_groupnorm_stats")
+    return stats
+
+
+def groupnorm_apply(x_pad, stats, gamma, beta, *, eps=1e-6, swish=True, round_out=True, compact_len=0, out=None, groups=32):
+    _need_cuda(x_pad, stats, gamma, beta)
+    B, Hp, Wp, C = x_pad.shape
+    H, W = Hp - 2, Wp - 2
+    flags = (GN_SWISH if swish else 0) | (ROUND_TF32 if round_out else 0) | (GN_COMPACT if compact_len else 0)
+    if out is None:
+        out = torch.empty((B, compact_len, C) if compact_len else (B, Hp, Wp, C), dtype=torch.float32, device=x_pad.device)
+    _lib.check(_lib.lib().dsb_groupnorm_apply(x_pad.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), B, H, W, C, groups,
+                                              eps, flags, compact_len, _stream()), "dsb_groupnorm_apply")
+    return out
+
+
+def upsample2x_padded(x_pad, *, round_out=True):
+    _need_cuda(x_pad)
+    B, Hp, Wp, C = x_pad.shape
+    H, W = Hp - 2, Wp - 2
+    out = torch.empty(B, 2 * H + 2, 2 * W + 2, C, dtype=torch.float32, device=x_pad.device)
+    _lib.check(_lib.lib().dsb_upsample2x_padded(x_pad.data_ptr(), out.data_ptr(), B, H, W, C, ROUND_TF32 if round_out else 0, _stream()),
+               "dsb_upsample2x_padded")
+    return out
+
+
+def softmax_rows_(x, n_valid, *, round_out=True):
+    _need_cuda(x)
+    assert x.is_contiguous()
+    ld = x.shape[-1]
+    _lib.check(_lib.lib().dsb_softmax_rows(x.data_ptr(), x.numel() // ld, n_valid, ld, ROUND_TF32 if round_out else 0, _stream()), "dsb_softmax_rows")
+    return x
+
+
+def tokens_add_to_padded_(tok, x_pad):
+    _need_cuda(tok, x_pad)
+    B, Hp, Wp, C = x_pad.shape
+    _lib.check(_lib.lib().dsb_tokens_add_to_padded(tok.data_ptr(), x_pad.data_ptr(), B, Hp - 2, Wp - 2, C, tok.shape[1], _stream()),
+               "dsb_tokens_add_to_padded")
+    return x_pad
+
+
+def lrelu_pad(x, pad, *, slope=0.2, reflect=True, channel_major=False, round_out=True):
+    """x (B,T,C) channels-last, or (B,C,T) with channel_major -> (B, T+2*pad, C)."""
+    _need_cuda(x)
+    x = x.contiguous()
+    if channel_major:
+        B, Cc, T = x.shape
+    else:
+        B, T, Cc = x.shape
+    out = torch.empty(B, T + 2 * pad, Cc, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().dsb_lrelu_pad(x.data_ptr(), out.data_ptr(), B, T, Cc, pad, slope, 1 if reflect else 0, 1 if channel_major else 0,
+                                        ROUND_TF32 if round_out else 0, _stream()), "dsb_lrelu_pad")
+    return out
