@@ -95,7 +95,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    v, cores, sample = cpu_port_clips_per_s(args.codebook, min(args.batch, 2), max(2, min(10, args.steps * 2)))
+    v, cores, sample = cpu_port_clips_per_s(args.codebook, min(args.batch, 2), max(2, min(10, args.steps * 2)), n_layer=args.layers)
     line = {"impl": "reference", "metric": "clips/sec (10s audio, 100 diffusion steps)", "value": v, "unit": "clips/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * args.batch / v, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -1,0 +1,178 @@
+"""CPU-side checks (no GPU): C-ABI surface, drop-in module construction / checkpoint-key compatibility, config factory,
+no-fallback behaviour, the sharded driver's host logic over gloo, and the reference-arm bench line."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from tests.helpers import ROOT, load_golden
+
+import _pkg
+
+_pkg.load()
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    from diffsound_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "diffsound_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|const char\*)\s+(dsb_\w+)\s*\(", hdr, flags=re.M))
+    assert len(declared) >= 20
+    L = _lib.lib()
+    for name in declared:
+        assert hasattr(L, name), f"libdiffsound_b200.so does not export {name}"
+    assert declared - {"dsb_last_error"} == set(_lib.SIGNATURES), "ctypes signatures out of sync with the header"
+    assert L.dsb_version() == 100
+
+
+def test_gemm_descriptor_layout_matches_header():
+    """sizeof(struct dsb_gemm_desc) as laid out by ctypes == what a C compiler produces for the header."""
+    from diffsound_b200 import _lib
+    import ctypes, tempfile
+    src = '#include <stdio.h>\n#include "diffsound_b200.h"\nint main(){printf("%zu %zu %zu", sizeof(dsb_gemm_desc), __builtin_offsetof(dsb_gemm_desc, tap_shift), __builtin_offsetof(dsb_gemm_desc, alpha));return 0;}'
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")], check=True)
+        out = subprocess.run([os.path.join(d, "t")], capture_output=True, text=True, check=True).stdout.split()
+    assert int(out[0]) == ctypes.sizeof(_lib.GemmDesc)
+    assert int(out[1]) == _lib.GemmDesc.tap_shift.offset and int(out[2]) == _lib.GemmDesc.alpha.offset
+
+
+def test_ops_refuse_cpu_tensors_no_fallback():
+    from diffsound_b200 import ops
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.round_tf32(torch.zeros(8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.gemm(torch.zeros(4, 32), torch.zeros(4, 32))
+
+
+def _dt(K, D, NL, NH, CD):
+    from tests.test_gpu_transformer import build_dt
+    real_cuda = torch.nn.Module.cuda
+    torch.nn.Module.cuda = lambda self, *a, **k: self
+    try:
+        return build_dt(K, D, NL, NH, CD)
+    finally:
+        torch.nn.Module.cuda = real_cuda
+
+
+def test_dropin_modules_keep_reference_state_dict_keys():
+    sd, g = load_golden("xf_tiny.npz")
+    K, D, NL, NH, CD, B, L = [int(v) for v in g["__cfg"]]
+    m = _dt(K, D, NL, NH, CD)
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all("attn2.mask" in k for k in missing)
+    assert m.num_classes == K + 1 and m.shape == 265 and m.num_timesteps == 100
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.sample(None, None, torch.zeros(B, 77, CD), filter_ratio=0, batch_size=B)
+    # decoder + vocoder
+    from tests.test_gpu_decoder import build_vq
+    from diffsound_b200.vocoder.modules import Generator
+    dsd, dg = load_golden("decoder_tiny.npz")
+    real_cuda = torch.nn.Module.cuda
+    torch.nn.Module.cuda = lambda self, *a, **k: self
+    try:
+        vq = build_vq(int(dg["__cfg"][0]), int(dg["__cfg"][1]), int(dg["__cfg"][2]), (1, 1, 1, 1, 2), dsd)
+    finally:
+        torch.nn.Module.cuda = real_cuda
+    assert not vq.engine.packed
+    msd, _ = load_golden("melgan_tiny.npz")
+    Generator(80, 4, 3).load_state_dict(msd, strict=True)
+    with pytest.raises(RuntimeError):
+        Generator(80, 4, 3)(torch.zeros(1, 80, 8))
+
+
+def test_stage_methods_stay_rebindable_and_truncation_parses():
+    from diffsound_b200.modeling.transformers.diffusion_transformer import parse_truncation
+    assert parse_truncation("top0.85r") == (1, 0.85, 0)
+    assert parse_truncation("top100p") == (2, 0.0, 100)
+    assert parse_truncation("top0.85r,fast3") == (1, 0.85, 0)
+    assert parse_truncation("normal") == (0, 0.0, 0) and parse_truncation(None) == (0, 0.0, 0)
+    m = _dt(32, 128, 1, 2, 64)
+    assert not m._stages_overridden()
+    m.predict_start = (lambda f: (lambda *a, **k: f(*a, **k)))(m.predict_start)  # what the reference DALLE does (dalle_spec.py:209)
+    assert m._stages_overridden()
+
+
+def test_config_factory_and_retarget():
+    from diffsound_b200.utils.misc import instantiate_from_config, retarget_config
+    cfg = {"target": "sound_synthesis.modeling.models.dalle_spec.DALLE", "params": {
+        "content_codec_config": {"target": "sound_synthesis.modeling.codecs.spec_codec.vqgan.VQModel", "params": {
+            "ckpt_path": None, "embed_dim": 64, "n_embed": 32, "lossconfig": {"target": "specvqgan.modules.losses.DummyLoss"},
+            "ddconfig": dict(double_z=False, z_channels=64, resolution=848, in_channels=1, out_ch=1, ch=32, ch_mult=[1, 1, 1, 1, 2],
+                             num_res_blocks=2, attn_resolutions=[53], dropout=0.0)}},
+        "condition_codec_config": None,
+        "first_stage_permuter_config": {"target": "specvqgan.modules.transformer.permuter.ColumnMajor", "params": {"H": 5, "W": 53}},
+        "diffusion_config": {"target": "sound_synthesis.modeling.transformers.diffusion_transformer.DiffusionTransformer", "params": {
+            "diffusion_step": 100, "alpha_init_type": "alpha1", "auxiliary_loss_weight": 5.0e-4, "adaptive_auxiliary_loss": True, "mask_weight": [1, 1],
+            "condition_emb_config": None,
+            "transformer_config": {"target": "sound_synthesis.modeling.transformers.transformer_utils.Text2ImageTransformer", "params": dict(
+                attn_type="selfcross", n_layer=1, condition_seq_len=77, content_seq_len=265, content_spatial_size=[5, 53], n_embd=64, condition_dim=64,
+                n_head=1, attn_pdrop=0.0, resid_pdrop=0.0, block_activate="GELU2", timestep_type="adalayernorm", mlp_hidden_times=4)},
+            "content_emb_config": {"target": "sound_synthesis.modeling.embeddings.dalle_mask_image_embedding.DalleMaskImageEmbedding", "params": dict(
+                num_embed=32, spatial_size=(5, 53), embed_dim=64, trainable=True, pos_emb_type="embedding")}}}}}
+    new = retarget_config(cfg)
+    assert new["target"].startswith("diffsound_b200.") and cfg["target"].startswith("sound_synthesis.")  # input not mutated
+    model = instantiate_from_config(new)
+    keys = set(model.state_dict().keys())
+    assert "transformer.transformer.blocks.0.attn1.query.weight" in keys and "content_codec.decoder.conv_in.weight" in keys
+    assert "first_stage_permuter.forward_shuffle_idx" in keys and "transformer.log_cumprod_at" in keys
+    ids = torch.arange(265).view(1, 265)
+    perm = model.first_stage_permuter
+    assert torch.equal(perm(perm(ids), reverse=True), ids)
+    assert perm(ids)[0, 1].item() == 53  # column-major: second token is row 1 of column 0
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import _pkg
+    _pkg.load()
+    from diffsound_b200 import pipeline
+
+    class FakeDalle:
+        device = torch.device("cpu")
+
+        def generate_content(self, *, batch, **kw):
+            c = batch["condition_embed"]
+            tok = (c[:, 0, :3].sum(-1, keepdim=True) * 1000).long().expand(-1, 5) + torch.randint(0, 1 << 20, (1,))  # seed-dependent
+            return {"content": torch.zeros(c.shape[0], 1, 2, 4), "content_token": tok}
+
+    cond = torch.arange(8 * 77 * 4, dtype=torch.float32).view(8, 77, 4) / 100
+    out = pipeline.synthesize_sharded(FakeDalle(), lambda s: s.sum(-1, keepdim=True).unsqueeze(1), cond, base_seed=7)
+    q.put((rank, out["tokens"].clone(), out["wav"].shape))
+    dist.destroy_process_group()
+
+
+def test_sharded_driver_over_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda r: r[0])
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    (r0, t0, s0), (r1, t1, s1) = res
+    assert torch.equal(t0, t1) and t0.shape == (8, 5) and s0 == s1  # every rank holds all 8 clips, in caption order
+    # rank-local seeds differ (base_seed + rank), captions are contiguous blocks of 4
+    torch.manual_seed(7); a = torch.randint(0, 1 << 20, (1,))
+    torch.manual_seed(8); b = torch.randint(0, 1 << 20, (1,))
+    cond = torch.arange(8 * 77 * 4, dtype=torch.float32).view(8, 77, 4) / 100
+    base = (cond[:, 0, :3].sum(-1, keepdim=True) * 1000).long().expand(-1, 5)
+    assert torch.equal(t0[:4], base[:4] + a) and torch.equal(t0[4:], base[4:] + b)
+
+
+def test_bench_reference_arm_prints_contract_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--layers", "1", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "clips/s" and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["value"] > 0

@@ -55,3 +55,43 @@ def test_decoder_full_config_matches_oracle(G):
     mse = float(((mel - ref) ** 2).mean())
     print("decoder full rel err", err, "mel MSE", mse, "ref rms", float(ref.pow(2).mean().sqrt()))
     assert err < 2e-3
+
+
+def test_melgan_tiny_matches_reference_golden(G):
+    from diffsound_b200.vocoder.modules import Generator
+    sd, g = load_golden("melgan_tiny.npz")
+    m = Generator(80, 4, 3)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    wav = m(torch.from_numpy(g["in_mel"]).cuda()).cpu()
+    ref = torch.from_numpy(g["out_wav"])
+    assert wav.shape == ref.shape
+    err = rel_err(wav, ref)
+    print("melgan tiny rel err", err)
+    assert err < 2e-3
+
+
+def test_melgan_real_checkpoint(G):
+    """The reference's shipped generator weights (staged in oracle/_ref by build()): reference-generated I/O golden, then a
+    full 848-frame clip against the oracle."""
+    from diffsound_b200.vocoder.modules import Generator
+    ck = os.path.join(ROOT, "oracle", "_ref", "best_netG.pt")
+    if not os.path.exists(ck):
+        pytest.skip("oracle/_ref/best_netG.pt not staged")
+    sd = torch.load(ck, map_location="cpu")
+    m = Generator(80, 32, 3)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    _, g = load_golden("melgan_real_io.npz")
+    wav = m(torch.from_numpy(g["in_mel"]).cuda()).cpu()
+    ref = torch.from_numpy(g["out_wav"])
+    err = rel_err(wav, ref)
+    print("melgan real (40 frames) rel err", err)
+    assert err < 3e-3
+    mel = torch.rand(2, 80, 848, generator=torch.Generator().manual_seed(21))
+    ref = O.melgan_forward(sd, mel)
+    wav = m(mel.cuda()).cpu()
+    assert wav.shape == (2, 1, 217088)
+    err = rel_err(wav, ref)
+    print("melgan real (848 frames, B=2) rel err", err, "rms ref", float(ref.pow(2).mean().sqrt()))
+    assert err < 3e-3

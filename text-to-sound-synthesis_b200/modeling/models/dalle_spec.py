@@ -1,0 +1,93 @@
+"""Drop-in for sound_synthesis/modeling/models/dalle_spec.py::DALLE (inference side): same constructor keys, the same
+`generate_content` / `decode_to_img` / `get_ema_model` surface and the same state_dict prefixes (`transformer.*`,
+`content_codec.*`, `first_stage_permuter.*`), so `ckpt["model"]` loads with strict=False and `ckpt["ema"]` overlays
+`get_ema_model()` exactly as generate_samples_batch.py:78-85 does.
+
+Differences that are deliberate (and documented in INTEGRATION.md):
+  * truncation (`sample_type` 'top0.85r' / 'top100p') is passed to the fused sampler kernel instead of monkey-patching
+    `predict_start` with sort/cumsum torch ops (reference :146-177, :207-210);
+  * the text tokenizer / CLIP tower is a 'next' row: without a `condition_codec`, captions arrive
+    as pre-computed embeddings `batch['condition_embed']` (B, 77, 512), the reference's own bypass
+    (diffusion_transformer.py:623-627).
+"""
+import torch
+from torch import nn
+
+from ...utils.misc import instantiate_from_config
+
+
+def disabled_train(self, mode=True):
+    return self
+
+
+class DALLE(nn.Module):
+    def __init__(self, *, content_info={"key": "image"}, condition_info={"key": "text"}, content_codec_config, condition_codec_config,
+                 first_stage_permuter_config, diffusion_config):
+        super().__init__()
+        self.content_info = content_info
+        self.condition_info = condition_info
+        model = instantiate_from_config(content_codec_config).eval()
+        model.train = disabled_train.__get__(model)
+        self.content_codec = model
+        self.condition_codec = instantiate_from_config(condition_codec_config)
+        self.transformer = instantiate_from_config(diffusion_config)
+        self.first_stage_permuter = instantiate_from_config(config=first_stage_permuter_config)
+        self.truncation_forward = False
+
+    @property
+    def device(self):
+        return self.transformer.device
+
+    def get_ema_model(self):
+        return self.transformer
+
+    @torch.no_grad()
+    def decode_to_img(self, index, zshape, stage="first"):
+        """Token ids in the transformer's (column-major) order -> mel (B,1,80,848)  (reference :80-91).  The un-permute and the
+        codebook gather are one kernel inside VQModel.decode_tokens."""
+        if stage != "first":
+            raise NotImplementedError
+        return self.content_codec.decode_tokens(index, (zshape[2], zshape[3]))
+
+    @torch.no_grad()
+    def prepare_condition(self, batch, condition=None):
+        if self.condition_codec is None:
+            emb = batch["condition_embed"] if condition is None else condition
+            return {"condition_token": None, "condition_mask": None, "condition_embed_token": emb.to(self.device)}
+        cond = batch[self.condition_info["key"]] if condition is None else condition
+        cond = self.condition_codec.get_tokens(cond)
+        return {"condition_" + k: (v.to(self.device) if torch.is_tensor(v) else v) for k, v in cond.items()}
+
+    @torch.no_grad()
+    def generate_content(self, *, batch, condition=None, filter_ratio=0.5, temperature=1.0, content_ratio=0.0, replicate=1,
+                         return_att_weight=False, sample_type="top0.85r"):
+        self.eval()
+        condition = self.prepare_condition(batch=batch, condition=condition)
+        if replicate != 1:
+            for k in condition.keys():
+                if condition[k] is not None:
+                    condition[k] = torch.cat([condition[k] for _ in range(replicate)], dim=0)
+        parts = sample_type.split(",")
+        if len(parts) > 1 and parts[1][:1] == "q":
+            raise NotImplementedError("'q' re-sampling (p_sample_with_truncation, reference :135-143) is a 'next' row (SURVEY 8f N1)")
+        self.transformer.truncation = parts[0] if parts[0][:3] == "top" else None
+        emb = condition.get("condition_embed_token", None)
+        bsz = (condition["condition_token"] if condition["condition_token"] is not None else emb).shape[0]
+        kw = dict(condition_token=condition["condition_token"], condition_mask=condition.get("condition_mask", None), condition_embed=emb,
+                  content_token=None, filter_ratio=filter_ratio, temperature=temperature, return_att_weight=return_att_weight, return_logits=False,
+                  print_log=False, sample_type=sample_type, batch_size=bsz)
+        if len(parts) == 2 and parts[1][:4] == "fast":
+            trans_out = self.transformer.sample_fast(skip_step=int(parts[1][4:]), **kw)
+        else:
+            trans_out = self.transformer.sample(**kw)
+        zshape = (trans_out["content_token"].shape[0], self.content_codec.quantize.e_dim, *self._grid())
+        content = self.decode_to_img(trans_out["content_token"], zshape)
+        self.train()
+        return {"content": content, "content_token": trans_out["content_token"]}
+
+    def _grid(self):
+        p = self.first_stage_permuter
+        return (p.H, p.W)
+
+    def forward(self, batch, name="none", **kwargs):
+        raise NotImplementedError("training forward (config 4) is SURVEY.md section 8 row A13 -- after the inference path")

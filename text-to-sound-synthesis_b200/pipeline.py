@@ -1,0 +1,44 @@
+"""caption embeddings -> token grid -> mel -> waveform on one GPU, and the sharded multi-GPU driver.
+
+Mirrors what Diffsound/evaluation/generate_samples_batch.py:143-187 does per caption batch, minus disk I/O: the reference
+decodes the mel, copies it to the host, and runs the vocoder at batch 1 through another host round trip (:178-185); here
+tokens, mel and waveform stay on the device and the vocoder is batched.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+
+@torch.no_grad()
+def synthesize(dalle, vocoder, cond_emb: torch.Tensor, *, sample_type: str = "top0.85r", seed: Optional[int] = None):
+    """cond_emb (B,77,512) on the device -> dict(tokens (B,265) int64, mel (B,1,80,848) in ~[-1,1], wav (B,1,217088))."""
+    if seed is not None:
+        torch.manual_seed(seed)
+    out = dalle.generate_content(batch={"condition_embed": cond_emb}, filter_ratio=0, replicate=1, sample_type=sample_type)
+    mel = out["content"]
+    spec01 = (mel[:, 0] + 1) / 2  # the script's (spec + 1) / 2 before saving / vocoding (generate_samples_batch.py:181)
+    wav = vocoder(spec01) if vocoder is not None else None
+    return {"tokens": out["content_token"], "mel": mel, "wav": wav}
+
+
+@torch.no_grad()
+def synthesize_sharded(dalle, vocoder, cond_emb_all: torch.Tensor, *, sample_type="top0.85r", base_seed=1234, gather="wav"):
+    """Shard captions over the ranks of the default process group (contiguous blocks), sample independently with seed
+    base_seed + rank, and all_gather the finished clips (the only collective of the path)."""
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    B = cond_emb_all.shape[0]
+    assert B % world == 0, "caption count must divide the world size"
+    per = B // world
+    local = synthesize(dalle, vocoder, cond_emb_all[rank * per:(rank + 1) * per].to(dalle.device), sample_type=sample_type, seed=base_seed + rank)
+    if world == 1:
+        return local
+    out = {}
+    for k in ("tokens",) + (("wav",) if gather == "wav" and local["wav"] is not None else ()):
+        parts = [torch.empty_like(local[k]) for _ in range(world)]
+        dist.all_gather(parts, local[k].contiguous())
+        out[k] = torch.cat(parts, 0)
+    return out

@@ -1,0 +1,103 @@
+"""MelGAN generator on sm_100a: every Conv1d / ConvTranspose1d is a tcgen05 GEMM over channels-last (B, T, C) activations.
+
+* weight_norm (w = g * v / ||v||, reference vocoder/modules.py:18-23) is folded once at pack time instead of every forward;
+* Conv1d(k, dilation d) = GEMM with k taps (row shifts 0, d, 2d, ...) over a reflection-padded copy of the input;
+* ConvTranspose1d(stride r, kernel 2r, padding r/2) is evaluated in polyphase form: output time q*r + ph only touches
+  inputs q-1, q (ph < r/2) or q, q+1 (ph >= r/2), so it is two GEMMs with 2 taps each whose (T, r*Cout) row-major output IS
+  the (r*T, Cout) channels-last result -- no zero-stuffing, no scatter;
+* LeakyReLU / tanh / bias / residual live in the GEMM epilogue; only the reflection pad of a ResnetBlock input needs its own
+  (HBM-bound) pass.
+Reference: vocoder/modules.py:72-85 (ResnetBlock), :88-130 (Generator).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+def _fold(m) -> torch.Tensor:
+    v, g = m.weight_v.detach().float(), m.weight_g.detach().float()
+    return g * v / v.flatten(1).norm(dim=1).view(-1, *([1] * (v.dim() - 1)))
+
+
+def _pack_conv1d(w) -> torch.Tensor:
+    return ops.round_tf32(w.permute(0, 2, 1).reshape(w.shape[0], -1).contiguous())  # (Cout, k*Cin), tap-major
+
+
+class VocoderEngine:
+    def __init__(self, gen):
+        self.gen = gen
+        self.packed = False
+        self.launches = 0
+
+    @torch.no_grad()
+    def repack(self):
+        mods = list(self.gen.model)
+        if mods[1].bias.device.type != "cuda":
+            raise RuntimeError("VocoderEngine needs the module on a CUDA device (no CPU fallback)")
+        f = lambda p: p.detach().float().contiguous()
+        self.first = (_pack_conv1d(_fold(mods[1])), f(mods[1].bias))
+        self.stages = []
+        i = 2
+        for r in self.gen.ratios:
+            ct = mods[i + 1]
+            w = _fold(ct)  # (Cin, Cout, 2r); weight_norm dim=0 -> norm over (Cout, k) per input channel
+            p = r // 2 + r % 2
+            assert r % 2 == 0, "polyphase split assumes even stride (the Diffsound ratios 8,8,2,2)"
+            half = r - p
+            # phases [0, half): taps (q-1 -> k=ph+p+r, q -> k=ph+p); phases [half, r): taps (q -> k=ph+p, q+1 -> k=ph+p-r)
+            wa = torch.stack([torch.cat([w[:, :, ph + p + r].t(), w[:, :, ph + p].t()], dim=1) for ph in range(half)], 0)
+            wb = torch.stack([torch.cat([w[:, :, ph + p].t(), w[:, :, ph + p - r].t()], dim=1) for ph in range(half, r)], 0)
+            cout = w.shape[1]
+            st = dict(r=r, cout=cout, half=half, wa=ops.round_tf32(wa.reshape(half * cout, -1).contiguous()),
+                      wb=ops.round_tf32(wb.reshape((r - half) * cout, -1).contiguous()),
+                      ba=f(ct.bias).repeat(half), bb=f(ct.bias).repeat(r - half), res=[])
+            i += 2
+            for _ in range(self.gen.n_residual_layers):
+                rb = mods[i]
+                st["res"].append(dict(d=rb.dilation, wd=_pack_conv1d(_fold(rb.block[2])), bd=f(rb.block[2].bias),
+                                      w1=_pack_conv1d(_fold(rb.block[4])), b1=f(rb.block[4].bias),
+                                      ws=_pack_conv1d(_fold(rb.shortcut)), bs=f(rb.shortcut.bias)))
+                i += 1
+            self.stages.append(st)
+        last = mods[i + 2]
+        self.last = (_pack_conv1d(_fold(last)), f(last.bias))
+        self.packed = True
+
+    @torch.no_grad()
+    def forward(self, mel: torch.Tensor) -> torch.Tensor:
+        if not self.packed:
+            self.repack()
+        if not mel.is_cuda:
+            raise RuntimeError("VocoderEngine.forward needs a CUDA tensor (no CPU fallback)")
+        mel = mel.detach().float().contiguous()
+        B, Cm, T = mel.shape
+        n = 0
+        xl = ops.lrelu_pad(mel, 3, slope=1.0, reflect=True, channel_major=True)          # ReflectionPad1d(3) of the mel, channels-last
+        w0, b0 = self.first
+        # conv k=7 -> LeakyReLU (the activation in front of the first ConvTranspose1d) fused in the epilogue
+        x = ops.gemm(xl, w0, b0, taps=list(range(7)), out_rows=T, lrelu=True, round_out=True)   # (B, T, 16*ngf)
+        n += 2
+        for si, st in enumerate(self.stages):
+            r, cout, half = st["r"], st["cout"], st["half"]
+            y = torch.empty(B, T, r * cout, dtype=torch.float32, device=mel.device)
+            ops.gemm(x, st["wa"], st["ba"], out=y[:, :, : half * cout], taps=[-1, 0], round_out=True)
+            ops.gemm(x, st["wb"], st["bb"], out=y[:, :, half * cout:], taps=[0, 1], round_out=True)
+            T = T * r
+            x = y.view(B, T, cout)
+            n += 2
+            for ri, rb in enumerate(st["res"]):
+                d = rb["d"]
+                xl = ops.lrelu_pad(x, d, slope=0.2, reflect=True)                          # LeakyReLU + ReflectionPad1d(d)
+                y1 = ops.gemm(xl, rb["wd"], rb["bd"], taps=[0, d, 2 * d], out_rows=T, lrelu=True, round_out=True)
+                tmp = ops.gemm(y1, rb["w1"], rb["b1"])
+                last_of_stage = ri == len(st["res"]) - 1
+                # shortcut(x) + block(x); after the last block of a stage the next consumer is LeakyReLU -> ConvT / final conv
+                x = ops.gemm(x, rb["ws"], rb["bs"], residual=tmp, round_out=True, lrelu=last_of_stage, res_before_act=last_of_stage)
+                n += 4
+        xl = ops.lrelu_pad(x, 3, slope=1.0, reflect=True)                                  # x already went through LeakyReLU
+        wl, bl = self.last
+        wav = ops.gemm(xl, wl, bl, taps=list(range(7)), out_rows=T, tanh=True)             # (B, T, 1)
+        self.launches = n + 2
+        return wav.view(B, 1, T)
