@@ -114,6 +114,10 @@ int dsb_silu(const float* in, float* out, long long n, void* stream);
 int dsb_attention(const float* q, long long ldq, const float* k, long long ldk, const float* v, long long ldv, float* o, long long ldo,
                   int B, int H, int Lq, int Lk, float scale, int flags, void* stream);
 
+/* Same attention core with fp16 q/k/v (row strides in halves, multiples of 8); o is fp16 (DSB_GEMM_OUT_F16) or fp32. */
+int dsb_attention_f16(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o, long long ldo,
+                      int B, int H, int Lq, int Lk, float scale, int flags, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Posterior + truncation + Gumbel-argmax sampler, one kernel (reference diffusion_transformer.py:285-289 predict_start tail,
  * models/dalle_spec.py:146-174 top-k / nucleus truncation, diffusion_transformer.py:293-339 q_posterior,

@@ -140,3 +140,25 @@ def test_posterior_sampler_k512_and_t_post(G):
     ref, post, _ = O.posterior_sample_step(sched, logits, x_t, t, u, T=T, truncation="top0.85r", t_posterior=tp)
     nxt = G.ops.posterior_sample(logits.permute(0, 2, 1).contiguous().cuda(), x_t.cuda(), t.cuda(), u.cuda(), _sched_tensor(sched).cuda(), T=T, t_post=tp.cuda())
     assert int((nxt.cpu() != ref).sum()) <= 1
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk", [(2, 2, 265, 265), (3, 16, 265, 77), (1, 1, 16, 5), (2, 4, 70, 130)])
+def test_attention_f16_matches_fp64(G, B, H, Lq, Lk):
+    D = H * 64
+    gen = torch.Generator().manual_seed(B * 100 + Lk)
+    qkv = torch.randn(B * Lq, 3 * D, generator=gen).half()
+    kv = torch.randn(B * Lk, 2 * D, generator=gen).half()
+    q = qkv[:, :D]
+    k, v = (kv[:, :D], kv[:, D:])
+    qh = q.double().view(B, Lq, H, 64).transpose(1, 2)
+    kh = k.double().view(B, Lk, H, 64).transpose(1, 2)
+    vh = v.double().view(B, Lk, H, 64).transpose(1, 2)
+    ref = (torch.softmax(qh @ kh.transpose(-1, -2) / 8.0, dim=-1) @ vh).transpose(1, 2).reshape(B * Lq, D)
+    qkv_d, kv_d = qkv.cuda(), kv.cuda()
+    out = torch.full((B * Lq, D), float("nan"), device="cuda", dtype=torch.float16)
+    G.ops.attention(qkv_d[:, :D], kv_d[:, :D], kv_d[:, D:], out, B=B, H=H, Lq=Lq, Lk=Lk, scale=0.125)
+    assert torch.isfinite(out).all()
+    assert G.relerr(out.float(), ref) < 1.5e-3  # fp16 P and fp16 output rounding
+    out32 = torch.empty(B * Lq, D, device="cuda")
+    G.ops.attention(qkv_d[:, :D], kv_d[:, :D], kv_d[:, D:], out32, B=B, H=H, Lq=Lq, Lk=Lk, scale=0.125)
+    assert G.relerr(out32, ref) < 1e-3

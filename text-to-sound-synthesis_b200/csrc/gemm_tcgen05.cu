@@ -19,6 +19,7 @@ constexpr int BLOCK_M = 128;
 constexpr int ROW_BYTES = 128;  // one swizzle-128B row of K per operand row
 constexpr int GEMM_THREADS = 192;
 constexpr int MAX_TAPS = 9;
+constexpr int EPI_LD = 36;  // padded row stride (floats) of the epilogue transpose tile: 16-byte aligned rows, conflict-free
 
 struct GemmParams {
   int M, N, batch;
@@ -47,7 +48,7 @@ struct GemmSmem {
   static constexpr int B_BYTES = BLOCK_N * ROW_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * 32 * EPI_LD * 4 /*epilogue transpose tiles*/;
 };
 
 template <int BLOCK_N, int KIND>  // KIND = DSB_DTYPE_*
@@ -63,6 +64,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* epi_smem = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + 256);  // 4 warps x 32 x EPI_LD floats
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -142,7 +144,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else {
     // ------------------------------------------------------------ epilogue warps (2..5): TMEM lane quadrant = warp % 4
+    // Each 32x32 accumulator chunk (lane = row) is transposed through a private smem tile so that every global access of
+    // the warp covers 4 rows x 128 contiguous bytes (float4 per lane) instead of 32 scattered 16-byte pieces.
     const int q = warp & 3;
+    float* sw = epi_smem + (warp - 2) * (32 * EPI_LD);
     const bool has_geo = p.geo_P > 0;
     const bool out_bf16 = (p.flags & DSB_GEMM_OUT_BF16) != 0;
     const bool out_f16 = (p.flags & DSB_GEMM_OUT_F16) != 0;
@@ -151,6 +156,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const bool do_lrelu = (p.flags & DSB_GEMM_LRELU) != 0;
     const bool do_tanh = (p.flags & DSB_GEMM_TANH) != 0;
     const bool res_first = (p.flags & DSB_GEMM_RES_BEFORE_ACT) != 0;
+    const int out_es = (out_bf16 || out_f16) ? 2 : 4;
+    const bool vec_ok = ((p.ldo & 3) == 0) && ((p.out_bstride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & (4 * out_es - 1)) == 0) &&
+                        (!p.residual || (((p.ld_res & 3) == 0) && ((p.res_bstride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0))) &&
+                        (!p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0));
+    const int c4 = lane & 7;    // float4 column slot inside the 32-column chunk
+    const int rsub = lane >> 3; // row inside each group of 4 rows
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile % p.tiles_m;
@@ -158,117 +169,134 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int b = tile / (p.tiles_m * p.tiles_n);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      const int row_base = m_blk * BLOCK_M + q * 32;
+      uint32_t ok_mask = 0, in_mask = 0;  // bit i: row (row_base + i*4 + rsub) exists / is an interior row
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = row_base + i * 4 + rsub;
+        if (row < p.M) ok_mask |= 1u << i;
+        bool interior = true;
+        if (has_geo) {
+          const int pp = row % p.geo_P;
+          const int y = pp / p.geo_Wp, x = pp - y * p.geo_Wp;
+          interior = (y >= p.geo_y0) && (y < p.geo_y1) && (x >= p.geo_x0) && (x < p.geo_x1);
+        }
+        if (interior) in_mask |= 1u << i;
+      }
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
+      const long long out_boff = (long long)b * p.out_bstride;
+      const float* res_b = p.residual ? p.residual + (long long)b * p.res_bstride : nullptr;
+      const int n_chunks = min(BLOCK_N / 32, (p.N - n_blk * BLOCK_N + 31) / 32);
+
+      // bias + residual of a chunk are fetched one chunk ahead (the first one before the accumulator is even complete), so
+      // their latency hides behind the mainloop / the previous chunk instead of stalling every row group.
+      float4 rz_next[8];
+      float4 bz_next = make_float4(0.f, 0.f, 0.f, 0.f);
+      auto prefetch = [&](int c) {
+        const int col = n_blk * BLOCK_N + c * 32 + c4 * 4;
+        const bool vec = vec_ok && (col + 3 < p.N);
+        bz_next = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) {
+          if (vec) bz_next = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+          else {
+            if (col < p.N) bz_next.x = __ldg(p.bias + col);
+            if (col + 1 < p.N) bz_next.y = __ldg(p.bias + col + 1);
+            if (col + 2 < p.N) bz_next.z = __ldg(p.bias + col + 2);
+            if (col + 3 < p.N) bz_next.w = __ldg(p.bias + col + 3);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          rz_next[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (res_b && ((ok_mask >> i) & 1u)) {
+            const float* rp = res_b + (long long)(row_base + i * 4 + rsub) * p.ld_res + col;
+            if (vec) rz_next[i] = *reinterpret_cast<const float4*>(rp);
+            else {
+              if (col < p.N) rz_next[i].x = rp[0];
+              if (col + 1 < p.N) rz_next[i].y = rp[1];
+              if (col + 2 < p.N) rz_next[i].z = rp[2];
+              if (col + 3 < p.N) rz_next[i].w = rp[3];
+            }
+          }
+        }
+      };
+      if (n_chunks > 0) prefetch(0);
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
-      const int row = m_blk * BLOCK_M + q * 32 + lane;
-      const bool row_ok = row < p.M;
-      bool interior = true;
-      if (has_geo) {
-        const int pp = row % p.geo_P;
-        const int y = pp / p.geo_Wp, x = pp - y * p.geo_Wp;
-        interior = (y >= p.geo_y0) && (y < p.geo_y1) && (x >= p.geo_x0) && (x < p.geo_x1);
-      }
-      const float* res_row = p.residual ? p.residual + (long long)b * p.res_bstride + (long long)row * p.ld_res : nullptr;
-      float* out_f = reinterpret_cast<float*>(p.out) + (long long)b * p.out_bstride + (long long)row * p.ldo;
-      __nv_bfloat16* out_h = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)b * p.out_bstride + (long long)row * p.ldo;
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
+      for (int c = 0; c < n_chunks; ++c) {
         const int col0 = n_blk * BLOCK_N + c * 32;
-        if (col0 >= p.N) break;  // warp-uniform
         uint32_t v[32];
-        __syncwarp();
         tmem_ld_32x32(t_row + c * 32, v);
         tmem_ld_wait();
-        if (row_ok) {
-        const bool full_chunk = (col0 + 32 <= p.N) && ((p.N & 3) == 0);
-        float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
-        if (p.bias) {
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(sw + lane * EPI_LD + j * 4) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        const int col = col0 + c4 * 4;
+        const bool vec = vec_ok && (col + 3 < p.N);
+        float4 rz_cur[8];
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (full_chunk || col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
-        }
-#define DSB_ADD_RESIDUAL()                                                                     \
-        if (res_row) {                                                                           \
-          if (full_chunk) {                                                                      \
-            _Pragma("unroll") for (int j = 0; j < 32; j += 4) {                                  \
-              const float4 r = *reinterpret_cast<const float4*>(res_row + col0 + j);             \
-              f[j] += r.x; f[j + 1] += r.y; f[j + 2] += r.z; f[j + 3] += r.w;                    \
-            }                                                                                    \
-          } else {                                                                               \
-            for (int j = 0; j < 32; ++j)                                                         \
-              if (col0 + j < p.N) f[j] += res_row[col0 + j];                                     \
-          }                                                                                      \
-        }
-        if (res_first) { DSB_ADD_RESIDUAL() }
-        if (do_gelu) {
+        for (int i = 0; i < 8; ++i) rz_cur[i] = rz_next[i];
+        const float bz[4] = {bz_next.x, bz_next.y, bz_next.z, bz_next.w};
+        float4 acc[8];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = f[j] / (1.0f + __expf(-1.702f * f[j]));
-        }
-        if (do_lrelu) {
+        for (int i = 0; i < 8; ++i) acc[i] = *reinterpret_cast<const float4*>(sw + (i * 4 + rsub) * EPI_LD + c4 * 4);
+        if (c + 1 < n_chunks) prefetch(c + 1);  // issued before this chunk's stores (out may alias residual)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = f[j] > 0.f ? f[j] : 0.2f * f[j];
-        }
-        if (do_tanh) {
+        for (int i = 0; i < 8; ++i) {
+          if (!((ok_mask >> i) & 1u)) continue;  // no warp-synchronous op below; lanes rejoin at the __syncwarp
+          const long long row = row_base + i * 4 + rsub;
+          float f[4] = {acc[i].x * p.alpha + bz[0], acc[i].y * p.alpha + bz[1], acc[i].z * p.alpha + bz[2], acc[i].w * p.alpha + bz[3]};
+          const float rz[4] = {rz_cur[i].x, rz_cur[i].y, rz_cur[i].z, rz_cur[i].w};
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = tanhf(f[j]);
-        }
-        if (!res_first) { DSB_ADD_RESIDUAL() }
-#undef DSB_ADD_RESIDUAL
-        if (do_round) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = round_tf32(f[j]);
-        }
-        if (!interior) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = 0.0f;
-        }
-        if (out_f16) {
-          __half* out_hh = reinterpret_cast<__half*>(p.out) + (long long)b * p.out_bstride + (long long)row * p.ldo;
-          if (full_chunk && (p.N & 7) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              __half2 h0 = __floats2half2_rn(f[j], f[j + 1]), h1 = __floats2half2_rn(f[j + 2], f[j + 3]);
-              __half2 h2 = __floats2half2_rn(f[j + 4], f[j + 5]), h3 = __floats2half2_rn(f[j + 6], f[j + 7]);
-              uint4 u;
+          for (int k = 0; k < 4; ++k) {
+            float x = f[k];
+            if (res_first) x += rz[k];
+            if (do_gelu) x = x / (1.0f + __expf(-1.702f * x));
+            if (do_lrelu) x = x > 0.f ? x : 0.2f * x;
+            if (do_tanh) x = tanhf(x);
+            if (!res_first) x += rz[k];
+            if (do_round) x = round_tf32(x);
+            if (!((in_mask >> i) & 1u)) x = 0.f;
+            f[k] = x;
+          }
+          if (out_f16) {
+            __half* op = reinterpret_cast<__half*>(p.out) + out_boff + row * p.ldo + col;
+            if (vec) {
+              __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]);
+              uint2 u;
               u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-              u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-              *reinterpret_cast<uint4*>(out_hh + col0 + j) = u;
+              *reinterpret_cast<uint2*>(op) = u;
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (col + k < p.N) op[k] = __float2half_rn(f[k]);
+            }
+          } else if (out_bf16) {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + out_boff + row * p.ldo + col;
+            if (vec) {
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+              uint2 u;
+              u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+              *reinterpret_cast<uint2*>(op) = u;
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (col + k < p.N) op[k] = __float2bfloat16(f[k]);
             }
           } else {
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) out_hh[col0 + j] = __float2half_rn(f[j]);
-          }
-        } else if (!out_bf16) {
-          if (full_chunk) {
+            float* op = reinterpret_cast<float*>(p.out) + out_boff + row * p.ldo + col;
+            if (vec) {
+              *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(out_f + col0 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) out_f[col0 + j] = f[j];
-          }
-        } else {
-          if (full_chunk && (p.N & 7) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(f[j], f[j + 1]);
-              __nv_bfloat162 h1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
-              __nv_bfloat162 h3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-              uint4 u;
-              u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-              u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-              *reinterpret_cast<uint4*>(out_h + col0 + j) = u;
+              for (int k = 0; k < 4; ++k)
+                if (col + k < p.N) op[k] = f[k];
             }
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) out_h[col0 + j] = __float2bfloat16(f[j]);
           }
         }
-        }  // row_ok
+        __syncwarp();  // the smem tile is rewritten by the next chunk
       }
       tc_fence_before();
       __syncwarp();

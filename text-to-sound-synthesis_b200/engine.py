@@ -100,7 +100,7 @@ class DenoiserEngine:
             dev, M, D = self.device, B * L, self.D
             e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
             a = (lambda *s: torch.empty(*s, dtype=torch.float16, device=dev)) if self.precision == "f16" else e  # GEMM A operands
-            ws = dict(x=e(B, L, D), h=a(B, L, D), qkv=e(M, 3 * D), att=a(M, D), q2=e(M, D), hid=a(M, self.layers[0]["w1"].shape[0]),
+            ws = dict(x=e(B, L, D), h=a(B, L, D), qkv=a(M, 3 * D), att=a(M, D), q2=a(M, D), hid=a(M, self.layers[0]["w1"].shape[0]),
                       logits=e(B, L, self.K), err=torch.zeros(1, dtype=torch.int32, device=dev))
             self._ws[key] = ws
         return ws
@@ -124,7 +124,8 @@ class DenoiserEngine:
             c = ops.round_tf32(c)
         elif self.precision == "f16":
             c = ops.to_f16(c)
-        return self._linear(c, self.wkv_all, self.bkv_all)
+        out = torch.empty(B * Lc, self.wkv_all.shape[0], dtype=torch.float16 if self.precision == "f16" else torch.float32, device=c.device)
+        return self._linear(c, self.wkv_all, self.bkv_all, out=out)
 
     @torch.no_grad()
     def forward(self, ids: torch.Tensor, kv_all: torch.Tensor, t: torch.Tensor, Lc: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -171,6 +171,12 @@ def attention(q, k, v, out, *, B, H, Lq, Lk, scale, round_out=False):
     for t_ in (q, k, v, out):
         if t_.stride(-1) != 1:
             raise RuntimeError("attention operands must be contiguous in the head dimension")
+    if q.dtype == torch.float16:
+        if k.dtype != torch.float16 or v.dtype != torch.float16:
+            raise RuntimeError("attention: q, k, v must share a dtype")
+        _lib.check(_lib.lib().dsb_attention_f16(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), out.data_ptr(),
+                                                out.stride(0), B, H, Lq, Lk, scale, _out_flags(out, False), _stream()), "dsb_attention_f16")
+        return out
     _lib.check(_lib.lib().dsb_attention(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), out.data_ptr(), out.stride(0),
                                         B, H, Lq, Lk, scale, _out_flags(out, round_out), _stream()), "dsb_attention")
     return out
