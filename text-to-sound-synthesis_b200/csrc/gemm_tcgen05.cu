@@ -17,7 +17,7 @@ namespace dsb {
 
 constexpr int BLOCK_M = 128;
 constexpr int ROW_BYTES = 128;  // one swizzle-128B row of K per operand row
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;  // warp0 TMA, warp1 MMA, warps 2..9 epilogue
 constexpr int MAX_TAPS = 9;
 constexpr int EPI_LD = 36;  // padded row stride (floats) of the epilogue transpose tile: 16-byte aligned rows, conflict-free
 
@@ -48,7 +48,7 @@ struct GemmSmem {
   static constexpr int B_BYTES = BLOCK_N * ROW_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * 32 * EPI_LD * 4 /*epilogue transpose tiles*/;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 8 * 32 * 32 * 4 /*epilogue transpose tiles*/;
 };
 
 template <int BLOCK_N, int KIND>  // KIND = DSB_DTYPE_*
@@ -64,7 +64,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* epi_smem = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + 256);  // 4 warps x 32 x EPI_LD floats
+  float* epi_smem = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + 256);  // 8 warps x 32 x 32 floats (XOR-swizzled)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -80,7 +80,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 4);
+      mbar_init(&tmem_empty[s], 8);
     }
     fence_barrier_init();
   }
@@ -143,20 +143,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue warps (2..5): TMEM lane quadrant = warp % 4
-    // Each 32x32 accumulator chunk (lane = row) is transposed through a private smem tile so that every global access of
-    // the warp covers 4 rows x 128 contiguous bytes (float4 per lane) instead of 32 scattered 16-byte pieces.
+    // ------------------------------------------------------------ epilogue warps (2..9): TMEM lane quadrant = warp % 4,
+    // two warps per quadrant splitting the 32-column chunks (even / odd).  Each chunk (lane = row) is transposed through a
+    // private XOR-swizzled smem tile so that every global access of the warp covers 4 rows x 128 contiguous bytes.
+    // Code-size discipline matters here: with one or two warps per scheduler the epilogue is instruction-fetch bound as
+    // soon as it leaves the L0/L1.5 instruction caches, so every runtime-flag switch sits OUTSIDE the unrolled loops.
     const int q = warp & 3;
-    float* sw = epi_smem + (warp - 2) * (32 * EPI_LD);
+    const int half = (warp - 2) >> 2;  // 0: even chunks, 1: odd chunks
+    float* sw = epi_smem + (warp - 2) * (32 * 32);
     const bool has_geo = p.geo_P > 0;
-    const bool out_bf16 = (p.flags & DSB_GEMM_OUT_BF16) != 0;
-    const bool out_f16 = (p.flags & DSB_GEMM_OUT_F16) != 0;
-    const bool do_gelu = (p.flags & DSB_GEMM_GELU2) != 0;
+    const int out_mode = (p.flags & DSB_GEMM_OUT_F16) ? 1 : ((p.flags & DSB_GEMM_OUT_BF16) ? 2 : 0);
+    const int act = (p.flags & DSB_GEMM_GELU2) ? 1 : ((p.flags & DSB_GEMM_LRELU) ? 2 : ((p.flags & DSB_GEMM_TANH) ? 3 : 0));
     const bool do_round = (p.flags & DSB_GEMM_ROUND_TF32) != 0;
-    const bool do_lrelu = (p.flags & DSB_GEMM_LRELU) != 0;
-    const bool do_tanh = (p.flags & DSB_GEMM_TANH) != 0;
     const bool res_first = (p.flags & DSB_GEMM_RES_BEFORE_ACT) != 0;
-    const int out_es = (out_bf16 || out_f16) ? 2 : 4;
+    const int out_es = out_mode ? 2 : 4;
     const bool vec_ok = ((p.ldo & 3) == 0) && ((p.out_bstride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & (4 * out_es - 1)) == 0) &&
                         (!p.residual || (((p.ld_res & 3) == 0) && ((p.res_bstride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0))) &&
                         (!p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0));
@@ -171,7 +171,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint32_t aphase = (it >> 1) & 1;
       const int row_base = m_blk * BLOCK_M + q * 32;
       uint32_t ok_mask = 0, in_mask = 0;  // bit i: row (row_base + i*4 + rsub) exists / is an interior row
-#pragma unroll
+#pragma unroll 1
       for (int i = 0; i < 8; ++i) {
         const int row = row_base + i * 4 + rsub;
         if (row < p.M) ok_mask |= 1u << i;
@@ -188,111 +188,133 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const float* res_b = p.residual ? p.residual + (long long)b * p.res_bstride : nullptr;
       const int n_chunks = min(BLOCK_N / 32, (p.N - n_blk * BLOCK_N + 31) / 32);
 
-      // bias + residual of a chunk are fetched one chunk ahead (the first one before the accumulator is even complete), so
-      // their latency hides behind the mainloop / the previous chunk instead of stalling every row group.
+      // bias + residual are fetched one chunk ahead (the first one while the mainloop still runs)
       float4 rz_next[8];
       float4 bz_next = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) rz_next[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       auto prefetch = [&](int c) {
         const int col = n_blk * BLOCK_N + c * 32 + c4 * 4;
-        const bool vec = vec_ok && (col + 3 < p.N);
-        bz_next = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias) {
-          if (vec) bz_next = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-          else {
-            if (col < p.N) bz_next.x = __ldg(p.bias + col);
-            if (col + 1 < p.N) bz_next.y = __ldg(p.bias + col + 1);
-            if (col + 2 < p.N) bz_next.z = __ldg(p.bias + col + 2);
-            if (col + 3 < p.N) bz_next.w = __ldg(p.bias + col + 3);
-          }
-        }
+        if (vec_ok && (col + 3 < p.N)) {  // tail / unaligned chunks fetch inside the slow path instead
+          if (p.bias) bz_next = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+          if (res_b) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          rz_next[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (res_b && ((ok_mask >> i) & 1u)) {
-            const float* rp = res_b + (long long)(row_base + i * 4 + rsub) * p.ld_res + col;
-            if (vec) rz_next[i] = *reinterpret_cast<const float4*>(rp);
-            else {
-              if (col < p.N) rz_next[i].x = rp[0];
-              if (col + 1 < p.N) rz_next[i].y = rp[1];
-              if (col + 2 < p.N) rz_next[i].z = rp[2];
-              if (col + 3 < p.N) rz_next[i].w = rp[3];
-            }
+            for (int i = 0; i < 8; ++i)
+              if ((ok_mask >> i) & 1u) rz_next[i] = *reinterpret_cast<const float4*>(res_b + (long long)(row_base + i * 4 + rsub) * p.ld_res + col);
           }
         }
       };
-      if (n_chunks > 0) prefetch(0);
+      if (half < n_chunks) prefetch(half);
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < n_chunks; ++c) {
+      for (int c = half; c < n_chunks; c += 2) {
         const int col0 = n_blk * BLOCK_N + c * 32;
-        uint32_t v[32];
-        tmem_ld_32x32(t_row + c * 32, v);
-        tmem_ld_wait();
+        {
+          uint32_t v[32];
+          tmem_ld_32x32(t_row + c * 32, v);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(sw + lane * EPI_LD + j * 4) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(sw + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
         __syncwarp();
         const int col = col0 + c4 * 4;
-        const bool vec = vec_ok && (col + 3 < p.N);
-        float4 rz_cur[8];
+        if (vec_ok && (col0 + 32 <= p.N)) {
+          // ---------------- fast path: whole chunk in range, 16-byte aligned everywhere
+          float x[32];
+          float4 rz_cur[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) rz_cur[i] = rz_next[i];
-        const float bz[4] = {bz_next.x, bz_next.y, bz_next.z, bz_next.w};
-        float4 acc[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = *reinterpret_cast<const float4*>(sw + (i * 4 + rsub) * EPI_LD + c4 * 4);
-        if (c + 1 < n_chunks) prefetch(c + 1);  // issued before this chunk's stores (out may alias residual)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (!((ok_mask >> i) & 1u)) continue;  // no warp-synchronous op below; lanes rejoin at the __syncwarp
-          const long long row = row_base + i * 4 + rsub;
-          float f[4] = {acc[i].x * p.alpha + bz[0], acc[i].y * p.alpha + bz[1], acc[i].z * p.alpha + bz[2], acc[i].w * p.alpha + bz[3]};
-          const float rz[4] = {rz_cur[i].x, rz_cur[i].y, rz_cur[i].z, rz_cur[i].w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            float x = f[k];
-            if (res_first) x += rz[k];
-            if (do_gelu) x = x / (1.0f + __expf(-1.702f * x));
-            if (do_lrelu) x = x > 0.f ? x : 0.2f * x;
-            if (do_tanh) x = tanhf(x);
-            if (!res_first) x += rz[k];
-            if (do_round) x = round_tf32(x);
-            if (!((in_mask >> i) & 1u)) x = 0.f;
-            f[k] = x;
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + rsub;
+            const float4 a4 = *reinterpret_cast<const float4*>(sw + r * 32 + ((c4 ^ (r & 7)) << 2));
+            rz_cur[i] = rz_next[i];
+            x[4 * i + 0] = fmaf(a4.x, p.alpha, bz_next.x); x[4 * i + 1] = fmaf(a4.y, p.alpha, bz_next.y);
+            x[4 * i + 2] = fmaf(a4.z, p.alpha, bz_next.z); x[4 * i + 3] = fmaf(a4.w, p.alpha, bz_next.w);
           }
-          if (out_f16) {
-            __half* op = reinterpret_cast<__half*>(p.out) + out_boff + row * p.ldo + col;
-            if (vec) {
-              __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]);
-              uint2 u;
-              u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-              *reinterpret_cast<uint2*>(op) = u;
-            } else {
+          if (c + 2 < n_chunks) prefetch(c + 2);  // issued before this chunk's stores (out may alias residual)
+          if (res_b && res_first) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (col + k < p.N) op[k] = __float2half_rn(f[k]);
-            }
-          } else if (out_bf16) {
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + out_boff + row * p.ldo + col;
-            if (vec) {
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
-              uint2 u;
-              u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-              *reinterpret_cast<uint2*>(op) = u;
-            } else {
+            for (int i = 0; i < 8; ++i) { x[4 * i] += rz_cur[i].x; x[4 * i + 1] += rz_cur[i].y; x[4 * i + 2] += rz_cur[i].z; x[4 * i + 3] += rz_cur[i].w; }
+          }
+          if (act == 1) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (col + k < p.N) op[k] = __float2bfloat16(f[k]);
+            for (int e = 0; e < 32; ++e) x[e] = __fdividef(x[e], 1.0f + __expf(-1.702f * x[e]));
+          } else if (act == 2) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) x[e] = x[e] > 0.f ? x[e] : 0.2f * x[e];
+          } else if (act == 3) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {  // tanh(x) = 1 - 2 / (1 + exp(2x)), clamped so exp stays finite
+              const float z = fminf(fmaxf(x[e], -15.f), 15.f);
+              x[e] = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * z));
             }
+          }
+          if (res_b && !res_first) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { x[4 * i] += rz_cur[i].x; x[4 * i + 1] += rz_cur[i].y; x[4 * i + 2] += rz_cur[i].z; x[4 * i + 3] += rz_cur[i].w; }
+          }
+          if (do_round) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) x[e] = round_tf32(x[e]);
+          }
+          if (has_geo) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (!((in_mask >> i) & 1u)) { x[4 * i] = 0.f; x[4 * i + 1] = 0.f; x[4 * i + 2] = 0.f; x[4 * i + 3] = 0.f; }
+          }
+          if (out_mode == 0) {
+            float* op = reinterpret_cast<float*>(p.out) + out_boff + (long long)(row_base + rsub) * p.ldo + col;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if ((ok_mask >> i) & 1u) *reinterpret_cast<float4*>(op + (long long)i * 4 * p.ldo) = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+          } else if (out_mode == 1) {
+            __half* op = reinterpret_cast<__half*>(p.out) + out_boff + (long long)(row_base + rsub) * p.ldo + col;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if ((ok_mask >> i) & 1u) {
+                __half2 h0 = __floats2half2_rn(x[4 * i], x[4 * i + 1]), h1 = __floats2half2_rn(x[4 * i + 2], x[4 * i + 3]);
+                uint2 u;
+                u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+                *reinterpret_cast<uint2*>(op + (long long)i * 4 * p.ldo) = u;
+              }
           } else {
-            float* op = reinterpret_cast<float*>(p.out) + out_boff + row * p.ldo + col;
-            if (vec) {
-              *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
-            } else {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + out_boff + (long long)(row_base + rsub) * p.ldo + col;
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (col + k < p.N) op[k] = f[k];
+            for (int i = 0; i < 8; ++i)
+              if ((ok_mask >> i) & 1u) {
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(x[4 * i], x[4 * i + 1]), h1 = __floats2bfloat162_rn(x[4 * i + 2], x[4 * i + 3]);
+                uint2 u;
+                u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+                *reinterpret_cast<uint2*>(op + (long long)i * 4 * p.ldo) = u;
+              }
+          }
+        } else {
+          // ---------------- slow path (N tail, unaligned leading dimensions): rolled scalar loops, rarely taken
+          if (c + 2 < n_chunks) prefetch(c + 2);
+#pragma unroll 1
+          for (int i = 0; i < 8; ++i) {
+            if (!((ok_mask >> i) & 1u)) continue;
+            const int r = i * 4 + rsub;
+            const long long row = row_base + r;
+            const float4 a4 = *reinterpret_cast<const float4*>(sw + r * 32 + ((c4 ^ (r & 7)) << 2));
+            const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll 1
+            for (int k = 0; k < 4; ++k) {
+              if (col + k >= p.N) break;
+              float xv = av[k] * p.alpha + (p.bias ? __ldg(p.bias + col + k) : 0.f);
+              const float rv = res_b ? res_b[row * p.ld_res + col + k] : 0.f;
+              if (res_first) xv += rv;
+              if (act == 1) xv = __fdividef(xv, 1.0f + __expf(-1.702f * xv));
+              else if (act == 2) xv = xv > 0.f ? xv : 0.2f * xv;
+              else if (act == 3) { const float z = fminf(fmaxf(xv, -15.f), 15.f); xv = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * z)); }
+              if (!res_first) xv += rv;
+              if (do_round) xv = round_tf32(xv);
+              if (!((in_mask >> i) & 1u)) xv = 0.f;
+              const long long o = out_boff + row * p.ldo + col + k;
+              if (out_mode == 0) reinterpret_cast<float*>(p.out)[o] = xv;
+              else if (out_mode == 1) reinterpret_cast<__half*>(p.out)[o] = __float2half_rn(xv);
+              else reinterpret_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16(xv);
             }
           }
         }
