@@ -27,22 +27,27 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-__device__ __forceinline__ void load_tile(__half* dst, const __half* src, long long ld, int row0, int nrows_valid) {
-  // 64 rows x 64 halves (8 x 16-byte vectors per row), 128 threads
-  for (int idx = threadIdx.x; idx < 64 * 8; idx += 128) {
+// asynchronous 64 x 64-half tile copy (global -> padded smem) with cp.async; rows past nrows_valid are zero-filled
+__device__ __forceinline__ void load_tile_async(__half* dst, const __half* src, long long ld, int row0, int nrows_valid) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int idx = threadIdx.x + it * 128;
     const int r = idx >> 3, c8 = (idx & 7) * 8;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (row0 + r < nrows_valid) v = *reinterpret_cast<const uint4*>(src + (long long)(row0 + r) * ld + c8);
-    *reinterpret_cast<uint4*>(dst + r * LDS + c8) = v;
+    const bool ok = row0 + r < nrows_valid;
+    const __half* g = src + (long long)(ok ? row0 + r : 0) * ld + c8;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst + r * LDS + c8)), "l"(g), "r"(ok ? 16 : 0) : "memory");
   }
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __global__ void __launch_bounds__(128)
 attention_f16_kernel(const __half* __restrict__ q, long long ldq, const __half* __restrict__ k, long long ldk, const __half* __restrict__ v,
                      long long ldv, void* __restrict__ o, long long ldo, int Lq, int Lk, float scale_log2e, int flags) {
   __shared__ __align__(16) __half Qs[QT * LDS];
-  __shared__ __align__(16) __half Ks[KT * LDS];
-  __shared__ __align__(16) __half Vs[KT * LDS];
+  __shared__ __align__(16) __half Ks[2][KT * LDS];
+  __shared__ __align__(16) __half Vs[2][KT * LDS];
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -50,14 +55,11 @@ attention_f16_kernel(const __half* __restrict__ q, long long ldq, const __half* 
   const __half* kb = k + (long long)b * Lk * ldk + h * HD;
   const __half* vb = v + (long long)b * Lk * ldv + h * HD;
 
-  load_tile(Qs, qb, ldq, qt * QT, Lq);
-  __syncthreads();
+  load_tile_async(Qs, qb, ldq, qt * QT, Lq);
+  load_tile_async(Ks[0], kb, ldk, 0, Lk);
+  load_tile_async(Vs[0], vb, ldv, 0, Lk);
+  cp_async_commit();
   uint32_t a[4][4];  // Q fragments: 4 k-steps of 16 head dims
-  {
-    const int row = warp * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) ldsm_x4(a[ks], Qs + row * LDS + ks * 16 + 8 * (lane >> 4));
-  }
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
   float oacc[8][4];
 #pragma unroll
@@ -65,17 +67,29 @@ attention_f16_kernel(const __half* __restrict__ q, long long ldq, const __half* 
 
   const int nchunks = (Lk + KT - 1) / KT;
   for (int kc = 0; kc < nchunks; ++kc) {
+    const __half* Kc = Ks[kc & 1];
+    const __half* Vc = Vs[kc & 1];
+    if (kc + 1 < nchunks) {  // prefetch the next K/V chunk into the other buffer while this one is consumed
+      load_tile_async(Ks[(kc + 1) & 1], kb, ldk, (kc + 1) * KT, Lk);
+      load_tile_async(Vs[(kc + 1) & 1], vb, ldv, (kc + 1) * KT, Lk);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     __syncthreads();
-    load_tile(Ks, kb, ldk, kc * KT, Lk);
-    load_tile(Vs, vb, ldv, kc * KT, Lk);
-    __syncthreads();
+    if (kc == 0) {
+      const int row = warp * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) ldsm_x4(a[ks], Qs + row * LDS + ks * 16 + 8 * (lane >> 4));
+    }
 
     float s[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
       uint32_t kf[4];
-      const __half* kp = Ks + (nt * 8 + (lane & 7)) * LDS + 8 * (lane >> 3);
+      const __half* kp = Kc + (nt * 8 + (lane & 7)) * LDS + 8 * (lane >> 3);
       ldsm_x4(kf, kp);            // head dims 0..31  -> (b0,b1) of k-step 0 and 1
       mma_f16(s[nt], a[0], kf[0], kf[1]);
       mma_f16(s[nt], a[1], kf[2], kf[3]);
@@ -111,7 +125,7 @@ attention_f16_kernel(const __half* __restrict__ q, long long ldq, const __half* 
     for (int kk = 0; kk < 4; ++kk) {  // 16 keys per step: score tiles 2kk and 2kk+1 re-packed as the fp16 A fragment
       const uint32_t pa[4] = {pack_h2(s[2 * kk][0], s[2 * kk][1]), pack_h2(s[2 * kk][2], s[2 * kk][3]),
                               pack_h2(s[2 * kk + 1][0], s[2 * kk + 1][1]), pack_h2(s[2 * kk + 1][2], s[2 * kk + 1][3])};
-      const __half* vp = Vs + (kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * LDS + 8 * (lane >> 4);
+      const __half* vp = Vc + (kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * LDS + 8 * (lane >> 4);
 #pragma unroll
       for (int np = 0; np < 4; ++np) {  // two 8-wide head-dim tiles per ldmatrix.x4.trans
         uint32_t vf[4];
@@ -120,6 +134,7 @@ attention_f16_kernel(const __half* __restrict__ q, long long ldq, const __half* 
         mma_f16(oacc[2 * np + 1], pa, vf[2], vf[3]);
       }
     }
+    __syncthreads();  // everyone is done with this buffer before the prefetch two iterations ahead overwrites it
   }
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);

@@ -39,26 +39,29 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// MODE 0: plain affine (gamma, beta); MODE 1: AdaLN (table row = scale | shift selected by t[b])
-template <int MODE>
-__global__ void layernorm_kernel(const float* __restrict__ x, void* __restrict__ out, const float* __restrict__ p0, const float* __restrict__ p1,
-                                 const int64_t* __restrict__ t, int rows, int L, int D, int T, float eps, int flags) {
+// MODE 0: plain affine (gamma, beta); MODE 1: AdaLN (table row = scale | shift selected by t[b]).
+// NV = D / 128 float4 vectors per lane, the whole row lives in registers: x is read from HBM exactly once.
+template <int MODE, int NV>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, void* __restrict__ out, const float* __restrict__ p0, const float* __restrict__ p1,
+                 const int64_t* __restrict__ t, int rows, int L, int D, int T, float eps, int flags) {
   const int warps_per_block = blockDim.x >> 5;
   const int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * D);
-  const int nv = D / 4;
+  float4 v[NV];
   float s = 0.f;
-  for (int i = lane; i < nv; i += 32) {
-    const float4 v = xr[i];
-    s += (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    v[j] = xr[lane + 32 * j];
+    s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
   }
   const float mean = warp_sum(s) / (float)D;
   float q = 0.f;
-  for (int i = lane; i < nv; i += 32) {
-    const float4 v = xr[i];
-    const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
     q += (a * a + b * b) + (c * c + d * d);
   }
   const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
@@ -73,25 +76,25 @@ __global__ void layernorm_kernel(const float* __restrict__ x, void* __restrict__
     b4 = reinterpret_cast<const float4*>(p0 + ti * 2LL * D + D);  // shift
   }
   const bool rnd = (flags & DSB_GEMM_ROUND_TF32) != 0;
-  const bool obf = (flags & DSB_GEMM_OUT_BF16) != 0;
-  const bool of16 = (flags & DSB_GEMM_OUT_F16) != 0;
-  for (int i = lane; i < nv; i += 32) {
-    const float4 v = xr[i];
+  const int omode = (flags & DSB_GEMM_OUT_F16) ? 1 : ((flags & DSB_GEMM_OUT_BF16) ? 2 : 0);
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int i = lane + 32 * j;
     const float4 g = __ldg(g4 + i), b = __ldg(b4 + i);
     float4 y;
     if (MODE == 0) {
-      y.x = (v.x - mean) * rstd * g.x + b.x; y.y = (v.y - mean) * rstd * g.y + b.y;
-      y.z = (v.z - mean) * rstd * g.z + b.z; y.w = (v.w - mean) * rstd * g.w + b.w;
+      y.x = (v[j].x - mean) * rstd * g.x + b.x; y.y = (v[j].y - mean) * rstd * g.y + b.y;
+      y.z = (v[j].z - mean) * rstd * g.z + b.z; y.w = (v[j].w - mean) * rstd * g.w + b.w;
     } else {
-      y.x = (v.x - mean) * rstd * (1.f + g.x) + b.x; y.y = (v.y - mean) * rstd * (1.f + g.y) + b.y;
-      y.z = (v.z - mean) * rstd * (1.f + g.z) + b.z; y.w = (v.w - mean) * rstd * (1.f + g.w) + b.w;
+      y.x = (v[j].x - mean) * rstd * (1.f + g.x) + b.x; y.y = (v[j].y - mean) * rstd * (1.f + g.y) + b.y;
+      y.z = (v[j].z - mean) * rstd * (1.f + g.z) + b.z; y.w = (v[j].w - mean) * rstd * (1.f + g.w) + b.w;
     }
-    if (of16) {
+    if (omode == 1) {
       __half2 h0 = __floats2half2_rn(y.x, y.y), h1 = __floats2half2_rn(y.z, y.w);
       uint2 u;
       u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
       reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out) + (long long)row * D)[i] = u;
-    } else if (obf) {
+    } else if (omode == 2) {
       __nv_bfloat162 h0 = __floats2bfloat162_rn(y.x, y.y), h1 = __floats2bfloat162_rn(y.z, y.w);
       uint2 u;
       u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
@@ -101,6 +104,21 @@ __global__ void layernorm_kernel(const float* __restrict__ x, void* __restrict__
       reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (long long)row * D)[i] = y;
     }
   }
+}
+
+template <int MODE>
+static int launch_ln(const float* x, void* out, const float* p0, const float* p1, const int64_t* t, int rows, int L, int D, int T, float eps,
+                     int flags, cudaStream_t st) {
+  const int grid = (rows + 7) / 8;
+  switch (D / 128) {
+#define DSB_LN_CASE(N) case N: layernorm_kernel<MODE, N><<<grid, 256, 0, st>>>(x, out, p0, p1, t, rows, L, D, T, eps, flags); break;
+    DSB_LN_CASE(1) DSB_LN_CASE(2) DSB_LN_CASE(3) DSB_LN_CASE(4) DSB_LN_CASE(5) DSB_LN_CASE(6) DSB_LN_CASE(7) DSB_LN_CASE(8)
+    DSB_LN_CASE(12) DSB_LN_CASE(16)
+#undef DSB_LN_CASE
+    default: set_error("layernorm: D=%d unsupported (need D %% 128 == 0 and D/128 in {1..8,12,16})", D); return 2;
+  }
+  DSB_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 }  // namespace dsb
 using namespace dsb;
@@ -115,16 +133,11 @@ extern "C" int dsb_embed_tokens(const int64_t* ids, const float* emb, const floa
   return 0;
 }
 extern "C" int dsb_layernorm(const float* x, void* out, const float* gamma, const float* beta, int rows, int D, float eps, int flags, void* stream) {
-  DSB_REQUIRE(D % 4 == 0, "dsb_layernorm: D must be a multiple of 4");
-  layernorm_kernel<0><<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, out, gamma, beta, nullptr, rows, 1, D, 0, eps, flags);
-  DSB_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  DSB_REQUIRE(D % 128 == 0, "dsb_layernorm: D must be a multiple of 128");
+  return launch_ln<0>(x, out, gamma, beta, nullptr, rows, 1, D, 0, eps, flags, (cudaStream_t)stream);
 }
 extern "C" int dsb_ada_layernorm(const float* x, void* out, const float* table, const int64_t* t, int B, int L, int D, int T, float eps, int flags,
                                  void* stream) {
-  DSB_REQUIRE(D % 4 == 0, "dsb_ada_layernorm: D must be a multiple of 4");
-  const int rows = B * L;
-  layernorm_kernel<1><<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, out, table, nullptr, t, rows, L, D, T, eps, flags);
-  DSB_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  DSB_REQUIRE(D % 128 == 0, "dsb_ada_layernorm: D must be a multiple of 128");
+  return launch_ln<1>(x, out, table, nullptr, t, B * L, L, D, T, eps, flags, (cudaStream_t)stream);
 }
