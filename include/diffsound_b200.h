@@ -69,8 +69,11 @@ typedef struct dsb_gemm_desc {
   long long a_batch_stride, w_batch_stride /* 0 = shared W */, out_batch_stride, res_batch_stride;
   int dtype;             /* DSB_DTYPE_* */
   int flags;             /* DSB_GEMM_* */
-  int num_taps;          /* 1..9 */
-  int tap_shift[9];
+  int num_taps;          /* 1..32 */
+  int tap_shift[32];     /* A row shift per tap */
+  int tap_acol[32];      /* A column offset per tap (elements); with a_cols this lets one A buffer hold several K-blocks side by
+                            side, e.g. the (hi | lo) halves of a split-TF32 operand */
+  long long a_cols;      /* columns of A that exist (0 -> K) */
   int geo_P, geo_Wp, geo_y0, geo_y1, geo_x0, geo_x1; /* optional zero-border row mask, geo_P = 0 disables */
   float alpha;           /* 0 -> 1 */
   int block_n;           /* 0 = auto, 128, 256 */
@@ -87,6 +90,11 @@ int dsb_gemm_f32(const float* A, const float* W, const float* bias, const float*
 int dsb_round_tf32(const float* in, float* out, long long n, void* stream);
 int dsb_f32_to_bf16(const float* in, void* out_bf16, long long n, void* stream);
 int dsb_f32_to_f16(const float* in, void* out_f16, long long n, void* stream);
+/* Split-TF32 operand: out[r, c] = hi = tf32(in[r, c]), out[r, Cp + c] = lo = tf32(in[r, c] - hi), zeros in the padding columns
+ * [C, Cp); out has 2*Cp columns (ld_out elements per row).  A*W ~ hi*Whi + lo*Whi + hi*Wlo recovers fp32-class accuracy on
+ * the TF32 tensor pipe (three K passes), used for the SpecVQGAN decoder / MelGAN convolutions.  w_format = 1 writes the
+ * weight-side layout [hi | hi | lo] (3*Cp columns) for an activation that is the W operand of a GEMM (attention K, V^T). */
+int dsb_split_tf32(const float* in, long long ld_in, float* out, long long ld_out, long long rows, int C, int Cp, int w_format, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Denoiser pieces (reference sound_synthesis/modeling/transformers/transformer_utils.py,

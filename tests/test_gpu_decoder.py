@@ -16,31 +16,33 @@ def G():
     return gpu_common
 
 
-def build_vq(K, E, ch, ch_mult, sd=None, z_channels=None, prefix="content_codec."):
+def build_vq(K, E, ch, ch_mult, sd=None, z_channels=None, prefix="content_codec.", precision="tf32x3"):
     from diffsound_b200.modeling.codecs.spec_codec.vqgan import VQModel
     dd = dict(double_z=False, z_channels=z_channels or E, resolution=848, in_channels=1, out_ch=1, ch=ch, ch_mult=list(ch_mult), num_res_blocks=2,
               attn_resolutions=[53], dropout=0.0)
-    m = VQModel(dd, None, n_embed=K, embed_dim=E)
+    m = VQModel(dd, None, n_embed=K, embed_dim=E, precision=precision)
     if sd is not None:
         m.load_state_dict({k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}, strict=True)
     return m.cuda().eval()
 
 
-def test_decoder_tiny_matches_reference_golden(G):
+@pytest.mark.parametrize("precision,tol", [("tf32x3", 1e-3), ("tf32", 1.5e-2)])
+def test_decoder_tiny_matches_reference_golden(G, precision, tol):
+    """north_star tolerance (1e-3 relative) holds in the default split-TF32 mode; single-pass TF32 is the fast, looser mode."""
     sd, g = load_golden("decoder_tiny.npz")
     K, E, ch, H, W = [int(v) for v in g["__cfg"]]
-    m = build_vq(K, E, ch, (1, 1, 1, 1, 2), sd)
+    m = build_vq(K, E, ch, (1, 1, 1, 1, 2), sd, precision=precision)
     mel = m.decode_tokens(torch.from_numpy(g["in_ids"]).long().cuda(), (H, W)).cpu()
     ref = torch.from_numpy(g["out_mel"])
     assert mel.shape == ref.shape
     err = rel_err(mel, ref)
-    print("decoder tiny rel err", err)
-    assert err < 2e-3  # TF32 operands through ~30 conv layers
+    print(f"decoder tiny [{precision}] rel err", err)
+    assert err < tol
     # the reference-shaped entry point (NCHW latents) agrees with the token fast path
     ids_rm = O.column_major_reverse(torch.from_numpy(g["in_ids"]).long(), H, W)
     z = O.codebook_lookup(sd, ids_rm, (ids_rm.shape[0], H, W, E))
     mel2 = m.decode(z.cuda()).cpu()
-    assert rel_err(mel2, mel) < 1e-6
+    assert rel_err(mel2, mel) < 1e-5
 
 
 def test_decoder_full_config_matches_oracle(G):
@@ -53,8 +55,8 @@ def test_decoder_full_config_matches_oracle(G):
     assert mel.shape == (1, 1, 80, 848)
     err = rel_err(mel, ref)
     mse = float(((mel - ref) ** 2).mean())
-    print("decoder full rel err", err, "mel MSE", mse, "ref rms", float(ref.pow(2).mean().sqrt()))
-    assert err < 2e-3
+    print("decoder full [tf32x3] rel err", err, "mel MSE", mse, "ref rms", float(ref.pow(2).mean().sqrt()))
+    assert err < 1e-3
 
 
 def test_melgan_tiny_matches_reference_golden(G):
@@ -67,8 +69,8 @@ def test_melgan_tiny_matches_reference_golden(G):
     ref = torch.from_numpy(g["out_wav"])
     assert wav.shape == ref.shape
     err = rel_err(wav, ref)
-    print("melgan tiny rel err", err)
-    assert err < 2e-3
+    print("melgan tiny [tf32x3] rel err", err)
+    assert err < 1e-3
 
 
 def test_melgan_real_checkpoint(G):
@@ -86,12 +88,12 @@ def test_melgan_real_checkpoint(G):
     wav = m(torch.from_numpy(g["in_mel"]).cuda()).cpu()
     ref = torch.from_numpy(g["out_wav"])
     err = rel_err(wav, ref)
-    print("melgan real (40 frames) rel err", err)
-    assert err < 3e-3
+    print("melgan real (40 frames) [tf32x3] rel err", err)
+    assert err < 1e-3
     mel = torch.rand(2, 80, 848, generator=torch.Generator().manual_seed(21))
     ref = O.melgan_forward(sd, mel)
     wav = m(mel.cuda()).cpu()
     assert wav.shape == (2, 1, 217088)
     err = rel_err(wav, ref)
-    print("melgan real (848 frames, B=2) rel err", err, "rms ref", float(ref.pow(2).mean().sqrt()))
-    assert err < 3e-3
+    print("melgan real (848 frames, B=2) [tf32x3] rel err", err, "rms ref", float(ref.pow(2).mean().sqrt()))
+    assert err < 1e-3

@@ -20,7 +20,7 @@ class GemmDesc(C.Structure):
         ("M", c_i), ("N", c_i), ("K", c_i), ("batch", c_i),
         ("a_rows", c_ll), ("lda", c_ll), ("ldw", c_ll), ("ldo", c_ll), ("ld_res", c_ll),
         ("a_batch_stride", c_ll), ("w_batch_stride", c_ll), ("out_batch_stride", c_ll), ("res_batch_stride", c_ll),
-        ("dtype", c_i), ("flags", c_i), ("num_taps", c_i), ("tap_shift", c_i * 9),
+        ("dtype", c_i), ("flags", c_i), ("num_taps", c_i), ("tap_shift", c_i * 32), ("tap_acol", c_i * 32), ("a_cols", c_ll),
         ("geo_P", c_i), ("geo_Wp", c_i), ("geo_y0", c_i), ("geo_y1", c_i), ("geo_x0", c_i), ("geo_x1", c_i),
         ("alpha", c_f), ("block_n", c_i), ("max_ctas", c_i),
     ]
@@ -36,6 +36,7 @@ SIGNATURES = {
     "dsb_f32_to_bf16": [c_vp, c_vp, c_ll, c_vp],
     "dsb_f32_to_f16": [c_vp, c_vp, c_ll, c_vp],
     "dsb_silu": [c_vp, c_vp, c_ll, c_vp],
+    "dsb_split_tf32": [c_vp, c_ll, c_vp, c_ll, c_ll, c_i, c_i, c_i, c_vp],
     "dsb_embed_tokens": [c_vp] * 5 + [c_i] * 6 + [c_vp, c_vp],
     "dsb_layernorm": [c_vp] * 4 + [c_i, c_i, c_f, c_i, c_vp],
     "dsb_ada_layernorm": [c_vp] * 4 + [c_i] * 4 + [c_f, c_i, c_vp],

@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cstdarg>
+#include <cstdlib>
 
 namespace dsb {
 static thread_local char g_err[512] = "";
@@ -12,6 +13,14 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DSB_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 int sm_count() {
   static int n = 0;
@@ -42,6 +51,26 @@ __global__ void f32_to_f16_kernel(const float* __restrict__ in, __half* __restri
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) out[i] = __float2half_rn(in[i]);
+}
+__global__ void split_tf32_kernel(const float* __restrict__ in, long long ld_in, float* __restrict__ out, long long ld_out, long long rows, int C, int Cp, int wfmt) {
+  const long long total = rows * Cp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / Cp;
+    const int c = (int)(i - r * Cp);
+    float hi = 0.f, lo = 0.f;
+    if (c < C) {
+      const float v = in[r * ld_in + c];
+      hi = round_tf32(v);
+      lo = round_tf32(v - hi);
+    }
+    out[r * ld_out + c] = hi;
+    if (wfmt) {  // weight-side layout [hi | hi | lo]
+      out[r * ld_out + Cp + c] = hi;
+      out[r * ld_out + 2 * Cp + c] = lo;
+    } else {     // activation-side layout [hi | lo]
+      out[r * ld_out + Cp + c] = lo;
+    }
+  }
 }
 __global__ void silu_kernel(const float* __restrict__ in, float* __restrict__ out, long long n) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -84,6 +113,12 @@ extern "C" int dsb_f32_to_bf16(const float* in, void* out, long long n, void* st
 }
 extern "C" int dsb_f32_to_f16(const float* in, void* out, long long n, void* stream) {
   f32_to_f16_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(in, (__half*)out, n);
+  DSB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int dsb_split_tf32(const float* in, long long ld_in, float* out, long long ld_out, long long rows, int C, int Cp, int wfmt, void* stream) {
+  DSB_REQUIRE(rows > 0 && C > 0 && Cp >= C && ld_out >= (wfmt ? 3LL : 2LL) * Cp, "dsb_split_tf32: bad shape");
+  split_tf32_kernel<<<grid_for(rows * Cp, 256), 256, 0, (cudaStream_t)stream>>>(in, ld_in, out, ld_out, rows, C, Cp, wfmt);
   DSB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -33,6 +33,8 @@ attention_kernel(const float* __restrict__ q, long long ldq, const float* __rest
   const float* kb = k + (long long)b * Lk * ldk + h * HD;
   const float* vb = v + (long long)b * Lk * ldv + h * HD;
 
+  pdl_wait();
+  pdl_trigger();
   uint32_t a[8][4];
 #pragma unroll
   for (int ks = 0; ks < 8; ++ks) {
@@ -144,7 +146,7 @@ extern "C" int dsb_attention(const float* q, long long ldq, const float* k, long
   DSB_REQUIRE(((reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) & 15) == 0 && (reinterpret_cast<uintptr_t>(o) & 3) == 0,
               "dsb_attention: k/v must be 16-byte aligned, o 8-byte aligned");
   dim3 grid((Lq + QT - 1) / QT, H, B);
-  attention_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(q, ldq, k, ldk, v, ldv, o, ldo, Lq, Lk, scale * 1.4426950408889634f, flags);
-  DSB_CHECK_CUDA(cudaGetLastError());
+  DSB_CHECK_CUDA(launch_pdl(attention_kernel, grid, dim3(128), 0, (cudaStream_t)stream, q, ldq, k, ldk, v, ldv, o, ldo, Lq, Lk,
+                            scale * 1.4426950408889634f, flags));
   return 0;
 }

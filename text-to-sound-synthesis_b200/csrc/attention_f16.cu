@@ -54,6 +54,8 @@ attention_f16_kernel(const __half* __restrict__ q, long long ldq, const __half* 
   const __half* qb = q + (long long)b * Lq * ldq + h * HD;
   const __half* kb = k + (long long)b * Lk * ldk + h * HD;
   const __half* vb = v + (long long)b * Lk * ldv + h * HD;
+  pdl_wait();
+  pdl_trigger();
 
   load_tile_async(Qs, qb, ldq, qt * QT, Lq);
   load_tile_async(Ks[0], kb, ldk, 0, Lk);
@@ -167,8 +169,7 @@ extern "C" int dsb_attention_f16(const void* q, long long ldq, const void* k, lo
   DSB_REQUIRE(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) & 15) == 0,
               "dsb_attention_f16: q/k/v must be 16-byte aligned");
   dim3 grid((Lq + QT - 1) / QT, H, B);
-  attention_f16_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const __half*)q, ldq, (const __half*)k, ldk, (const __half*)v, ldv, o, ldo, Lq, Lk,
-                                                               scale * 1.4426950408889634f, flags);
-  DSB_CHECK_CUDA(cudaGetLastError());
+  DSB_CHECK_CUDA(launch_pdl(attention_f16_kernel, grid, dim3(128), 0, (cudaStream_t)stream, (const __half*)q, ldq, (const __half*)k, ldk,
+                            (const __half*)v, ldv, o, ldo, Lq, Lk, scale * 1.4426950408889634f, flags));
   return 0;
 }

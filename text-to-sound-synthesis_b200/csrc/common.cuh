@@ -27,6 +27,24 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 int sm_count();
+bool pdl_enabled();  // programmatic dependent launch (env DSB_PDL=0 disables)
+
+// Launch with the programmatic-stream-serialization attribute: the grid may be scheduled while its predecessor drains; the
+// kernel calls pdl_wait() before touching anything the predecessor wrote.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 
 // ---------------------------------------------------------------- small device utils
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -50,6 +68,10 @@ __device__ __forceinline__ float round_tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
+
+// programmatic dependent launch: wait for the predecessor grid(s) to complete and flush; let the successor start launching
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -18,7 +18,7 @@ namespace dsb {
 constexpr int BLOCK_M = 128;
 constexpr int ROW_BYTES = 128;  // one swizzle-128B row of K per operand row
 constexpr int GEMM_THREADS = 320;  // warp0 TMA, warp1 MMA, warps 2..9 epilogue
-constexpr int MAX_TAPS = 9;
+constexpr int MAX_TAPS = 32;
 constexpr int EPI_LD = 36;  // padded row stride (floats) of the epilogue transpose tile: 16-byte aligned rows, conflict-free
 
 struct GemmParams {
@@ -28,6 +28,7 @@ struct GemmParams {
   int block_k;     // elements per k-block (32 tf32 / 64 bf16)
   int num_taps;
   int tap_shift[MAX_TAPS];
+  int tap_acol[MAX_TAPS];
   int kc;          // channels per tap (B column offset per tap)
   int b_batched;
   const float* bias;
@@ -92,6 +93,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // everything above (barrier init, TMEM allocation, tensor-map prefetch) overlapped the predecessor's tail
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -108,7 +112,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
           uint8_t* sa = smem + stage * S::STAGE_BYTES;
-          tma_load_3d(&tmap_a, &full_bar[stage], sa, c0, m_blk * BLOCK_M + p.tap_shift[tap], b);
+          tma_load_3d(&tmap_a, &full_bar[stage], sa, c0 + p.tap_acol[tap], m_blk * BLOCK_M + p.tap_shift[tap], b);
           tma_load_3d(&tmap_b, &full_bar[stage], sa + S::A_BYTES, tap * p.kc + c0, n_blk * BLOCK_N, p.b_batched ? b : 0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -381,8 +385,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams
   }
   const int tiles = p.tiles_m * p.tiles_n * p.batch;
   int grid = tiles < max_ctas ? tiles : max_ctas;
-  kern<<<grid, GEMM_THREADS, S::TOTAL, st>>>(ma, mb, p);
-  DSB_CHECK_CUDA(cudaGetLastError());
+  DSB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), S::TOTAL, st, ma, mb, p));
   return 0;
 }
 
@@ -404,7 +407,10 @@ extern "C" int dsb_gemm_ex(const dsb_gemm_desc* d, void* stream) {
   p.kb_per_tap = (d->K + block_k - 1) / block_k;
   p.block_k = block_k;
   p.num_taps = d->num_taps;
-  for (int i = 0; i < MAX_TAPS; ++i) p.tap_shift[i] = i < d->num_taps ? d->tap_shift[i] : 0;
+  for (int i = 0; i < MAX_TAPS; ++i) {
+    p.tap_shift[i] = i < d->num_taps ? d->tap_shift[i] : 0;
+    p.tap_acol[i] = i < d->num_taps ? d->tap_acol[i] : 0;
+  }
   p.kc = d->K;
   p.b_batched = d->w_batch_stride != 0;
   p.bias = d->bias; p.residual = d->residual; p.ld_res = d->ld_res; p.res_bstride = d->res_batch_stride;
@@ -430,7 +436,7 @@ extern "C" int dsb_gemm_ex(const dsb_gemm_desc* d, void* stream) {
 
   CUtensorMap ma, mb;
   const long long a_rows = d->a_rows > 0 ? d->a_rows : d->M;
-  if (make_operand_map(&ma, d->A, kind, d->K, a_rows, d->batch, d->lda, d->a_batch_stride, BLOCK_M)) return 3;
+  if (make_operand_map(&ma, d->A, kind, d->a_cols > 0 ? d->a_cols : d->K, a_rows, d->batch, d->lda, d->a_batch_stride, BLOCK_M)) return 3;
   if (make_operand_map(&mb, d->W, kind, (long long)d->K * d->num_taps, d->N, p.b_batched ? d->batch : 1, d->ldw, d->w_batch_stride, block_n)) return 3;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int max_ctas = d->max_ctas > 0 ? d->max_ctas : sms;

@@ -16,6 +16,8 @@ __global__ void embed_tokens_kernel(const int64_t* __restrict__ ids, const float
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const int l = row % L;
+  pdl_wait();
+  pdl_trigger();
   long long id = ids[row];
   if (id < 0) id = 0;  // index[index < 0] = 0  (dalle_mask_image_embedding.py:40)
   if (id >= num_embed) {
@@ -50,6 +52,8 @@ layernorm_kernel(const float* __restrict__ x, void* __restrict__ out, const floa
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * D);
+  pdl_wait();
+  pdl_trigger();
   float4 v[NV];
   float s = 0.f;
 #pragma unroll
@@ -111,7 +115,7 @@ static int launch_ln(const float* x, void* out, const float* p0, const float* p1
                      int flags, cudaStream_t st) {
   const int grid = (rows + 7) / 8;
   switch (D / 128) {
-#define DSB_LN_CASE(N) case N: layernorm_kernel<MODE, N><<<grid, 256, 0, st>>>(x, out, p0, p1, t, rows, L, D, T, eps, flags); break;
+#define DSB_LN_CASE(N) case N: DSB_CHECK_CUDA(launch_pdl(layernorm_kernel<MODE, N>, dim3(grid), dim3(256), 0, st, x, out, p0, p1, t, rows, L, D, T, eps, flags)); break;
     DSB_LN_CASE(1) DSB_LN_CASE(2) DSB_LN_CASE(3) DSB_LN_CASE(4) DSB_LN_CASE(5) DSB_LN_CASE(6) DSB_LN_CASE(7) DSB_LN_CASE(8)
     DSB_LN_CASE(12) DSB_LN_CASE(16)
 #undef DSB_LN_CASE
@@ -128,8 +132,8 @@ extern "C" int dsb_embed_tokens(const int64_t* ids, const float* emb, const floa
   DSB_REQUIRE(D % 4 == 0, "dsb_embed_tokens: D must be a multiple of 4");
   DSB_REQUIRE(L <= H * W, "dsb_embed_tokens: L=%d exceeds the %dx%d grid", L, H, W);
   const int rows = B * L;
-  embed_tokens_kernel<<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(ids, emb, hemb, wemb, out, rows, L, D, W, num_embed, err_flag);
-  DSB_CHECK_CUDA(cudaGetLastError());
+  DSB_CHECK_CUDA(launch_pdl(embed_tokens_kernel, dim3((rows + 7) / 8), dim3(256), 0, (cudaStream_t)stream, ids, emb, hemb, wemb, out, rows, L, D, W,
+                            num_embed, err_flag));
   return 0;
 }
 extern "C" int dsb_layernorm(const float* x, void* out, const float* gamma, const float* beta, int rows, int D, float eps, int flags, void* stream) {

@@ -54,6 +54,8 @@ posterior_sample_kernel(const float* __restrict__ logits, const int64_t* __restr
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int l = l0 + warp;
   const bool active = l < L;
+  pdl_wait();
+  pdl_trigger();
 
   // stage the (C x SW) tile of uniforms: u[b, k, l0 + j]
   if (do_sample) {
@@ -237,8 +239,7 @@ static int launch_sampler(const float* logits, const int64_t* x_t, const int64_t
   auto kern = posterior_sample_kernel<NJ>;
   if (smem > 48 * 1024) DSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((L + SW - 1) / SW, B);
-  kern<<<grid, SW * 32, smem, st>>>(logits, x_t, t, t_post, uniform, sched, x_next, lpo, K, L, T, mode, r, kk, stage);
-  DSB_CHECK_CUDA(cudaGetLastError());
+  DSB_CHECK_CUDA(launch_pdl(kern, grid, dim3(SW * 32), smem, st, logits, x_t, t, t_post, uniform, sched, x_next, lpo, K, L, T, mode, r, kk, stage));
   return 0;
 }
 }  // namespace dsb

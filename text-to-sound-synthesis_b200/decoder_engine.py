@@ -13,16 +13,29 @@ import torch
 from . import ops
 
 
-def _pack_conv(conv) -> torch.Tensor:
-    w = conv.weight.detach().float()  # (Cout, Cin, kh, kw) -> (Cout, kh*kw*Cin), tap-major
-    return ops.round_tf32(w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous())
-
-
 class DecoderEngine:
-    def __init__(self, vq):
+    def __init__(self, vq, precision: str = "tf32x3"):
+        """precision: 'tf32x3' -- split-TF32 operands (A = hi+lo, W = hi+lo; hi*Whi + lo*Whi + hi*Wlo on the tensor pipe): fp32-class
+                                   accuracy, needed for the 1e-3 mel tolerance through ~30 conv + GroupNorm layers;
+                      'tf32'   -- single-pass TF32 (3x fewer MMAs; mel error ~4e-3 relative)."""
+        if precision not in ("tf32x3", "tf32"):
+            raise ValueError("precision must be 'tf32x3' or 'tf32'")
         self.vq = vq
+        self.precision = precision
         self.packed = False
         self.launches = 0
+
+    def _pack_conv(self, conv) -> torch.Tensor:
+        w = conv.weight.detach().float()  # (Cout, Cin, kh, kw) -> (Cout, kh*kw*Cin), tap-major
+        ntaps = w.shape[2] * w.shape[3]
+        w = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
+        return ops.pack_split_weight(w, ntaps) if self.precision == "tf32x3" else ops.round_tf32(w)
+
+    def _mm(self, a, w, bias=None, residual=None, out=None, **kw):
+        """a: fp32 activation (rows, C) or batched; w: packed weight (split or rounded)."""
+        if self.precision == "tf32x3":
+            return ops.gemm_split(ops.split_tf32(a), w, bias, residual, out, **kw)
+        return ops.gemm(a, w, bias, residual, out, **kw)
 
     @torch.no_grad()
     def repack(self):
@@ -33,7 +46,7 @@ class DecoderEngine:
         self.w = {}
 
         def conv(name, m):
-            self.w[name] = (_pack_conv(m), f(m.bias), m.kernel_size[0])
+            self.w[name] = (self._pack_conv(m), f(m.bias), m.kernel_size[0])
 
         def gn(name, m):
             self.w[name] = (f(m.weight), f(m.bias), m.eps)
@@ -70,23 +83,26 @@ class DecoderEngine:
         R = B * Hp * Wp
         taps = [dy * Wp + dx for dy in (-1, 0, 1) for dx in (-1, 0, 1)] if k == 3 else [0]
         out = torch.empty(B, Hp, Wp, w.shape[0], dtype=torch.float32, device=x.device)
-        ops.gemm(x.view(R, C), w, b, None if residual is None else residual.view(R, -1), out.view(R, -1), taps=taps,
-                 geo=(Hp * Wp, Wp, 1, Hp - 1, 1, Wp - 1), round_out=round_out)
-        self.launches += 1
+        self._mm(x.view(R, C), w, b, None if residual is None else residual.view(R, -1), out.view(R, -1), taps=taps,
+                 geo=(Hp * Wp, Wp, 1, Hp - 1, 1, Wp - 1), round_out=round_out and self.precision == "tf32")
+        self.launches += 2 if self.precision == "tf32x3" else 1
         return out
 
     def _gn(self, x, name, swish=True, compact_len=0):
         g, b, eps = self.w[name]
         st = ops.groupnorm_stats(x)
         self.launches += 3  # memset + stats + apply
-        return ops.groupnorm_apply(x, st, g, b, eps=eps, swish=swish, round_out=True, compact_len=compact_len)
+        return ops.groupnorm_apply(x, st, g, b, eps=eps, swish=swish, round_out=self.precision == "tf32", compact_len=compact_len)
 
     def _res(self, x, name):
         h = self._conv(self._gn(x, name + ".norm1"), name + ".conv1")
         h = self._gn(h, name + ".norm2")
         if (name + ".nin") in self.w:
-            self.launches += 1
-            x = self._conv(ops.round_tf32(x), name + ".nin")
+            if self.precision == "tf32":
+                self.launches += 1
+                x = self._conv(ops.round_tf32(x), name + ".nin")
+            else:
+                x = self._conv(x, name + ".nin")
         return self._conv(h, name + ".conv2", residual=x)
 
     def _attn(self, x, name):
@@ -96,13 +112,20 @@ class DecoderEngine:
         Lp = (L + 15) // 16 * 16  # token rows padded so every TMA stride is a multiple of 16 bytes
         h = self._gn(x, name + ".norm", swish=False, compact_len=Lp).view(B * Lp, C)
         (wq, bq, _), (wk, bk, _), (wv, bv, _), (wp, bp, _) = (self.w[name + "." + n] for n in ("q", "k", "v", "proj_out"))
-        q = ops.gemm(h, wq, bq, round_out=True).view(B, Lp, C)
-        k = ops.gemm(h, wk, bk, round_out=True).view(B, Lp, C)
-        vT = ops.gemm(wv, h, round_out=True)  # (C, B*Lp) = Wv h^T: V transposed, bias folded in after P V (softmax rows sum to 1)
-        s = ops.gemm(q, k, alpha=float(C) ** -0.5)  # (B, Lp, Lp)
-        ops.softmax_rows_(s, L)
-        o = ops.gemm(s, vT.view(C, B, Lp).permute(1, 0, 2), bv, round_out=True)  # (B, Lp, C)
-        proj = ops.gemm(o.view(B * Lp, C), wp, bp).view(B, Lp, C)
+        rnd = self.precision == "tf32"
+        q = self._mm(h, wq, bq, round_out=rnd).view(B, Lp, C)
+        k = self._mm(h, wk, bk, round_out=rnd).view(B, Lp, C)
+        v = self._mm(h, wv, bv, round_out=rnd).view(B, Lp, C)
+        vT = v.transpose(1, 2).contiguous()  # (B, C, Lp): data movement only (token rows >= L are masked by the softmax below)
+        if self.precision == "tf32x3":
+            s_ = ops.gemm_split(ops.split_tf32(q), ops.split_tf32(k, w_format=True), alpha=float(C) ** -0.5)  # (B, Lp, Lp)
+            ops.softmax_rows_(s_, L, round_out=False)
+            o = ops.gemm_split(ops.split_tf32(s_), ops.split_tf32(vT, w_format=True))  # (B, Lp, C)
+        else:
+            s_ = ops.gemm(q, k, alpha=float(C) ** -0.5)
+            ops.softmax_rows_(s_, L)
+            o = ops.gemm(s_, vT, round_out=True)
+        proj = self._mm(o.view(B * Lp, C), wp, bp).view(B, Lp, C)
         ops.tokens_add_to_padded_(proj, x)
         self.launches += 8
         return x
@@ -122,7 +145,7 @@ class DecoderEngine:
                 if len(d.up[lvl].attn) > 0:
                     h = self._attn(h, f"up.{lvl}.attn.{j}")
             if lvl != 0:
-                h = self._conv(ops.upsample2x_padded(h), f"up.{lvl}.upsample")
+                h = self._conv(ops.upsample2x_padded(h, round_out=self.precision == "tf32"), f"up.{lvl}.upsample")
                 self.launches += 1
         out = self._conv(self._gn(h, "norm_out"), "conv_out")  # (B, Hp, Wp, out_ch)
         return out[:, 1:-1, 1:-1, :].permute(0, 3, 1, 2).contiguous()
@@ -134,7 +157,7 @@ class DecoderEngine:
         self.launches = 1
         H, W = grid
         err = torch.zeros(1, dtype=torch.int32, device=ids.device)
-        z = ops.codebook_gather_padded(ids, self.codebook, H, W, round_out=True, err_flag=err)
+        z = ops.codebook_gather_padded(ids, self.codebook, H, W, round_out=self.precision == "tf32", err_flag=err)
         mel = self._decode_padded(z)
         if int(err.item()):
             raise RuntimeError("codebook index out of range")
@@ -147,4 +170,4 @@ class DecoderEngine:
             self.repack()
         self.launches = 1
         z = torch.nn.functional.pad(quant.detach().float().permute(0, 2, 3, 1), (0, 0, 1, 1, 1, 1)).contiguous()
-        return self._decode_padded(ops.round_tf32(z))
+        return self._decode_padded(ops.round_tf32(z) if self.precision == "tf32" else z)

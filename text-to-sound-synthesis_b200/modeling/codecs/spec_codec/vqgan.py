@@ -121,14 +121,14 @@ class VectorQuantizer(nn.Module):
 
 class VQModel(nn.Module):
     def __init__(self, ddconfig, lossconfig=None, n_embed=256, embed_dim=256, ckpt_path=None, ignore_keys=[], image_key="image",
-                 colorize_nlabels=None, monitor=None):
+                 colorize_nlabels=None, monitor=None, precision="tf32x3"):
         super().__init__()
         self.image_key = image_key
         self.ddconfig = dict(ddconfig)
         self.decoder = Decoder(**ddconfig)
         self.quantize = VectorQuantizer(n_embed, embed_dim, beta=0.25)
         self.post_quant_conv = nn.Conv2d(embed_dim, ddconfig["z_channels"], 1)
-        self.engine = DecoderEngine(self)
+        self.engine = DecoderEngine(self, precision=precision)
         self.register_load_state_dict_post_hook(lambda module, inc: module.engine.__setattr__("packed", False))
         if ckpt_path is not None:
             self.init_from_ckpt(ckpt_path, ignore_keys=ignore_keys)

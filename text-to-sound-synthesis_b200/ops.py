@@ -59,6 +59,47 @@ def to_f16(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def split_tf32(x: torch.Tensor, w_format: bool = False) -> torch.Tensor:
+    """(..., C) fp32 -> (..., 2*Cp) [hi | lo] split-TF32 A operand (or (..., 3*Cp) [hi | hi | lo] W operand), Cp = C rounded up to 32."""
+    _need_cuda(x)
+    C = x.shape[-1]
+    Cp = (C + 31) // 32 * 32
+    x2 = x.reshape(-1, C) if x.is_contiguous() else x
+    if x2.dim() != 2:
+        raise RuntimeError("split_tf32 needs a contiguous tensor or a 2-D row-strided view")
+    nb = 3 if w_format else 2
+    out = torch.empty(*x.shape[:-1], nb * Cp, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().dsb_split_tf32(x2.data_ptr(), x2.stride(0), out.data_ptr(), nb * Cp, x2.shape[0], C, Cp, 1 if w_format else 0, _stream()),
+               "dsb_split_tf32")
+    return out
+
+
+def pack_split_weight(w: torch.Tensor, ntaps: int) -> torch.Tensor:
+    """(N, ntaps*C) fp32 tap-major weight -> (N, 3*ntaps*Cp): per tap [Whi | Whi | Wlo] (pairs with gemm_split's tap list)."""
+    N = w.shape[0]
+    C = w.shape[1] // ntaps
+    Cp = (C + 31) // 32 * 32
+    w3 = w.reshape(N, ntaps, C).float()
+    hi = round_tf32(w3.contiguous())
+    lo = round_tf32((w3 - hi).contiguous())
+    out = torch.zeros(N, ntaps, 3, Cp, dtype=torch.float32, device=w.device)
+    out[:, :, 0, :C] = hi
+    out[:, :, 1, :C] = hi
+    out[:, :, 2, :C] = lo
+    return out.reshape(N, ntaps * 3 * Cp).contiguous()
+
+
+def gemm_split(a_split: torch.Tensor, w_split: torch.Tensor, bias=None, residual=None, out=None, *, taps=None, **kw) -> torch.Tensor:
+    """3xTF32 GEMM: a_split from split_tf32 (.., 2*Cp), w_split from pack_split_weight; same epilogue options as gemm()."""
+    Cp = a_split.shape[-1] // 2
+    taps = list(taps) if taps is not None else [0]
+    t3, ac = [], []
+    for s_ in taps:
+        t3 += [s_, s_, s_]
+        ac += [0, Cp, 0]  # hi*Whi, lo*Whi, hi*Wlo
+    return gemm(a_split, w_split, bias, residual, out, dtype=TF32, taps=t3, tap_acol=ac, k_per_tap=Cp, **kw)
+
+
 def silu(x: torch.Tensor) -> torch.Tensor:
     _need_cuda(x)
     x = x.contiguous()
@@ -69,7 +110,8 @@ def silu(x: torch.Tensor) -> torch.Tensor:
 
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
          out: Optional[torch.Tensor] = None, *, dtype: int = TF32, gelu: bool = False, round_out: bool = False, out_bf16: bool = False, out_f16: bool = False,
-         lrelu: bool = False, tanh: bool = False, res_before_act: bool = False, taps: Optional[Sequence[int]] = None, out_rows: Optional[int] = None, geo: Optional[Sequence[int]] = None, alpha: float = 1.0,
+         lrelu: bool = False, tanh: bool = False, res_before_act: bool = False, taps: Optional[Sequence[int]] = None,
+         tap_acol: Optional[Sequence[int]] = None, k_per_tap: Optional[int] = None, out_rows: Optional[int] = None, geo: Optional[Sequence[int]] = None, alpha: float = 1.0,
          block_n: int = 0, max_ctas: int = 0) -> torch.Tensor:
     """out = epi(alpha * A @ W^T + bias) (+ residual) on tcgen05.  a: (M,K) or (batch,M,K); w: (N, taps*K) or (batch,N,K)."""
     _need_cuda(a, w, bias, residual, out)
@@ -78,7 +120,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         raise RuntimeError("gemm operands must be K-contiguous")
     ntaps = 1 if taps is None else len(taps)
     batch = a.shape[0] if batched else 1
-    a_rows, K = a.shape[-2], a.shape[-1]
+    a_rows, a_cols = a.shape[-2], a.shape[-1]
+    K = a_cols if k_per_tap is None else k_per_tap  # reduction length per tap (A may hold several K blocks side by side)
     N = w.shape[-2]
     if w.shape[-1] != K * ntaps:
         raise RuntimeError(f"gemm: W has {w.shape[-1]} columns, expected {K}*{ntaps}")
@@ -103,6 +146,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     d.num_taps = ntaps
     for i, s in enumerate(taps or [0]):
         d.tap_shift[i] = int(s)
+        d.tap_acol[i] = int(tap_acol[i]) if tap_acol is not None else 0
+    d.a_cols = a_cols
     if geo is not None:
         d.geo_P, d.geo_Wp, d.geo_y0, d.geo_y1, d.geo_x0, d.geo_x1 = [int(v) for v in geo]
     d.alpha = alpha

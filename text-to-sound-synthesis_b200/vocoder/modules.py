@@ -28,7 +28,7 @@ class ResnetBlock(_Holder):
 
 
 class Generator(nn.Module):
-    def __init__(self, input_size, ngf, n_residual_layers):
+    def __init__(self, input_size, ngf, n_residual_layers, precision="tf32x3"):
         super().__init__()
         ratios = [8, 8, 2, 2]
         self.ratios = ratios
@@ -47,7 +47,7 @@ class Generator(nn.Module):
         for m in self.modules():  # weights_init of the reference (modules.py:9-15)
             if isinstance(m, (nn.Conv1d, nn.ConvTranspose1d)):
                 m.weight_v.data.normal_(0.0, 0.02)
-        self.engine = VocoderEngine(self)
+        self.engine = VocoderEngine(self, precision=precision)
         self.register_load_state_dict_post_hook(lambda module, inc: module.engine.__setattr__("packed", False))
 
     def _apply(self, fn, *a, **k):

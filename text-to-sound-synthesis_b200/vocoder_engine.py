@@ -21,15 +21,30 @@ def _fold(m) -> torch.Tensor:
     return g * v / v.flatten(1).norm(dim=1).view(-1, *([1] * (v.dim() - 1)))
 
 
-def _pack_conv1d(w) -> torch.Tensor:
-    return ops.round_tf32(w.permute(0, 2, 1).reshape(w.shape[0], -1).contiguous())  # (Cout, k*Cin), tap-major
-
-
 class VocoderEngine:
-    def __init__(self, gen):
+    def __init__(self, gen, precision: str = "tf32x3"):
+        """precision 'tf32x3' (split-TF32, fp32-class accuracy: the shipped checkpoint's weights span a wide dynamic range and
+        single-pass TF32 gives 2.6e-2 waveform error) or 'tf32' (single pass)."""
+        if precision not in ("tf32x3", "tf32"):
+            raise ValueError("precision must be 'tf32x3' or 'tf32'")
         self.gen = gen
+        self.precision = precision
         self.packed = False
         self.launches = 0
+
+    def _pack(self, w2d: torch.Tensor, ntaps: int) -> torch.Tensor:
+        """(N, ntaps*Cin) tap-major fp32 -> packed GEMM weight for the selected precision."""
+        w2d = w2d.contiguous().float()
+        return ops.pack_split_weight(w2d, ntaps) if self.precision == "tf32x3" else ops.round_tf32(w2d)
+
+    def _pack_conv1d(self, w) -> torch.Tensor:
+        return self._pack(w.permute(0, 2, 1).reshape(w.shape[0], -1), w.shape[2])  # (Cout, k*Cin), tap-major
+
+    def _mm(self, a, w, bias=None, residual=None, out=None, **kw):
+        if self.precision == "tf32x3":
+            kw.pop("round_out", None)
+            return ops.gemm_split(ops.split_tf32(a), w, bias, residual, out, **kw)
+        return ops.gemm(a, w, bias, residual, out, **kw)
 
     @torch.no_grad()
     def repack(self):
@@ -37,7 +52,7 @@ class VocoderEngine:
         if mods[1].bias.device.type != "cuda":
             raise RuntimeError("VocoderEngine needs the module on a CUDA device (no CPU fallback)")
         f = lambda p: p.detach().float().contiguous()
-        self.first = (_pack_conv1d(_fold(mods[1])), f(mods[1].bias))
+        self.first = (self._pack_conv1d(_fold(mods[1])), f(mods[1].bias))
         self.stages = []
         i = 2
         for r in self.gen.ratios:
@@ -50,19 +65,19 @@ class VocoderEngine:
             wa = torch.stack([torch.cat([w[:, :, ph + p + r].t(), w[:, :, ph + p].t()], dim=1) for ph in range(half)], 0)
             wb = torch.stack([torch.cat([w[:, :, ph + p].t(), w[:, :, ph + p - r].t()], dim=1) for ph in range(half, r)], 0)
             cout = w.shape[1]
-            st = dict(r=r, cout=cout, half=half, wa=ops.round_tf32(wa.reshape(half * cout, -1).contiguous()),
-                      wb=ops.round_tf32(wb.reshape((r - half) * cout, -1).contiguous()),
+            st = dict(r=r, cout=cout, half=half, wa=self._pack(wa.reshape(half * cout, -1), 2),
+                      wb=self._pack(wb.reshape((r - half) * cout, -1), 2),
                       ba=f(ct.bias).repeat(half), bb=f(ct.bias).repeat(r - half), res=[])
             i += 2
             for _ in range(self.gen.n_residual_layers):
                 rb = mods[i]
-                st["res"].append(dict(d=rb.dilation, wd=_pack_conv1d(_fold(rb.block[2])), bd=f(rb.block[2].bias),
-                                      w1=_pack_conv1d(_fold(rb.block[4])), b1=f(rb.block[4].bias),
-                                      ws=_pack_conv1d(_fold(rb.shortcut)), bs=f(rb.shortcut.bias)))
+                st["res"].append(dict(d=rb.dilation, wd=self._pack_conv1d(_fold(rb.block[2])), bd=f(rb.block[2].bias),
+                                      w1=self._pack_conv1d(_fold(rb.block[4])), b1=f(rb.block[4].bias),
+                                      ws=self._pack_conv1d(_fold(rb.shortcut)), bs=f(rb.shortcut.bias)))
                 i += 1
             self.stages.append(st)
         last = mods[i + 2]
-        self.last = (_pack_conv1d(_fold(last)), f(last.bias))
+        self.last = (self._pack_conv1d(_fold(last)), f(last.bias))
         self.packed = True
 
     @torch.no_grad()
@@ -74,30 +89,31 @@ class VocoderEngine:
         mel = mel.detach().float().contiguous()
         B, Cm, T = mel.shape
         n = 0
-        xl = ops.lrelu_pad(mel, 3, slope=1.0, reflect=True, channel_major=True)          # ReflectionPad1d(3) of the mel, channels-last
+        rnd = self.precision == "tf32"
+        xl = ops.lrelu_pad(mel, 3, slope=1.0, reflect=True, channel_major=True, round_out=rnd)          # ReflectionPad1d(3) of the mel, channels-last
         w0, b0 = self.first
         # conv k=7 -> LeakyReLU (the activation in front of the first ConvTranspose1d) fused in the epilogue
-        x = ops.gemm(xl, w0, b0, taps=list(range(7)), out_rows=T, lrelu=True, round_out=True)   # (B, T, 16*ngf)
+        x = self._mm(xl, w0, b0, taps=list(range(7)), out_rows=T, lrelu=True, round_out=rnd)   # (B, T, 16*ngf)
         n += 2
         for si, st in enumerate(self.stages):
             r, cout, half = st["r"], st["cout"], st["half"]
             y = torch.empty(B, T, r * cout, dtype=torch.float32, device=mel.device)
-            ops.gemm(x, st["wa"], st["ba"], out=y[:, :, : half * cout], taps=[-1, 0], round_out=True)
-            ops.gemm(x, st["wb"], st["bb"], out=y[:, :, half * cout:], taps=[0, 1], round_out=True)
+            self._mm(x, st["wa"], st["ba"], out=y[:, :, : half * cout], taps=[-1, 0], round_out=rnd)
+            self._mm(x, st["wb"], st["bb"], out=y[:, :, half * cout:], taps=[0, 1], round_out=rnd)
             T = T * r
             x = y.view(B, T, cout)
             n += 2
             for ri, rb in enumerate(st["res"]):
                 d = rb["d"]
-                xl = ops.lrelu_pad(x, d, slope=0.2, reflect=True)                          # LeakyReLU + ReflectionPad1d(d)
-                y1 = ops.gemm(xl, rb["wd"], rb["bd"], taps=[0, d, 2 * d], out_rows=T, lrelu=True, round_out=True)
-                tmp = ops.gemm(y1, rb["w1"], rb["b1"])
+                xl = ops.lrelu_pad(x, d, slope=0.2, reflect=True, round_out=rnd)                          # LeakyReLU + ReflectionPad1d(d)
+                y1 = self._mm(xl, rb["wd"], rb["bd"], taps=[0, d, 2 * d], out_rows=T, lrelu=True, round_out=rnd)
+                tmp = self._mm(y1, rb["w1"], rb["b1"])
                 last_of_stage = ri == len(st["res"]) - 1
                 # shortcut(x) + block(x); after the last block of a stage the next consumer is LeakyReLU -> ConvT / final conv
-                x = ops.gemm(x, rb["ws"], rb["bs"], residual=tmp, round_out=True, lrelu=last_of_stage, res_before_act=last_of_stage)
+                x = self._mm(x, rb["ws"], rb["bs"], residual=tmp, round_out=rnd, lrelu=last_of_stage, res_before_act=last_of_stage)
                 n += 4
-        xl = ops.lrelu_pad(x, 3, slope=1.0, reflect=True)                                  # x already went through LeakyReLU
+        xl = ops.lrelu_pad(x, 3, slope=1.0, reflect=True, round_out=rnd)                                  # x already went through LeakyReLU
         wl, bl = self.last
-        wav = ops.gemm(xl, wl, bl, taps=list(range(7)), out_rows=T, tanh=True)             # (B, T, 1)
+        wav = self._mm(xl, wl, bl, taps=list(range(7)), out_rows=T, tanh=True)             # (B, T, 1)
         self.launches = n + 2
         return wav.view(B, 1, T)
