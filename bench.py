@@ -192,6 +192,45 @@ def gemm_roofline(model, B, peaks, peaks_src):
             "flop_per_launch_avg": tot_flop / launches, "us_per_launch_avg": round(tot_ms * 1e3 / launches, 2)}
 
 
+def full_pipeline_probe(model, cond_dev, B):
+    """Secondary figure (BASELINE configs[2] shape at this batch): tokens -> SpecVQGAN decoder -> MelGAN on top of the sampler."""
+    import _pkg
+    _pkg.load()
+    from diffsound_b200.modeling.codecs.spec_codec.vqgan import VQModel
+    from diffsound_b200.vocoder.modules import Generator
+    from oracle import diffsound_oracle as O
+    dd = dict(double_z=False, z_channels=256, resolution=848, in_channels=1, out_ch=1, ch=128, ch_mult=[1, 1, 2, 2, 4], num_res_blocks=2,
+              attn_resolutions=[53], dropout=0.0)
+    torch.manual_seed(0)
+    vq = VQModel(dd, None, n_embed=256, embed_dim=256).cuda().eval()
+    ck = os.path.join(ROOT, "oracle", "_ref", "best_netG.pt")
+    voc = Generator(80, 32, 3)
+    voc.load_state_dict(torch.load(ck, map_location="cpu") if os.path.exists(ck) else O.make_melgan_state_dict(seed=1), strict=True)
+    voc = voc.cuda().eval()
+
+    def run():
+        tok = model.sample(condition_token=None, condition_mask=None, condition_embed=cond_dev, filter_ratio=0, batch_size=B)["content_token"]
+        tok = tok % 256
+        mel = vq.decode_tokens(tok, (5, 53))
+        return voc((mel[:, 0] + 1) / 2)
+
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    run(); torch.cuda.synchronize()
+    st = torch.cuda.current_stream()
+    ev[0].record(st)
+    tok = model.sample(condition_token=None, condition_mask=None, condition_embed=cond_dev, filter_ratio=0, batch_size=B)["content_token"] % 256
+    ev[1].record(st)
+    mel = vq.decode_tokens(tok, (5, 53))
+    ev[2].record(st)
+    wav = voc((mel[:, 0] + 1) / 2)
+    ev[3].record(st)
+    torch.cuda.synchronize()
+    t = [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
+    return {"clips_per_s": B / (sum(t) * 1e-3), "batch": B, "ms": {"sampler_100_steps": round(t[0], 2), "decoder": round(t[1], 2), "vocoder": round(t[2], 2)},
+            "precision": "sampler f16 operands; decoder/vocoder split-TF32 (3-pass)", "wav_shape": list(wav.shape),
+            "launches": {"decoder": vq.engine.launches, "vocoder": voc.engine.launches}}
+
+
 def run_gpu_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -250,6 +289,7 @@ def run_gpu_arm(args):
     clips = B * world * args.steps
     value = clips / (ms_dev * 1e-3)
     e2e_v = clips / (ms_e2e * 1e-3)
+    full = full_pipeline_probe(model, cond_dev, B) if (rank == 0 and not args.no_full_pipeline) else None
     if rank == 0:
         peaks, src = load_peaks()
         roof = gemm_roofline(model, B, peaks, src)
@@ -269,7 +309,7 @@ def run_gpu_arm(args):
                            "l2_policy": "working set per diffusion step (1.53 GB fp32 weights) exceeds the 126 MB L2; no explicit flush"},
                 "e2e": {"value": e2e_v, "unit": "clips/s", "h2d_bytes_per_step": cond_host.numel() * 4, "d2h_bytes_per_step": tok_host.numel() * 8,
                         "api": "DiffusionTransformer.sample(condition_embed=<pinned host tensor -> device>) -> tokens copied to pinned host"},
-                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clk}
+                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clk, "full_pipeline": full}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -285,6 +325,7 @@ def main():
     ap.add_argument("--layers", type=int, default=19)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full-pipeline", action="store_true")
     ap.add_argument("--precision", default="f16", choices=["f16", "tf32", "fp32"])
     args = ap.parse_args()
     if args.impl == "reference":
