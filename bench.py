@@ -238,6 +238,7 @@ def run_gpu_arm(args):
     dist = None
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("DSB_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         import torch.distributed as dist
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)

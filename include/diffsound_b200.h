@@ -78,6 +78,7 @@ typedef struct dsb_gemm_desc {
   float alpha;           /* 0 -> 1 */
   int block_n;           /* 0 = auto, 128, 256 */
   int max_ctas;          /* 0 = one per SM */
+  int cta_pair;          /* 0 = auto (pairs for 256-wide tiles), 1 = force cta_group::2 pairs (256x256 tiles), -1 = single-CTA kernel */
 } dsb_gemm_desc;
 int dsb_gemm_ex(const dsb_gemm_desc* desc, void* stream);
 

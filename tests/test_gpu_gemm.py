@@ -41,9 +41,51 @@ def test_gemm_tf32(G, M, N, K, bn):
     a = G.tf32_round_ref(torch.randn(M, K, generator=g))
     w = G.tf32_round_ref(torch.randn(N, K, generator=g) * 0.05)
     bias = torch.randn(N, generator=g)
-    out = G.ops.gemm(a.cuda(), w.cuda(), bias.cuda(), block_n=bn)
+    out = G.ops.gemm(a.cuda(), w.cuda(), bias.cuda(), block_n=bn, cta_pair=-1)  # single-CTA kernel
     torch.cuda.synchronize()
     assert G.relerr(out, _ref(a, w, bias)) < 2e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (512, 256, 1024), (530, 256, 1024), (4240, 1024, 1024), (1000, 3072, 1024), (300, 1024, 4096),
+                                   (77 * 3, 2048, 512), (200, 33, 64), (130, 260, 100), (129, 512, 96)])
+@pytest.mark.parametrize("dtype", ["tf32", "f16"])
+def test_gemm_cta_pair(G, M, N, K, dtype):
+    """cta_group::2 kernel (256 x 256 pair tiles), forced: same answers as the fp64 reference, incl. M / N / K tails."""
+    g = torch.Generator().manual_seed(M * 7 + N + K)
+    a, w = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * 0.05
+    bias, res = torch.randn(N, generator=g), torch.randn(M, N, generator=g)
+    if dtype == "tf32":
+        a, w = G.tf32_round_ref(a), G.tf32_round_ref(w)
+        if (K * 4) % 16:
+            pytest.skip("leading dimension must be a multiple of 16 bytes")
+        out = G.ops.gemm(a.cuda(), w.cuda(), bias.cuda(), res.cuda(), cta_pair=1)
+    else:
+        a, w = a.half(), w.half()
+        if (K * 2) % 16:
+            pytest.skip("leading dimension must be a multiple of 16 bytes")
+        out = G.ops.gemm(a.cuda(), w.cuda(), bias.cuda(), res.cuda(), dtype=G.ops.F16, cta_pair=1)
+    torch.cuda.synchronize()
+    assert G.relerr(out, _ref(a.float(), w.float(), bias, res)) < 2e-5
+
+
+def test_gemm_cta_pair_persistent_and_taps(G):
+    g = torch.Generator().manual_seed(11)
+    M, N, K = 3000, 1024, 512
+    a = torch.randn(M, K, generator=g).half()
+    w = (torch.randn(N, K, generator=g) * 0.05).half()
+    bias = torch.randn(N, generator=g)
+    ref = _ref(a.float(), w.float(), bias, gelu=True)
+    out = G.ops.gemm(a.cuda(), w.cuda(), bias.cuda(), dtype=G.ops.F16, gelu=True, cta_pair=1, max_ctas=6)  # 3 pairs, many tiles each
+    assert G.relerr(out, ref) < 2e-5
+    rows, C, Nn = 7 * 60, 64, 96
+    a = G.tf32_round_ref(torch.randn(rows, C, generator=g))
+    w = G.tf32_round_ref(torch.randn(Nn, 3 * C, generator=g) * 0.1)
+    out = G.ops.gemm(a.cuda(), w.cuda(), taps=[-7, 0, 7], cta_pair=1)
+    assert G.relerr(out, _ref(a, w, taps=[-7, 0, 7])) < 2e-5
+    Bt = 3
+    a = G.tf32_round_ref(torch.randn(Bt, 265, 512, generator=g)); w = G.tf32_round_ref(torch.randn(Bt, 265, 512, generator=g))
+    out = G.ops.gemm(a.cuda(), w.cuda(), alpha=0.5, cta_pair=1)
+    assert G.relerr(out, 0.5 * torch.einsum("bmk,bnk->bmn", a.double(), w.double())) < 2e-5
 
 
 def test_gemm_epilogues_and_persistence(G):

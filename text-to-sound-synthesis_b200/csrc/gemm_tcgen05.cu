@@ -12,6 +12,7 @@
 #include "diffsound_b200.h"
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 namespace dsb {
 
@@ -51,6 +52,174 @@ struct GemmSmem {
   static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 8 * 32 * 32 * 4 /*epilogue transpose tiles*/;
 };
+
+// One output tile's epilogue for one warp: TMEM -> registers -> XOR-swizzled smem transpose -> bias / activation / residual ->
+// coalesced global stores.  Shared by the 1-CTA and the CTA-pair kernels (row_base = first row of this warp's 32-row slab).
+template <int BLOCK_N>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, float* sw, uint32_t tmem_acc, uint64_t* tmem_full_bar, uint32_t aphase,
+                                              int row_base, int n_blk, int b, int q, int half, int lane) {
+  const bool has_geo = p.geo_P > 0;
+  const int out_mode = (p.flags & DSB_GEMM_OUT_F16) ? 1 : ((p.flags & DSB_GEMM_OUT_BF16) ? 2 : 0);
+  const int act = (p.flags & DSB_GEMM_GELU2) ? 1 : ((p.flags & DSB_GEMM_LRELU) ? 2 : ((p.flags & DSB_GEMM_TANH) ? 3 : 0));
+  const bool do_round = (p.flags & DSB_GEMM_ROUND_TF32) != 0;
+  const bool res_first = (p.flags & DSB_GEMM_RES_BEFORE_ACT) != 0;
+  const int out_es = out_mode ? 2 : 4;
+  const bool vec_ok = ((p.ldo & 3) == 0) && ((p.out_bstride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & (4 * out_es - 1)) == 0) &&
+                      (!p.residual || (((p.ld_res & 3) == 0) && ((p.res_bstride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0))) &&
+                      (!p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0));
+  const int c4 = lane & 7;    // float4 column slot inside the 32-column chunk
+  const int rsub = lane >> 3; // row inside each group of 4 rows
+      uint32_t ok_mask = 0, in_mask = 0;  // bit i: row (row_base + i*4 + rsub) exists / is an interior row
+#pragma unroll 1
+  for (int i = 0; i < 8; ++i) {
+    const int row = row_base + i * 4 + rsub;
+    if (row < p.M) ok_mask |= 1u << i;
+    bool interior = true;
+    if (has_geo) {
+      const int pp = row % p.geo_P;
+      const int y = pp / p.geo_Wp, x = pp - y * p.geo_Wp;
+      interior = (y >= p.geo_y0) && (y < p.geo_y1) && (x >= p.geo_x0) && (x < p.geo_x1);
+    }
+    if (interior) in_mask |= 1u << i;
+  }
+  const uint32_t t_row = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
+  const long long out_boff = (long long)b * p.out_bstride;
+  const float* res_b = p.residual ? p.residual + (long long)b * p.res_bstride : nullptr;
+  const int n_chunks = min(BLOCK_N / 32, (p.N - n_blk * BLOCK_N + 31) / 32);
+
+  // bias + residual are fetched one chunk ahead (the first one while the mainloop still runs)
+  float4 rz_next[8];
+  float4 bz_next = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) rz_next[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto prefetch = [&](int c) {
+    const int col = n_blk * BLOCK_N + c * 32 + c4 * 4;
+    if (vec_ok && (col + 3 < p.N)) {  // tail / unaligned chunks fetch inside the slow path instead
+      if (p.bias) bz_next = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+      if (res_b) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if ((ok_mask >> i) & 1u) rz_next[i] = *reinterpret_cast<const float4*>(res_b + (long long)(row_base + i * 4 + rsub) * p.ld_res + col);
+      }
+    }
+  };
+  if (half < n_chunks) prefetch(half);
+  mbar_wait(tmem_full_bar, aphase);
+  tc_fence_after();
+#pragma unroll 1
+  for (int c = half; c < n_chunks; c += 2) {
+    const int col0 = n_blk * BLOCK_N + c * 32;
+    {
+      uint32_t v[32];
+      tmem_ld_32x32(t_row + c * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<uint4*>(sw + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+    __syncwarp();
+    const int col = col0 + c4 * 4;
+    if (vec_ok && (col0 + 32 <= p.N)) {
+      // ---------------- fast path: whole chunk in range, 16-byte aligned everywhere
+      float x[32];
+      float4 rz_cur[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + rsub;
+    const float4 a4 = *reinterpret_cast<const float4*>(sw + r * 32 + ((c4 ^ (r & 7)) << 2));
+    rz_cur[i] = rz_next[i];
+    x[4 * i + 0] = fmaf(a4.x, p.alpha, bz_next.x); x[4 * i + 1] = fmaf(a4.y, p.alpha, bz_next.y);
+    x[4 * i + 2] = fmaf(a4.z, p.alpha, bz_next.z); x[4 * i + 3] = fmaf(a4.w, p.alpha, bz_next.w);
+      }
+      if (c + 2 < n_chunks) prefetch(c + 2);  // issued before this chunk's stores (out may alias residual)
+      if (res_b && res_first) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { x[4 * i] += rz_cur[i].x; x[4 * i + 1] += rz_cur[i].y; x[4 * i + 2] += rz_cur[i].z; x[4 * i + 3] += rz_cur[i].w; }
+      }
+      if (act == 1) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) x[e] = __fdividef(x[e], 1.0f + __expf(-1.702f * x[e]));
+      } else if (act == 2) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) x[e] = x[e] > 0.f ? x[e] : 0.2f * x[e];
+      } else if (act == 3) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {  // tanh(x) = 1 - 2 / (1 + exp(2x)), clamped so exp stays finite
+      const float z = fminf(fmaxf(x[e], -15.f), 15.f);
+      x[e] = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * z));
+    }
+      }
+      if (res_b && !res_first) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { x[4 * i] += rz_cur[i].x; x[4 * i + 1] += rz_cur[i].y; x[4 * i + 2] += rz_cur[i].z; x[4 * i + 3] += rz_cur[i].w; }
+      }
+      if (do_round) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) x[e] = round_tf32(x[e]);
+      }
+      if (has_geo) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (!((in_mask >> i) & 1u)) { x[4 * i] = 0.f; x[4 * i + 1] = 0.f; x[4 * i + 2] = 0.f; x[4 * i + 3] = 0.f; }
+      }
+      if (out_mode == 0) {
+    float* op = reinterpret_cast<float*>(p.out) + out_boff + (long long)(row_base + rsub) * p.ldo + col;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if ((ok_mask >> i) & 1u) *reinterpret_cast<float4*>(op + (long long)i * 4 * p.ldo) = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+      } else if (out_mode == 1) {
+    __half* op = reinterpret_cast<__half*>(p.out) + out_boff + (long long)(row_base + rsub) * p.ldo + col;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if ((ok_mask >> i) & 1u) {
+        __half2 h0 = __floats2half2_rn(x[4 * i], x[4 * i + 1]), h1 = __floats2half2_rn(x[4 * i + 2], x[4 * i + 3]);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(op + (long long)i * 4 * p.ldo) = u;
+      }
+      } else {
+    __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + out_boff + (long long)(row_base + rsub) * p.ldo + col;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if ((ok_mask >> i) & 1u) {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(x[4 * i], x[4 * i + 1]), h1 = __floats2bfloat162_rn(x[4 * i + 2], x[4 * i + 3]);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(op + (long long)i * 4 * p.ldo) = u;
+      }
+      }
+    } else {
+      // ---------------- slow path (N tail, unaligned leading dimensions): rolled scalar loops, rarely taken
+      if (c + 2 < n_chunks) prefetch(c + 2);
+#pragma unroll 1
+      for (int i = 0; i < 8; ++i) {
+    if (!((ok_mask >> i) & 1u)) continue;
+    const int r = i * 4 + rsub;
+    const long long row = row_base + r;
+    const float4 a4 = *reinterpret_cast<const float4*>(sw + r * 32 + ((c4 ^ (r & 7)) << 2));
+    const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+      if (col + k >= p.N) break;
+      float xv = av[k] * p.alpha + (p.bias ? __ldg(p.bias + col + k) : 0.f);
+      const float rv = res_b ? res_b[row * p.ld_res + col + k] : 0.f;
+      if (res_first) xv += rv;
+      if (act == 1) xv = __fdividef(xv, 1.0f + __expf(-1.702f * xv));
+      else if (act == 2) xv = xv > 0.f ? xv : 0.2f * xv;
+      else if (act == 3) { const float z = fminf(fmaxf(xv, -15.f), 15.f); xv = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * z)); }
+      if (!res_first) xv += rv;
+      if (do_round) xv = round_tf32(xv);
+      if (!((in_mask >> i) & 1u)) xv = 0.f;
+      const long long o = out_boff + row * p.ldo + col + k;
+      if (out_mode == 0) reinterpret_cast<float*>(p.out)[o] = xv;
+      else if (out_mode == 1) reinterpret_cast<__half*>(p.out)[o] = __float2half_rn(xv);
+      else reinterpret_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16(xv);
+    }
+      }
+    }
+    __syncwarp();  // the smem tile is rewritten by the next chunk
+  }
+}
 
 template <int BLOCK_N, int KIND>  // KIND = DSB_DTYPE_*
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -148,24 +317,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else {
     // ------------------------------------------------------------ epilogue warps (2..9): TMEM lane quadrant = warp % 4,
-    // two warps per quadrant splitting the 32-column chunks (even / odd).  Each chunk (lane = row) is transposed through a
-    // private XOR-swizzled smem tile so that every global access of the warp covers 4 rows x 128 contiguous bytes.
-    // Code-size discipline matters here: with one or two warps per scheduler the epilogue is instruction-fetch bound as
-    // soon as it leaves the L0/L1.5 instruction caches, so every runtime-flag switch sits OUTSIDE the unrolled loops.
+    // two warps per quadrant splitting the 32-column chunks (even / odd).
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;  // 0: even chunks, 1: odd chunks
     float* sw = epi_smem + (warp - 2) * (32 * 32);
-    const bool has_geo = p.geo_P > 0;
-    const int out_mode = (p.flags & DSB_GEMM_OUT_F16) ? 1 : ((p.flags & DSB_GEMM_OUT_BF16) ? 2 : 0);
-    const int act = (p.flags & DSB_GEMM_GELU2) ? 1 : ((p.flags & DSB_GEMM_LRELU) ? 2 : ((p.flags & DSB_GEMM_TANH) ? 3 : 0));
-    const bool do_round = (p.flags & DSB_GEMM_ROUND_TF32) != 0;
-    const bool res_first = (p.flags & DSB_GEMM_RES_BEFORE_ACT) != 0;
-    const int out_es = out_mode ? 2 : 4;
-    const bool vec_ok = ((p.ldo & 3) == 0) && ((p.out_bstride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & (4 * out_es - 1)) == 0) &&
-                        (!p.residual || (((p.ld_res & 3) == 0) && ((p.res_bstride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0))) &&
-                        (!p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0));
-    const int c4 = lane & 7;    // float4 column slot inside the 32-column chunk
-    const int rsub = lane >> 3; // row inside each group of 4 rows
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile % p.tiles_m;
@@ -173,157 +328,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int b = tile / (p.tiles_m * p.tiles_n);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int row_base = m_blk * BLOCK_M + q * 32;
-      uint32_t ok_mask = 0, in_mask = 0;  // bit i: row (row_base + i*4 + rsub) exists / is an interior row
-#pragma unroll 1
-      for (int i = 0; i < 8; ++i) {
-        const int row = row_base + i * 4 + rsub;
-        if (row < p.M) ok_mask |= 1u << i;
-        bool interior = true;
-        if (has_geo) {
-          const int pp = row % p.geo_P;
-          const int y = pp / p.geo_Wp, x = pp - y * p.geo_Wp;
-          interior = (y >= p.geo_y0) && (y < p.geo_y1) && (x >= p.geo_x0) && (x < p.geo_x1);
-        }
-        if (interior) in_mask |= 1u << i;
-      }
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
-      const long long out_boff = (long long)b * p.out_bstride;
-      const float* res_b = p.residual ? p.residual + (long long)b * p.res_bstride : nullptr;
-      const int n_chunks = min(BLOCK_N / 32, (p.N - n_blk * BLOCK_N + 31) / 32);
-
-      // bias + residual are fetched one chunk ahead (the first one while the mainloop still runs)
-      float4 rz_next[8];
-      float4 bz_next = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) rz_next[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      auto prefetch = [&](int c) {
-        const int col = n_blk * BLOCK_N + c * 32 + c4 * 4;
-        if (vec_ok && (col + 3 < p.N)) {  // tail / unaligned chunks fetch inside the slow path instead
-          if (p.bias) bz_next = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-          if (res_b) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if ((ok_mask >> i) & 1u) rz_next[i] = *reinterpret_cast<const float4*>(res_b + (long long)(row_base + i * 4 + rsub) * p.ld_res + col);
-          }
-        }
-      };
-      if (half < n_chunks) prefetch(half);
-      mbar_wait(&tmem_full[as], aphase);
-      tc_fence_after();
-#pragma unroll 1
-      for (int c = half; c < n_chunks; c += 2) {
-        const int col0 = n_blk * BLOCK_N + c * 32;
-        {
-          uint32_t v[32];
-          tmem_ld_32x32(t_row + c * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<uint4*>(sw + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
-        __syncwarp();
-        const int col = col0 + c4 * 4;
-        if (vec_ok && (col0 + 32 <= p.N)) {
-          // ---------------- fast path: whole chunk in range, 16-byte aligned everywhere
-          float x[32];
-          float4 rz_cur[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = i * 4 + rsub;
-            const float4 a4 = *reinterpret_cast<const float4*>(sw + r * 32 + ((c4 ^ (r & 7)) << 2));
-            rz_cur[i] = rz_next[i];
-            x[4 * i + 0] = fmaf(a4.x, p.alpha, bz_next.x); x[4 * i + 1] = fmaf(a4.y, p.alpha, bz_next.y);
-            x[4 * i + 2] = fmaf(a4.z, p.alpha, bz_next.z); x[4 * i + 3] = fmaf(a4.w, p.alpha, bz_next.w);
-          }
-          if (c + 2 < n_chunks) prefetch(c + 2);  // issued before this chunk's stores (out may alias residual)
-          if (res_b && res_first) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { x[4 * i] += rz_cur[i].x; x[4 * i + 1] += rz_cur[i].y; x[4 * i + 2] += rz_cur[i].z; x[4 * i + 3] += rz_cur[i].w; }
-          }
-          if (act == 1) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) x[e] = __fdividef(x[e], 1.0f + __expf(-1.702f * x[e]));
-          } else if (act == 2) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) x[e] = x[e] > 0.f ? x[e] : 0.2f * x[e];
-          } else if (act == 3) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {  // tanh(x) = 1 - 2 / (1 + exp(2x)), clamped so exp stays finite
-              const float z = fminf(fmaxf(x[e], -15.f), 15.f);
-              x[e] = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * z));
-            }
-          }
-          if (res_b && !res_first) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { x[4 * i] += rz_cur[i].x; x[4 * i + 1] += rz_cur[i].y; x[4 * i + 2] += rz_cur[i].z; x[4 * i + 3] += rz_cur[i].w; }
-          }
-          if (do_round) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) x[e] = round_tf32(x[e]);
-          }
-          if (has_geo) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (!((in_mask >> i) & 1u)) { x[4 * i] = 0.f; x[4 * i + 1] = 0.f; x[4 * i + 2] = 0.f; x[4 * i + 3] = 0.f; }
-          }
-          if (out_mode == 0) {
-            float* op = reinterpret_cast<float*>(p.out) + out_boff + (long long)(row_base + rsub) * p.ldo + col;
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if ((ok_mask >> i) & 1u) *reinterpret_cast<float4*>(op + (long long)i * 4 * p.ldo) = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
-          } else if (out_mode == 1) {
-            __half* op = reinterpret_cast<__half*>(p.out) + out_boff + (long long)(row_base + rsub) * p.ldo + col;
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if ((ok_mask >> i) & 1u) {
-                __half2 h0 = __floats2half2_rn(x[4 * i], x[4 * i + 1]), h1 = __floats2half2_rn(x[4 * i + 2], x[4 * i + 3]);
-                uint2 u;
-                u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-                *reinterpret_cast<uint2*>(op + (long long)i * 4 * p.ldo) = u;
-              }
-          } else {
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + out_boff + (long long)(row_base + rsub) * p.ldo + col;
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if ((ok_mask >> i) & 1u) {
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(x[4 * i], x[4 * i + 1]), h1 = __floats2bfloat162_rn(x[4 * i + 2], x[4 * i + 3]);
-                uint2 u;
-                u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-                *reinterpret_cast<uint2*>(op + (long long)i * 4 * p.ldo) = u;
-              }
-          }
-        } else {
-          // ---------------- slow path (N tail, unaligned leading dimensions): rolled scalar loops, rarely taken
-          if (c + 2 < n_chunks) prefetch(c + 2);
-#pragma unroll 1
-          for (int i = 0; i < 8; ++i) {
-            if (!((ok_mask >> i) & 1u)) continue;
-            const int r = i * 4 + rsub;
-            const long long row = row_base + r;
-            const float4 a4 = *reinterpret_cast<const float4*>(sw + r * 32 + ((c4 ^ (r & 7)) << 2));
-            const float av[4] = {a4.x, a4.y, a4.z, a4.w};
-#pragma unroll 1
-            for (int k = 0; k < 4; ++k) {
-              if (col + k >= p.N) break;
-              float xv = av[k] * p.alpha + (p.bias ? __ldg(p.bias + col + k) : 0.f);
-              const float rv = res_b ? res_b[row * p.ld_res + col + k] : 0.f;
-              if (res_first) xv += rv;
-              if (act == 1) xv = __fdividef(xv, 1.0f + __expf(-1.702f * xv));
-              else if (act == 2) xv = xv > 0.f ? xv : 0.2f * xv;
-              else if (act == 3) { const float z = fminf(fmaxf(xv, -15.f), 15.f); xv = 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * z)); }
-              if (!res_first) xv += rv;
-              if (do_round) xv = round_tf32(xv);
-              if (!((in_mask >> i) & 1u)) xv = 0.f;
-              const long long o = out_boff + row * p.ldo + col + k;
-              if (out_mode == 0) reinterpret_cast<float*>(p.out)[o] = xv;
-              else if (out_mode == 1) reinterpret_cast<__half*>(p.out)[o] = __float2half_rn(xv);
-              else reinterpret_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16(xv);
-            }
-          }
-        }
-        __syncwarp();  // the smem tile is rewritten by the next chunk
-      }
+      epilogue_tile<BLOCK_N>(p, sw, tmem_base + as * BLOCK_N, &tmem_full[as], aphase, m_blk * BLOCK_M + q * 32, n_blk, b, q, half, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
@@ -335,6 +340,190 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ CTA-pair (cta_group::2) kernel
+// Two CTAs of a cluster (one TPC) cooperate on a 256 x 256 output tile: CTA r loads its own 128 rows of A and HALF of the
+// B tile (128 of the 256 N rows); the leader (rank 0) issues tcgen05.mma.cta_group::2 with M = 256, which reads A / B halves
+// from both CTAs' shared memory and accumulates rows [128 r, 128 r + 128) into CTA r's TMEM.  Per k-block each SM now moves
+// 32 KB in + 32 KB out of shared memory instead of 48 + 48 KB -- the 1-CTA kernel is bound by exactly that (760 vs 542
+// cycles per k-block).  Protocol: both producers' TMA loads complete_tx on the LEADER's full barrier (.cta_group::2 form);
+// MMA completion is multicast to both CTAs' empty / tmem_full barriers; epilogue warps of both CTAs arrive on the leader's
+// tmem_empty barrier.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {  // same smem offset in CTA `rank` of the cluster
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void tma_load_3d_2sm(const CUtensorMap* m, uint32_t bar_cluster_addr, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+template <bool kTf32>
+__device__ __forceinline__ void umma_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (kTf32) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+  }
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {  // arrives on `bar` (same offset) in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+
+struct PairSmem {
+  static constexpr int BLOCK_N = 256;
+  static constexpr int A_BYTES = BLOCK_M * ROW_BYTES;        // this CTA's 128 rows of A
+  static constexpr int B_BYTES = (BLOCK_N / 2) * ROW_BYTES;  // this CTA's half of the B tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = 6;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + 256 + 8 * 32 * 32 * 4;
+};
+
+template <int KIND>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ GemmParams p) {
+  using S = PairSmem;
+  constexpr int BLOCK_N = S::BLOCK_N;
+  constexpr int STAGES = S::STAGES;
+  constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* epi_smem = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int num_tiles = p.tiles_m * p.tiles_n * p.batch;  // tiles_m counts 256-row pair tiles
+  const int num_kb = p.kb_per_tap * p.num_taps;
+  const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);   // leader's copy is the one in use: its producer arms expect_tx for both CTAs' bytes
+      mbar_init(&empty_bar[s], 1);  // one multicast tcgen05.commit per phase
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 16);  // 8 epilogue warps x 2 CTAs (leader's copy is the one in use)
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast commit / peer TMA signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+        const int m_blk = tile % p.tiles_m;
+        const int n_blk = (tile / p.tiles_m) % p.tiles_n;
+        const int b = tile / (p.tiles_m * p.tiles_n);
+        const int row0 = m_blk * (2 * BLOCK_M) + (int)rank * BLOCK_M;
+        const int nrow0 = n_blk * BLOCK_N + (int)rank * (BLOCK_N / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int tap = kb / p.kb_per_tap;
+          const int c0 = (kb - tap * p.kb_per_tap) * p.block_k;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
+          const uint32_t bar = map_to_cta(smem_u32(&full_bar[stage]), 0);
+          uint8_t* sa = smem + stage * S::STAGE_BYTES;
+          tma_load_3d_2sm(&tmap_a, bar, sa, c0 + p.tap_acol[tap], row0 + p.tap_shift[tap], b);
+          tma_load_3d_2sm(&tmap_b, bar, sa + S::A_BYTES, tap * p.kc + c0, nrow0, p.b_batched ? b : 0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer: one thread of the leader CTA
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc(KIND, 2 * BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint64_t da = make_sw128_kmajor_desc(sa);
+          const uint64_t db = make_sw128_kmajor_desc(sa + S::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_2sm<KIND == DSB_DTYPE_TF32>(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2sm(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&tmem_full[as]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps of both CTAs (rows [128 rank, 128 rank + 128) of the pair tile)
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    float* sw = epi_smem + (warp - 2) * (32 * 32);
+    int it = 0;
+    for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++it) {
+      const int m_blk = tile % p.tiles_m;
+      const int n_blk = (tile / p.tiles_m) % p.tiles_n;
+      const int b = tile / (p.tiles_m * p.tiles_n);
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      epilogue_tile<BLOCK_N>(p, sw, tmem_base + as * BLOCK_N, &tmem_full[as], aphase, m_blk * (2 * BLOCK_M) + (int)rank * BLOCK_M + q * 32, n_blk, b, q,
+                             half, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[as]), 0));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // nobody leaves (or frees TMEM) while the peer may still signal / read
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -389,6 +578,31 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams
   return 0;
 }
 
+template <int KIND>
+static int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int max_ctas, cudaStream_t st) {
+  auto kern = gemm_tcgen05_pair_kernel<KIND>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PairSmem::TOTAL));
+    attr_done = true;
+  }
+  const int tiles = p.tiles_m * p.tiles_n * p.batch;
+  int pairs = max_ctas / 2;
+  if (pairs < 1) pairs = 1;
+  if (tiles < pairs) pairs = tiles;
+  DSB_CHECK_CUDA(launch_pdl(kern, dim3(2 * pairs), dim3(GEMM_THREADS), PairSmem::TOTAL, st, ma, mb, p));
+  return 0;
+}
+
+static bool pair_default() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DSB_GEMM_PAIR");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 }  // namespace dsb
 
 using namespace dsb;
@@ -432,14 +646,26 @@ extern "C" int dsb_gemm_ex(const dsb_gemm_desc* d, void* stream) {
     }
   }
   DSB_REQUIRE(block_n == 128 || block_n == 256, "dsb_gemm_ex: block_n must be 0, 128 or 256");
+  // CTA pairs (cta_group::2, 256 x 256 tiles): default whenever the tile width is 256 and the problem is at least one pair tile tall
+  const bool use_pair = d->cta_pair > 0 || (d->cta_pair == 0 && d->block_n == 0 && block_n == 256 && d->M > BLOCK_M && pair_default());
+  if (use_pair) {
+    block_n = 256;
+    p.tiles_m = (d->M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  }
   p.tiles_n = (d->N + block_n - 1) / block_n;
 
   CUtensorMap ma, mb;
   const long long a_rows = d->a_rows > 0 ? d->a_rows : d->M;
   if (make_operand_map(&ma, d->A, kind, d->a_cols > 0 ? d->a_cols : d->K, a_rows, d->batch, d->lda, d->a_batch_stride, BLOCK_M)) return 3;
-  if (make_operand_map(&mb, d->W, kind, (long long)d->K * d->num_taps, d->N, p.b_batched ? d->batch : 1, d->ldw, d->w_batch_stride, block_n)) return 3;
+  if (make_operand_map(&mb, d->W, kind, (long long)d->K * d->num_taps, d->N, p.b_batched ? d->batch : 1, d->ldw, d->w_batch_stride,
+                       use_pair ? block_n / 2 : block_n)) return 3;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int max_ctas = d->max_ctas > 0 ? d->max_ctas : sms;
+  if (use_pair) {
+    if (kind == DSB_DTYPE_TF32) return launch_pair<DSB_DTYPE_TF32>(ma, mb, p, max_ctas, st);
+    if (kind == DSB_DTYPE_BF16) return launch_pair<DSB_DTYPE_BF16>(ma, mb, p, max_ctas, st);
+    return launch_pair<DSB_DTYPE_F16>(ma, mb, p, max_ctas, st);
+  }
   if (block_n == 256) {
     if (kind == DSB_DTYPE_TF32) return launch<256, DSB_DTYPE_TF32>(ma, mb, p, max_ctas, st);
     if (kind == DSB_DTYPE_BF16) return launch<256, DSB_DTYPE_BF16>(ma, mb, p, max_ctas, st);

@@ -112,7 +112,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
          out: Optional[torch.Tensor] = None, *, dtype: int = TF32, gelu: bool = False, round_out: bool = False, out_bf16: bool = False, out_f16: bool = False,
          lrelu: bool = False, tanh: bool = False, res_before_act: bool = False, taps: Optional[Sequence[int]] = None,
          tap_acol: Optional[Sequence[int]] = None, k_per_tap: Optional[int] = None, out_rows: Optional[int] = None, geo: Optional[Sequence[int]] = None, alpha: float = 1.0,
-         block_n: int = 0, max_ctas: int = 0) -> torch.Tensor:
+         block_n: int = 0, max_ctas: int = 0, cta_pair: int = 0) -> torch.Tensor:
     """out = epi(alpha * A @ W^T + bias) (+ residual) on tcgen05.  a: (M,K) or (batch,M,K); w: (N, taps*K) or (batch,N,K)."""
     _need_cuda(a, w, bias, residual, out)
     batched = a.dim() == 3
@@ -151,7 +151,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     if geo is not None:
         d.geo_P, d.geo_Wp, d.geo_y0, d.geo_y1, d.geo_x0, d.geo_x1 = [int(v) for v in geo]
     d.alpha = alpha
-    d.block_n, d.max_ctas = block_n, max_ctas
+    d.block_n, d.max_ctas, d.cta_pair = block_n, max_ctas, cta_pair
     _lib.check(_lib.lib().dsb_gemm_ex(C.byref(d), _stream()), "dsb_gemm_ex")
     return out
 
