@@ -62,6 +62,7 @@ attention_f16_kernel(const __half* __restrict__ q, long long ldq, const __half* 
   load_tile_async(Vs[0], vb, ldv, 0, Lk);
   cp_async_commit();
   uint32_t a[4][4];  // Q fragments: 4 k-steps of 16 head dims
+  const bool warp_live = qt * QT + warp * 16 < Lq;  // warps whose 16 query rows are all out of range only help with the tile copies
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
   float oacc[8][4];
 #pragma unroll
@@ -86,10 +87,15 @@ attention_f16_kernel(const __half* __restrict__ q, long long ldq, const __half* 
       for (int ks = 0; ks < 4; ++ks) ldsm_x4(a[ks], Qs + row * LDS + ks * 16 + 8 * (lane >> 4));
     }
 
+    // key tiles (8 keys) / key steps (16 keys) that lie entirely beyond Lk are skipped (warp-uniform): the last chunk of a
+    // 265-key sequence holds 9 keys, of a 77-key sequence 13
+    const int keys_left = Lk - kc * KT;
+    const int n_live = keys_left >= KT ? 8 : (keys_left + 7) >> 3;
     float s[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      if (!warp_live || nt >= n_live) continue;
       uint32_t kf[4];
       const __half* kp = Kc + (nt * 8 + (lane & 7)) * LDS + 8 * (lane >> 3);
       ldsm_x4(kf, kp);            // head dims 0..31  -> (b0,b1) of k-step 0 and 1
@@ -124,7 +130,8 @@ attention_f16_kernel(const __half* __restrict__ q, long long ldq, const __half* 
       l1 += s[nt][2] + s[nt][3];
     }
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {  // 16 keys per step: score tiles 2kk and 2kk+1 re-packed as the fp16 A fragment
+    for (int kk = 0; kk < 4; ++kk) {  // 16 keys per step
+      if (!warp_live || kk * 2 >= n_live) continue;: score tiles 2kk and 2kk+1 re-packed as the fp16 A fragment
       const uint32_t pa[4] = {pack_h2(s[2 * kk][0], s[2 * kk][1]), pack_h2(s[2 * kk][2], s[2 * kk][3]),
                               pack_h2(s[2 * kk + 1][0], s[2 * kk + 1][1]), pack_h2(s[2 * kk + 1][2], s[2 * kk + 1][3])};
       const __half* vp = Vc + (kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * LDS + 8 * (lane >> 4);

@@ -647,7 +647,10 @@ extern "C" int dsb_gemm_ex(const dsb_gemm_desc* d, void* stream) {
   }
   DSB_REQUIRE(block_n == 128 || block_n == 256, "dsb_gemm_ex: block_n must be 0, 128 or 256");
   // CTA pairs (cta_group::2, 256 x 256 tiles): default whenever the tile width is 256 and the problem is at least one pair tile tall
-  const bool use_pair = d->cta_pair > 0 || (d->cta_pair == 0 && d->block_n == 0 && block_n == 256 && d->M > BLOCK_M && pair_default());
+  // measured (tools/gemm_microbench.py): pairs win once the mainloop dominates (K >= 2048: 33.3 -> 31.3 us at N=1024, K=4096) and
+  // lose ~1 us of extra prologue (cluster barriers) on short-K launches
+  const bool use_pair = d->cta_pair > 0 || (d->cta_pair == 0 && d->block_n == 0 && block_n == 256 && d->M > BLOCK_M &&
+                                            (long long)d->K * d->num_taps >= 2048 && pair_default());
   if (use_pair) {
     block_n = 256;
     p.tiles_m = (d->M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);

@@ -11,6 +11,7 @@ from __future__ import annotations
 import torch
 
 from . import ops
+from .graphs import GraphCache
 
 
 class DecoderEngine:
@@ -24,6 +25,8 @@ class DecoderEngine:
         self.precision = precision
         self.packed = False
         self.launches = 0
+        self.use_cuda_graph = True
+        self._graphs = GraphCache()
 
     def _pack_conv(self, conv) -> torch.Tensor:
         w = conv.weight.detach().float()  # (Cout, Cin, kh, kw) -> (Cout, kh*kw*Cin), tap-major
@@ -75,6 +78,7 @@ class DecoderEngine:
         conv("conv_out", d.conv_out)
         self.codebook = f(vq.quantize.embedding.weight)
         self.packed = True
+        self._graphs.clear()
 
     # ------------------------------------------------------------------ building blocks (all on padded NHWC tensors)
     def _conv(self, x, name, residual=None, round_out=False):
@@ -154,11 +158,19 @@ class DecoderEngine:
     def decode_tokens(self, ids, grid):
         if not self.packed:
             self.repack()
-        self.launches = 1
         H, W = grid
-        err = torch.zeros(1, dtype=torch.int32, device=ids.device)
-        z = ops.codebook_gather_padded(ids, self.codebook, H, W, round_out=self.precision == "tf32", err_flag=err)
-        mel = self._decode_padded(z)
+        ids = ids.contiguous()
+
+        def body(ids_):
+            self.launches = 1
+            err = torch.zeros(1, dtype=torch.int32, device=ids_.device)
+            z = ops.codebook_gather_padded(ids_, self.codebook, H, W, round_out=self.precision == "tf32", err_flag=err)
+            return self._decode_padded(z), err
+
+        if self.use_cuda_graph:
+            mel, err = self._graphs.run(("tok", tuple(ids.shape), H, W), body, ids)
+        else:
+            mel, err = body(ids)
         if int(err.item()):
             raise RuntimeError("codebook index out of range")
         return mel

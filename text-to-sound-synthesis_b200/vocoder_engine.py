@@ -14,6 +14,7 @@ from __future__ import annotations
 import torch
 
 from . import ops
+from .graphs import GraphCache
 
 
 def _fold(m) -> torch.Tensor:
@@ -31,6 +32,8 @@ class VocoderEngine:
         self.precision = precision
         self.packed = False
         self.launches = 0
+        self.use_cuda_graph = True
+        self._graphs = GraphCache()
 
     def _pack(self, w2d: torch.Tensor, ntaps: int) -> torch.Tensor:
         """(N, ntaps*Cin) tap-major fp32 -> packed GEMM weight for the selected precision."""
@@ -79,6 +82,7 @@ class VocoderEngine:
         last = mods[i + 2]
         self.last = (self._pack_conv1d(_fold(last)), f(last.bias))
         self.packed = True
+        self._graphs.clear()
 
     @torch.no_grad()
     def forward(self, mel: torch.Tensor) -> torch.Tensor:
@@ -87,6 +91,11 @@ class VocoderEngine:
         if not mel.is_cuda:
             raise RuntimeError("VocoderEngine.forward needs a CUDA tensor (no CPU fallback)")
         mel = mel.detach().float().contiguous()
+        if self.use_cuda_graph:
+            return self._graphs.run(tuple(mel.shape), self._forward, mel)
+        return self._forward(mel)
+
+    def _forward(self, mel: torch.Tensor) -> torch.Tensor:
         B, Cm, T = mel.shape
         n = 0
         rnd = self.precision == "tf32"

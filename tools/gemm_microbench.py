@@ -42,14 +42,12 @@ for N, K in [(1024, 64), (1024, 256), (1024, 1024), (1024, 4096), (3072, 1024), 
         it[0] += 1
         return ws[it[0] % 8]
 
-    cases = [("f32 out, no bias", lambda: ops.gemm(a, w(), None, None, out32, dtype=ops.F16)),
-             ("f32 out, bias", lambda: ops.gemm(a, w(), bias, None, out32, dtype=ops.F16)),
-             ("f32 out, bias, residual (in place)", lambda: ops.gemm(a, w(), bias, out32, out32, dtype=ops.F16)),
-             ("f16 out, bias", lambda: ops.gemm(a, w(), bias, None, out16, dtype=ops.F16)),
-             ("f16 out, bias, gelu", lambda: ops.gemm(a, w(), bias, None, out16, dtype=ops.F16, gelu=True)),
-             ("f16 out, bias, BN=128", lambda: ops.gemm(a, w(), bias, None, out16, dtype=ops.F16, block_n=128)),
-             ("f32 out, bias, residual, BN=128", lambda: ops.gemm(a, w(), bias, out32, out32, dtype=ops.F16, block_n=128)),
-             ("f16 out, bias, max_ctas=74", lambda: ops.gemm(a, w(), bias, None, out16, dtype=ops.F16, max_ctas=74))]
+    cases = [("1cta f32 out, bias, residual (in place)", lambda: ops.gemm(a, w(), bias, out32, out32, dtype=ops.F16, cta_pair=-1)),
+             ("pair f32 out, bias, residual (in place)", lambda: ops.gemm(a, w(), bias, out32, out32, dtype=ops.F16, cta_pair=1)),
+             ("1cta f16 out, bias", lambda: ops.gemm(a, w(), bias, None, out16, dtype=ops.F16, cta_pair=-1)),
+             ("pair f16 out, bias", lambda: ops.gemm(a, w(), bias, None, out16, dtype=ops.F16, cta_pair=1)),
+             ("1cta f16 out, bias, gelu", lambda: ops.gemm(a, w(), bias, None, out16, dtype=ops.F16, gelu=True, cta_pair=-1)),
+             ("pair f16 out, bias, gelu", lambda: ops.gemm(a, w(), bias, None, out16, dtype=ops.F16, gelu=True, cta_pair=1))]
     for name, fn in cases:
         us = timeit(fn)
         print(f"N={N:5d} K={K:5d} {name:42s} {us:8.1f} {2.0 * M * N * K / us / 1e6:9.1f}")
