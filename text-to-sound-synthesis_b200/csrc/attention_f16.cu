@@ -131,7 +131,7 @@ attention_f16_kernel(const __half* __restrict__ q, long long ldq, const __half* 
     }
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {  // 16 keys per step
-      if (!warp_live || kk * 2 >= n_live) continue;: score tiles 2kk and 2kk+1 re-packed as the fp16 A fragment
+      if (!warp_live || kk * 2 >= n_live) continue;  // score tiles 2kk and 2kk+1 re-packed as the fp16 A fragment
       const uint32_t pa[4] = {pack_h2(s[2 * kk][0], s[2 * kk][1]), pack_h2(s[2 * kk][2], s[2 * kk][3]),
                               pack_h2(s[2 * kk + 1][0], s[2 * kk + 1][1]), pack_h2(s[2 * kk + 1][2], s[2 * kk + 1][3])};
       const __half* vp = Vc + (kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * LDS + 8 * (lane >> 4);
