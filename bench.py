@@ -185,7 +185,10 @@ def gemm_roofline(model, B, peaks, peaks_src):
     tf32 = eng.precision == "tf32"
     peak = peak_bf16 / 2.0 if tf32 else peak_bf16  # kind::tf32 issues at half the kind::f16 rate; fp16 == bf16 rate
     return {"bound": "tensor", "kernel": f"gemm_tcgen05_kernel<{eng.precision}>", "achieved": round(achieved, 1), "peak": round(peak, 1), "unit": "TFLOP/s",
-            "frac": round(achieved / peak, 4), "traffic": None,
+            "frac": round(achieved / peak, 4),
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the six layer GEMMs of one `ncu --set full` capture
+            # (profiles/r1_d_ncu_full_layer.md; B=16 f16 run; outputs stay L2-resident, so this is below the 46.6 MB algorithmic bytes)
+            "traffic": 27.0e6 if (B == 16 and eng.precision == "f16") else None, "traffic_unit": "bytes/launch",
             "peak_source": f"{peaks_src} MEASURED_PEAKS.json bf16_tflops_sustained={peak_bf16}" + (" / 2 (tf32 dense rate is half of bf16)" if tf32 else
                            " (cuBLAS bf16 GEMM inside a long loop; kind::f16 fp16 operands issue at the same rate)"),
             "per_gemm": per,
@@ -303,9 +306,10 @@ def run_gpu_arm(args):
             cpu = {"value": v, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample}
         line = {"metric": "clips/sec (10s audio, 100 diffusion steps)", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": {"f16": "f16 (fp16 operands, fp32 accumulate)", "tf32": "tf32", "fp32": "f32"}[args.precision], "data": "synthetic",
+                "dtype": {"f16": "f16", "tf32": "tf32", "fp32": "f32"}[args.precision], "data": "synthetic",
                 "config": {"workload": f"Diffsound AudioCaps inference: batch {B}/GPU, 100 steps, K={K} codebook, 265-token grid, top0.85r "
                                        f"(BASELINE.json configs[1]); {args.layers}-layer D=1024 denoiser, random-init weights, synthetic caption embeddings",
+                           "arithmetic": "GEMM operands fp16 (11-bit significand, = TF32), fp32 accumulation; residual stream / LayerNorm / softmax fp32; log_softmax fp64",
                            "global_batch": B * world, "parallelism": f"dp{world} (independent captions per rank, all_gather of tokens)",
                            "l2_policy": "working set per diffusion step (1.53 GB fp32 weights) exceeds the 126 MB L2; no explicit flush"},
                 "e2e": {"value": e2e_v, "unit": "clips/s", "h2d_bytes_per_step": cond_host.numel() * 4, "d2h_bytes_per_step": tok_host.numel() * 8,

@@ -111,33 +111,51 @@ posterior_sample_kernel(const float* __restrict__ logits, const int64_t* __restr
     }  // !in_logprob
     // A.2: truncation
     if (trunc_mode != 0) {
-      float* vw = v_s + warp * C;
-      double* ew = e_s + warp * C;
+      // Keep-set = a prefix of the (value desc, index asc) order: element k is kept iff P(key_k), with key = (orderable value bits,
+      // 0xFFFF - index) a strict total order, T(key) = fp64 sum of exp(v_i) over keys_i > key, and
+      //   nucleus:  P = (float)T(key) < r  (top element always kept)      top-k:  P = #{keys_i > key} < k.
+      // P is monotone in key, so the boundary is found by bisection over the 48-bit key space (48 warp-wide reductions) instead
+      // of ranking every element against every other one (O(K^2)); the predicate itself is unchanged.
+      unsigned long long key[NJ];
+      double ex[NJ];
+      unsigned long long kmax = 0ull;
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         const int k = lane + 32 * j;
-        if (k < C) { vw[k] = lp[j]; ew[k] = (double)expf(lp[j]); }
-      }
-      __syncwarp();
-      double ahead_sum[NJ];
-      int ahead_cnt[NJ];
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) { ahead_sum[j] = 0.0; ahead_cnt[j] = 0; }
-      for (int i = 0; i < C; ++i) {
-        const float vi = vw[i];
-        const double ei = ew[i];
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-          const int k = lane + 32 * j;
-          const bool ahead = (vi > lp[j]) || (vi == lp[j] && i < k);
-          if (ahead) { ahead_sum[j] += ei; ahead_cnt[j] += 1; }
+        if (k < C) {
+          const uint32_t bits = __float_as_uint(lp[j] + 0.0f);
+          const uint32_t u = (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
+          key[j] = ((unsigned long long)u << 16) | (unsigned long long)(0xFFFF - k);
+          ex[j] = (double)expf(lp[j]);
+        } else {
+          key[j] = 0ull;  // below every real key (real keys have index bits <= 0xFFFF and u >= 1 for finite values)
+          ex[j] = 0.0;
         }
+        kmax = key[j] > kmax ? key[j] : kmax;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, kmax, o);
+        kmax = other > kmax ? other : kmax;
+      }
+      // invariant: P(hi) true (the top key: nothing ahead of it), P(lo) false or lo below all keys
+      unsigned long long lo = 0ull, hi = kmax;
+      while (hi - lo > 1ull) {
+        const unsigned long long mid = lo + ((hi - lo) >> 1);
+        double tsum = 0.0;
+        int tcnt = 0;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+          if (key[j] > mid) { tsum += ex[j]; tcnt += 1; }
+        tsum = wsumd(tsum);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tcnt += __shfl_xor_sync(0xffffffffu, tcnt, o);
+        const bool pm = (trunc_mode == 1) ? ((float)tsum < trunc_r) : (tcnt < trunc_k);
+        if (pm) hi = mid; else lo = mid;
       }
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
-        bool keep;
-        if (trunc_mode == 1) keep = (ahead_cnt[j] == 0) || ((float)ahead_sum[j] < trunc_r);
-        else keep = ahead_cnt[j] < trunc_k;
+        const bool keep = key[j] >= hi;  // includes the top element (key == kmax >= hi)
         if (!keep) lp[j] = -70.f;
       }
     }
