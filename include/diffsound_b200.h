@@ -41,6 +41,7 @@ extern "C" {
 /* GroupNorm-apply flags (share the ROUND_TF32 bit) */
 #define DSB_GN_SWISH 32       /* x * sigmoid(x) after the affine (reference model.py:29-31) */
 #define DSB_GN_COMPACT 64     /* write (B, Lp, C) tokens instead of the zero-padded image */
+#define DSB_SPLIT_OUT 512     /* elementwise producers: write the split-TF32 operand (hi | lo), 2*Cp floats per row (see dsb_split_tf32) */
 
 const char* dsb_last_error(void);
 int dsb_version(void);

@@ -53,22 +53,30 @@ __global__ void f32_to_f16_kernel(const float* __restrict__ in, __half* __restri
   for (; i < n; i += stride) out[i] = __float2half_rn(in[i]);
 }
 __global__ void split_tf32_kernel(const float* __restrict__ in, long long ld_in, float* __restrict__ out, long long ld_out, long long rows, int C, int Cp, int wfmt) {
-  const long long total = rows * Cp;
+  const int c4n = Cp / 4;
+  const bool vec = ((C & 3) == 0) && ((ld_in & 3) == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
+  const long long total = rows * c4n;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / Cp;
-    const int c = (int)(i - r * Cp);
-    float hi = 0.f, lo = 0.f;
-    if (c < C) {
-      const float v = in[r * ld_in + c];
-      hi = round_tf32(v);
-      lo = round_tf32(v - hi);
+    const long long r = i / c4n;
+    const int c = (int)(i - r * c4n) * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (vec && c + 3 < C) {
+      const float4 t = *reinterpret_cast<const float4*>(in + r * ld_in + c);
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (c + k < C) v[k] = in[r * ld_in + c + k];
     }
-    out[r * ld_out + c] = hi;
+    float4 hi = make_float4(round_tf32(v[0]), round_tf32(v[1]), round_tf32(v[2]), round_tf32(v[3]));
+    float4 lo = make_float4(round_tf32(v[0] - hi.x), round_tf32(v[1] - hi.y), round_tf32(v[2] - hi.z), round_tf32(v[3] - hi.w));
+    float* o = out + r * ld_out + c;  // ld_out and Cp are multiples of 4 -> 16-byte aligned
+    *reinterpret_cast<float4*>(o) = hi;
     if (wfmt) {  // weight-side layout [hi | hi | lo]
-      out[r * ld_out + Cp + c] = hi;
-      out[r * ld_out + 2 * Cp + c] = lo;
+      *reinterpret_cast<float4*>(o + Cp) = hi;
+      *reinterpret_cast<float4*>(o + 2 * Cp) = lo;
     } else {     // activation-side layout [hi | lo]
-      out[r * ld_out + Cp + c] = lo;
+      *reinterpret_cast<float4*>(o + Cp) = lo;
     }
   }
 }
@@ -118,7 +126,8 @@ extern "C" int dsb_f32_to_f16(const float* in, void* out, long long n, void* str
 }
 extern "C" int dsb_split_tf32(const float* in, long long ld_in, float* out, long long ld_out, long long rows, int C, int Cp, int wfmt, void* stream) {
   DSB_REQUIRE(rows > 0 && C > 0 && Cp >= C && ld_out >= (wfmt ? 3LL : 2LL) * Cp, "dsb_split_tf32: bad shape");
-  split_tf32_kernel<<<grid_for(rows * Cp, 256), 256, 0, (cudaStream_t)stream>>>(in, ld_in, out, ld_out, rows, C, Cp, wfmt);
+  DSB_REQUIRE(Cp % 4 == 0 && ld_out % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "dsb_split_tf32: output must be 16-byte aligned with Cp %% 4 == 0");
+  split_tf32_kernel<<<grid_for(rows * (Cp / 4), 256), 256, 0, (cudaStream_t)stream>>>(in, ld_in, out, ld_out, rows, C, Cp, wfmt);
   DSB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -22,6 +22,11 @@ __device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], u
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ float ex2(float x) {  // 2^x, single MUFU (inputs are <= 0 here; flush-to-zero underflow is exact enough)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -42,7 +47,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 attention_f16_kernel(const __half* __restrict__ q, long long ldq, const __half* __restrict__ k, long long ldk, const __half* __restrict__ v,
                      long long ldv, void* __restrict__ o, long long ldo, int Lq, int Lk, float scale_log2e, int flags) {
   __shared__ __align__(16) __half Qs[QT * LDS];
@@ -117,15 +122,16 @@ attention_f16_kernel(const __half* __restrict__ q, long long ldq, const __half* 
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
     const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
-    const float c0 = exp2f((m0 - mn0) * scale_log2e), c1 = exp2f((m1 - mn1) * scale_log2e);
+    const float c0 = ex2((m0 - mn0) * scale_log2e), c1 = ex2((m1 - mn1) * scale_log2e);
+    const float ms0 = mn0 * scale_log2e, ms1 = mn1 * scale_log2e;
     m0 = mn0; m1 = mn1;
     l0 *= c0; l1 *= c1;
 #pragma unroll
     for (int nd = 0; nd < 8; ++nd) { oacc[nd][0] *= c0; oacc[nd][1] *= c0; oacc[nd][2] *= c1; oacc[nd][3] *= c1; }
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      s[nt][0] = exp2f((s[nt][0] - mn0) * scale_log2e); s[nt][1] = exp2f((s[nt][1] - mn0) * scale_log2e);
-      s[nt][2] = exp2f((s[nt][2] - mn1) * scale_log2e); s[nt][3] = exp2f((s[nt][3] - mn1) * scale_log2e);
+      s[nt][0] = ex2(fmaf(s[nt][0], scale_log2e, -ms0)); s[nt][1] = ex2(fmaf(s[nt][1], scale_log2e, -ms0));
+      s[nt][2] = ex2(fmaf(s[nt][2], scale_log2e, -ms1)); s[nt][3] = ex2(fmaf(s[nt][3], scale_log2e, -ms1));
       l0 += s[nt][0] + s[nt][1];
       l1 += s[nt][2] + s[nt][3];
     }

@@ -18,9 +18,10 @@ __global__ void codebook_gather_padded_kernel(const int64_t* __restrict__ ids, c
   const int b = row / (Hp * Wp);
   const int p = row % (Hp * Wp);
   const int y = p / Wp - 1, x = p % Wp - 1;
-  float4* o = reinterpret_cast<float4*>(out + row * E);
+  const bool split = flags & DSB_SPLIT_OUT;
+  float4* o = reinterpret_cast<float4*>(out + row * (split ? 2 * E : E));
   if (y < 0 || y >= H || x < 0 || x >= W) {
-    for (int i = lane; i < E / 4; i += 32) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = lane; i < (split ? E / 2 : E / 4); i += 32) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     return;
   }
   // ColumnMajor reverse: row-major position (y, x) holds the token at column-major index x*H + y
@@ -33,6 +34,12 @@ __global__ void codebook_gather_padded_kernel(const int64_t* __restrict__ ids, c
   const bool rnd = flags & DSB_GEMM_ROUND_TF32;
   for (int i = lane; i < E / 4; i += 32) {
     float4 v = __ldg(c + i);
+    if (split) {
+      const float4 hi = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+      o[i] = hi;
+      o[E / 4 + i] = make_float4(round_tf32(v.x - hi.x), round_tf32(v.y - hi.y), round_tf32(v.z - hi.z), round_tf32(v.w - hi.w));
+      continue;
+    }
     if (rnd) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
     o[i] = v;
   }
@@ -117,6 +124,13 @@ __global__ void groupnorm_apply_kernel(const float* __restrict__ x, const double
       }
       r = make_float4(o[0], o[1], o[2], o[3]);
     }
+    if (flags & DSB_SPLIT_OUT) {  // rows of 2*C floats: [hi | lo]
+      const float4 hi = make_float4(round_tf32(r.x), round_tf32(r.y), round_tf32(r.z), round_tf32(r.w));
+      *reinterpret_cast<float4*>(out + orow * 2 * C + c4 * 4) = hi;
+      *reinterpret_cast<float4*>(out + orow * 2 * C + C + c4 * 4) =
+          make_float4(round_tf32(r.x - hi.x), round_tf32(r.y - hi.y), round_tf32(r.z - hi.z), round_tf32(r.w - hi.w));
+      continue;
+    }
     *reinterpret_cast<float4*>(out + orow * C + c4 * 4) = r;
   }
 }
@@ -134,6 +148,13 @@ __global__ void upsample2x_padded_kernel(const float* __restrict__ in, float* __
     if (y >= 0 && y < 2 * H && x >= 0 && x < 2 * W) {
       v = *reinterpret_cast<const float4*>(in + (((long long)b * Hi + (y >> 1) + 1) * Wi + (x >> 1) + 1) * C + c4 * 4);
       if (flags & DSB_GEMM_ROUND_TF32) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+    }
+    if (flags & DSB_SPLIT_OUT) {
+      const float4 hi = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+      *reinterpret_cast<float4*>(out + orow * 2 * C + c4 * 4) = hi;
+      *reinterpret_cast<float4*>(out + orow * 2 * C + C + c4 * 4) =
+          make_float4(round_tf32(v.x - hi.x), round_tf32(v.y - hi.y), round_tf32(v.z - hi.z), round_tf32(v.w - hi.w));
+      continue;
     }
     *reinterpret_cast<float4*>(out + orow * C + c4 * 4) = v;
   }
@@ -208,6 +229,7 @@ extern "C" int dsb_groupnorm_stats(const float* x, double* stats, int B, int P, 
 extern "C" int dsb_groupnorm_apply(const float* x, const double* stats, const float* gamma, const float* beta, float* out, int B, int H, int W, int C,
                                    int groups, float eps, int flags, int Lp, void* stream) {
   DSB_REQUIRE(C % 4 == 0 && C % groups == 0, "dsb_groupnorm_apply: unsupported channel count %d", C);
+  DSB_REQUIRE(!(flags & DSB_SPLIT_OUT) || C % 32 == 0, "dsb_groupnorm_apply: split output needs C %% 32 == 0");
   DSB_REQUIRE(!(flags & DSB_GN_COMPACT) || Lp >= H * W, "dsb_groupnorm_apply: Lp too small");
   const long long total = ((flags & DSB_GN_COMPACT) ? (long long)B * Lp : (long long)B * (H + 2) * (W + 2)) * (C / 4);
   groupnorm_apply_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(x, stats, gamma, beta, out, B, H, W, C, groups, eps, flags, Lp);

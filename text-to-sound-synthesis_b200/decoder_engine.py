@@ -34,10 +34,10 @@ class DecoderEngine:
         w = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
         return ops.pack_split_weight(w, ntaps) if self.precision == "tf32x3" else ops.round_tf32(w)
 
-    def _mm(self, a, w, bias=None, residual=None, out=None, **kw):
-        """a: fp32 activation (rows, C) or batched; w: packed weight (split or rounded)."""
+    def _mm(self, a, w, bias=None, residual=None, out=None, presplit=False, **kw):
+        """a: fp32 activation (rows, C) or batched (already in (hi | lo) form when presplit); w: packed weight (split or rounded)."""
         if self.precision == "tf32x3":
-            return ops.gemm_split(ops.split_tf32(a), w, bias, residual, out, **kw)
+            return ops.gemm_split(a if presplit else ops.split_tf32(a), w, bias, residual, out, **kw)
         return ops.gemm(a, w, bias, residual, out, **kw)
 
     @torch.no_grad()
@@ -81,25 +81,28 @@ class DecoderEngine:
         self._graphs.clear()
 
     # ------------------------------------------------------------------ building blocks (all on padded NHWC tensors)
-    def _conv(self, x, name, residual=None, round_out=False):
+    def _conv(self, x, name, residual=None, round_out=False, presplit=False):
+        """x: padded image (B, Hp, Wp, C), or its split form (B, Hp, Wp, 2C) from a producer that fused the (hi | lo) split."""
         w, b, k = self.w[name]
-        B, Hp, Wp, C = x.shape
+        B, Hp, Wp, C = x.shape  # C counts the (hi | lo) columns when presplit; only used to flatten
         R = B * Hp * Wp
         taps = [dy * Wp + dx for dy in (-1, 0, 1) for dx in (-1, 0, 1)] if k == 3 else [0]
         out = torch.empty(B, Hp, Wp, w.shape[0], dtype=torch.float32, device=x.device)
-        self._mm(x.view(R, C), w, b, None if residual is None else residual.view(R, -1), out.view(R, -1), taps=taps,
+        self._mm(x.view(R, C), w, b, None if residual is None else residual.view(R, -1), out.view(R, -1), taps=taps, presplit=presplit,
                  geo=(Hp * Wp, Wp, 1, Hp - 1, 1, Wp - 1), round_out=round_out and self.precision == "tf32")
-        self.launches += 2 if self.precision == "tf32x3" else 1
+        self.launches += 2 if (self.precision == "tf32x3" and not presplit) else 1
         return out
 
     def _gn(self, x, name, swish=True, compact_len=0):
         g, b, eps = self.w[name]
         st = ops.groupnorm_stats(x)
         self.launches += 3  # memset + stats + apply
-        return ops.groupnorm_apply(x, st, g, b, eps=eps, swish=swish, round_out=self.precision == "tf32", compact_len=compact_len)
+        split = self.precision == "tf32x3" and not compact_len  # conv inputs leave GroupNorm already in (hi | lo) form
+        return ops.groupnorm_apply(x, st, g, b, eps=eps, swish=swish, round_out=self.precision == "tf32", compact_len=compact_len, split=split)
 
     def _res(self, x, name):
-        h = self._conv(self._gn(x, name + ".norm1"), name + ".conv1")
+        sp = self.precision == "tf32x3"
+        h = self._conv(self._gn(x, name + ".norm1"), name + ".conv1", presplit=sp)
         h = self._gn(h, name + ".norm2")
         if (name + ".nin") in self.w:
             if self.precision == "tf32":
@@ -107,7 +110,7 @@ class DecoderEngine:
                 x = self._conv(ops.round_tf32(x), name + ".nin")
             else:
                 x = self._conv(x, name + ".nin")
-        return self._conv(h, name + ".conv2", residual=x)
+        return self._conv(h, name + ".conv2", residual=x, presplit=sp)
 
     def _attn(self, x, name):
         """AttnBlock (model.py:202-226): single head over the H*W interior tokens, scale C^-0.5; x is updated in place."""
@@ -138,7 +141,7 @@ class DecoderEngine:
     @torch.no_grad()
     def _decode_padded(self, z):
         d = self.vq.decoder
-        z = self._conv(z, "post_quant", round_out=True)
+        z = self._conv(z, "post_quant", round_out=True, presplit=self.precision == "tf32x3")
         h = self._conv(z, "conv_in")
         h = self._res(h, "mid.block_1")
         h = self._attn(h, "mid.attn_1")
@@ -149,9 +152,10 @@ class DecoderEngine:
                 if len(d.up[lvl].attn) > 0:
                     h = self._attn(h, f"up.{lvl}.attn.{j}")
             if lvl != 0:
-                h = self._conv(ops.upsample2x_padded(h, round_out=self.precision == "tf32"), f"up.{lvl}.upsample")
+                sp = self.precision == "tf32x3"
+                h = self._conv(ops.upsample2x_padded(h, round_out=not sp, split=sp), f"up.{lvl}.upsample", presplit=sp)
                 self.launches += 1
-        out = self._conv(self._gn(h, "norm_out"), "conv_out")  # (B, Hp, Wp, out_ch)
+        out = self._conv(self._gn(h, "norm_out"), "conv_out", presplit=self.precision == "tf32x3")  # (B, Hp, Wp, out_ch)
         return out[:, 1:-1, 1:-1, :].permute(0, 3, 1, 2).contiguous()
 
     @torch.no_grad()
@@ -164,7 +168,7 @@ class DecoderEngine:
         def body(ids_):
             self.launches = 1
             err = torch.zeros(1, dtype=torch.int32, device=ids_.device)
-            z = ops.codebook_gather_padded(ids_, self.codebook, H, W, round_out=self.precision == "tf32", err_flag=err)
+            z = ops.codebook_gather_padded(ids_, self.codebook, H, W, round_out=self.precision == "tf32", split=self.precision == "tf32x3", err_flag=err)
             return self._decode_padded(z), err
 
         if self.use_cuda_graph:
@@ -182,4 +186,4 @@ class DecoderEngine:
             self.repack()
         self.launches = 1
         z = torch.nn.functional.pad(quant.detach().float().permute(0, 2, 3, 1), (0, 0, 1, 1, 1, 1)).contiguous()
-        return self._decode_padded(ops.round_tf32(z) if self.precision == "tf32" else z)
+        return self._decode_padded(ops.round_tf32(z) if self.precision == "tf32" else ops.split_tf32(z))

@@ -12,7 +12,7 @@ import torch
 from . import _lib
 
 TF32, BF16, F16 = 0, 1, 2
-GELU2, ROUND_TF32, OUT_BF16, LRELU, TANH, GN_SWISH, GN_COMPACT, RES_BEFORE_ACT, OUT_F16 = 1, 2, 4, 8, 16, 32, 64, 128, 256
+GELU2, ROUND_TF32, OUT_BF16, LRELU, TANH, GN_SWISH, GN_COMPACT, RES_BEFORE_ACT, OUT_F16, SPLIT_OUT = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512
 
 
 def _stream() -> int:
@@ -255,13 +255,14 @@ def posterior_sample(inp, x_t, t, uniform, sched, *, T, trunc_mode=1, trunc_r=0.
 
 
 # ---------------------------------------------------------------------------------------------- decoder / vocoder support
-def codebook_gather_padded(ids, codebook, H, W, *, round_out=True, err_flag=None):
+def codebook_gather_padded(ids, codebook, H, W, *, round_out=True, split=False, err_flag=None):
     _need_cuda(ids, codebook)
     B = ids.shape[0]
     E = codebook.shape[1]
-    out = torch.empty(B, H + 2, W + 2, E, dtype=torch.float32, device=ids.device)
+    out = torch.empty(B, H + 2, W + 2, 2 * E if split else E, dtype=torch.float32, device=ids.device)
     _lib.check(_lib.lib().dsb_codebook_gather_padded(ids.contiguous().data_ptr(), codebook.data_ptr(), out.data_ptr(), B, H, W, E, codebook.shape[0],
-                                                     ROUND_TF32 if round_out else 0, _ptr(err_flag), _stream()), "dsb_codebook_gather_padded")
+                                                     SPLIT_OUT if split else (ROUND_TF32 if round_out else 0), _ptr(err_flag), _stream()),
+               "dsb_codebook_gather_padded")
     return out
 
 
@@ -274,24 +275,25 @@ def groupnorm_stats(x_pad, stats=None, groups=32):
     return stats
 
 
-def groupnorm_apply(x_pad, stats, gamma, beta, *, eps=1e-6, swish=True, round_out=True, compact_len=0, out=None, groups=32):
+def groupnorm_apply(x_pad, stats, gamma, beta, *, eps=1e-6, swish=True, round_out=True, compact_len=0, out=None, groups=32, split=False):
     _need_cuda(x_pad, stats, gamma, beta)
     B, Hp, Wp, C = x_pad.shape
     H, W = Hp - 2, Wp - 2
-    flags = (GN_SWISH if swish else 0) | (ROUND_TF32 if round_out else 0) | (GN_COMPACT if compact_len else 0)
+    flags = (GN_SWISH if swish else 0) | (ROUND_TF32 if round_out and not split else 0) | (GN_COMPACT if compact_len else 0) | (SPLIT_OUT if split else 0)
     if out is None:
-        out = torch.empty((B, compact_len, C) if compact_len else (B, Hp, Wp, C), dtype=torch.float32, device=x_pad.device)
+        Co = 2 * C if split else C
+        out = torch.empty((B, compact_len, Co) if compact_len else (B, Hp, Wp, Co), dtype=torch.float32, device=x_pad.device)
     _lib.check(_lib.lib().dsb_groupnorm_apply(x_pad.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), B, H, W, C, groups,
                                               eps, flags, compact_len, _stream()), "dsb_groupnorm_apply")
     return out
 
 
-def upsample2x_padded(x_pad, *, round_out=True):
+def upsample2x_padded(x_pad, *, round_out=True, split=False):
     _need_cuda(x_pad)
     B, Hp, Wp, C = x_pad.shape
     H, W = Hp - 2, Wp - 2
-    out = torch.empty(B, 2 * H + 2, 2 * W + 2, C, dtype=torch.float32, device=x_pad.device)
-    _lib.check(_lib.lib().dsb_upsample2x_padded(x_pad.data_ptr(), out.data_ptr(), B, H, W, C, ROUND_TF32 if round_out else 0, _stream()),
+    out = torch.empty(B, 2 * H + 2, 2 * W + 2, 2 * C if split else C, dtype=torch.float32, device=x_pad.device)
+    _lib.check(_lib.lib().dsb_upsample2x_padded(x_pad.data_ptr(), out.data_ptr(), B, H, W, C, SPLIT_OUT if split else (ROUND_TF32 if round_out else 0), _stream()),
                "dsb_upsample2x_padded")
     return out
 
@@ -312,15 +314,16 @@ def tokens_add_to_padded_(tok, x_pad):
     return x_pad
 
 
-def lrelu_pad(x, pad, *, slope=0.2, reflect=True, channel_major=False, round_out=True):
-    """x (B,T,C) channels-last, or (B,C,T) with channel_major -> (B, T+2*pad, C)."""
+def lrelu_pad(x, pad, *, slope=0.2, reflect=True, channel_major=False, round_out=True, split=False):
+    """x (B,T,C) channels-last, or (B,C,T) with channel_major -> (B, T+2*pad, C), or the split-TF32 operand (B, T+2*pad, 2*Cp)."""
     _need_cuda(x)
     x = x.contiguous()
     if channel_major:
         B, Cc, T = x.shape
     else:
         B, T, Cc = x.shape
-    out = torch.empty(B, T + 2 * pad, Cc, dtype=torch.float32, device=x.device)
+    Co = 2 * ((Cc + 31) // 32 * 32) if split else Cc
+    out = torch.empty(B, T + 2 * pad, Co, dtype=torch.float32, device=x.device)
     _lib.check(_lib.lib().dsb_lrelu_pad(x.data_ptr(), out.data_ptr(), B, T, Cc, pad, slope, 1 if reflect else 0, 1 if channel_major else 0,
-                                        ROUND_TF32 if round_out else 0, _stream()), "dsb_lrelu_pad")
+                                        SPLIT_OUT if split else (ROUND_TF32 if round_out else 0), _stream()), "dsb_lrelu_pad")
     return out

@@ -43,10 +43,10 @@ class VocoderEngine:
     def _pack_conv1d(self, w) -> torch.Tensor:
         return self._pack(w.permute(0, 2, 1).reshape(w.shape[0], -1), w.shape[2])  # (Cout, k*Cin), tap-major
 
-    def _mm(self, a, w, bias=None, residual=None, out=None, **kw):
+    def _mm(self, a, w, bias=None, residual=None, out=None, presplit=False, **kw):
         if self.precision == "tf32x3":
             kw.pop("round_out", None)
-            return ops.gemm_split(ops.split_tf32(a), w, bias, residual, out, **kw)
+            return ops.gemm_split(a if presplit else ops.split_tf32(a), w, bias, residual, out, **kw)
         return ops.gemm(a, w, bias, residual, out, **kw)
 
     @torch.no_grad()
@@ -99,10 +99,11 @@ class VocoderEngine:
         B, Cm, T = mel.shape
         n = 0
         rnd = self.precision == "tf32"
-        xl = ops.lrelu_pad(mel, 3, slope=1.0, reflect=True, channel_major=True, round_out=rnd)          # ReflectionPad1d(3) of the mel, channels-last
+        sp = not rnd
+        xl = ops.lrelu_pad(mel, 3, slope=1.0, reflect=True, channel_major=True, round_out=rnd, split=sp)          # ReflectionPad1d(3) of the mel, channels-last
         w0, b0 = self.first
         # conv k=7 -> LeakyReLU (the activation in front of the first ConvTranspose1d) fused in the epilogue
-        x = self._mm(xl, w0, b0, taps=list(range(7)), out_rows=T, lrelu=True, round_out=rnd)   # (B, T, 16*ngf)
+        x = self._mm(xl, w0, b0, taps=list(range(7)), out_rows=T, lrelu=True, round_out=rnd, presplit=sp)   # (B, T, 16*ngf)
         n += 2
         for si, st in enumerate(self.stages):
             r, cout, half = st["r"], st["cout"], st["half"]
@@ -114,15 +115,15 @@ class VocoderEngine:
             n += 2
             for ri, rb in enumerate(st["res"]):
                 d = rb["d"]
-                xl = ops.lrelu_pad(x, d, slope=0.2, reflect=True, round_out=rnd)                          # LeakyReLU + ReflectionPad1d(d)
-                y1 = self._mm(xl, rb["wd"], rb["bd"], taps=[0, d, 2 * d], out_rows=T, lrelu=True, round_out=rnd)
+                xl = ops.lrelu_pad(x, d, slope=0.2, reflect=True, round_out=rnd, split=sp)                          # LeakyReLU + ReflectionPad1d(d)
+                y1 = self._mm(xl, rb["wd"], rb["bd"], taps=[0, d, 2 * d], out_rows=T, lrelu=True, round_out=rnd, presplit=sp)
                 tmp = self._mm(y1, rb["w1"], rb["b1"])
                 last_of_stage = ri == len(st["res"]) - 1
                 # shortcut(x) + block(x); after the last block of a stage the next consumer is LeakyReLU -> ConvT / final conv
                 x = self._mm(x, rb["ws"], rb["bs"], residual=tmp, round_out=rnd, lrelu=last_of_stage, res_before_act=last_of_stage)
                 n += 4
-        xl = ops.lrelu_pad(x, 3, slope=1.0, reflect=True, round_out=rnd)                                  # x already went through LeakyReLU
+        xl = ops.lrelu_pad(x, 3, slope=1.0, reflect=True, round_out=rnd, split=sp)                                  # x already went through LeakyReLU
         wl, bl = self.last
-        wav = self._mm(xl, wl, bl, taps=list(range(7)), out_rows=T, tanh=True)             # (B, T, 1)
+        wav = self._mm(xl, wl, bl, taps=list(range(7)), out_rows=T, tanh=True, presplit=sp)             # (B, T, 1)
         self.launches = n + 2
         return wav.view(B, 1, T)
