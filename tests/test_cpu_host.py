@@ -188,3 +188,21 @@ def test_bench_reference_arm_prints_contract_line():
     assert line["impl"] == "reference" and line["unit"] == "clips/s" and line["higher_is_better"] is True
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["value"] > 0
+
+
+def test_save_clip_writes_reference_layout(tmp_path):
+    import wave
+    import numpy as np
+    from diffsound_b200 import pipeline
+    mel = torch.linspace(-1, 1, 80 * 848).view(1, 80, 848)
+    wav = torch.sin(torch.linspace(0, 100, 22050)).view(1, -1) * 0.5
+    stem = pipeline.save_clip(str(tmp_path), "Y123", 3, mel, wav)
+    assert stem.endswith("Y123_mel_sample_3")
+    spec = np.load(stem + ".npy")
+    assert spec.shape == (80, 848) and abs(float(spec.min())) < 1e-6 and abs(float(spec.max()) - 1.0) < 1e-6  # [0,1] as generate_samples_batch.py:181
+    with wave.open(stem + ".wav", "rb") as f:
+        assert (f.getnchannels(), f.getsampwidth(), f.getframerate(), f.getnframes()) == (1, 3, 22050, 22050)
+        raw = np.frombuffer(f.readframes(4), dtype=np.uint8).reshape(-1, 3).astype(np.int32)
+    val = raw[:, 0] | (raw[:, 1] << 8) | (raw[:, 2] << 16)
+    val = np.where(val >= 1 << 23, val - (1 << 24), val)
+    assert np.allclose(val / 8388607.0, wav[0, :4].numpy(), atol=2e-7)

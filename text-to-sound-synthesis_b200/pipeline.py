@@ -42,3 +42,30 @@ def synthesize_sharded(dalle, vocoder, cond_emb_all: torch.Tensor, *, sample_typ
         dist.all_gather(parts, local[k].contiguous())
         out[k] = torch.cat(parts, 0)
     return out
+
+
+def save_clip(save_root: str, base_name: str, index: int, mel: torch.Tensor, wav: Optional[torch.Tensor], sample_rate: int = 22050):
+    """Write one clip the way Diffsound/evaluation/generate_samples_batch.py:173-187 does:
+    ``{base}_mel_sample_{n}.npy`` = the (80, 848) mel scaled to [0,1] with (spec + 1) / 2 (the layout/range Codebook/evaluate.py and
+    Codebook/evaluation/datasets/fakes.py read back), and ``{base}_mel_sample_{n}.wav`` = mono 24-bit PCM at 22 050 Hz (what
+    ``soundfile.write(..., 'PCM_24')`` produces; written here with the standard library, soundfile is not a dependency)."""
+    import os
+    import wave
+
+    import numpy as np
+    os.makedirs(save_root, exist_ok=True)
+    stem = os.path.join(save_root, f"{base_name}_mel_sample_{index}")
+    spec = mel.detach().float().cpu().numpy()
+    spec = spec.reshape(spec.shape[-2], spec.shape[-1])
+    np.save(stem + ".npy", (spec + 1) / 2)
+    if wav is not None:
+        x = np.clip(wav.detach().float().cpu().numpy().reshape(-1), -1.0, 1.0)
+        q = np.round(x * 8388607.0).astype(np.int32)  # 2^23 - 1
+        b = np.empty((q.size, 3), dtype=np.uint8)
+        b[:, 0], b[:, 1], b[:, 2] = q & 0xFF, (q >> 8) & 0xFF, (q >> 16) & 0xFF
+        with wave.open(stem + ".wav", "wb") as f:
+            f.setnchannels(1)
+            f.setsampwidth(3)
+            f.setframerate(sample_rate)
+            f.writeframes(b.tobytes())
+    return stem
