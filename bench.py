@@ -104,14 +104,16 @@ def cpu_port_clips_per_s(K, B, steps_sample, n_layer=19, threads=None):
         O.sample(sd, cond, gen, n_layer=n_layer, n_head=16, spatial=(5, 53), steps=steps)
         dt = time.perf_counter() - t0
     per_step = dt / len(steps)
-    return B / (per_step * 100.0), threads, f"B={B}, {len(steps)} of 100 p_sample steps (t=99..{steps[-1]}), x{100 // len(steps)} linear extrapolation, {dt:.1f} s of CPU work"
+    return B / (per_step * 100.0), threads, f"B={B}, {len(steps)} of 100 p_sample steps (t=99..{steps[-1]}), x{100 / len(steps):g} linear extrapolation, {dt:.1f} s of CPU work"
 
 
 def run_reference_arm(args):
+    """CPU arm: the reference algorithm (oracle port -- the reference itself is Python under /root/reference and cannot travel to the
+    GPU box) on the host cores.  One bounded sample (B=4, 5 x steps diffusion steps, linearly extrapolated to 100) keeps the run short."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    v, cores, sample = cpu_port_clips_per_s(args.codebook, min(args.batch, 2), max(2, min(10, args.steps * 2)), n_layer=args.layers)
+    v, cores, sample = cpu_port_clips_per_s(args.codebook, min(args.batch, 4), max(5, min(50, 5 * args.steps)), n_layer=args.layers)
     line = {"impl": "reference", "metric": "clips/sec (10s audio, 100 diffusion steps)", "value": v, "unit": "clips/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * args.batch / v, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -302,7 +304,7 @@ def run_gpu_arm(args):
         if args.no_cpu_baseline:
             cpu = None
         else:
-            v, cores, sample = cpu_port_clips_per_s(K, 2, 8, n_layer=args.layers)
+            v, cores, sample = cpu_port_clips_per_s(K, 4, 20, n_layer=args.layers)  # ~10-20 s of CPU work
             cpu = {"value": v, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample}
         line = {"metric": "clips/sec (10s audio, 100 diffusion steps)", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
