@@ -146,3 +146,76 @@ def test_free_running_full_size_tokens_vs_oracle(G):
         assert agree >= floor, f"{prec}: {agree}"
         del m, eng
         torch.cuda.empty_cache()
+
+
+def _run_chain(m, cond, us, steps):
+    """Fused step on supplied uniforms (no torch RNG): returns the token grid after `steps` diffusion steps."""
+    eng = m.transformer.engine
+    B = cond.shape[0]
+    K, L = m.num_classes - 1, m.shape
+    kv = eng.encode_condition(cond)
+    x = torch.full((B, L), K, dtype=torch.long, device="cuda")
+    mode, r, k = m._trunc()
+    for i, ti in enumerate(range(99, 99 - steps, -1)):
+        t = torch.full((B,), ti, dtype=torch.long, device="cuda")
+        x = G_ops().posterior_sample(eng.forward(x, kv, t, cond.shape[1]), x, t, us[i], m._sched(), T=100, trunc_mode=mode, trunc_r=r, trunc_k=k)
+    return x
+
+
+def G_ops():
+    from tests import gpu_common
+    return gpu_common.ops
+
+
+def test_full_config_batch_invariance_and_properties(G):
+    """BASELINE configs[1] shape (19 layers, D=1024, K=256, B=16): properties that do not need the CPU oracle at full size.
+    (1) batch invariance: clip j sampled inside a batch of 16 gets exactly the tokens it gets alone (same per-clip uniforms) -- every
+        kernel on the path reduces each row in an order that does not depend on the other rows;
+    (2) determinism: two runs are bit-identical;  (3) after the full 100 steps no [MASK] id survives and ids < K;
+    (4) the public sample() (CUDA graph, torch RNG) returns the same shape / range at B=16 and B=64."""
+    K, D, NL, NH, CD, L = 256, 1024, 19, 16, 512, 265
+    torch.manual_seed(0)
+    m = build_dt(K, D, NL, NH, CD)
+    m.truncation = "top0.85r"
+    g = torch.Generator().manual_seed(9)
+    B = 16
+    cond = torch.randn(B, 77, CD, generator=g)
+    cond = (cond / cond.norm(dim=-1, keepdim=True)).cuda()
+    steps = 12
+    us = [torch.rand(B, K + 1, L, generator=g).cuda() for _ in range(steps)]
+    full = _run_chain(m, cond, us, steps)
+    again = _run_chain(m, cond, us, steps)
+    assert torch.equal(full, again)
+    for j in (0, 7, 15):
+        solo = _run_chain(m, cond[j:j + 1], [u[j:j + 1].contiguous() for u in us], steps)
+        assert torch.equal(solo[0], full[j]), f"clip {j} depends on its batch neighbours"
+    for Bs in (16, 64):
+        c = torch.randn(Bs, 77, CD, generator=g)
+        c = (c / c.norm(dim=-1, keepdim=True)).cuda()
+        torch.manual_seed(1234)
+        tok = m.sample(None, None, c, filter_ratio=0, batch_size=Bs)["content_token"]
+        assert tok.shape == (Bs, L) and int(tok.min()) >= 0 and int(tok.max()) < K
+
+
+def test_k512_codebook_config_runs(G):
+    """caps_512.yaml's codebook (BASELINE configs[4]): K=512 logits head + K+1=513-class sampler (NJ=17 instantiation), 2 layers."""
+    K, D, NL, NH, CD, B, L = 512, 1024, 2, 16, 512, 4, 265
+    sd = O.make_transformer_state_dict(K=K, D=D, n_layer=NL, n_head=NH, cond_dim=CD, seed=2)
+    m = build_dt(K, D, NL, NH, CD, sd)
+    g = torch.Generator().manual_seed(4)
+    cond = torch.randn(B, 77, CD, generator=g)
+    cond = cond / cond.norm(dim=-1, keepdim=True)
+    x = torch.where(torch.rand(B, L, generator=g) < 0.5, torch.full((B, L), K), torch.randint(0, K, (B, L), generator=g))
+    t = torch.tensor([80, 40, 10, 0])
+    ref_logits = O.transformer_forward(sd, x, cond, t, n_layer=NL, n_head=NH, spatial=(5, 53))
+    eng = m.transformer.engine
+    logits = eng.forward(x.cuda(), eng.encode_condition(cond.cuda()), t.cuda(), 77)
+    assert rel_err(logits.permute(0, 2, 1).cpu(), ref_logits) < 2e-3
+    u = torch.rand(B, K + 1, L, generator=g)
+    sched = {k: sd[k] for k in sd if k.startswith("log_")}
+    ref_next, _, _ = O.posterior_sample_step(sched, ref_logits, x, t, u, T=100)
+    nxt = G.ops.posterior_sample(logits, x.cuda(), t.cuda(), u.cuda(), m._sched(), T=100).cpu()
+    assert (nxt != ref_next).float().mean() < 0.02
+    m.truncation = "top0.85r"
+    tok = m.sample(None, None, cond.cuda(), filter_ratio=0, batch_size=B)["content_token"]
+    assert int(tok.max()) < K
