@@ -295,13 +295,13 @@ def run_gpu_arm(args):
     clips = B * world * args.steps
     value = clips / (ms_dev * 1e-3)
     e2e_v = clips / (ms_e2e * 1e-3)
-    full = full_pipeline_probe(model, cond_dev, B) if (rank == 0 and not args.no_full_pipeline) else None
+    full = full_pipeline_probe(model, cond_dev, B) if (rank == 0 and world == 1 and not args.no_full_pipeline) else None
     if rank == 0:
         peaks, src = load_peaks()
         roof = gemm_roofline(model, B, peaks, src)
         flops = FLOP_PER_CLIP_STEP.get(K, 158.3e9) * 100 * (args.layers / 19.0)
         roof["pipeline_tflops"] = round(value * flops / 1e12 / world, 1)
-        if args.no_cpu_baseline:
+        if args.no_cpu_baseline or world > 1:  # the CPU arm is timed at N=1 only
             cpu = None
         else:
             v, cores, sample = cpu_port_clips_per_s(K, 4, 20, n_layer=args.layers)  # ~10-20 s of CPU work
