@@ -128,6 +128,11 @@ int dsb_attention(const float* q, long long ldq, const float* k, long long ldk, 
 int dsb_attention_f16(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o, long long ldo,
                       int B, int H, int Lq, int Lk, float scale, int flags, void* stream);
 
+/* tcgen05 / TMEM version of the same core: S = Q K^T and O = P V on the 5th-gen tensor cores (P is written back into TMEM by
+ * the softmax warps and read as the A operand), one CTA per (batch, head), Lk <= 272.  q/k/v/o fp16. */
+int dsb_attention_tc(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o, long long ldo,
+                     int B, int H, int Lq, int Lk, float scale, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Posterior + truncation + Gumbel-argmax sampler, one kernel (reference diffusion_transformer.py:285-289 predict_start tail,
  * models/dalle_spec.py:146-174 top-k / nucleus truncation, diffusion_transformer.py:293-339 q_posterior,
