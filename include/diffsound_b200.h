@@ -132,6 +132,10 @@ int dsb_attention_f16(const void* q, long long ldq, const void* k, long long ldk
  * the softmax warps and read as the A operand), one CTA per (batch, head), Lk <= 272.  q/k/v/o fp16. */
 int dsb_attention_tc(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o, long long ldo,
                      int B, int H, int Lq, int Lk, float scale, void* stream);
+/* pipelined version: TMA-fed, warp-specialised (producer / MMA issuer / 8 softmax warps / 4 epilogue warps), persistent over a
+ * balanced slice of the (batch, head, query tile) list */
+int dsb_attention_tc2(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o, long long ldo,
+                      int B, int H, int Lq, int Lk, float scale, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Posterior + truncation + Gumbel-argmax sampler, one kernel (reference diffusion_transformer.py:285-289 predict_start tail,

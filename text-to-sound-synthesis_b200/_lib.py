@@ -49,6 +49,7 @@ SIGNATURES = {
     "dsb_tokens_add_to_padded": [c_vp, c_vp] + [c_i] * 5 + [c_vp],
     "dsb_lrelu_pad": [c_vp, c_vp] + [c_i] * 4 + [c_f, c_i, c_i, c_i, c_vp],
     "dsb_attention_f16": [c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_i, c_i, c_i, c_i, c_f, c_i, c_vp],
+    "dsb_attention_tc2": [c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_i, c_i, c_i, c_i, c_f, c_vp],
     "dsb_attention_tc": [c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_i, c_i, c_i, c_i, c_f, c_vp],
     "dsb_posterior_sample": [c_vp] * 8 + [c_i] * 5 + [c_f, c_i, c_i, c_vp],
 }

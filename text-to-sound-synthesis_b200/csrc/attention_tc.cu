@@ -221,3 +221,256 @@ extern "C" int dsb_attention_tc(const void* q, long long ldq, const void* k, lon
                             (const __half*)v, ldv, (__half*)o, ldo, Lq, Lk, scale * 1.4426950408889634f));
   return 0;
 }
+
+// ================================================================================================================================
+// Pipelined version.  Work list = (batch, head, 128-row query tile), flattened head-major so that consecutive tiles share K/V; every
+// CTA takes a contiguous, equally sized slice of it.  Roles (14 warps):
+//   warps 0-7  softmax: warp w owns TMEM lanes 32*(w%4).., half (w/4) of the key columns; row max / row sum exchanged through smem
+//   warps 8-11 epilogue: O / rowsum -> fp16 -> HBM
+//   warp 12    TMA producer: K/V (double-buffered per (batch, head)) and Q tiles (double-buffered)
+//   warp 13    tcgen05.mma issuer (+ TMEM owner): S(t) ... [softmax(t)] ... P.V(t), S(t+1) back to back
+// TMEM: S columns [0,272), P (packed fp16) [272,408), O [416,480).
+namespace dsb {
+namespace {
+constexpr int T2_THREADS = 448;
+constexpr int T2_KV_BYTES = TC_KMAX * 128;   // one K or V buffer
+struct T2Params {
+  int B, H, Lq, Lk, kpad, n_qt, total_tiles, box_rows, n_box;
+  long long ldo;
+  __half* o;
+  float scale_log2e;
+};
+
+__global__ void __launch_bounds__(T2_THREADS, 1)
+attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+                     const __grid_constant__ T2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                               // 2 x 16 KB
+  uint8_t* sK = sQ + 2 * TC_QM * 128;               // 2 x 34 KB
+  uint8_t* sV = sK + 2 * T2_KV_BYTES;               // 2 x 34 KB
+  float* s_max = reinterpret_cast<float*>(sV + 2 * T2_KV_BYTES);  // [2 halves][128 rows]
+  float* s_sum = s_max + 256;                       // [2 tile parities][2 halves][128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_sum + 512);
+  uint64_t* kv_full = bars;        // [2]
+  uint64_t* kv_empty = bars + 2;   // [2]
+  uint64_t* q_full = bars + 4;     // [2]
+  uint64_t* q_empty = bars + 6;    // [2]
+  uint64_t* s_full = bars + 8;
+  uint64_t* p_full = bars + 9;
+  uint64_t* o_full = bars + 10;
+  uint64_t* o_empty = bars + 11;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g0 = (int)((long long)p.total_tiles * blockIdx.x / gridDim.x);
+  const int g1 = (int)((long long)p.total_tiles * (blockIdx.x + 1) / gridDim.x);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
+      mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1);
+    }
+    mbar_init(s_full, 1); mbar_init(p_full, 8); mbar_init(o_full, 1); mbar_init(o_empty, 4);
+    fence_barrier_init();
+    prefetch_tmap(&map_q); prefetch_tmap(&map_k); prefetch_tmap(&map_v);
+  }
+  if (warp == 13) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tS = tmem_base, tP = tmem_base + 272, tO = tmem_base + 416;
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp == 12) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int prev_u = -1, kv_n = 0;
+      for (int g = g0, t = 0; g < g1; ++g, ++t) {
+        const int u = g / p.n_qt, qt = g - u * p.n_qt;
+        const int b = u / p.H, h = u - b * p.H;
+        if (u != prev_u) {
+          const int kb = kv_n & 1;
+          mbar_wait(&kv_empty[kb], ((kv_n >> 1) & 1) ^ 1);
+          mbar_arrive_expect_tx(&kv_full[kb], 2 * p.kpad * 128);
+          for (int bx = 0; bx < p.n_box; ++bx) {
+            tma_load_3d(&map_k, &kv_full[kb], sK + kb * T2_KV_BYTES + bx * p.box_rows * 128, h * TC_HD, b * p.Lk + bx * p.box_rows, 0);
+            tma_load_3d(&map_v, &kv_full[kb], sV + kb * T2_KV_BYTES + bx * p.box_rows * 128, h * TC_HD, b * p.Lk + bx * p.box_rows, 0);
+          }
+          ++kv_n;
+          prev_u = u;
+        }
+        const int qb = t & 1;
+        mbar_wait(&q_empty[qb], ((t >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&q_full[qb], TC_QM * 128);
+        tma_load_3d(&map_q, &q_full[qb], sQ + qb * TC_QM * 128, h * TC_HD, b * p.Lq + qt * TC_QM, 0);
+      }
+    }
+  } else if (warp == 13) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const int n_hi = p.kpad > 256 ? 256 : p.kpad, n_lo = p.kpad - n_hi;
+      const uint32_t id_hi = idesc_f16(TC_QM, n_hi, false), id_lo = idesc_f16(TC_QM, n_lo > 0 ? n_lo : 16, false);
+      const uint32_t id_pv = idesc_f16(TC_QM, TC_HD, true);
+      const int ksteps = p.kpad >> 4;
+      int prev_u = -1, kv_n = 0, kb = 0;
+      for (int g = g0, t = 0; g < g1; ++g, ++t) {
+        const int u = g / p.n_qt;
+        if (u != prev_u) {
+          kb = kv_n & 1;
+          mbar_wait(&kv_full[kb], (kv_n >> 1) & 1);
+          ++kv_n;
+          prev_u = u;
+        }
+        const int qb = t & 1;
+        mbar_wait(&q_full[qb], (t >> 1) & 1);
+        // S(t) may overwrite S(t-1): softmax(t-1) finished reading it before it arrived on p_full, which this thread observed before P.V(t-1)
+        tc_fence_after();
+        const uint64_t dq = make_sw128_kmajor_desc(smem_u32(sQ + qb * TC_QM * 128));
+        const uint64_t dk = make_sw128_kmajor_desc(smem_u32(sK + kb * T2_KV_BYTES));
+        const uint64_t dk2 = make_sw128_kmajor_desc(smem_u32(sK + kb * T2_KV_BYTES) + 256 * 128);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          umma<false>(tS, dq + 2 * ks, dk + 2 * ks, id_hi, ks != 0);
+          if (n_lo > 0) umma<false>(tS + 256, dq + 2 * ks, dk2 + 2 * ks, id_lo, ks != 0);
+        }
+        umma_commit(s_full);
+        umma_commit(&q_empty[qb]);
+        // P(t) ready, O free (epilogue of tile t-1 has read it)
+        mbar_wait(p_full, t & 1);
+        mbar_wait(o_empty, (t & 1) ^ 1);
+        tc_fence_after();
+        const uint64_t dv = make_sw128_kmajor_desc(smem_u32(sV + kb * T2_KV_BYTES));
+        for (int ks = 0; ks < ksteps; ++ks) umma_ts_f16(tO, tP + ks * 8, dv + (uint64_t)(ks * 128), id_pv, ks != 0);
+        umma_commit(o_full);
+        const bool last_of_unit = (g + 1 == g1) || ((g + 1) / p.n_qt != u);
+        if (last_of_unit) umma_commit(&kv_empty[kb]);
+      }
+    }
+  } else if (warp < 8) {
+    // ------------------------------------------------------------------ softmax: 2 warps per 32-row slab, each half of the key columns
+    const int quad = warp & 3, half = warp >> 2;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const int row_in_tile = quad * 32 + lane;
+    const int csplit = (((p.kpad + 31) >> 5) + 1) / 2 * 32;  // columns [0, csplit) -> half 0, [csplit, kpad) -> half 1
+    const int c_begin = half == 0 ? 0 : csplit, c_end = half == 0 ? (csplit < p.kpad ? csplit : p.kpad) : p.kpad;
+    for (int g = g0, t = 0; g < g1; ++g, ++t) {
+      mbar_wait(s_full, t & 1);
+      tc_fence_after();
+      float mx = -INFINITY;
+      for (int c = c_begin; c < c_end; c += 32) {
+        uint32_t sv[32];
+        tmem_ld_32x32(tS + lane_off + c, sv);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c + j < p.Lk) mx = fmaxf(mx, __uint_as_float(sv[j]));
+      }
+      s_max[half * 128 + row_in_tile] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mx = fmaxf(mx, s_max[(half ^ 1) * 128 + row_in_tile]);
+      const float ms = mx * p.scale_log2e;
+      float sum = 0.f;
+      for (int c = c_begin; c < c_end; c += 32) {
+        uint32_t sv[32];
+        tmem_ld_32x32(tS + lane_off + c, sv);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float p0 = (c + 2 * j < p.Lk) ? ex2f(fmaf(__uint_as_float(sv[2 * j]), p.scale_log2e, -ms)) : 0.f;
+          const float p1 = (c + 2 * j + 1 < p.Lk) ? ex2f(fmaf(__uint_as_float(sv[2 * j + 1]), p.scale_log2e, -ms)) : 0.f;
+          sum += p0 + p1;
+          __half2 hh = __floats2half2_rn(p0, p1);
+          pk[j] = *reinterpret_cast<uint32_t*>(&hh);
+        }
+        tmem_st_32x32_x16(tP + lane_off + (c >> 1), pk);
+      }
+      s_sum[((t & 1) * 2 + half) * 128 + row_in_tile] = sum;
+      tmem_st_wait();
+      tc_fence_before();
+      asm volatile("bar.sync 2, 256;" ::: "memory");  // nobody overwrites s_max for the next tile before both halves have read it
+      if (lane == 0) mbar_arrive(p_full);
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 8-11)
+    const int quad = warp & 3;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const int row_in_tile = quad * 32 + lane;
+    for (int g = g0, t = 0; g < g1; ++g, ++t) {
+      const int u = g / p.n_qt, qt = g - u * p.n_qt;
+      const int b = u / p.H, h = u - b * p.H;
+      mbar_wait(o_full, t & 1);
+      tc_fence_after();
+      const float inv = 1.0f / (s_sum[((t & 1) * 2) * 128 + row_in_tile] + s_sum[((t & 1) * 2 + 1) * 128 + row_in_tile]);
+      const int row = qt * TC_QM + row_in_tile;
+      __half* orow = p.o + ((long long)b * p.Lq + row) * p.ldo + h * TC_HD;
+#pragma unroll
+      for (int c = 0; c < TC_HD; c += 32) {
+        uint32_t ov[32];
+        tmem_ld_32x32(tO + lane_off + c, ov);
+        tmem_ld_wait();
+        if (row < p.Lq) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            __half2 h0 = __floats2half2_rn(__uint_as_float(ov[j]) * inv, __uint_as_float(ov[j + 1]) * inv);
+            __half2 h1 = __floats2half2_rn(__uint_as_float(ov[j + 2]) * inv, __uint_as_float(ov[j + 3]) * inv);
+            __half2 h2 = __floats2half2_rn(__uint_as_float(ov[j + 4]) * inv, __uint_as_float(ov[j + 5]) * inv);
+            __half2 h3 = __floats2half2_rn(__uint_as_float(ov[j + 6]) * inv, __uint_as_float(ov[j + 7]) * inv);
+            uint4 uu;
+            uu.x = *reinterpret_cast<uint32_t*>(&h0); uu.y = *reinterpret_cast<uint32_t*>(&h1);
+            uu.z = *reinterpret_cast<uint32_t*>(&h2); uu.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(orow + c + j) = uu;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 13) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+}  // namespace
+}  // namespace dsb
+
+extern "C" int dsb_attention_tc2(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o, long long ldo,
+                                 int B, int H, int Lq, int Lk, float scale, void* stream) {
+  using namespace dsb;
+  DSB_REQUIRE(B > 0 && H > 0 && Lq > 0 && Lk > 0 && Lk <= TC_KMAX, "dsb_attention_tc2: need 0 < Lk <= %d", TC_KMAX);
+  DSB_REQUIRE(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0, "dsb_attention_tc2: o must be 16-byte aligned with ldo %% 8 == 0");
+  T2Params p{};
+  p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk;
+  p.kpad = (Lk + 15) & ~15;
+  p.n_qt = (Lq + TC_QM - 1) / TC_QM;
+  p.total_tiles = B * H * p.n_qt;
+  p.n_box = p.kpad > 256 ? 2 : 1;
+  p.box_rows = p.kpad / p.n_box;
+  DSB_REQUIRE(p.box_rows % 8 == 0, "dsb_attention_tc2: internal box size");
+  p.ldo = ldo; p.o = (__half*)o;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  CUtensorMap mq, mk, mv;
+  if (make_operand_map(&mq, q, DSB_DTYPE_F16, (long long)H * TC_HD, (long long)B * Lq, 1, ldq, 0, TC_QM)) return 3;
+  if (make_operand_map(&mk, k, DSB_DTYPE_F16, (long long)H * TC_HD, (long long)B * Lk, 1, ldk, 0, p.box_rows)) return 3;
+  if (make_operand_map(&mv, v, DSB_DTYPE_F16, (long long)H * TC_HD, (long long)B * Lk, 1, ldv, 0, p.box_rows)) return 3;
+  const int smem = 2 * TC_QM * 128 + 4 * T2_KV_BYTES + (256 + 512) * 4 + 16 * 8 + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DSB_CHECK_CUDA(cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_done = true;
+  }
+  int grid = sm_count();
+  if (grid > p.total_tiles) grid = p.total_tiles;
+  DSB_CHECK_CUDA(launch_pdl(attention_tc2_kernel, dim3(grid), dim3(T2_THREADS), smem, (cudaStream_t)stream, mq, mk, mv, p));
+  return 0;
+}

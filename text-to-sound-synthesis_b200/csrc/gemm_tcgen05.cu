@@ -544,7 +544,7 @@ static PFN_encodeTiled get_encode() {
 }
 
 // 3-D map (K, rows, batch) over a K-contiguous matrix; box = (128 bytes of K, box_rows, 1); SWIZZLE_128B; OOB -> 0
-static int make_operand_map(CUtensorMap* map, const void* ptr, int kind, long long kdim, long long rows, long long batch,
+int make_operand_map(CUtensorMap* map, const void* ptr, int kind, long long kdim, long long rows, long long batch,
                             long long ld_elems, long long bstride_elems, int box_rows) {
   PFN_encodeTiled enc = get_encode();
   DSB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");

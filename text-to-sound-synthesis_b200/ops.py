@@ -230,13 +230,14 @@ def attention(q, k, v, out, *, B, H, Lq, Lk, scale, round_out=False):
 STAGE_INPUT_LOGPROB, STAGE_SKIP_POSTERIOR, STAGE_SKIP_SAMPLE = 1, 2, 4
 
 
-def attention_tc(q, k, v, out, *, B, H, Lq, Lk, scale):
+def attention_tc(q, k, v, out, *, B, H, Lq, Lk, scale, pipelined=True):
     """tcgen05/TMEM attention core (fp16 in/out); same argument conventions as attention()."""
     _need_cuda(q, k, v, out)
     if not all(t_.dtype == torch.float16 and t_.stride(-1) == 1 for t_ in (q, k, v, out)):
         raise RuntimeError("attention_tc needs fp16 tensors contiguous in the head dimension")
-    _lib.check(_lib.lib().dsb_attention_tc(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), out.data_ptr(), out.stride(0),
-                                           B, H, Lq, Lk, scale, _stream()), "dsb_attention_tc")
+    fn = _lib.lib().dsb_attention_tc2 if pipelined else _lib.lib().dsb_attention_tc
+    _lib.check(fn(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), out.data_ptr(), out.stride(0),
+                  B, H, Lq, Lk, scale, _stream()), "dsb_attention_tc")
     return out
 
 

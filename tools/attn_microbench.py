@@ -3,7 +3,21 @@ import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import _pkg; _pkg.load()
 from diffsound_b200 import ops
-from tools.gemm_microbench import timeit
+
+def timeit(fn, reps=20):
+    fn(); torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            fn()
+    g.replay(); torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(3):
+        g.replay()
+    e.record(); e.synchronize()
+    return s.elapsed_time(e) / (3 * reps) * 1e3  # us
+
 B, H, L, Lc, D = 16, 16, 265, 77, 1024
 qkv = torch.randn(B * L, 3 * D, device="cuda").half()
 kv = torch.randn(B * Lc, 38912, device="cuda").half()
@@ -13,6 +27,11 @@ us = timeit(lambda: ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], o
 print(f"self-attention  f16: {us:7.1f} us  {4 * B * H * L * L * 64 / us / 1e6:7.1f} TFLOP/s")
 us = timeit(lambda: ops.attention(q2, kv[:, :D], kv[:, D:2 * D], out, B=B, H=H, Lq=L, Lk=Lc, scale=0.125))
 print(f"cross-attention f16: {us:7.1f} us  {4 * B * H * L * Lc * 64 / us / 1e6:7.1f} TFLOP/s")
+us = timeit(lambda: ops.attention_tc(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], out, B=B, H=H, Lq=L, Lk=L, scale=0.125))
+print(f"self-attention  tcgen05: {us:7.1f} us  {4 * B * H * L * L * 64 / us / 1e6:7.1f} TFLOP/s")
+us = timeit(lambda: ops.attention_tc(q2, kv[:, :D], kv[:, D:2 * D], out, B=B, H=H, Lq=L, Lk=Lc, scale=0.125))
+print(f"cross-attention tcgen05: {us:7.1f} us  {4 * B * H * L * Lc * 64 / us / 1e6:7.1f} TFLOP/s")
+if len(sys.argv) > 1: sys.exit(0)
 x = torch.randn(B, L, D, device="cuda"); tab = torch.randn(100, 2 * D, device="cuda"); t = torch.full((B,), 5, device="cuda", dtype=torch.long)
 h = torch.empty(B, L, D, device="cuda", dtype=torch.float16)
 print(f"ada_layernorm (L2-warm x): {timeit(lambda: ops.ada_layernorm(x, tab, t, out=h)):7.1f} us")

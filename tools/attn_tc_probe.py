@@ -4,18 +4,19 @@ import _pkg; _pkg.load()
 from diffsound_b200 import ops
 torch.manual_seed(0)
 def relerr(a, b): return float((a.double() - b.double()).abs().max() / b.double().abs().max())
-for (B, H, Lq, Lk) in [(1, 1, 128, 64), (1, 1, 128, 272), (2, 2, 265, 265), (2, 16, 265, 77), (1, 1, 16, 5)]:
+for (B, H, Lq, Lk) in [(1, 1, 128, 64), (1, 1, 128, 272), (2, 2, 265, 265), (2, 16, 265, 77), (1, 1, 16, 5), (16, 16, 265, 265), (16, 16, 265, 77)]:
     D = H * 64
     qkv = torch.randn(B * Lq, 3 * D, device="cuda").half(); kv = torch.randn(B * Lk, 2 * D, device="cuda").half()
     q, k, v = qkv[:, :D], kv[:, :D], kv[:, D:]
     qh = q.double().view(B, Lq, H, 64).transpose(1, 2); kh = k.double().view(B, Lk, H, 64).transpose(1, 2); vh = v.double().view(B, Lk, H, 64).transpose(1, 2)
     s = qh @ kh.transpose(-1, -2) / 8.0
     ref = (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(B * Lq, D)
+  for pipelined in (False, True):
     out = torch.full((B * Lq, D), float("nan"), device="cuda", dtype=torch.float16)
     try:
-        ops.attention_tc(q, k, v, out, B=B, H=H, Lq=Lq, Lk=Lk, scale=0.125); torch.cuda.synchronize()
+        ops.attention_tc(q, k, v, out, B=B, H=H, Lq=Lq, Lk=Lk, scale=0.125, pipelined=pipelined); torch.cuda.synchronize()
         e = relerr(out.float().cpu(), ref.cpu())
-        print(f"B={B} H={H} Lq={Lq} Lk={Lk}: rel err {e:.3e} nan {int(torch.isnan(out).sum())}", "OK" if e < 2e-3 else "MISMATCH")
+        print(f"pipelined={pipelined} B={B} H={H} Lq={Lq} Lk={Lk}: rel err {e:.3e} nan {int(torch.isnan(out).sum())}", "OK" if e < 2e-3 else "MISMATCH")
         if e >= 2e-3:
             o = out.float().cpu(); r = ref.float().cpu()
             print("  out[0,:8]", o[0, :8].tolist()); print("  ref[0,:8]", r[0, :8].tolist())
