@@ -250,7 +250,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   uint8_t* sK = sQ + 2 * TC_QM * 128;               // 2 x 34 KB
   uint8_t* sV = sK + 2 * T2_KV_BYTES;               // 2 x 34 KB
   float* s_max = reinterpret_cast<float*>(sV + 2 * T2_KV_BYTES);  // [2 halves][128 rows]
-  float* s_sum = s_max + 256;                       // [2 tile parities][2 halves][128 rows]
+  float* s_sum = s_max + 512;                       // [2 tile parities][2 halves][128 rows]   (s_max: [2 tile parities][2 halves][128])
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_sum + 512);
   uint64_t* kv_full = bars;        // [2]
   uint64_t* kv_empty = bars + 2;   // [2]
@@ -319,7 +319,8 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       const uint32_t id_pv = idesc_f16(TC_QM, TC_HD, true);
       const int ksteps = p.kpad >> 4;
       int prev_u = -1, kv_n = 0, kb = 0;
-      for (int g = g0, t = 0; g < g1; ++g, ++t) {
+      // issue S for local tile t (global tile g): waits for its K/V and Q, then 4 (x2) MMAs; returns the K/V buffer it used
+      auto issue_s = [&](int g, int t) {
         const int u = g / p.n_qt;
         if (u != prev_u) {
           kb = kv_n & 1;
@@ -329,7 +330,6 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         }
         const int qb = t & 1;
         mbar_wait(&q_full[qb], (t >> 1) & 1);
-        // S(t) may overwrite S(t-1): softmax(t-1) finished reading it before it arrived on p_full, which this thread observed before P.V(t-1)
         tc_fence_after();
         const uint64_t dq = make_sw128_kmajor_desc(smem_u32(sQ + qb * TC_QM * 128));
         const uint64_t dk = make_sw128_kmajor_desc(smem_u32(sK + kb * T2_KV_BYTES));
@@ -341,15 +341,23 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         }
         umma_commit(s_full);
         umma_commit(&q_empty[qb]);
-        // P(t) ready, O free (epilogue of tile t-1 has read it)
+        return kb;
+      };
+      int kb_cur = (g0 < g1) ? issue_s(g0, 0) : 0;
+      for (int g = g0, t = 0; g < g1; ++g, ++t) {
+        const int u = g / p.n_qt;
+        // P(t) is in TMEM and softmax(t) no longer reads S: the next tile's S can go first, P.V(t) then runs under softmax(t+1)
         mbar_wait(p_full, t & 1);
-        mbar_wait(o_empty, (t & 1) ^ 1);
+        int kb_next = kb_cur;
+        if (g + 1 < g1) kb_next = issue_s(g + 1, t + 1);
+        mbar_wait(o_empty, (t & 1) ^ 1);  // epilogue(t-1) has read O
         tc_fence_after();
-        const uint64_t dv = make_sw128_kmajor_desc(smem_u32(sV + kb * T2_KV_BYTES));
+        const uint64_t dv = make_sw128_kmajor_desc(smem_u32(sV + kb_cur * T2_KV_BYTES));
         for (int ks = 0; ks < ksteps; ++ks) umma_ts_f16(tO, tP + ks * 8, dv + (uint64_t)(ks * 128), id_pv, ks != 0);
         umma_commit(o_full);
         const bool last_of_unit = (g + 1 == g1) || ((g + 1) / p.n_qt != u);
-        if (last_of_unit) umma_commit(&kv_empty[kb]);
+        if (last_of_unit) umma_commit(&kv_empty[kb_cur]);
+        kb_cur = kb_next;
       }
     }
   } else if (warp < 8) {
@@ -360,41 +368,87 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     const int csplit = (((p.kpad + 31) >> 5) + 1) / 2 * 32;  // columns [0, csplit) -> half 0, [csplit, kpad) -> half 1
     const int c_begin = half == 0 ? 0 : csplit, c_end = half == 0 ? (csplit < p.kpad ? csplit : p.kpad) : p.kpad;
     for (int g = g0, t = 0; g < g1; ++g, ++t) {
+      const int qt = g % p.n_qt;
+      // a 32-row slab that lies entirely beyond Lq (most of the last query tile of a 265-row head) does no exp work at all:
+      // its P rows stay whatever they were, the rows are independent in the MMA and are never stored
+      const bool live = qt * TC_QM + quad * 32 < p.Lq;
       mbar_wait(s_full, t & 1);
       tc_fence_after();
-      float mx = -INFINITY;
-      for (int c = c_begin; c < c_end; c += 32) {
-        uint32_t sv[32];
-        tmem_ld_32x32(tS + lane_off + c, sv);
-        tmem_ld_wait();
+      float mx = -INFINITY, sum = 0.f;
+      float* smx = s_max + (t & 1) * 256;  // double-buffered by tile parity: no second barrier needed
+      if (live) {
+        for (int c = c_begin; c < c_end; c += 64) {
+          uint32_t sa[32], sb[32];
+          const bool two = c + 32 < c_end;
+          tmem_ld_32x32(tS + lane_off + c, sa);
+          if (two) tmem_ld_32x32(tS + lane_off + c + 32, sb);
+          tmem_ld_wait();
+          if (c + 32 <= p.Lk) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c + j < p.Lk) mx = fmaxf(mx, __uint_as_float(sv[j]));
-      }
-      s_max[half * 128 + row_in_tile] = mx;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      mx = fmaxf(mx, s_max[(half ^ 1) * 128 + row_in_tile]);
-      const float ms = mx * p.scale_log2e;
-      float sum = 0.f;
-      for (int c = c_begin; c < c_end; c += 32) {
-        uint32_t sv[32];
-        tmem_ld_32x32(tS + lane_off + c, sv);
-        tmem_ld_wait();
-        uint32_t pk[16];
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(sa[j]));
+          } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float p0 = (c + 2 * j < p.Lk) ? ex2f(fmaf(__uint_as_float(sv[2 * j]), p.scale_log2e, -ms)) : 0.f;
-          const float p1 = (c + 2 * j + 1 < p.Lk) ? ex2f(fmaf(__uint_as_float(sv[2 * j + 1]), p.scale_log2e, -ms)) : 0.f;
-          sum += p0 + p1;
-          __half2 hh = __floats2half2_rn(p0, p1);
-          pk[j] = *reinterpret_cast<uint32_t*>(&hh);
+            for (int j = 0; j < 32; ++j)
+              if (c + j < p.Lk) mx = fmaxf(mx, __uint_as_float(sa[j]));
+          }
+          if (two) {
+            if (c + 64 <= p.Lk) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(sb[j]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (c + 32 + j < p.Lk) mx = fmaxf(mx, __uint_as_float(sb[j]));
+            }
+          }
         }
-        tmem_st_32x32_x16(tP + lane_off + (c >> 1), pk);
+      }
+      smx[half * 128 + row_in_tile] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (t > 0) {  // P.V(t-1) still reads the P region this pass is about to overwrite
+        mbar_wait(o_full, (t - 1) & 1);
+        tc_fence_after();
+      }
+      if (live) {
+        mx = fmaxf(mx, smx[(half ^ 1) * 128 + row_in_tile]);
+        const float ms = mx * p.scale_log2e;
+        auto do_chunk = [&](const uint32_t (&sv)[32], int c) {
+          uint32_t pk[16];
+          if (c + 32 <= p.Lk) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float p0 = ex2f(fmaf(__uint_as_float(sv[2 * j]), p.scale_log2e, -ms));
+              const float p1 = ex2f(fmaf(__uint_as_float(sv[2 * j + 1]), p.scale_log2e, -ms));
+              sum += p0 + p1;
+              __half2 hh = __floats2half2_rn(p0, p1);
+              pk[j] = *reinterpret_cast<uint32_t*>(&hh);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float p0 = (c + 2 * j < p.Lk) ? ex2f(fmaf(__uint_as_float(sv[2 * j]), p.scale_log2e, -ms)) : 0.f;
+              const float p1 = (c + 2 * j + 1 < p.Lk) ? ex2f(fmaf(__uint_as_float(sv[2 * j + 1]), p.scale_log2e, -ms)) : 0.f;
+              sum += p0 + p1;
+              __half2 hh = __floats2half2_rn(p0, p1);
+              pk[j] = *reinterpret_cast<uint32_t*>(&hh);
+            }
+          }
+          tmem_st_32x32_x16(tP + lane_off + (c >> 1), pk);
+        };
+        for (int c = c_begin; c < c_end; c += 64) {
+          uint32_t sa[32], sb[32];
+          const bool two = c + 32 < c_end;
+          tmem_ld_32x32(tS + lane_off + c, sa);
+          if (two) tmem_ld_32x32(tS + lane_off + c + 32, sb);
+          tmem_ld_wait();
+          do_chunk(sa, c);
+          if (two) do_chunk(sb, c + 32);
+        }
+        tmem_st_wait();
       }
       s_sum[((t & 1) * 2 + half) * 128 + row_in_tile] = sum;
-      tmem_st_wait();
       tc_fence_before();
-      asm volatile("bar.sync 2, 256;" ::: "memory");  // nobody overwrites s_max for the next tile before both halves have read it
+      __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
     }
   } else {
@@ -463,7 +517,7 @@ extern "C" int dsb_attention_tc2(const void* q, long long ldq, const void* k, lo
   if (make_operand_map(&mq, q, DSB_DTYPE_F16, (long long)H * TC_HD, (long long)B * Lq, 1, ldq, 0, TC_QM)) return 3;
   if (make_operand_map(&mk, k, DSB_DTYPE_F16, (long long)H * TC_HD, (long long)B * Lk, 1, ldk, 0, p.box_rows)) return 3;
   if (make_operand_map(&mv, v, DSB_DTYPE_F16, (long long)H * TC_HD, (long long)B * Lk, 1, ldv, 0, p.box_rows)) return 3;
-  const int smem = 2 * TC_QM * 128 + 4 * T2_KV_BYTES + (256 + 512) * 4 + 16 * 8 + 1024;
+  const int smem = 2 * TC_QM * 128 + 4 * T2_KV_BYTES + (512 + 512) * 4 + 16 * 8 + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     DSB_CHECK_CUDA(cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
