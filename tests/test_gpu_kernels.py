@@ -162,3 +162,24 @@ def test_attention_f16_matches_fp64(G, B, H, Lq, Lk):
     out32 = torch.empty(B * Lq, D, device="cuda")
     G.ops.attention(qkv_d[:, :D], kv_d[:, :D], kv_d[:, D:], out32, B=B, H=H, Lq=Lq, Lk=Lk, scale=0.125)
     assert G.relerr(out32, ref) < 1e-3
+
+
+@pytest.mark.parametrize("pipelined", [False, True])
+@pytest.mark.parametrize("B,H,Lq,Lk", [(2, 2, 265, 265), (3, 16, 265, 77), (1, 1, 16, 5), (2, 4, 70, 130), (1, 2, 128, 272), (16, 16, 265, 265)])
+def test_attention_tcgen05_matches_fp64(G, B, H, Lq, Lk, pipelined):
+    """tcgen05 / TMEM attention (S = Q K^T and O = P V on the tensor cores, P written back to TMEM, V read MN-major); both the
+    single-phase probe kernel and the TMA-fed warp-specialised one, repeated launches included (barrier phases, K/V double buffers)."""
+    D = H * 64
+    gen = torch.Generator().manual_seed(B * 1000 + Lq + Lk)
+    qkv = torch.randn(B * Lq, 3 * D, generator=gen).half()
+    kv = torch.randn(B * Lk, 2 * D, generator=gen).half()
+    qh = qkv[:, :D].double().view(B, Lq, H, 64).transpose(1, 2)
+    kh = kv[:, :D].double().view(B, Lk, H, 64).transpose(1, 2)
+    vh = kv[:, D:].double().view(B, Lk, H, 64).transpose(1, 2)
+    ref = (torch.softmax(qh @ kh.transpose(-1, -2) / 8.0, dim=-1) @ vh).transpose(1, 2).reshape(B * Lq, D)
+    qkv_d, kv_d = qkv.cuda(), kv.cuda()
+    for _ in range(3):
+        out = torch.full((B * Lq, D), float("nan"), device="cuda", dtype=torch.float16)
+        G.ops.attention_tc(qkv_d[:, :D], kv_d[:, :D], kv_d[:, D:], out, B=B, H=H, Lq=Lq, Lk=Lk, scale=0.125, pipelined=pipelined)
+        assert torch.isfinite(out).all()
+        assert G.relerr(out.float(), ref) < 1.5e-3

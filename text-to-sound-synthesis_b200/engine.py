@@ -146,7 +146,11 @@ class DenoiserEngine:
         for li, lay in enumerate(self.layers):
             ops.ada_layernorm(x, lay["tab1"], t, out=h, round_out=rnd)
             self._linear(h2, lay["wqkv"], lay["bqkv"], out=qkv)
-            ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], att, B=B, H=H, Lq=L, Lk=L, scale=scale, round_out=rnd)
+            if self.precision == "f16" and L <= 272:
+                # tcgen05 / TMEM attention (S and P.V on the 5th-gen tensor cores, P kept in TMEM): 25.5 us vs 33.7 us for mma.sync at B=16
+                ops.attention_tc(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], att, B=B, H=H, Lq=L, Lk=L, scale=scale)
+            else:
+                ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], att, B=B, H=H, Lq=L, Lk=L, scale=scale, round_out=rnd)
             self._linear(att, lay["wo1"], lay["bo1"], residual=x2, out=x2)
             ops.ada_layernorm(x, lay["tab2"], t, out=h, round_out=rnd)
             self._linear(h2, lay["wq2"], lay["bq2"], out=q2)

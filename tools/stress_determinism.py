@@ -21,6 +21,8 @@ def run_all():
     ops.attention(qkv16[:, :D], qkv16[:, D:2 * D], qkv16[:, 2 * D:], o16, B=B, H=H, Lq=L, Lk=L, scale=0.125); outs.append(o16)
     o16c = torch.full((B * L, D), float("nan"), device="cuda", dtype=torch.float16)
     ops.attention(a16, kv16[:, :D], kv16[:, D:], o16c, B=B, H=H, Lq=L, Lk=Lc, scale=0.125); outs.append(o16c)
+    otc = torch.full((B * L, D), float("nan"), device="cuda", dtype=torch.float16)
+    ops.attention_tc(qkv16[:, :D], qkv16[:, D:2 * D], qkv16[:, 2 * D:], otc, B=B, H=H, Lq=L, Lk=L, scale=0.125); outs.append(otc)
     xx = res.clone()
     ops.gemm(a16, w16, bias, xx, xx, dtype=ops.F16); outs.append(xx)
     ops.gemm(a16, w16, bias, None, None, dtype=ops.F16, gelu=True, out_f16=True, cta_pair=1)
