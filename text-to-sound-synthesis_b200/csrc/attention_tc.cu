@@ -232,14 +232,120 @@ extern "C" int dsb_attention_tc(const void* q, long long ldq, const void* k, lon
 // TMEM: S columns [0,272), P (packed fp16) [272,408), O [416,480).
 namespace dsb {
 namespace {
-constexpr int T2_THREADS = 448;
+constexpr int T2_THREADS = 480;   // 15 warps: 0-7 softmax, 8-11 epilogue, 12 producer, 13 MMA issuer, 14 remainder rows
 constexpr int T2_KV_BYTES = TC_KMAX * 128;   // one K or V buffer
 struct T2Params {
   int B, H, Lq, Lk, kpad, n_qt, total_tiles, box_rows, n_box;
-  long long ldo;
+  int rem_rows;         // > 0: the last (Lq % 128 <= 16) query rows of every head are computed by the remainder warp, not by a tensor tile
+  long long ldo, ldq;
   __half* o;
+  const __half* q;
   float scale_log2e;
 };
+
+// ---- mma.sync helpers for the remainder warp (same fragments as attention_f16.cu, addresses follow the SW128 tile layout)
+__device__ __forceinline__ void t2_ldsm_x4(uint32_t (&r)[4], const uint8_t* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void t2_ldsm_x4_t(uint32_t (&r)[4], const uint8_t* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void t2_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t t2_pack(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// One warp: rows [row0, row0 + 16) of one head (rows >= Lq masked) against the K / V tiles in shared memory, flash-style over
+// 64-key chunks, written straight to HBM.  Runs concurrently with the tensor-core tiles of the same head.
+__device__ __forceinline__ void remainder_rows(const T2Params& p, const uint8_t* sKb, const uint8_t* sVb, int b, int h, int row0, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  const __half* qb = p.q + (long long)b * p.Lq * p.ldq + h * TC_HD;
+  uint32_t a[4][4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const int ra = row0 + g, rb = row0 + g + 8, c = ks * 16 + 2 * t;
+    a[ks][0] = ra < p.Lq ? *reinterpret_cast<const uint32_t*>(qb + (long long)ra * p.ldq + c) : 0u;
+    a[ks][1] = rb < p.Lq ? *reinterpret_cast<const uint32_t*>(qb + (long long)rb * p.ldq + c) : 0u;
+    a[ks][2] = ra < p.Lq ? *reinterpret_cast<const uint32_t*>(qb + (long long)ra * p.ldq + c + 8) : 0u;
+    a[ks][3] = rb < p.Lq ? *reinterpret_cast<const uint32_t*>(qb + (long long)rb * p.ldq + c + 8) : 0u;
+  }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  float oacc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.f;
+  for (int kc = 0; kc * 64 < p.kpad; ++kc) {
+    const int keys_left = p.Lk - kc * 64;
+    const int n_live = keys_left >= 64 ? 8 : (keys_left + 7) >> 3;
+    float s[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      if (nt >= n_live) continue;
+      const int row = kc * 64 + nt * 8 + (lane & 7);
+      uint32_t kf[4];
+      t2_ldsm_x4(kf, sKb + sw128_off(row, lane >> 3));
+      t2_mma(s[nt], a[0], kf[0], kf[1]);
+      t2_mma(s[nt], a[1], kf[2], kf[3]);
+      t2_ldsm_x4(kf, sKb + sw128_off(row, 4 + (lane >> 3)));
+      t2_mma(s[nt], a[2], kf[0], kf[1]);
+      t2_mma(s[nt], a[3], kf[2], kf[3]);
+    }
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int key = kc * 64 + nt * 8 + 2 * t;
+      if (key >= p.Lk) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+      if (key + 1 >= p.Lk) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    const float c0 = ex2f((m0 - mn0) * p.scale_log2e), c1 = ex2f((m1 - mn1) * p.scale_log2e);
+    const float ms0 = mn0 * p.scale_log2e, ms1 = mn1 * p.scale_log2e;
+    m0 = mn0; m1 = mn1;
+    l0 *= c0; l1 *= c1;
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd) { oacc[nd][0] *= c0; oacc[nd][1] *= c0; oacc[nd][2] *= c1; oacc[nd][3] *= c1; }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = ex2f(fmaf(s[nt][0], p.scale_log2e, -ms0)); s[nt][1] = ex2f(fmaf(s[nt][1], p.scale_log2e, -ms0));
+      s[nt][2] = ex2f(fmaf(s[nt][2], p.scale_log2e, -ms1)); s[nt][3] = ex2f(fmaf(s[nt][3], p.scale_log2e, -ms1));
+      l0 += s[nt][0] + s[nt][1];
+      l1 += s[nt][2] + s[nt][3];
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      if (kk * 2 >= n_live) continue;
+      const uint32_t pa[4] = {t2_pack(s[2 * kk][0], s[2 * kk][1]), t2_pack(s[2 * kk][2], s[2 * kk][3]),
+                              t2_pack(s[2 * kk + 1][0], s[2 * kk + 1][1]), t2_pack(s[2 * kk + 1][2], s[2 * kk + 1][3])};
+      const int row = kc * 64 + kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t vf[4];
+        t2_ldsm_x4_t(vf, sVb + sw128_off(row, 2 * np + (lane >> 4)));
+        t2_mma(oacc[2 * np], pa, vf[0], vf[1]);
+        t2_mma(oacc[2 * np + 1], pa, vf[2], vf[3]);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+  const int ra = row0 + g, rb = row0 + g + 8;
+  __half* ob = p.o + (long long)b * p.Lq * p.ldo + h * TC_HD;
+#pragma unroll
+  for (int nd = 0; nd < 8; ++nd) {
+    if (ra < p.Lq) *reinterpret_cast<__half2*>(ob + (long long)ra * p.ldo + nd * 8 + 2 * t) = __floats2half2_rn(oacc[nd][0] * i0, oacc[nd][1] * i0);
+    if (rb < p.Lq) *reinterpret_cast<__half2*>(ob + (long long)rb * p.ldo + nd * 8 + 2 * t) = __floats2half2_rn(oacc[nd][2] * i1, oacc[nd][3] * i1);
+  }
+}
 
 __global__ void __launch_bounds__(T2_THREADS, 1)
 attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
@@ -268,7 +374,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
+      mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], p.rem_rows > 0 ? 2 : 1);  // MMA commit (+ the remainder warp)
       mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1);
     }
     mbar_init(s_full, 1); mbar_init(p_full, 8); mbar_init(o_full, 1); mbar_init(o_empty, 4);
@@ -358,6 +464,26 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         const bool last_of_unit = (g + 1 == g1) || ((g + 1) / p.n_qt != u);
         if (last_of_unit) umma_commit(&kv_empty[kb_cur]);
         kb_cur = kb_next;
+      }
+    }
+  } else if (warp == 14) {
+    // ------------------------------------------------------------------ remainder rows (Lq % 128 <= 16) of every head whose last tile is ours
+    if (p.rem_rows > 0) {
+      int prev_u = -1, kv_n = 0, kb = 0;
+      for (int g = g0; g < g1; ++g) {
+        const int u = g / p.n_qt, qt = g - u * p.n_qt;
+        if (u != prev_u) {
+          kb = kv_n & 1;
+          mbar_wait(&kv_full[kb], (kv_n >> 1) & 1);
+          ++kv_n;
+          prev_u = u;
+        }
+        const bool last_of_unit = (g + 1 == g1) || ((g + 1) / p.n_qt != u);
+        if (qt == p.n_qt - 1) remainder_rows(p, sK + kb * T2_KV_BYTES, sV + kb * T2_KV_BYTES, u / p.H, u % p.H, p.n_qt * TC_QM, lane);
+        if (last_of_unit) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&kv_empty[kb]);
+        }
       }
     }
   } else if (warp < 8) {
@@ -506,8 +632,16 @@ extern "C" int dsb_attention_tc2(const void* q, long long ldq, const void* k, lo
   T2Params p{};
   p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk;
   p.kpad = (Lk + 15) & ~15;
-  p.n_qt = (Lq + TC_QM - 1) / TC_QM;
+  const int rem = Lq % TC_QM;
+  if (Lq > TC_QM && rem > 0 && rem <= 16) {  // e.g. 265 = 2 x 128 + 9: the 9 rows go to the remainder warp, not to a third tensor tile
+    p.n_qt = Lq / TC_QM;
+    p.rem_rows = rem;
+  } else {
+    p.n_qt = (Lq + TC_QM - 1) / TC_QM;
+    p.rem_rows = 0;
+  }
   p.total_tiles = B * H * p.n_qt;
+  p.q = (const __half*)q; p.ldq = ldq;
   p.n_box = p.kpad > 256 ? 2 : 1;
   p.box_rows = p.kpad / p.n_box;
   DSB_REQUIRE(p.box_rows % 8 == 0, "dsb_attention_tc2: internal box size");
