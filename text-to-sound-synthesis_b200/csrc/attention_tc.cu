@@ -232,7 +232,7 @@ extern "C" int dsb_attention_tc(const void* q, long long ldq, const void* k, lon
 // TMEM: S columns [0,272), P (packed fp16) [272,408), O [416,480).
 namespace dsb {
 namespace {
-constexpr int T2_THREADS = 480;   // 15 warps: 0-7 softmax, 8-11 epilogue, 12 producer, 13 MMA issuer, 14 remainder rows
+constexpr int T2_THREADS = 512;   // 16 warps: 0-7 softmax, 8-11 epilogue, 12 producer, 13 MMA issuer, 14-15 remainder rows
 constexpr int T2_KV_BYTES = TC_KMAX * 128;   // one K or V buffer
 struct T2Params {
   int B, H, Lq, Lk, kpad, n_qt, total_tiles, box_rows, n_box;
@@ -466,18 +466,20 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         kb_cur = kb_next;
       }
     }
-  } else if (warp == 14) {
-    // ------------------------------------------------------------------ remainder rows (Lq % 128 <= 16) of every head whose last tile is ours
+  } else if (warp >= 14) {
+    // ------------------------------------------------------------------ remainder rows (Lq % 128 <= 16) of every head whose last tile is
+    // ours.  Two warps, one per K/V buffer (warp 14 serves buffer 0 = even local heads, warp 15 buffer 1), so each observes every phase
+    // of "its" kv_full barrier in order and has two heads' worth of tensor time to finish one remainder.
     if (p.rem_rows > 0) {
-      int prev_u = -1, kv_n = 0, kb = 0;
+      const int mine = warp - 14;
+      int prev_u = -1, kv_n = 0;
       for (int g = g0; g < g1; ++g) {
         const int u = g / p.n_qt, qt = g - u * p.n_qt;
-        if (u != prev_u) {
-          kb = kv_n & 1;
-          mbar_wait(&kv_full[kb], (kv_n >> 1) & 1);
-          ++kv_n;
-          prev_u = u;
-        }
+        bool first_of_unit = false;
+        if (u != prev_u) { first_of_unit = true; prev_u = u; ++kv_n; }
+        const int n = kv_n - 1, kb = n & 1;
+        if (kb != mine) continue;
+        if (first_of_unit) mbar_wait(&kv_full[kb], (n >> 1) & 1);
         const bool last_of_unit = (g + 1 == g1) || ((g + 1) / p.n_qt != u);
         if (qt == p.n_qt - 1) remainder_rows(p, sK + kb * T2_KV_BYTES, sV + kb * T2_KV_BYTES, u / p.H, u % p.H, p.n_qt * TC_QM, lane);
         if (last_of_unit) {
