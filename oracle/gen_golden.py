@@ -79,6 +79,40 @@ def gen_xf_tiny():
     return model
 
 
+def gen_train_tiny(model):
+    """A13: DiffusionTransformer.forward(return_loss=True) of the reference on the xf_tiny weights, with sample_time pinned
+    (harness-side rebinding of the instance attribute; no reference file is edited) and the q_sample uniforms reproduced by seeding
+    the global CPU generator.  Stores loss, log_model_prob, x_t and the autograd gradient of every parameter."""
+    tr = model.transformer
+    K, D, NL, NH, CD, B, L = np.load(os.path.join(GOLD, "xf_tiny.npz"))["__cfg"].tolist()
+    g = torch.Generator().manual_seed(11)
+    cond = torch.randn(B, 77, CD, generator=g)
+    cond = cond / cond.norm(dim=-1, keepdim=True)
+    x0 = torch.randint(0, K, (B, L), generator=g)
+    t = torch.tensor([57, 0, 99])
+    pt = torch.tensor([0.013, 0.004, 0.01])
+    tr.__dict__.pop("predict_start", None)  # gen_xf_tiny rebound it to the truncating wrapper; training uses the plain method
+    tr.sample_time = lambda b, device, method="uniform": (t, pt)
+    tr.Lt_history.zero_(); tr.Lt_count.zero_()
+    for p_ in tr.parameters():
+        p_.requires_grad_(True)
+        p_.grad = None
+    seed = 4321
+    torch.manual_seed(seed)
+    u = torch.rand(B, K + 1, L)
+    torch.manual_seed(seed)
+    with torch.enable_grad():
+        out = tr({"content_token": x0, "condition_embed_token": cond}, return_loss=True)
+        out["loss"].backward()
+    grads = {"grad." + n: p_.grad.numpy() for n, p_ in tr.named_parameters() if p_.grad is not None}
+    missing = [n for n, p_ in tr.named_parameters() if p_.grad is None]
+    np.savez_compressed(os.path.join(GOLD, "train_tiny.npz"), in_cond=cond.numpy(), in_x0=x0.numpy().astype(np.int16), in_t=t.numpy(),
+                        in_pt=pt.numpy(), in_uniform=u.numpy(), out_loss=out["loss"].detach().numpy(), out_probs=out["logits"].detach().numpy(),
+                        out_Lt_history=tr.Lt_history.numpy(), out_Lt_count=tr.Lt_count.numpy(),
+                        cfg_aux=np.array([tr.auxiliary_loss_weight, float(tr.adaptive_auxiliary_loss), *tr.mask_weight]), **grads)
+    print("train_tiny: loss", float(out["loss"]), "params with grad", len(grads), "without", missing)
+
+
 def gen_sampler_cases():
     """K=256 posterior + nucleus + Gumbel sampler through the reference's own methods."""
     model, _ = rh.build_dalle(K=256, overrides=dict(n_layer=1, n_embd=64, n_head=1, dec_ch=32, dec_ch_mult=[1, 1, 1, 1, 2]), seed=0)
@@ -165,7 +199,7 @@ if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     torch.set_grad_enabled(False)
     gen_schedule()
-    gen_xf_tiny()
+    gen_train_tiny(gen_xf_tiny())
     gen_sampler_cases()
     gen_decoder_tiny()
     gen_melgan()

@@ -95,3 +95,28 @@ def test_synthetic_state_dicts_have_reference_keys():
     msd, _ = load_golden("melgan_tiny.npz")
     mine = O.make_melgan_state_dict(ngf=4)
     assert set(msd) == set(mine) and all(mine[k].shape == msd[k].shape for k in msd), set(msd) ^ set(mine)
+
+
+def test_train_loss_and_gradients_match_reference():
+    """A13: oracle _train_loss (+ torch autograd through it) vs the reference's forward(return_loss=True) / backward()."""
+    sd, _ = load_golden("xf_tiny.npz")
+    _, g = load_golden("train_tiny.npz")
+    K, D, NL, NH, CD, B, L = [int(v) for v in load_golden("xf_tiny.npz")[1]["__cfg"]]
+    aux, adaptive, mw0, mw1 = [float(v) for v in g["cfg_aux"]]
+    names = [k[5:] for k in g if k.startswith("grad.")]
+    leaf = {k: (v.clone().requires_grad_(True) if k in names else v) for k, v in sd.items()}
+    sched = {k: sd[k] for k in sd if k.startswith("log_")}
+    out = O.train_loss(leaf, sched, torch.from_numpy(g["in_x0"]).long(), torch.from_numpy(g["in_cond"]), torch.from_numpy(g["in_t"]),
+                       torch.from_numpy(g["in_pt"]), torch.from_numpy(g["in_uniform"]), n_layer=NL, n_head=NH, spatial=(5, 53), T=100,
+                       aux_weight=aux, adaptive_aux=bool(adaptive), mask_weight=(mw0, mw1))
+    ref_loss = float(g["out_loss"])
+    assert abs(float(out["loss"]) - ref_loss) <= 2e-6 * abs(ref_loss)
+    assert (out["log_model_prob"].exp() - torch.from_numpy(g["out_probs"])).abs().max() < 2e-6
+    # Lt bookkeeping (:450-454): history = 0.1 * kl_loss^2 on a zeroed buffer, count += 1
+    hist = torch.zeros(100).scatter_(0, torch.from_numpy(g["in_t"]), 0.1 * out["kl_loss"].detach() ** 2)
+    assert torch.allclose(hist, torch.from_numpy(g["out_Lt_history"]), rtol=1e-5)
+    out["loss"].backward()
+    for n in names:
+        ref = torch.from_numpy(g["grad." + n])
+        err = (leaf[n].grad - ref).abs().max() / ref.abs().max().clamp_min(1e-12)
+        assert err < 5e-4, (n, float(err))
