@@ -10,7 +10,7 @@ NVFLAGS   := -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -X
 
 all: $(OUT)
 
-build/%.o: $(CSRC)/%.cu $(CSRC)/common.cuh include/diffsound_b200.h
+build/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) include/diffsound_b200.h
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
 

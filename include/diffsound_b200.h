@@ -193,6 +193,57 @@ int dsb_tokens_add_to_padded(const float* tok, float* xpad, int B, int H, int W,
 int dsb_lrelu_pad(const float* in, float* out, int B, int T, int C, int pad, float slope, int reflect, int in_channel_major, int flags,
                   void* stream);
 
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Training (reference sound_synthesis/modeling/transformers/diffusion_transformer.py:370-377, :408-476).
+ * The reference obtains every gradient below from torch autograd; these entry points are the hand-written backward passes.
+ * "dtype" selects the activation storage: DSB_DTYPE_TF32 (fp32 containers, tf32-rounded on store) or DSB_DTYPE_BF16.
+ * ------------------------------------------------------------------------------------------------------------- */
+/* q_sample (:370-377): x_t[b,l] = argmax_k(gumbel(uniform[b,k,l]) + q_pred(log_onehot(x0), t)[k]); uniform is (B, K+1, L). */
+int dsb_q_sample(const int64_t* x0, const int64_t* t, const float* uniform, const float* sched, int64_t* x_t, int B, int K, int L, int T,
+                 void* stream);
+/* Fused _train_loss (:408-476) + the normalisation of forward() (:568-569), from the denoiser logits (B, L, K) on:
+ *   fp64 log_softmax/clamp, q_posterior of the model and of the true x0, KL / decoder NLL / auxiliary KL, mask weights, 1/pt importance
+ *   weights, and the analytic gradient d loss / d logits (dlogits, may be NULL for validation).
+ * Outputs: log_model_prob (B, K+1, L) or NULL (exp() of it when prob_as_exp: forward()'s out['logits'], :573-574); col_loss (B, L, 2) per-column (main, aux) terms; hits (B, L, 2) int flags
+ *   (argmax(log_x0_recon) == x0, argmax(log_model_prob) == x_t; :424-433) or NULL; kl_loss (B), vb_loss (B), loss (1).
+ * lt_history / lt_count (T floats each, updated in place as :448-454 does) may be NULL; scratch_b is B floats.
+ * aux_weight = 0 disables the auxiliary term (is_train=False or auxiliary_loss_weight=0). */
+int dsb_train_loss(const float* logits, const int64_t* x0, const int64_t* x_t, const int64_t* t, const float* pt, const float* sched,
+                   float* dlogits, float* log_model_prob, float* col_loss, int* hits, float* kl_loss, float* vb_loss, float* loss,
+                   float* lt_history, float* lt_count, float* scratch_b, int B, int K, int L, int T, float aux_weight, int adaptive,
+                   float mw0, float mw1, int prob_as_exp, void* stream);
+/* out[b][c, r] = in[b][r, c] (2- or 4-byte elements): the K-major operand copies the weight-gradient GEMMs need. */
+int dsb_transpose(const void* in, long long ld_in, long long in_batch_stride, void* out, long long ld_out, long long out_batch_stride,
+                  int rows, int cols, int batch, int elem_bytes, void* stream);
+/* token-major (B*Lx, ld) with head h in columns [64h, 64h+64)  <->  head-major (B*H, Lx, 64) */
+int dsb_heads_split(const void* tok, long long ld, void* heads, int B, int H, int Lx, int elem_bytes, void* stream);
+int dsb_heads_merge(const void* heads, void* tok, long long ld, int B, int H, int Lx, int elem_bytes, void* stream);
+/* out = dtype(in * (scale ? *scale : 1)); scale is a device scalar (the upstream d loss of autograd / GradScaler) */
+int dsb_cast_scale(const float* in, void* out, long long n, const float* scale, int dtype, void* stream);
+/* out[n] = sum over rows of in[rows, N] (bias gradients); out is overwritten */
+int dsb_colsum(const void* in, long long ld, float* out, long long rows, int N, int dtype, void* stream);
+/* GELU2 (transformer_utils.py:111-115) as separate forward / backward passes (training keeps the pre-activation) */
+int dsb_gelu2_fwd(const void* u, void* a, long long n, int dtype, void* stream);
+int dsb_gelu2_bwd(const void* u, const void* da, void* du, long long n, int dtype, void* stream);
+/* timestep-MLP pieces of AdaLayerNorm (transformer_utils.py:145-147) */
+int dsb_silu_bwd(const float* x, const float* dy, float* dx, long long n, void* stream);
+int dsb_gather_rows(const float* table, const int64_t* idx, float* out, int n, int D, void* stream);
+int dsb_scatter_add_rows(float* table, const int64_t* idx, const float* src, int n, int D, void* stream);
+/* LayerNorm backward: dx_io += dLN/dx (dx_io already holds the residual branch's gradient); dgamma / dbeta are ACCUMULATED. */
+int dsb_layernorm_bwd(const float* x, const float* dy, float* dx_io, const float* gamma, float* dgamma, float* dbeta, long long rows, int D,
+                      float eps, void* stream);
+/* AdaLayerNorm backward: table (n, 2D) = (scale | shift) rows selected by idx[b]; dtable (same shape) is ACCUMULATED. */
+int dsb_ada_layernorm_bwd(const float* x, const float* dy, float* dx_io, const float* table, const int64_t* idx, float* dtable, int B, int L,
+                          int D, float eps, void* stream);
+/* attention rows: P = softmax(S) and dS = alpha * P * (dP - sum(dP * P)) */
+int dsb_softmax_fwd(const float* S, long long ld_s, void* P, long long ld_p, long long rows, int n, int dtype, void* stream);
+int dsb_softmax_bwd(const void* P, long long ld_p, const float* dP, long long ld_dp, void* dS, long long ld_ds, long long rows, int n,
+                    float alpha, int dtype, void* stream);
+/* DalleMaskImageEmbedding backward (dalle_mask_image_embedding.py:36-58): demb / dheight / dwidth are ACCUMULATED. */
+int dsb_embed_bwd(const int64_t* ids, const float* dx, float* demb, float* dheight, float* dwidth, int B, int L, int D, int H, int W,
+                  int num_embed, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -254,18 +254,13 @@ def q_sample_ids(sched, x_start: Tensor, t: Tensor, uniform: Tensor, *, T: int, 
     return gumbel_argmax(q_pred(sched, index_to_log_onehot(x_start, num_classes), t, T), uniform)
 
 
-def train_loss(sd, sched, x_start: Tensor, cond_emb: Tensor, t: Tensor, pt: Tensor, uniform: Tensor, *, n_layer: int, n_head: int,
-               spatial, T: int = 100, aux_weight: float = 0.0, adaptive_aux: bool = False, mask_weight=(1.0, 1.0),
-               is_train: bool = True, prefix: str = "transformer."):
-    """DiffusionTransformer._train_loss + the normalisation of forward() (:408-476, :568-569) with (t, pt) = sample_time(...) and the
-    q_sample uniforms supplied by the caller.  Differentiable in ``sd`` (torch autograd) -- that is how the gradient goldens and
-    the GPU backward parity references are produced.  Returns a dict; 'loss' is the scalar forward() puts in out['loss']."""
+def train_loss_from_logits(sched, out: Tensor, x_start: Tensor, x_t: Tensor, t: Tensor, pt: Tensor, *, T: int = 100,
+                            aux_weight: float = 0.0, adaptive_aux: bool = False, mask_weight=(1.0, 1.0), is_train: bool = True):
+    """_train_loss after the denoiser call (:420-474): out = transformer logits (B, K, L).  Differentiable in ``out``."""
     B, L = x_start.shape
-    C = sd[prefix + "to_logits.1.weight"].shape[0] + 1
+    C = out.shape[1] + 1
     log_x_start = index_to_log_onehot(x_start, C)
-    x_t = q_sample_ids(sched, x_start, t, uniform, T=T, num_classes=C)
     log_xt = index_to_log_onehot(x_t, C)
-    out = transformer_forward(sd, x_t, cond_emb, t, n_layer=n_layer, n_head=n_head, spatial=spatial, prefix=prefix)
     log_x0_recon = predict_start_tail(out)                                        # :269-291 (no truncation in training)
     log_model_prob = q_posterior(sched, log_x0_recon, log_xt, t, T)                 # :421
     log_true_prob = q_posterior(sched, log_x_start, log_xt, t, T)                   # :439
@@ -277,13 +272,27 @@ def train_loss(sd, sched, x_start: Tensor, cond_emb: Tensor, t: Tensor, pt: Tens
     is0 = (t == 0).float()
     kl_loss = is0 * decoder_nll + (1.0 - is0) * kl
     vb = kl_loss / pt
+    kl_aux_loss = None
     if aux_weight != 0 and is_train:
         kl_aux = (multinomial_kl(log_x_start[:, :-1, :], log_x0_recon[:, :-1, :]) * mw).sum(-1)
         kl_aux_loss = is0 * decoder_nll + (1.0 - is0) * kl_aux
         w = (t / T + 1.0) if adaptive_aux else 1.0
         vb = vb + w * aux_weight * kl_aux_loss / pt
-    return dict(loss=vb.sum() / (B * L), vb_loss=vb, kl_loss=kl_loss, log_model_prob=log_model_prob, x_t=x_t,
+    return dict(loss=vb.sum() / (B * L), vb_loss=vb, kl_loss=kl_loss, kl_aux_loss=kl_aux_loss, log_model_prob=log_model_prob, x_t=x_t,
                 x0_recon=log_x0_recon.argmax(1), xt_1_recon=log_model_prob.argmax(1))
+
+
+def train_loss(sd, sched, x_start: Tensor, cond_emb: Tensor, t: Tensor, pt: Tensor, uniform: Tensor, *, n_layer: int, n_head: int,
+               spatial, T: int = 100, aux_weight: float = 0.0, adaptive_aux: bool = False, mask_weight=(1.0, 1.0),
+               is_train: bool = True, prefix: str = "transformer."):
+    """DiffusionTransformer._train_loss + the normalisation of forward() (:408-476, :568-569) with (t, pt) = sample_time(...) and the
+    q_sample uniforms supplied by the caller.  Differentiable in ``sd`` (torch autograd) -- that is how the gradient goldens and
+    the GPU backward parity references are produced.  Returns a dict; 'loss' is the scalar forward() puts in out['loss']."""
+    C = sd[prefix + "to_logits.1.weight"].shape[0] + 1
+    x_t = q_sample_ids(sched, x_start, t, uniform, T=T, num_classes=C)
+    out = transformer_forward(sd, x_t, cond_emb, t, n_layer=n_layer, n_head=n_head, spatial=spatial, prefix=prefix)
+    return train_loss_from_logits(sched, out, x_start, x_t, t, pt, T=T, aux_weight=aux_weight, adaptive_aux=adaptive_aux,
+                                  mask_weight=mask_weight, is_train=is_train)
 
 
 def sample(sd, cond_emb: Tensor, uniforms, *, n_layer: int, n_head: int, spatial, num_timesteps: int = 100,

@@ -52,6 +52,24 @@ SIGNATURES = {
     "dsb_attention_tc2": [c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_i, c_i, c_i, c_i, c_f, c_vp],
     "dsb_attention_tc": [c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_i, c_i, c_i, c_i, c_f, c_vp],
     "dsb_posterior_sample": [c_vp] * 8 + [c_i] * 5 + [c_f, c_i, c_i, c_vp],
+    # training (A13)
+    "dsb_q_sample": [c_vp] * 5 + [c_i] * 4 + [c_vp],
+    "dsb_train_loss": [c_vp] * 16 + [c_i] * 4 + [c_f, c_i, c_f, c_f, c_i, c_vp],
+    "dsb_transpose": [c_vp, c_ll, c_ll, c_vp, c_ll, c_ll, c_i, c_i, c_i, c_i, c_vp],
+    "dsb_heads_split": [c_vp, c_ll, c_vp, c_i, c_i, c_i, c_i, c_vp],
+    "dsb_heads_merge": [c_vp, c_vp, c_ll, c_i, c_i, c_i, c_i, c_vp],
+    "dsb_cast_scale": [c_vp, c_vp, c_ll, c_vp, c_i, c_vp],
+    "dsb_colsum": [c_vp, c_ll, c_vp, c_ll, c_i, c_i, c_vp],
+    "dsb_gelu2_fwd": [c_vp, c_vp, c_ll, c_i, c_vp],
+    "dsb_gelu2_bwd": [c_vp, c_vp, c_vp, c_ll, c_i, c_vp],
+    "dsb_silu_bwd": [c_vp, c_vp, c_vp, c_ll, c_vp],
+    "dsb_gather_rows": [c_vp, c_vp, c_vp, c_i, c_i, c_vp],
+    "dsb_scatter_add_rows": [c_vp, c_vp, c_vp, c_i, c_i, c_vp],
+    "dsb_layernorm_bwd": [c_vp] * 6 + [c_ll, c_i, c_f, c_vp],
+    "dsb_ada_layernorm_bwd": [c_vp] * 6 + [c_i, c_i, c_i, c_f, c_vp],
+    "dsb_softmax_fwd": [c_vp, c_ll, c_vp, c_ll, c_ll, c_i, c_i, c_vp],
+    "dsb_softmax_bwd": [c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_ll, c_i, c_f, c_i, c_vp],
+    "dsb_embed_bwd": [c_vp] * 5 + [c_i] * 6 + [c_vp],
 }
 
 _lib = None

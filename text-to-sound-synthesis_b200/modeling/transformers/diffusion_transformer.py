@@ -14,6 +14,7 @@ import torch
 from torch import nn
 
 from ... import ops
+from ... import train_ops
 from ...utils.misc import instantiate_from_config
 
 _SCHED_ROWS = ["log_at", "log_bt", "log_ct", "log_1_min_ct", "log_cumprod_at", "log_cumprod_bt", "log_cumprod_ct", "log_1_min_cumprod_ct"]
@@ -161,8 +162,47 @@ class DiffusionTransformer(nn.Module):
     def p_sample(self, log_x, cond_emb, t):
         return self.log_sample_categorical(self.p_pred(log_x, cond_emb, t))
 
-    def q_pred(self, log_x_start, t):
-        raise NotImplementedError("q_pred is only reached from training / content-conditioned sampling (SURVEY.md section 8 row A13: next)")
+    @torch.no_grad()
+    def q_sample(self, log_x_start, t, return_index=False):
+        """x_t ~ q(x_t | x_0) (diffusion_transformer.py:370-377): q_pred + Gumbel-argmax in one kernel, uniforms from torch.rand_like's stream."""
+        x0 = log_x_start.argmax(1).contiguous()
+        uniform = torch.rand_like(log_x_start, memory_format=torch.contiguous_format)
+        ids = train_ops.q_sample(x0, t.contiguous(), uniform, self._sched(), self.num_timesteps)
+        return ids if return_index else index_to_log_onehot(ids, self.num_classes)
+
+    def sample_time(self, b, device, method="uniform"):
+        """Importance-sampled timesteps (diffusion_transformer.py:379-406); host-side policy on two 100-element buffers."""
+        if method == "importance":
+            if not (self.Lt_count > 10).all():
+                return self.sample_time(b, device, method="uniform")
+            Lt_sqrt = torch.sqrt(self.Lt_history + 1e-10) + 0.0001
+            Lt_sqrt[0] = Lt_sqrt[1]
+            pt_all = Lt_sqrt / Lt_sqrt.sum()
+            t = torch.multinomial(pt_all, num_samples=b, replacement=True)
+            return t, pt_all.gather(dim=0, index=t)
+        if method == "uniform":
+            t = torch.randint(0, self.num_timesteps, (b,), device=device).long()
+            return t, torch.ones_like(t).float() / self.num_timesteps
+        raise ValueError(method)
+
+    def _train_loss(self, x, cond_emb, is_train=True, want_prob=True):
+        """KL training loss (diffusion_transformer.py:408-476).  Returns (exp(log_model_prob) or None, vb_loss (B,), loss scalar) where the scalar
+        already carries forward()'s normalisation (:568-569) and is differentiable w.r.t. the transformer parameters."""
+        assert self.loss_type == "vb_stochastic"
+        B, L = x.shape
+        x = x.contiguous()
+        t, pt = self.sample_time(B, x.device, "importance")
+        uniform = torch.rand(B, self.num_classes, L, dtype=torch.float32, device=x.device)  # == rand_like(log_EV_qxt_x0), :360
+        x_t = train_ops.q_sample(x, t.contiguous(), uniform, self._sched(), self.num_timesteps)
+        names, params = zip(*self.transformer.named_parameters())
+        loss, prob, vb, hits = _DenoiserLoss.apply(self, x, x_t, cond_emb, t.contiguous(), pt.float().contiguous(), bool(is_train), bool(want_prob),
+                                                   names, *params)
+        # accuracy bookkeeping of :424-436 (one small D2H copy instead of 2B .item() calls)
+        rate = hits.float().mean(dim=1).cpu()
+        for i, this_t in enumerate(t.tolist()):
+            self.diffusion_acc_list[this_t] = float(rate[i, 0]) * 0.1 + self.diffusion_acc_list[this_t] * 0.9
+            self.diffusion_keep_list[this_t] = float(rate[i, 1]) * 0.1 + self.diffusion_keep_list[this_t] * 0.9
+        return prob, vb, loss
 
     # ------------------------------------------------------------------ fused fast path
     def _stages_overridden(self) -> bool:
@@ -241,13 +281,15 @@ class DiffusionTransformer(nn.Module):
         batch_size = condition_token.shape[0] if condition_token is not None else kwargs["batch_size"]
         start_step = int(self.num_timesteps * filter_ratio)
         cond_emb = self._cond(condition_token, condition_embed)
-        if start_step != 0:
-            raise NotImplementedError("content-conditioned sampling (filter_ratio > 0) needs q_sample: SURVEY.md section 8 'next'")
-        steps = list(range(self.num_timesteps - 1, -1, -1))
+        x_init = None
+        if start_step != 0:  # content-conditioned: noise the given tokens to t = start_step-1, then denoise from there (:647-655)
+            t0 = torch.full((batch_size,), start_step - 1, device=self.device, dtype=torch.long)
+            x_init = self.q_sample(index_to_log_onehot(content_token, self.num_classes), t0, return_index=True)
+        steps = list(range((start_step or self.num_timesteps) - 1, -1, -1))
         if self._stages_overridden():
-            content_token = self._sample_unfused(cond_emb, batch_size, steps, steps)
+            content_token = self._sample_unfused(cond_emb, batch_size, steps, steps, x_init=x_init)
         else:
-            content_token = self._run_steps(cond_emb, batch_size, steps, steps)
+            content_token = self._run_steps(cond_emb, batch_size, steps, steps, x_init=x_init)
         output = {"content_token": content_token}
         if return_logits:
             output["logits"] = torch.exp(index_to_log_onehot(content_token, self.num_classes))
@@ -274,11 +316,11 @@ class DiffusionTransformer(nn.Module):
         return output
 
     @torch.no_grad()
-    def _sample_unfused(self, cond_emb, batch_size, steps, post_steps):
+    def _sample_unfused(self, cond_emb, batch_size, steps, post_steps, x_init=None):
         """Stage-by-stage loop through the (possibly re-bound) reference-named methods; every stage is still a CUDA kernel."""
         dev = self.device
         K, L = self.num_classes - 1, self.shape
-        log_z = index_to_log_onehot(torch.full((batch_size, L), K, dtype=torch.int64, device=dev), self.num_classes)
+        log_z = index_to_log_onehot(torch.full((batch_size, L), K, dtype=torch.int64, device=dev) if x_init is None else x_init, self.num_classes)
         for ti, tp in zip(steps, post_steps):
             t = torch.full((batch_size,), ti, device=dev, dtype=torch.long)
             if ti == tp:
@@ -289,8 +331,80 @@ class DiffusionTransformer(nn.Module):
                                                                      t=torch.full((batch_size,), tp, device=dev, dtype=torch.long)))
         return log_z.argmax(1)
 
+    def parameters(self, recurse=True, name=None):
+        """Reference override (diffusion_transformer.py:483-537): with a name, return AdamW groups -- Linear weights decayed (0.01), biases /
+        LayerNorm / Embedding weights not."""
+        if name is None or name == "none":
+            return super().parameters(recurse=recurse)
+        decay, no_decay = set(), set()
+        for mn, m in self.named_modules():
+            for pn, _ in m.named_parameters(recurse=False):
+                fpn = f"{mn}.{pn}" if mn else pn
+                if pn.endswith("bias"):
+                    no_decay.add(fpn)
+                elif pn.endswith("weight") and isinstance(m, nn.Linear):
+                    decay.add(fpn)
+                elif pn.endswith("weight") and isinstance(m, (nn.LayerNorm, nn.Embedding)):
+                    no_decay.add(fpn)
+        strip = lambda names: {n[len("transformer."):] for n in names if n.startswith("transformer.")}
+        decay, no_decay = strip(decay), strip(no_decay)
+        param_dict = dict(self.transformer.named_parameters())
+        assert not (decay & no_decay) and not (param_dict.keys() - (decay | no_decay))
+        return [{"params": [param_dict[pn] for pn in sorted(decay)], "weight_decay": 0.01},
+                {"params": [param_dict[pn] for pn in sorted(no_decay)], "weight_decay": 0.0}]
+
     def forward(self, input, return_loss=False, return_logits=True, return_att_weight=False, is_train=True, **kwargs):
-        raise NotImplementedError("training forward/_train_loss (config 4) is SURVEY.md section 8 row A13 -- after the inference path")
+        """Training / validation entry (diffusion_transformer.py:539-584): {'logits': exp(log_model_prob), 'loss': scalar}."""
+        if kwargs.get("autocast") is True:
+            self.amp = True  # kept for interface parity; the engine's GEMM precision is fixed at construction (train_precision)
+        sample_image = input["content_token"]
+        if self.condition_emb is not None:
+            with torch.no_grad():
+                cond_emb = self.condition_emb(input["condition_token"]).float()
+        else:
+            cond_emb = input["condition_embed_token"].float() if input.get("condition_embed_token") is not None else None
+        out = {}
+        if is_train:
+            prob, _, loss = self._train_loss(sample_image, cond_emb, want_prob=return_logits)
+            if return_logits:
+                out["logits"] = prob
+            if return_loss:
+                out["loss"] = loss
+        self.amp = False
+        return out
+
+
+class _DenoiserLoss(torch.autograd.Function):
+    """loss = _train_loss(denoiser(x_t, cond, t)) with a hand-written backward: forward runs DenoiserTrainEngine.forward and the fused loss
+    kernel (which also emits d loss / d logits); backward runs DenoiserTrainEngine.backward and hands every parameter its gradient."""
+
+    @staticmethod
+    def forward(ctx, dt, x0, x_t, cond_emb, t, pt, is_train, want_prob, names, *params):
+        eng = dt.transformer.train_engine
+        B, L = x0.shape
+        K = dt.num_classes - 1
+        dev = x0.device
+        logits = eng.forward(x_t, cond_emb, t)
+        need_grad = any(ctx.needs_input_grad[9:])
+        dlogits = torch.empty(B, L, K, dtype=torch.float32, device=dev) if need_grad else None
+        prob = torch.empty(B, K + 1, L, dtype=torch.float32, device=dev) if want_prob else None
+        hits = torch.empty(B, L, 2, dtype=torch.int32, device=dev)
+        aux = float(dt.auxiliary_loss_weight) if is_train else 0.0
+        res = train_ops.train_loss(logits, x0, x_t, t, pt, dt._sched(), dt.num_timesteps, aux_weight=aux, adaptive=bool(dt.adaptive_auxiliary_loss),
+                                   mask_weight=dt.mask_weight, dlogits=dlogits, log_model_prob=prob, hits=hits, lt_history=dt.Lt_history,
+                                   lt_count=dt.Lt_count, prob_as_exp=True)
+        ctx.eng, ctx.dlogits, ctx.names = eng, dlogits, names
+        loss = res["loss"].clone().reshape(())
+        vb = res["vb_loss"].clone()
+        if prob is None:
+            prob = torch.empty(0, device=dev)
+        ctx.mark_non_differentiable(prob, vb, hits)
+        return loss, prob, vb, hits
+
+    @staticmethod
+    def backward(ctx, gloss, gprob, gvb, ghits):
+        grads = ctx.eng.backward(ctx.dlogits, scale=gloss.detach().float().reshape(1).contiguous())
+        return (None,) * 9 + tuple(grads[n] for n in ctx.names)
 
 
 def index_to_log_onehot(x, num_classes):

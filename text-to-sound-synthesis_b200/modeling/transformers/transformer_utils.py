@@ -1,7 +1,8 @@
 """Drop-in for sound_synthesis/modeling/transformers/transformer_utils.py::Text2ImageTransformer.
 
 Same constructor arguments and the same state_dict keys, so reference checkpoints load unchanged;
-``forward`` runs the hand-written sm_100a kernels through ``DenoiserEngine`` instead of ATen ops.  The sub-modules
+``forward`` runs the hand-written sm_100a kernels through ``DenoiserEngine`` instead of ATen ops (inference);
+training goes through ``DenoiserTrainEngine`` (called from DiffusionTransformer._train_loss).  The sub-modules
 below only HOLD parameters under the reference's names -- they have no torch forward (there is no fallback path).
 """
 import math
@@ -10,6 +11,7 @@ import torch
 from torch import nn
 
 from ...engine import DenoiserEngine
+from ...train_engine import DenoiserTrainEngine
 from ...utils.misc import instantiate_from_config
 
 
@@ -70,7 +72,7 @@ class Text2ImageTransformer(nn.Module):
     def __init__(self, condition_seq_len=77, n_layer=14, n_embd=1024, n_head=16, content_seq_len=1024, attn_pdrop=0, resid_pdrop=0,
                  mlp_hidden_times=4, block_activate=None, attn_type="selfcross", content_spatial_size=[32, 32], condition_dim=512,
                  diffusion_step=1000, timestep_type="adalayernorm", content_emb_config=None, mlp_type="fc", checkpoint=False,
-                 precision="f16"):
+                 precision="f16", train_precision="bf16"):
         super().__init__()
         assert attn_type == "selfcross"
         assert mlp_type == "fc", "conv_mlp is not used by the Diffsound configs"
@@ -91,6 +93,7 @@ class Text2ImageTransformer(nn.Module):
         self.n_embd, self.n_head, self.diffusion_step = n_embd, n_head, diffusion_step
         self.apply(self._init_weights)
         self.engine = DenoiserEngine(self, precision=precision)
+        self.train_engine = DenoiserTrainEngine(self, precision=train_precision)  # forward-with-activations + backward (A13)
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.engine.__setattr__("packed", False))
 
     def _init_weights(self, module):  # same distribution as the reference (:355-363)
@@ -106,6 +109,8 @@ class Text2ImageTransformer(nn.Module):
         out = super()._apply(fn, *a, **k)
         if hasattr(self, "engine"):
             self.engine.packed = False
+        if hasattr(self, "train_engine"):
+            self.train_engine.reset()
         return out
 
     @torch.no_grad()

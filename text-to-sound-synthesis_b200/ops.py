@@ -100,10 +100,10 @@ def gemm_split(a_split: torch.Tensor, w_split: torch.Tensor, bias=None, residual
     return gemm(a_split, w_split, bias, residual, out, dtype=TF32, taps=t3, tap_acol=ac, k_per_tap=Cp, **kw)
 
 
-def silu(x: torch.Tensor) -> torch.Tensor:
-    _need_cuda(x)
+def silu(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(x, out)
     x = x.contiguous()
-    out = torch.empty_like(x)
+    out = torch.empty_like(x) if out is None else out
     _lib.check(_lib.lib().dsb_silu(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "dsb_silu")
     return out
 
