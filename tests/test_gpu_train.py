@@ -194,6 +194,24 @@ def test_q_sample_and_fused_loss_match_oracle(G, TO, K):
 
 
 # ------------------------------------------------------------------------------------------------ whole model
+def _grad_report(tag, grads, ref_of, tol):
+    """Per-parameter max-abs error relative to that parameter's reference gradient scale.  Parameters whose true gradient is zero
+    (attention key biases: softmax is invariant to a shift common to all keys) only carry rounding noise in the reference, so the scale
+    is floored at 1e-4 of the largest gradient in the model."""
+    refs = {n: ref_of(n) for n in grads}
+    gmax = max(float(r.abs().max()) for r in refs.values())
+    rows = []
+    for n, gr in grads.items():
+        r = refs[n]
+        assert gr is not None and gr.shape == r.shape, n
+        abs_err = float((gr.detach().cpu() - r).abs().max())
+        rows.append((abs_err / max(float(r.abs().max()), 1e-4 * gmax), n, float(r.abs().max()), abs_err))
+    rows.sort(reverse=True)
+    for e, n, rm, ae in rows[:6]:
+        print(f"[{tag}] {n}: rel {e:.3e} (ref max {rm:.3e}, abs err {ae:.3e})")
+    assert rows[0][0] < tol, rows[0]
+
+
 def _run_loss_and_grads(m, x0, x_t, cond, t, pt):
     from diffsound_b200.modeling.transformers.diffusion_transformer import _DenoiserLoss
     for p in m.parameters():
@@ -221,15 +239,7 @@ def test_tiny_training_step_matches_reference_loss_and_gradients(G, TO, precisio
     print(f"[{precision}] loss {float(loss):.6f} vs reference {ref_loss:.6f}")
     assert abs(float(loss) - ref_loss) <= tol_loss * abs(ref_loss)
     assert float((prob.cpu() - torch.from_numpy(g["out_probs"])).abs().max()) < (5e-3 if precision == "tf32" else 5e-2)
-    worst = ("", 0.0)
-    for n, gr in grads.items():
-        ref = torch.from_numpy(g["grad.transformer." + n])
-        assert gr is not None and gr.shape == ref.shape, n
-        err = float((gr.cpu() - ref).abs().max() / ref.abs().max().clamp_min(1e-12))
-        if err > worst[1]:
-            worst = (n, err)
-    print(f"[{precision}] worst gradient rel err {worst[1]:.3e} at {worst[0]}")
-    assert worst[1] < tol_grad, worst
+    _grad_report(precision, grads, lambda n: torch.from_numpy(g["grad.transformer." + n]), tol_grad)
     assert torch.allclose(m.Lt_history.cpu(), torch.from_numpy(g["out_Lt_history"]), rtol=10 * tol_loss, atol=1e-3)
 
 
@@ -259,14 +269,7 @@ def test_midsize_training_step_matches_oracle_autograd(G, TO):
     rl = float(ref["loss"].detach())
     print(f"midsize loss {float(loss):.6f} vs oracle {rl:.6f}")
     assert abs(float(loss) - rl) <= 2e-3 * abs(rl)
-    worst = ("", 0.0)
-    for n, gr in grads.items():
-        r = leaf["transformer." + n].grad
-        err = float((gr.cpu() - r).abs().max() / r.abs().max().clamp_min(1e-12))
-        if err > worst[1]:
-            worst = (n, err)
-    print(f"midsize worst gradient rel err {worst[1]:.3e} at {worst[0]}")
-    assert worst[1] < 2e-2, worst
+    _grad_report("midsize", grads, lambda n: leaf["transformer." + n].grad, 2e-2)
 
 
 def test_module_forward_backward_and_optimizer_steps(G, TO):
@@ -291,7 +294,7 @@ def test_module_forward_backward_and_optimizer_steps(G, TO):
         out["loss"].backward()
         assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.transformer.parameters())
         opt.step()
-        losses.append(float(out["loss"]))
+        losses.append(float(out["loss"].detach()))
     print("losses", [round(v, 4) for v in losses])
     assert losses[-1] < losses[0]
     assert float(m.Lt_count.sum()) == 12 * B
@@ -307,6 +310,16 @@ def test_content_conditioned_sampling_runs(G, TO):
     m.truncation = "top0.85r"
     tok = torch.randint(0, K, (B, L)).cuda()
     cond = torch.randn(B, 77, CD).cuda()
-    out = m.sample(condition_token=None, condition_mask=None, condition_embed=cond, content_token=tok, filter_ratio=0.3, batch_size=B)["content_token"]
-    assert out.shape == (B, L) and int(out.max()) < K and int(out.min()) >= 0
-    assert float((out == tok).float().mean()) > 0.3  # most tokens survive 30 noising steps at the start of the schedule
+    run = lambda: m.sample(condition_token=None, condition_mask=None, condition_embed=cond, content_token=tok, filter_ratio=0.3, batch_size=B)["content_token"]
+    torch.manual_seed(77)
+    fused = run()
+    assert fused.shape == (B, L) and int(fused.max()) < K and int(fused.min()) >= 0
+    m.p_sample = m.p_sample  # re-bound instance attribute -> the stage-by-stage path (what a monkey-patching caller triggers)
+    torch.manual_seed(77)
+    staged = run()
+    assert torch.equal(fused, staged)
+    # the start state really is q_sample at t = 29: with the same seed the first RNG draw is q_sample's
+    torch.manual_seed(77)
+    x29 = m.q_sample(O.index_to_log_onehot(tok.cpu(), K + 1).cuda(), torch.full((B,), 29, device="cuda", dtype=torch.long), return_index=True)
+    frac_masked = float((x29 == K).float().mean())
+    assert 0.15 < frac_masked < 0.40 and float((x29[x29 != K] == tok[x29 != K]).float().mean()) > 0.9

@@ -386,7 +386,7 @@ class _DenoiserLoss(torch.autograd.Function):
         dev = x0.device
         logits = eng.forward(x_t, cond_emb, t)
         need_grad = any(ctx.needs_input_grad[9:])
-        dlogits = torch.empty(B, L, K, dtype=torch.float32, device=dev) if need_grad else None
+        dlogits = eng.dlogits_buffer() if need_grad else None  # engine-owned: the static input of its backward graph
         prob = torch.empty(B, K + 1, L, dtype=torch.float32, device=dev) if want_prob else None
         hits = torch.empty(B, L, 2, dtype=torch.int32, device=dev)
         aux = float(dt.auxiliary_loss_weight) if is_train else 0.0

@@ -38,6 +38,8 @@ class DenoiserTrainEngine:
         self.adt = torch.bfloat16 if precision == "bf16" else torch.float32
         self.gd = ops.BF16 if precision == "bf16" else ops.TF32
         self._ws: Dict[tuple, dict] = {}
+        self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
+        self.use_cuda_graph = True  # replay forward / backward as two CUDA graphs (~2.5k launches per step otherwise)
 
     # ------------------------------------------------------------------ small helpers
     @property
@@ -57,8 +59,10 @@ class DenoiserTrainEngine:
     def reset(self) -> None:
         """Drop packed operands and workspaces (the module moved to another device / dtype)."""
         self._ws.clear()
-        if hasattr(self, "layers"):
-            del self.layers
+        self._graphs.clear()
+        for attr in ("layers", "_layout"):
+            if hasattr(self, attr):
+                delattr(self, attr)
 
     # ------------------------------------------------------------------ weights
     @torch.no_grad()
@@ -127,6 +131,10 @@ class DenoiserTrainEngine:
         ws = dict(
             layers=per_layer, x_out=f(B, L, D), hf=a(M, D), logits=f(B, L, K), cond=a(Mc, self.Cd), kv_all=a(Mc, NL * 2 * D),
             arange=torch.arange(B, dtype=torch.int64, device=self.device),
+            # static inputs / outputs of the two CUDA graphs
+            ids=torch.zeros(B, L, dtype=torch.int64, device=self.device), t=torch.zeros(B, dtype=torch.int64, device=self.device),
+            cond_in=f(Mc, self.Cd), dlogits=f(B, L, K), scale=torch.ones(1, dtype=torch.float32, device=self.device),
+            grad_flat=torch.zeros(self._grad_layout()[1], dtype=torch.float32, device=self.device),
             # scratch shared by every layer
             S=f(BH, L, Lp), vT=a(BH, 64, Lp), oh=a(BH, L, 64),
             dx=f(B, L, D), dy=a(M, D), dbig=a(M, Dh), dbig2=a(M, Dh), dh=f(M, D), dqkv=a(M, 3 * D), dq2=a(M, D), datt=a(M, D),
@@ -135,8 +143,59 @@ class DenoiserTrainEngine:
             doh=a(BH, L, 64), dP=f(BH, L, Lp), dS=a(BH, L, Lp), PT=a(BH, Lp, Lp), doT=a(BH, 64, Lp), kT=a(BH, 64, Lp), qT=a(BH, 64, Lp),
             dST=a(BH, Lp, Lp), dqh=a(BH, L, 64), dkh=a(BH, L, 64), dvh=a(BH, L, 64),
             dtab=f(B, 2 * D), dtabT=f(2 * D, Bp), sT=f(D, Bp), ds=f(B, D), de=f(B, D))
+        ws["grads"] = self._grad_views(ws["grad_flat"])
         self._ws[key] = ws
         return ws
+
+    # ------------------------------------------------------------------ gradient storage: one flat fp32 buffer, parameters are views
+    def _grad_layout(self):
+        """[(key, shape, offset)], total.  attn1 q/k/v and every layer's attn2 k/v gradients come out of fused wgrad GEMMs, so they are
+        slices of the fused regions '_qkv_w.{li}' / '_kv_w' rather than regions of their own."""
+        if hasattr(self, "_layout"):
+            return self._layout
+        D, NL, Cd = self.D, self.n_layer, self.Cd
+        fused = (".attn1.query.", ".attn1.key.", ".attn1.value.", ".attn2.key.", ".attn2.value.")
+        specs = [(n, tuple(p.shape)) for n, p in self.m.named_parameters() if not any(f_ in n for f_ in fused)]
+        for li in range(NL):
+            specs += [(f"_qkv_w.{li}", (3 * D, D)), (f"_qkv_b.{li}", (3 * D,))]
+        specs += [("_kv_w", (NL * 2 * D, Cd)), ("_kv_b", (NL * 2 * D,))]
+        out, off = [], 0
+        for k, shp in specs:
+            out.append((k, shp, off))
+            off += _rup(math.prod(shp), 64)
+        self._layout = (out, off)
+        return self._layout
+
+    def _grad_views(self, flat: torch.Tensor) -> Dict[str, torch.Tensor]:
+        D = self.D
+        v = {k: flat[o:o + math.prod(shp)].view(shp) for k, shp, o in self._grad_layout()[0]}
+        for li in range(self.n_layer):
+            for j, nm in enumerate(("query", "key", "value")):
+                v[f"blocks.{li}.attn1.{nm}.weight"] = v[f"_qkv_w.{li}"][j * D:(j + 1) * D]
+                v[f"blocks.{li}.attn1.{nm}.bias"] = v[f"_qkv_b.{li}"][j * D:(j + 1) * D]
+            o = li * 2 * D
+            v[f"blocks.{li}.attn2.key.weight"], v[f"blocks.{li}.attn2.value.weight"] = v["_kv_w"][o:o + D], v["_kv_w"][o + D:o + 2 * D]
+            v[f"blocks.{li}.attn2.key.bias"], v[f"blocks.{li}.attn2.value.bias"] = v["_kv_b"][o:o + D], v["_kv_b"][o + D:o + 2 * D]
+        return v
+
+    def _replay(self, key, fn):
+        """Run fn() through a CUDA graph captured on first use (after one eager warm-up for lazy initialisation)."""
+        ptrs = tuple(p.data_ptr() for p in self.m.parameters())
+        ent = self._graphs.get(key)
+        if ent is not None and ent[1] != ptrs:
+            ent = None  # a parameter was re-allocated (EMA swap, .data assignment): the captured pointers are stale
+        if ent is None:
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                fn()
+            cur.wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            ent = self._graphs[key] = (g, ptrs)
+        ent[0].replay()
 
     # ------------------------------------------------------------------ forward
     def _lin(self, a, w, bias, out, residual=None):
@@ -165,17 +224,30 @@ class DenoiserTrainEngine:
 
     @torch.no_grad()
     def forward(self, ids: torch.Tensor, cond_emb: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
-        """ids (B, L) int64, cond_emb (B, Lc, Cd) fp32, t (B,) int64 -> logits (B, L, K) fp32; activations are kept for backward()."""
-        self.pack()
-        m = self.m
+        """ids (B, L) int64, cond_emb (B, Lc, Cd) fp32, t (B,) int64 -> logits (B, L, K) fp32 (engine-owned buffer, valid until the next
+        forward); activations are kept for backward()."""
+        if not hasattr(self, "layers"):
+            self.pack()  # allocates the packed operands; sizes the workspaces
         B, L = ids.shape
         Lc = cond_emb.shape[1]
-        D = self.D
         ws = self.workspace(B, L, Lc)
         self._shape = (B, L, Lc)
-        self._ids, self._t = ids.contiguous(), t.contiguous()
+        ws["ids"].copy_(ids)
+        ws["t"].copy_(t)
+        ws["cond_in"].copy_(cond_emb.detach().reshape(B * Lc, -1))
+        if self.use_cuda_graph:
+            self._replay(("fwd", B, L, Lc), lambda: self._forward_impl(ws, B, L, Lc))
+        else:
+            self._forward_impl(ws, B, L, Lc)
+        return ws["logits"]
+
+    def _forward_impl(self, ws, B, L, Lc):
+        self.pack()
+        m = self.m
+        D = self.D
+        self._ids, self._t = ws["ids"], ws["t"]
         ar = ws["arange"]
-        T.cast_scale(cond_emb.detach().float().reshape(B * Lc, -1).contiguous(), ws["cond"])
+        T.cast_scale(ws["cond_in"], ws["cond"])
         self._lin(ws["cond"], self.wkv_all, self.bkv_all, ws["kv_all"])
         ce = m.content_emb
         x = ws["layers"][0]["x1"] if self.n_layer else ws["x_out"]
@@ -269,20 +341,38 @@ class DenoiserTrainEngine:
         g.zero_()
         T.scatter_add_rows(g, self._t, ws["de"])
 
+    def dlogits_buffer(self) -> torch.Tensor:
+        """(B, L, K) fp32 buffer the loss kernel writes d loss / d logits into (static input of the backward graph)."""
+        return self.workspace(*self._shape)["dlogits"]
+
     @torch.no_grad()
     def backward(self, dlogits: torch.Tensor, scale: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         """dlogits (B, L, K) fp32 = d loss / d logits for unit upstream gradient, scale = upstream d loss (device scalar or None).
-        Returns {parameter name (relative to the Text2ImageTransformer): fp32 gradient}."""
-        m = self.m
+        Returns {parameter name (relative to the Text2ImageTransformer): fp32 gradient}; the tensors are views of one freshly cloned
+        flat buffer, so the caller (autograd) owns them."""
         B, L, Lc = self._shape
+        ws = self.workspace(B, L, Lc)
+        if dlogits.data_ptr() != ws["dlogits"].data_ptr():
+            ws["dlogits"].copy_(dlogits)
+        if scale is None:
+            ws["scale"].fill_(1.0)
+        else:
+            ws["scale"].copy_(scale.reshape(1))
+        if self.use_cuda_graph:
+            self._replay(("bwd", B, L, Lc), lambda: self._backward_impl(ws, B, L, Lc))
+        else:
+            self._backward_impl(ws, B, L, Lc)
+        out = self._grad_views(ws["grad_flat"].clone())
+        return {n: out[n] for n, _ in self.m.named_parameters()}
+
+    def _backward_impl(self, ws, B, L, Lc):
+        m = self.m
         D, K, NL = self.D, self.K, self.n_layer
         M, Mc = B * L, B * Lc
-        ws = self.workspace(B, L, Lc)
-        dev = self.device
-        grads: Dict[str, torch.Tensor] = {n: torch.empty_like(p, dtype=torch.float32) for n, p in m.named_parameters()}
+        grads = ws["grads"]
         dx = ws["dx"]
         # ---- head: logits = LN_f(x) Wlog^T + b
-        T.cast_scale(dlogits.reshape(M, K), ws["dlog"], scale)
+        T.cast_scale(ws["dlogits"].view(M, K), ws["dlog"], ws["scale"])
         self._linear_bwd(ws["dlog"], ws["hf"], self.wlogT, grads["to_logits.1.weight"], grads["to_logits.1.bias"], ws["dh"], ws)
         dx.zero_()
         lnf = m.to_logits[0]
@@ -312,21 +402,11 @@ class DenoiserTrainEngine:
             self._linear_bwd(ws["dy"], sv["att1"], lay["wo1T"], grads[p + "attn1.proj.weight"], grads[p + "attn1.proj.bias"], ws["datt"], ws)
             dqkv = ws["dqkv"]
             self._attn_bwd(ws["datt"], dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], sv["qh1"], sv["kh1"], sv["vh1"], sv["P1"], ws, B, L, L)
-            gw, gb = self._f32(3 * D, D), self._f32(3 * D)
-            self._linear_bwd(dqkv, sv["h1"], lay["wqkvT"], gw, gb, ws["dh"], ws)
-            for j, nm in enumerate(("query", "key", "value")):
-                grads[p + f"attn1.{nm}.weight"] = gw[j * D:(j + 1) * D]
-                grads[p + f"attn1.{nm}.bias"] = gb[j * D:(j + 1) * D]
+            self._linear_bwd(dqkv, sv["h1"], lay["wqkvT"], grads[f"_qkv_w.{li}"], grads[f"_qkv_b.{li}"], ws["dh"], ws)
             self._ada_bwd(blk.ln1, lay["lin1T"], sv["x1"], ws["dh"], sv["e1"], sv["s1"], sv["tab1"], grads, p + "ln1.", ws, B)
         # ---- cross-attention K/V projections of every layer in one wgrad: kv_all = cond Wkv^T + b
-        gkv, gbkv = self._f32(NL * 2 * D, self.Cd), self._f32(NL * 2 * D)
-        self._linear_bwd(dkv_all, ws["cond"], None, gkv, gbkv, None, ws, yT=ws["ykvT"], xT=ws["condT"])
-        for li in range(NL):
-            o = li * 2 * D
-            grads[f"blocks.{li}.attn2.key.weight"], grads[f"blocks.{li}.attn2.value.weight"] = gkv[o:o + D], gkv[o + D:o + 2 * D]
-            grads[f"blocks.{li}.attn2.key.bias"], grads[f"blocks.{li}.attn2.value.bias"] = gbkv[o:o + D], gbkv[o + D:o + 2 * D]
+        self._linear_bwd(dkv_all, ws["cond"], None, grads["_kv_w"], grads["_kv_b"], None, ws, yT=ws["ykvT"], xT=ws["condT"])
         # ---- embedding
         for n in ("content_emb.emb.weight", "content_emb.height_emb.weight", "content_emb.width_emb.weight"):
             grads[n].zero_()
         T.embed_bwd(self._ids, dx, grads["content_emb.emb.weight"], grads["content_emb.height_emb.weight"], grads["content_emb.width_emb.weight"])
-        return grads

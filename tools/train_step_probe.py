@@ -22,10 +22,12 @@ def main():
     ap.add_argument("--layers", type=int, default=19)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--no-graph", action="store_true")
     a = ap.parse_args()
     K, D, NH, CD, L = 256, 1024, 16, 512, 265
     m = build_dt(K, D, a.layers, NH, CD)
     m.transformer.train_engine.__init__(m.transformer, precision=a.precision)
+    m.transformer.train_engine.use_cuda_graph = not a.no_graph
     m.train()
     for p in m.parameters():
         p.requires_grad_(True)
@@ -51,10 +53,10 @@ def main():
         if it >= 2:
             times.append(e[0].elapsed_time(e[3]))
             parts.append((e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), e[2].elapsed_time(e[3]), wall))
-        print(f"step {it}: loss {float(out['loss']):.4f} gpu {e[0].elapsed_time(e[3]):.1f} ms (fwd {e[0].elapsed_time(e[1]):.1f} bwd {e[1].elapsed_time(e[2]):.1f} "
+        print(f"step {it}: loss {float(out["loss"].detach()):.4f} gpu {e[0].elapsed_time(e[3]):.1f} ms (fwd {e[0].elapsed_time(e[1]):.1f} bwd {e[1].elapsed_time(e[2]):.1f} "
               f"opt {e[2].elapsed_time(e[3]):.1f}) wall {wall:.1f} ms", flush=True)
     ms = sum(times) / len(times)
-    print(json.dumps({"train_step_ms": ms, "samples_per_s": a.batch / ms * 1e3, "batch": a.batch, "layers": a.layers, "precision": a.precision,
+    print(json.dumps({"train_step_ms": ms, "samples_per_s": a.batch / ms * 1e3, "batch": a.batch, "layers": a.layers, "precision": a.precision, "cuda_graph": not a.no_graph,
                       "fwd_ms": sum(p[0] for p in parts) / len(parts), "bwd_ms": sum(p[1] for p in parts) / len(parts),
                       "opt_ms": sum(p[2] for p in parts) / len(parts), "wall_ms": sum(p[3] for p in parts) / len(parts),
                       "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30}))
