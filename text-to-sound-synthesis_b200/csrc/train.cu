@@ -30,6 +30,36 @@ template <class T> __device__ __forceinline__ void st_act(T* p, float v);
 template <> __device__ __forceinline__ void st_act<float>(float* p, float v) { *p = round_tf32(v); }
 template <> __device__ __forceinline__ void st_act<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
+// 8 consecutive activations <-> 8 floats (16-byte access for bf16, 2 x 16 bytes for fp32); p must be 8-element aligned
+template <class T> __device__ __forceinline__ void ld_act8(const T* p, float (&v)[8]);
+template <> __device__ __forceinline__ void ld_act8<float>(const float* p, float (&v)[8]) {
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <> __device__ __forceinline__ void ld_act8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+template <class T> __device__ __forceinline__ void st_act8(T* p, const float (&v)[8]);
+template <> __device__ __forceinline__ void st_act8<float>(float* p, const float (&v)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(round_tf32(v[0]), round_tf32(v[1]), round_tf32(v[2]), round_tf32(v[3]));
+  reinterpret_cast<float4*>(p)[1] = make_float4(round_tf32(v[4]), round_tf32(v[5]), round_tf32(v[6]), round_tf32(v[7]));
+}
+template <> __device__ __forceinline__ void st_act8<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 u;
+  __nv_bfloat162 h;
+  h = __floats2bfloat162_rn(v[0], v[1]); u.x = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(v[2], v[3]); u.y = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(v[4], v[5]); u.z = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(v[6], v[7]); u.w = *reinterpret_cast<uint32_t*>(&h);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
 struct WarpCtx {  // lane context of train_loss_math.cuh: one warp per column
   int ln;
   __device__ __forceinline__ int lane() const { return ln; }
@@ -174,6 +204,54 @@ transpose_kernel(const E* __restrict__ in, long long ld_in, long long in_bs, E* 
   }
 }
 
+// 2-byte elements, 64x64 tiles, 16-byte global accesses on both sides (the wgrad operand copies are the bulk of the backward's
+// non-GEMM traffic).  Requires 16-byte aligned bases / leading dimensions / batch strides; ragged edges fall back to element accesses.
+__global__ void __launch_bounds__(256)
+transpose16_kernel(const uint16_t* __restrict__ in, long long ld_in, long long in_bs, uint16_t* __restrict__ out, long long ld_out, long long out_bs,
+                   int rows, int cols) {
+  constexpr int PITCH = 66;  // elements; 33 words: the 8 row-groups a warp reads per column land on 4 banks (2-way conflict at worst)
+  __shared__ __align__(16) uint16_t tile[64 * PITCH];
+  in += (long long)blockIdx.z * in_bs;
+  out += (long long)blockIdx.z * out_bs;
+  const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int q = threadIdx.x + 256 * it;
+    const int r = q >> 3, cc = (q & 7) * 8;
+    const int gr = r0 + r, gc = c0 + cc;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(tile + r * PITCH + cc);
+    if (gr < rows && gc + 7 < cols) {
+      const uint4 v = *reinterpret_cast<const uint4*>(in + (long long)gr * ld_in + gc);
+      dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tile[r * PITCH + cc + i] = (gr < rows && gc + i < cols) ? in[(long long)gr * ld_in + gc + i] : (uint16_t)0;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int q = threadIdx.x + 256 * it;
+    const int c = q >> 3, rg = (q & 7) * 8;   // output row c (= input column), 8 consecutive input rows
+    const int gc = c0 + c, gr = r0 + rg;
+    if (gc >= cols) continue;
+    uint16_t e[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) e[i] = tile[(rg + i) * PITCH + c];
+    uint16_t* dst = out + (long long)gc * ld_out + gr;
+    if (gr + 7 < rows) {
+      uint4 v;
+      v.x = e[0] | ((uint32_t)e[1] << 16); v.y = e[2] | ((uint32_t)e[3] << 16);
+      v.z = e[4] | ((uint32_t)e[5] << 16); v.w = e[6] | ((uint32_t)e[7] << 16);
+      *reinterpret_cast<uint4*>(dst) = v;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (gr + i < rows) dst[i] = e[i];
+    }
+  }
+}
+
 // heads: token-major (B*Lx, ld) columns [h*64, h*64+64)  <->  head-major (B*H, Lx, 64); 16-byte chunks
 template <int TO_HEADS>
 __global__ void __launch_bounds__(256)
@@ -195,47 +273,80 @@ template <class T>
 __global__ void __launch_bounds__(256)
 cast_scale_kernel(const float* __restrict__ in, T* __restrict__ out, long long n, const float* __restrict__ scale) {
   const float s = scale ? *scale : 1.f;
-  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += 256LL * gridDim.x) st_act<T>(out + i, in[i] * s);
+  const bool vec = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  const long long n4 = vec ? n / 4 : 0;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n4; i += 256LL * gridDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(in)[i];
+    st_act<T>(out + 4 * i, v.x * s); st_act<T>(out + 4 * i + 1, v.y * s); st_act<T>(out + 4 * i + 2, v.z * s); st_act<T>(out + 4 * i + 3, v.w * s);
+  }
+  for (long long i = n4 * 4 + blockIdx.x * 256LL + threadIdx.x; i < n; i += 256LL * gridDim.x) st_act<T>(out + i, in[i] * s);
 }
 
-// column sums of a (rows, N) matrix into fp32 out[N] (atomic accumulation; out zeroed by the host wrapper)
-template <class T>
+// column sums of a (rows, N) matrix into fp32 out[N] (atomic accumulation; out zeroed by the host wrapper).
+// VEC: each thread owns 8 consecutive columns (16-byte loads: a warp row covers 256 columns); otherwise one column per thread.
+template <class T, bool VEC>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const T* __restrict__ in, long long ld, float* __restrict__ out, long long rows, int N, int rows_per_cta) {
-  __shared__ float red[8][32];
+  constexpr int CPT = VEC ? 8 : 1;
+  __shared__ float red[8][32 * CPT];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + tx;
+  const int c = (blockIdx.x * 32 + tx) * CPT;
   const long long r0 = (long long)blockIdx.y * rows_per_cta;
   const long long r1 = r0 + rows_per_cta < rows ? r0 + rows_per_cta : rows;
-  float acc = 0.f;
-  if (c < N)
-    for (long long r = r0 + ty; r < r1; r += 8) acc += ld_act<T>(in + r * ld + c);
-  red[ty][tx] = acc;
-  __syncthreads();
-  if (ty == 0 && c < N) {
-    float s = 0.f;
+  float acc[CPT];
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += red[w][tx];
-    atomicAdd(out + c, s);
+  for (int i = 0; i < CPT; ++i) acc[i] = 0.f;
+  if (c < N) {
+    for (long long r = r0 + ty; r < r1; r += 8) {
+      if (VEC) {
+        float v[8];
+        ld_act8<T>(in + r * ld + c, v);
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) acc[i] += v[i];
+      } else {
+        acc[0] += ld_act<T>(in + r * ld + c);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < CPT; ++i) red[ty][tx * CPT + i] = acc[i];
+  __syncthreads();
+  for (int j = threadIdx.x; j < 32 * CPT; j += 256) {
+    const int cg = blockIdx.x * 32 * CPT + j;
+    if (cg < N) {
+      float sacc = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) sacc += red[w][j];
+      atomicAdd(out + cg, sacc);
+    }
   }
 }
 
 // ---------------------------------------------------------------------------------------------- GELU2  (transformer_utils.py:111-115)
 template <class T>
 __global__ void __launch_bounds__(256)
-gelu2_fwd_kernel(const T* __restrict__ u, T* __restrict__ a, long long n) {
-  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += 256LL * gridDim.x) {
-    const float x = ld_act<T>(u + i);
-    st_act<T>(a + i, x / (1.f + __expf(-1.702f * x)));
+gelu2_fwd_kernel(const T* __restrict__ u, T* __restrict__ a, long long n) {  // n % 8 == 0, 16-byte aligned (checked by the host wrapper)
+  for (long long i = (blockIdx.x * 256LL + threadIdx.x) * 8; i < n; i += 256LL * 8 * gridDim.x) {
+    float x[8];
+    ld_act8<T>(u + i, x);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = x[j] / (1.f + __expf(-1.702f * x[j]));
+    st_act8<T>(a + i, x);
   }
 }
 template <class T>
 __global__ void __launch_bounds__(256)
 gelu2_bwd_kernel(const T* __restrict__ u, const T* __restrict__ da, T* __restrict__ du, long long n) {
-  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += 256LL * gridDim.x) {
-    const float x = ld_act<T>(u + i);
-    const float s = 1.f / (1.f + __expf(-1.702f * x));
-    st_act<T>(du + i, ld_act<T>(da + i) * (s + 1.702f * x * s * (1.f - s)));
+  for (long long i = (blockIdx.x * 256LL + threadIdx.x) * 8; i < n; i += 256LL * 8 * gridDim.x) {
+    float x[8], d[8];
+    ld_act8<T>(u + i, x);
+    ld_act8<T>(da + i, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float sg = 1.f / (1.f + __expf(-1.702f * x[j]));
+      d[j] *= sg + 1.702f * x[j] * sg * (1.f - sg);
+    }
+    st_act8<T>(du + i, d);
   }
 }
 __global__ void __launch_bounds__(256)
@@ -260,7 +371,8 @@ scatter_add_rows_kernel(float* __restrict__ table, const int64_t* __restrict__ i
 // y = xhat * g + beta with g = gamma (MODE 0) or 1 + table[idx[b], 0:D] (MODE 1, beta = table[idx[b], D:2D]).
 //   dx    = rstd * (dy g - mean(dy g) - xhat mean(dy g xhat));   dx_io += dx   (the residual branch's gradient is already in dx_io)
 //   dg   += sum_rows dy xhat ;  dbeta += sum_rows dy                 (MODE 0: dgamma[D], dbeta[D];  MODE 1: dtable[idx[b]] = (dscale | dshift))
-// grid (ceil(L / 128), B): a CTA never straddles two batch elements; 8 warps x 16 rows.
+// grid (ceil(L / 32), B): a CTA never straddles two batch elements; 8 warps x 4 rows (enough CTAs to fill 148 SMs at B = 20).
+constexpr int LNB_ROWS = 32;
 template <int MODE, int NV>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx_io, const float* __restrict__ p0,
@@ -273,8 +385,8 @@ layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, 
   float4 dg[NV], db[NV];
 #pragma unroll
   for (int j = 0; j < NV; ++j) dg[j] = db[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int l_end = min(L, (int)(blockIdx.x + 1) * 128);
-  for (int l = blockIdx.x * 128 + warp; l < l_end; l += 8) {
+  const int l_end = min(L, (int)(blockIdx.x + 1) * LNB_ROWS);
+  for (int l = blockIdx.x * LNB_ROWS + warp; l < l_end; l += 8) {
     const long long row = (long long)b * L + l;
     const float4* xr = reinterpret_cast<const float4*>(x + row * D);
     const float4* dr = reinterpret_cast<const float4*>(dy + row * D);
@@ -415,14 +527,20 @@ template <class T> static void run_cast_scale(const float* in, void* out, long l
   cast_scale_kernel<T><<<grid_for(n), 256, 0, st>>>(in, (T*)out, n, scale);
 }
 template <class T> static void run_colsum(const void* in, long long ld, float* out, long long rows, int N, int rpc, cudaStream_t st) {
-  dim3 grid((N + 31) / 32, (unsigned)((rows + rpc - 1) / rpc));
-  colsum_kernel<T><<<grid, 256, 0, st>>>((const T*)in, ld, out, rows, N, rpc);
+  const bool vec = N % 8 == 0 && ld % 8 == 0 && ((uintptr_t)in & 31) == 0;
+  if (vec) {
+    dim3 grid((N + 255) / 256, (unsigned)((rows + rpc - 1) / rpc));
+    colsum_kernel<T, true><<<grid, 256, 0, st>>>((const T*)in, ld, out, rows, N, rpc);
+  } else {
+    dim3 grid((N + 31) / 32, (unsigned)((rows + rpc - 1) / rpc));
+    colsum_kernel<T, false><<<grid, 256, 0, st>>>((const T*)in, ld, out, rows, N, rpc);
+  }
 }
 template <class T> static void run_gelu2_fwd(const void* u, void* a, long long n, cudaStream_t st) {
-  gelu2_fwd_kernel<T><<<grid_for(n), 256, 0, st>>>((const T*)u, (T*)a, n);
+  gelu2_fwd_kernel<T><<<grid_for(n / 8), 256, 0, st>>>((const T*)u, (T*)a, n);
 }
 template <class T> static void run_gelu2_bwd(const void* u, const void* da, void* du, long long n, cudaStream_t st) {
-  gelu2_bwd_kernel<T><<<grid_for(n), 256, 0, st>>>((const T*)u, (const T*)da, (T*)du, n);
+  gelu2_bwd_kernel<T><<<grid_for(n / 8), 256, 0, st>>>((const T*)u, (const T*)da, (T*)du, n);
 }
 template <class T> static void run_softmax_fwd(const float* S, long long ld_s, void* P, long long ld_p, long long rows, int n, cudaStream_t st) {
   softmax_fwd_kernel<T><<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(S, ld_s, (T*)P, ld_p, rows, n);
@@ -479,7 +597,12 @@ extern "C" int dsb_transpose(const void* in, long long ld_in, long long in_batch
   DSB_REQUIRE(elem_bytes == 2 || elem_bytes == 4, "dsb_transpose: elem_bytes must be 2 or 4");
   DSB_REQUIRE(batch <= 65535, "dsb_transpose: batch=%d exceeds 65535", batch);
   dim3 grid((cols + 31) / 32, (rows + 31) / 32, batch);
-  if (elem_bytes == 2)
+  const bool vec_ok = elem_bytes == 2 && ((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0 && ld_in % 8 == 0 && ld_out % 8 == 0 &&
+                      (batch == 1 || (in_batch_stride % 8 == 0 && out_batch_stride % 8 == 0));
+  if (vec_ok)
+    transpose16_kernel<<<dim3((cols + 63) / 64, (rows + 63) / 64, batch), 256, 0, (cudaStream_t)stream>>>(
+        (const uint16_t*)in, ld_in, in_batch_stride, (uint16_t*)out, ld_out, out_batch_stride, rows, cols);
+  else if (elem_bytes == 2)
     transpose_kernel<uint16_t><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint16_t*)in, ld_in, in_batch_stride, (uint16_t*)out, ld_out, out_batch_stride, rows, cols);
   else
     transpose_kernel<uint32_t><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint32_t*)in, ld_in, in_batch_stride, (uint32_t*)out, ld_out, out_batch_stride, rows, cols);
@@ -518,10 +641,12 @@ extern "C" int dsb_colsum(const void* in, long long ld, float* out, long long ro
 }
 
 extern "C" int dsb_gelu2_fwd(const void* u, void* a, long long n, int dtype, void* stream) {
+  DSB_REQUIRE(n % 8 == 0 && (((uintptr_t)u | (uintptr_t)a) & 31) == 0, "dsb_gelu2_fwd: n must be a multiple of 8 and the buffers 32-byte aligned");
   DSB_ACT_CALL(dtype, run_gelu2_fwd, u, a, n, (cudaStream_t)stream);
   return 0;
 }
 extern "C" int dsb_gelu2_bwd(const void* u, const void* da, void* du, long long n, int dtype, void* stream) {
+  DSB_REQUIRE(n % 8 == 0 && (((uintptr_t)u | (uintptr_t)da | (uintptr_t)du) & 31) == 0, "dsb_gelu2_bwd: n must be a multiple of 8 and the buffers 32-byte aligned");
   DSB_ACT_CALL(dtype, run_gelu2_bwd, u, da, du, n, (cudaStream_t)stream);
   return 0;
 }
@@ -544,7 +669,7 @@ extern "C" int dsb_scatter_add_rows(float* table, const int64_t* idx, const floa
 template <int MODE>
 static int launch_ln_bwd(const float* x, const float* dy, float* dx_io, const float* p0, const int64_t* idx, float* dg, float* db, int B, int L, int D,
                          float eps, cudaStream_t st) {
-  dim3 grid((L + 127) / 128, B);
+  dim3 grid((L + LNB_ROWS - 1) / LNB_ROWS, B);
   switch (D / 128) {
 #define DSB_LNB_CASE(N) case N: layernorm_bwd_kernel<MODE, N><<<grid, 256, 0, st>>>(x, dy, dx_io, p0, idx, dg, db, L, D, eps); break;
     DSB_LNB_CASE(1) DSB_LNB_CASE(2) DSB_LNB_CASE(3) DSB_LNB_CASE(4) DSB_LNB_CASE(5) DSB_LNB_CASE(6) DSB_LNB_CASE(7) DSB_LNB_CASE(8)

@@ -206,7 +206,8 @@ class DenoiserTrainEngine:
     def _ada_table(self, ln, t, e, s, tab):
         T.gather_rows(ln.emb.weight.detach(), t, e)
         ops.silu(e, out=s)
-        return ops.gemm_f32(s, ln.linear.weight.detach(), ln.linear.bias.detach(), out=tab)
+        # skinny (B rows) but K = D deep: the tcgen05 TF32 path reads the fp32 parameters directly (no packing) and is ~10x the SIMT GEMM here
+        return ops.gemm(s, ln.linear.weight.detach(), ln.linear.bias.detach(), None, tab, dtype=ops.TF32)
 
     def _attn_fwd(self, q_tok, k_tok, v_tok, att_tok, qh, kh, vh, P, ws, B, Lq, Lk):
         H = self.H
@@ -333,9 +334,9 @@ class DenoiserTrainEngine:
         dtabT, sT = ws["dtabT"][:, :Bp], ws["sT"][:, :Bp]
         T.transpose(dtab, dtabT)
         T.transpose(sv_s, sT)
-        ops.gemm_f32(dtabT[:, :B], sT[:, :B], out=grads[prefix + "linear.weight"])
+        ops.gemm(dtabT[:, :B], sT[:, :B], None, None, grads[prefix + "linear.weight"], dtype=ops.TF32)
         T.colsum(dtab, grads[prefix + "linear.bias"])
-        ops.gemm_f32(dtab, linT, out=ws["ds"])
+        ops.gemm(dtab, linT, None, None, ws["ds"], dtype=ops.TF32)
         T.silu_bwd(sv_e, ws["ds"], ws["de"])
         g = grads[prefix + "emb.weight"]
         g.zero_()
