@@ -80,6 +80,9 @@ typedef struct dsb_gemm_desc {
   int block_n;           /* 0 = auto, 128, 256 */
   int max_ctas;          /* 0 = one per SM */
   int cta_pair;          /* 0 = auto (pairs for 256-wide tiles), 1 = force cta_group::2 pairs (256x256 tiles), -1 = single-CTA kernel */
+  int a_mn_major;        /* 1: A lies in memory as (K rows, M columns), lda = row stride: out[m, n] = sum_k A[k, m] W[n, k]; 2-byte dtypes, 1 tap */
+  int b_mn_major;        /* 1: W lies in memory as (K rows, N columns), ldw = row stride (e.g. dW = dY^T X with both operands token-major,
+                            dX = dY W with torch's (out, in) weight as stored) */
 } dsb_gemm_desc;
 int dsb_gemm_ex(const dsb_gemm_desc* desc, void* stream);
 

@@ -193,3 +193,43 @@ def test_gemm_split_tf32_recovers_fp32_accuracy(G):
     q = torch.randn(2, 40, 64, generator=g); k = torch.randn(2, 48, 64, generator=g)
     s = G.ops.gemm_split(G.ops.split_tf32(q.cuda()), G.ops.split_tf32(k.cuda(), w_format=True), alpha=0.125)
     assert G.relerr(s, 0.125 * torch.einsum("bmk,bnk->bmn", q.double(), k.double())) < 5e-6
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 512, 200), (1024, 1024, 5300), (4096, 1024, 795), (77, 64, 265), (265, 64, 77), (96, 200, 130)])
+def test_gemm_mn_major_operands(G, dt, M, N, K):
+    """Operands as they lie in memory with the reduction dimension as ROWS (weight-gradient / P^T dO shapes): out = a^T w, a^T w_k, a w."""
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    code = G.ops.BF16 if dt == torch.bfloat16 else G.ops.F16
+    ld_a, ld_w = (M + 7) // 8 * 8 + 8, (N + 7) // 8 * 8 + 16  # padded leading dimensions: garbage beyond the extents must never be read
+    a_store = torch.full((K, ld_a), float("nan")).to(dt)
+    w_store = torch.full((K, ld_w), float("nan")).to(dt)
+    a_store[:, :M] = torch.randn(K, M, generator=g).to(dt)
+    w_store[:, :N] = (torch.randn(K, N, generator=g) * 0.1).to(dt)
+    a_km, w_km = a_store.cuda()[:, :M], w_store.cuda()[:, :N]            # (K, M), (K, N) row-strided views of the padded buffers
+    ref = a_store[:, :M].double().T @ w_store[:, :N].double()
+    out = G.ops.gemm(a_km, w_km, dtype=code, a_mn=True, w_mn=True)
+    assert out.shape == (M, N) and G.relerr(out, ref) < 2e-5
+    # mixed: A K-major (M, K) with W MN-major (K, N), and A MN-major with W K-major (N, K)
+    a_rm = a_store[:, :M].T.contiguous().cuda()
+    w_rm = w_store[:, :N].T.contiguous().cuda()
+    if K % 8 == 0:
+        assert G.relerr(G.ops.gemm(a_rm, w_km, dtype=code, w_mn=True), ref) < 2e-5
+        assert G.relerr(G.ops.gemm(a_km, w_rm, dtype=code, a_mn=True), ref) < 2e-5
+    bias = torch.randn(N, generator=g)
+    outb = G.ops.gemm(a_km, w_km, bias.cuda(), dtype=code, a_mn=True, w_mn=True, alpha=0.5, block_n=128)
+    assert G.relerr(outb, 0.5 * ref + bias.double()) < 2e-5
+
+
+def test_gemm_mn_major_batched(G):
+    g = torch.Generator().manual_seed(11)
+    Bt, Lq, Lk = 5, 265, 77
+    P = torch.rand(Bt, Lq, 80, generator=g).bfloat16()       # (Lq rows = reduction, Lk columns) inside an 80-wide buffer
+    dO = torch.randn(Bt, Lq, 64, generator=g).bfloat16()
+    Pc = P.cuda()[:, :, :Lk]
+    out = G.ops.gemm(Pc, dO.cuda(), dtype=G.ops.BF16, a_mn=True, w_mn=True)   # dV = P^T dO
+    ref = torch.einsum("bqk,bqd->bkd", P[:, :, :Lk].double(), dO.double())
+    assert out.shape == (Bt, Lk, 64) and G.relerr(out, ref) < 2e-5
+    V = torch.randn(Bt, Lk, 64, generator=g).bfloat16()
+    out2 = G.ops.gemm(Pc, V.cuda(), dtype=G.ops.BF16, w_mn=True)             # O = P V with V as stored
+    assert G.relerr(out2, torch.einsum("bqk,bkd->bqd", P[:, :, :Lk].double(), V.double())) < 2e-5

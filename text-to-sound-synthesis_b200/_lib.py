@@ -22,7 +22,7 @@ class GemmDesc(C.Structure):
         ("a_batch_stride", c_ll), ("w_batch_stride", c_ll), ("out_batch_stride", c_ll), ("res_batch_stride", c_ll),
         ("dtype", c_i), ("flags", c_i), ("num_taps", c_i), ("tap_shift", c_i * 32), ("tap_acol", c_i * 32), ("a_cols", c_ll),
         ("geo_P", c_i), ("geo_Wp", c_i), ("geo_y0", c_i), ("geo_y1", c_i), ("geo_x0", c_i), ("geo_x1", c_i),
-        ("alpha", c_f), ("block_n", c_i), ("max_ctas", c_i), ("cta_pair", c_i),
+        ("alpha", c_f), ("block_n", c_i), ("max_ctas", c_i), ("cta_pair", c_i), ("a_mn_major", c_i), ("b_mn_major", c_i),
     ]
 
 

@@ -16,11 +16,25 @@
 
 namespace dsb {
 
+constexpr int MN_BOX_BYTES_C = 64 * 128;
 constexpr int BLOCK_M = 128;
 constexpr int ROW_BYTES = 128;  // one swizzle-128B row of K per operand row
 constexpr int GEMM_THREADS = 320;  // warp0 TMA, warp1 MMA, warps 2..9 epilogue
 constexpr int MAX_TAPS = 32;
+constexpr int MN_BOX_BYTES = 64 * ROW_BYTES;  // one MN-major TMA box: 64 K rows x 64 two-byte columns
 constexpr int EPI_LD = 36;  // padded row stride (floats) of the epilogue transpose tile: 16-byte aligned rows, conflict-free
+
+// SW128 MN-major UMMA descriptor (canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units): a 64-column block is 64 K rows of
+// 128 bytes; LBO = distance between 64-column blocks (one TMA box, 8 KB), SBO = distance between groups of 8 K rows (1 KB).
+__device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(MN_BOX_BYTES_C >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 
 struct GemmParams {
   int M, N, batch;
@@ -42,6 +56,10 @@ struct GemmParams {
   // rows outside [y0,y1) x [x0,x1) are written as zeros.  geo_P == 0 disables.
   int geo_P, geo_Wp, geo_y0, geo_y1, geo_x0, geo_x1;
   float alpha;     // scale applied to the accumulator before bias (1.0 for Linear)
+  // MN-major operands (2-byte types, one tap): the operand lies in HBM as (K rows, MN columns) -- e.g. dY and X of a weight-gradient GEMM
+  // dW = dY^T X, which contract over the token dimension.  Loaded as 64-column x 64-row TMA boxes (SWIZZLE_128B), consumed through MN-major
+  // UMMA descriptors: no transposed copies.
+  int a_mn, b_mn;
 };
 
 template <int BLOCK_N>
@@ -281,8 +299,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
           uint8_t* sa = smem + stage * S::STAGE_BYTES;
-          tma_load_3d(&tmap_a, &full_bar[stage], sa, c0 + p.tap_acol[tap], m_blk * BLOCK_M + p.tap_shift[tap], b);
-          tma_load_3d(&tmap_b, &full_bar[stage], sa + S::A_BYTES, tap * p.kc + c0, n_blk * BLOCK_N, p.b_batched ? b : 0);
+          if (p.a_mn) {
+#pragma unroll
+            for (int j = 0; j < BLOCK_M / 64; ++j) tma_load_3d(&tmap_a, &full_bar[stage], sa + j * MN_BOX_BYTES, m_blk * BLOCK_M + j * 64, c0, b);
+          } else {
+            tma_load_3d(&tmap_a, &full_bar[stage], sa, c0 + p.tap_acol[tap], m_blk * BLOCK_M + p.tap_shift[tap], b);
+          }
+          if (p.b_mn) {
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_3d(&tmap_b, &full_bar[stage], sa + S::A_BYTES + j * MN_BOX_BYTES, n_blk * BLOCK_N + j * 64, c0, p.b_batched ? b : 0);
+          } else {
+            tma_load_3d(&tmap_b, &full_bar[stage], sa + S::A_BYTES, tap * p.kc + c0, n_blk * BLOCK_N, p.b_batched ? b : 0);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -290,7 +319,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(KIND, BLOCK_M, BLOCK_N);
+      const uint32_t idesc = make_idesc(KIND, BLOCK_M, BLOCK_N) | (p.a_mn ? (1u << 15) : 0u) | (p.b_mn ? (1u << 16) : 0u);
+      // descriptor step per 16-element K slice: K-major = 32 bytes inside the swizzle row, MN-major = 16 rows of 128 bytes
+      const uint32_t a_step = p.a_mn ? (16 * ROW_BYTES) >> 4 : 2, b_step = p.b_mn ? (16 * ROW_BYTES) >> 4 : 2;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -304,11 +335,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
-          const uint64_t da = make_sw128_kmajor_desc(sa);
-          const uint64_t db = make_sw128_kmajor_desc(sa + S::A_BYTES);
+          const uint64_t da = p.a_mn ? make_sw128_mnmajor_desc(sa) : make_sw128_kmajor_desc(sa);
+          const uint64_t db = p.b_mn ? make_sw128_mnmajor_desc(sa + S::A_BYTES) : make_sw128_kmajor_desc(sa + S::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)  // 4 x 32-byte K slices per 128-byte swizzle row
-            umma<KIND == DSB_DTYPE_TF32>(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)  // 4 K slices (16 elements of 2 bytes / 8 of 4 bytes) per 64-deep k-block
+            umma<KIND == DSB_DTYPE_TF32>(d_tmem, da + a_step * k, db + b_step * k, idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -563,6 +594,26 @@ int make_operand_map(CUtensorMap* map, const void* ptr, int kind, long long kdim
   return 0;
 }
 
+// 3-D map (MN, K rows, batch) over an MN-contiguous operand; box = (64 columns = 128 bytes, 64 K rows, 1); SWIZZLE_128B; OOB -> 0
+int make_operand_map_mn(CUtensorMap* map, const void* ptr, int kind, long long mn, long long krows, long long batch, long long ld_elems,
+                        long long bstride_elems) {
+  PFN_encodeTiled enc = get_encode();
+  DSB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  DSB_REQUIRE(kind != DSB_DTYPE_TF32, "MN-major GEMM operands are implemented for the 2-byte types only");
+  DSB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "GEMM operand pointer must be 16-byte aligned");
+  DSB_REQUIRE((ld_elems * 2) % 16 == 0, "GEMM operand leading dimension must be a multiple of 16 bytes (ld=%lld)", ld_elems);
+  DSB_REQUIRE(batch == 1 || (bstride_elems * 2) % 16 == 0, "GEMM batch stride must be a multiple of 16 bytes");
+  cuuint64_t gdim[3] = {(cuuint64_t)mn, (cuuint64_t)krows, (cuuint64_t)batch};
+  cuuint64_t gstr[2] = {(cuuint64_t)(ld_elems * 2), (cuuint64_t)((batch == 1 ? ld_elems * krows : bstride_elems) * 2)};
+  cuuint32_t box[3] = {64, 64, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, kind == DSB_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), gdim, gstr,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DSB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (MN-major) failed (%d): mn=%lld k=%lld batch=%lld ld=%lld", (int)r, mn, krows, batch, ld_elems);
+  return 0;
+}
+
 template <int BLOCK_N, int KIND>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int max_ctas, cudaStream_t st) {
   using S = GemmSmem<BLOCK_N>;
@@ -632,6 +683,11 @@ extern "C" int dsb_gemm_ex(const dsb_gemm_desc* d, void* stream) {
   p.flags = d->flags;
   p.geo_P = d->geo_P; p.geo_Wp = d->geo_Wp; p.geo_y0 = d->geo_y0; p.geo_y1 = d->geo_y1; p.geo_x0 = d->geo_x0; p.geo_x1 = d->geo_x1;
   p.alpha = d->alpha == 0.0f ? 1.0f : d->alpha;
+  p.a_mn = d->a_mn_major != 0;
+  p.b_mn = d->b_mn_major != 0;
+  const bool any_mn = p.a_mn || p.b_mn;
+  DSB_REQUIRE(!any_mn || (kind != DSB_DTYPE_TF32 && d->num_taps == 1 && d->tap_shift[0] == 0 && d->tap_acol[0] == 0),
+              "dsb_gemm_ex: MN-major operands need a 2-byte dtype and a single unshifted tap");
 
   // tile-N choice: fewest waves, then the wider tile (less A re-read)
   const int sms = sm_count();
@@ -649,8 +705,9 @@ extern "C" int dsb_gemm_ex(const dsb_gemm_desc* d, void* stream) {
   // CTA pairs (cta_group::2, 256 x 256 tiles): default whenever the tile width is 256 and the problem is at least one pair tile tall
   // measured (tools/gemm_microbench.py): pairs win once the mainloop dominates (K >= 2048: 33.3 -> 31.3 us at N=1024, K=4096) and
   // lose ~1 us of extra prologue (cluster barriers) on short-K launches
-  const bool use_pair = d->cta_pair > 0 || (d->cta_pair == 0 && d->block_n == 0 && block_n == 256 && d->M > BLOCK_M &&
-                                            (long long)d->K * d->num_taps >= 2048 && pair_default());
+  DSB_REQUIRE(!(any_mn && d->cta_pair > 0), "dsb_gemm_ex: the cta_group::2 kernel takes K-major operands only");
+  const bool use_pair = !any_mn && (d->cta_pair > 0 || (d->cta_pair == 0 && d->block_n == 0 && block_n == 256 && d->M > BLOCK_M &&
+                                                        (long long)d->K * d->num_taps >= 2048 && pair_default()));
   if (use_pair) {
     block_n = 256;
     p.tiles_m = (d->M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
@@ -659,9 +716,13 @@ extern "C" int dsb_gemm_ex(const dsb_gemm_desc* d, void* stream) {
 
   CUtensorMap ma, mb;
   const long long a_rows = d->a_rows > 0 ? d->a_rows : d->M;
-  if (make_operand_map(&ma, d->A, kind, d->a_cols > 0 ? d->a_cols : d->K, a_rows, d->batch, d->lda, d->a_batch_stride, BLOCK_M)) return 3;
-  if (make_operand_map(&mb, d->W, kind, (long long)d->K * d->num_taps, d->N, p.b_batched ? d->batch : 1, d->ldw, d->w_batch_stride,
-                       use_pair ? block_n / 2 : block_n)) return 3;
+  if (p.a_mn) {
+    if (make_operand_map_mn(&ma, d->A, kind, a_rows, d->K, d->batch, d->lda, d->a_batch_stride)) return 3;
+  } else if (make_operand_map(&ma, d->A, kind, d->a_cols > 0 ? d->a_cols : d->K, a_rows, d->batch, d->lda, d->a_batch_stride, BLOCK_M)) return 3;
+  if (p.b_mn) {
+    if (make_operand_map_mn(&mb, d->W, kind, d->N, d->K, p.b_batched ? d->batch : 1, d->ldw, d->w_batch_stride)) return 3;
+  } else if (make_operand_map(&mb, d->W, kind, (long long)d->K * d->num_taps, d->N, p.b_batched ? d->batch : 1, d->ldw, d->w_batch_stride,
+                              use_pair ? block_n / 2 : block_n)) return 3;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int max_ctas = d->max_ctas > 0 ? d->max_ctas : sms;
   if (use_pair) {

@@ -112,19 +112,21 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
          out: Optional[torch.Tensor] = None, *, dtype: int = TF32, gelu: bool = False, round_out: bool = False, out_bf16: bool = False, out_f16: bool = False,
          lrelu: bool = False, tanh: bool = False, res_before_act: bool = False, taps: Optional[Sequence[int]] = None,
          tap_acol: Optional[Sequence[int]] = None, k_per_tap: Optional[int] = None, out_rows: Optional[int] = None, geo: Optional[Sequence[int]] = None, alpha: float = 1.0,
-         block_n: int = 0, max_ctas: int = 0, cta_pair: int = 0) -> torch.Tensor:
-    """out = epi(alpha * A @ W^T + bias) (+ residual) on tcgen05.  a: (M,K) or (batch,M,K); w: (N, taps*K) or (batch,N,K)."""
+         block_n: int = 0, max_ctas: int = 0, cta_pair: int = 0, a_mn: bool = False, w_mn: bool = False) -> torch.Tensor:
+    """out = epi(alpha * A @ W^T + bias) (+ residual) on tcgen05.  a: (M,K) or (batch,M,K); w: (N, taps*K) or (batch,N,K).
+    a_mn / w_mn: that operand is given MN-major, i.e. as it lies in memory with the reduction dimension as rows -- a: (K, M), w: (K, N)
+    (2-byte dtypes): out = a^T @ w with no transposed copies."""
     _need_cuda(a, w, bias, residual, out)
     batched = a.dim() == 3
     if a.stride(-1) != 1 or w.stride(-1) != 1:
-        raise RuntimeError("gemm operands must be K-contiguous")
+        raise RuntimeError("gemm operands must be contiguous in their last dimension")
     ntaps = 1 if taps is None else len(taps)
     batch = a.shape[0] if batched else 1
-    a_rows, a_cols = a.shape[-2], a.shape[-1]
+    a_rows, a_cols = (a.shape[-1], a.shape[-2]) if a_mn else (a.shape[-2], a.shape[-1])  # (M, K)
     K = a_cols if k_per_tap is None else k_per_tap  # reduction length per tap (A may hold several K blocks side by side)
-    N = w.shape[-2]
-    if w.shape[-1] != K * ntaps:
-        raise RuntimeError(f"gemm: W has {w.shape[-1]} columns, expected {K}*{ntaps}")
+    N = w.shape[-1] if w_mn else w.shape[-2]
+    if (w.shape[-2] if w_mn else w.shape[-1]) != K * ntaps:
+        raise RuntimeError(f"gemm: W has reduction length {w.shape[-2] if w_mn else w.shape[-1]}, expected {K}*{ntaps}")
     M = a_rows if out_rows is None else out_rows
     odt = torch.bfloat16 if out_bf16 else (torch.float16 if out_f16 else torch.float32)
     if out is None:
@@ -152,6 +154,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         d.geo_P, d.geo_Wp, d.geo_y0, d.geo_y1, d.geo_x0, d.geo_x1 = [int(v) for v in geo]
     d.alpha = alpha
     d.block_n, d.max_ctas, d.cta_pair = block_n, max_ctas, cta_pair
+    d.a_mn_major, d.b_mn_major = int(a_mn), int(w_mn)
     _lib.check(_lib.lib().dsb_gemm_ex(C.byref(d), _stream()), "dsb_gemm_ex")
     return out
 

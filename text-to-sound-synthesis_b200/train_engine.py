@@ -37,6 +37,9 @@ class DenoiserTrainEngine:
         self.precision = precision
         self.adt = torch.bfloat16 if precision == "bf16" else torch.float32
         self.gd = ops.BF16 if precision == "bf16" else ops.TF32
+        # 2-byte operands can be fed MN-major (token-major dY / X for wgrad, torch's (out, in) weights for dgrad, V / K / Q / dO as stored for
+        # attention): no transposed copies at all.  The TF32 accuracy mode keeps explicit transposes (dsb_transpose).
+        self.mn = precision == "bf16"
         self._ws: Dict[tuple, dict] = {}
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self.use_cuda_graph = True  # replay forward / backward as two CUDA graphs (~2.5k launches per step otherwise)
@@ -96,10 +99,12 @@ class DenoiserTrainEngine:
             for j, lin in enumerate((a1.query, a1.key, a1.value)):
                 self._cast_w(lin.weight, lay["wqkv"][j * D:(j + 1) * D])
                 lay["bqkv"][j * D:(j + 1) * D].copy_(lin.bias.detach())
-            T.transpose(lay["wqkv"], lay["wqkvT"])
+            if not self.mn:
+                T.transpose(lay["wqkv"], lay["wqkvT"])
             for name, lin in (("wo1", a1.proj), ("wq2", a2.query), ("wo2", a2.proj), ("w1", blk.mlp[0]), ("w2", blk.mlp[2])):
                 self._cast_w(lin.weight, lay[name])
-                T.transpose(lay[name], lay[name + "T"])
+                if not self.mn:
+                    T.transpose(lay[name], lay[name + "T"])
             self._cast_w(a2.key.weight, self.wkv_all[li * 2 * D:li * 2 * D + D])
             self._cast_w(a2.value.weight, self.wkv_all[li * 2 * D + D:(li + 1) * 2 * D])
             self.bkv_all[li * 2 * D:li * 2 * D + D].copy_(a2.key.bias.detach())
@@ -107,7 +112,8 @@ class DenoiserTrainEngine:
             T.transpose(blk.ln1.linear.weight.detach(), lay["lin1T"])
             T.transpose(blk.ln1_1.linear.weight.detach(), lay["lin2T"])
         self._cast_w(m.to_logits[1].weight, self.wlog)
-        T.transpose(self.wlog, self.wlogT)
+        if not self.mn:
+            T.transpose(self.wlog, self.wlogT)
 
     # ------------------------------------------------------------------ workspaces (allocated once per shape; nothing is allocated per step)
     def workspace(self, B: int, L: int, Lc: int) -> dict:
@@ -215,12 +221,15 @@ class DenoiserTrainEngine:
         T.heads_split(q_tok, qh, B, H, Lq)
         T.heads_split(k_tok, kh, B, H, Lk)
         T.heads_split(v_tok, vh, B, H, Lk)
-        vT = ws["vT"][:, :, :Lkp]
-        T.transpose(vh, vT)
         S = ws["S"][:, :, :Lkp]
         ops.gemm(qh, kh, None, None, S, dtype=self.gd, alpha=1.0 / math.sqrt(64))
         T.softmax_fwd(S, P, Lk)
-        ops.gemm(P[:, :, :Lk], vT[:, :, :Lk], None, None, ws["oh"], dtype=self.gd, round_out=self.adt == torch.float32)
+        if self.mn:
+            ops.gemm(P[:, :, :Lk], vh, None, None, ws["oh"], dtype=self.gd, w_mn=True)          # O = P V, V as stored (Lk, 64)
+        else:
+            vT = ws["vT"][:, :, :Lkp]
+            T.transpose(vh, vT)
+            ops.gemm(P[:, :, :Lk], vT[:, :, :Lk], None, None, ws["oh"], dtype=self.gd, round_out=True)
         T.heads_merge(ws["oh"], att_tok, B, H, Lq)
 
     @torch.no_grad()
@@ -279,21 +288,27 @@ class DenoiserTrainEngine:
         return ws["logits"]
 
     # ------------------------------------------------------------------ backward
-    def _linear_bwd(self, dy, x_act, wT, dW, db, dx_out, ws, *, yT=None, xT=None):
+    def _linear_bwd(self, dy, x_act, w, wT, dW, db, dx_out, ws, *, yT=None, xT=None):
         """dy (M, N), x_act (M, K): dW (N, K) = dy^T x, db (N) = colsum(dy), dx_out (M, K) = dy W (if dx_out is not None).
         dx_out is either ws['dh'] (fp32, consumed by a LayerNorm backward) or an activation-typed buffer feeding another GEMM."""
         M, N = dy.shape
         Kin = x_act.shape[1]
-        Mp = _rup(M, 8)
-        yT = (ws["yT"] if yT is None else yT)[:N, :Mp]
-        xT = (ws["xT"] if xT is None else xT)[:Kin, :Mp]
-        T.transpose(dy, yT)
-        T.transpose(x_act, xT)
-        ops.gemm(yT[:, :M], xT[:, :M], None, None, dW, dtype=self.gd)
+        if self.mn:
+            ops.gemm(dy, x_act, None, None, dW, dtype=self.gd, a_mn=True, w_mn=True)              # both operands token-major, read in place
+        else:
+            Mp = _rup(M, 8)
+            yT = (ws["yT"] if yT is None else yT)[:N, :Mp]
+            xT = (ws["xT"] if xT is None else xT)[:Kin, :Mp]
+            T.transpose(dy, yT)
+            T.transpose(x_act, xT)
+            ops.gemm(yT[:, :M], xT[:, :M], None, None, dW, dtype=self.gd)
         if db is not None:
             T.colsum(dy, db)
         if dx_out is not None:
-            ops.gemm(dy, wT, None, None, dx_out, dtype=self.gd, round_out=(dx_out.dtype == torch.float32 and dx_out is not ws["dh"]))
+            if self.mn:
+                ops.gemm(dy, w, None, None, dx_out, dtype=self.gd, w_mn=True)                      # W (N, Kin) as torch stores it
+            else:
+                ops.gemm(dy, wT, None, None, dx_out, dtype=self.gd, round_out=(dx_out.dtype == torch.float32 and dx_out is not ws["dh"]))
 
     def _attn_bwd(self, datt_tok, dq_tok, dk_tok, dv_tok, qh, kh, vh, P, ws, B, Lq, Lk):
         H = self.H
@@ -306,20 +321,25 @@ class DenoiserTrainEngine:
         ops.gemm(doh, vh, None, None, dP, dtype=self.gd)                                  # dP = dO V^T
         dS = ws["dS"][:, :, :Lkp]
         T.softmax_bwd(P, dP, dS, Lk, scale)
-        PT, doT = ws["PT"][:, :Lk, :Lqp], ws["doT"][:, :, :Lqp]
-        T.transpose(P[:, :, :Lk], PT)
-        T.transpose(doh, doT)
         BH = B * H
         dvh = ws["dvh"].view(-1)[:BH * Lk * 64].view(BH, Lk, 64)
-        ops.gemm(PT[:, :, :Lq], doT[:, :, :Lq], None, None, dvh, dtype=self.gd, round_out=rnd)     # dV = P^T dO
-        kT = ws["kT"][:, :, :Lkp]
-        T.transpose(kh, kT)
-        ops.gemm(dS[:, :, :Lk], kT[:, :, :Lk], None, None, ws["dqh"], dtype=self.gd, round_out=rnd)  # dQ = dS K
-        dST, qT = ws["dST"][:, :Lk, :Lqp], ws["qT"][:, :, :Lqp]
-        T.transpose(dS[:, :, :Lk], dST)
-        T.transpose(qh, qT)
         dkh = ws["dkh"].view(-1)[:BH * Lk * 64].view(BH, Lk, 64)
-        ops.gemm(dST[:, :, :Lq], qT[:, :, :Lq], None, None, dkh, dtype=self.gd, round_out=rnd)     # dK = dS^T Q
+        if self.mn:
+            ops.gemm(P[:, :, :Lk], doh, None, None, dvh, dtype=self.gd, a_mn=True, w_mn=True)        # dV = P^T dO
+            ops.gemm(dS[:, :, :Lk], kh, None, None, ws["dqh"], dtype=self.gd, w_mn=True)            # dQ = dS K
+            ops.gemm(dS[:, :, :Lk], qh, None, None, dkh, dtype=self.gd, a_mn=True, w_mn=True)       # dK = dS^T Q
+        else:
+            PT, doT = ws["PT"][:, :Lk, :Lqp], ws["doT"][:, :, :Lqp]
+            T.transpose(P[:, :, :Lk], PT)
+            T.transpose(doh, doT)
+            ops.gemm(PT[:, :, :Lq], doT[:, :, :Lq], None, None, dvh, dtype=self.gd, round_out=rnd)
+            kT = ws["kT"][:, :, :Lkp]
+            T.transpose(kh, kT)
+            ops.gemm(dS[:, :, :Lk], kT[:, :, :Lk], None, None, ws["dqh"], dtype=self.gd, round_out=rnd)
+            dST, qT = ws["dST"][:, :Lk, :Lqp], ws["qT"][:, :, :Lqp]
+            T.transpose(dS[:, :, :Lk], dST)
+            T.transpose(qh, qT)
+            ops.gemm(dST[:, :, :Lq], qT[:, :, :Lq], None, None, dkh, dtype=self.gd, round_out=rnd)
         T.heads_merge(ws["dqh"], dq_tok, B, H, Lq)
         T.heads_merge(dkh, dk_tok, B, H, Lk)
         T.heads_merge(dvh, dv_tok, B, H, Lk)
@@ -374,7 +394,7 @@ class DenoiserTrainEngine:
         dx = ws["dx"]
         # ---- head: logits = LN_f(x) Wlog^T + b
         T.cast_scale(ws["dlogits"].view(M, K), ws["dlog"], ws["scale"])
-        self._linear_bwd(ws["dlog"], ws["hf"], self.wlogT, grads["to_logits.1.weight"], grads["to_logits.1.bias"], ws["dh"], ws)
+        self._linear_bwd(ws["dlog"], ws["hf"], self.wlog, self.wlogT, grads["to_logits.1.weight"], grads["to_logits.1.bias"], ws["dh"], ws)
         dx.zero_()
         lnf = m.to_logits[0]
         grads["to_logits.0.weight"].zero_(); grads["to_logits.0.bias"].zero_()
@@ -386,27 +406,27 @@ class DenoiserTrainEngine:
             Dh = lay["w1"].shape[0]
             # ---- MLP: x_next = x3 + W2 gelu2(W1 LN2(x3))
             T.cast_scale(dx.view(M, D), ws["dy"])
-            self._linear_bwd(ws["dy"], sv["act"], lay["w2T"], grads[p + "mlp.2.weight"], grads[p + "mlp.2.bias"], ws["dbig"], ws)
+            self._linear_bwd(ws["dy"], sv["act"], lay["w2"], lay["w2T"], grads[p + "mlp.2.weight"], grads[p + "mlp.2.bias"], ws["dbig"], ws)
             T.gelu2_bwd(sv["u"], ws["dbig"], ws["dbig2"])
-            self._linear_bwd(ws["dbig2"], sv["h3"], lay["w1T"], grads[p + "mlp.0.weight"], grads[p + "mlp.0.bias"], ws["dh"], ws)
+            self._linear_bwd(ws["dbig2"], sv["h3"], lay["w1"], lay["w1T"], grads[p + "mlp.0.weight"], grads[p + "mlp.0.bias"], ws["dh"], ws)
             grads[p + "ln2.weight"].zero_(); grads[p + "ln2.bias"].zero_()
             T.layernorm_bwd(sv["x3"], ws["dh"].view(B, L, D), dx, blk.ln2.weight.detach(), grads[p + "ln2.weight"], grads[p + "ln2.bias"], blk.ln2.eps)
             # ---- cross-attention: x3 = x2 + Wo2 attn(q2, kv)
             T.cast_scale(dx.view(M, D), ws["dy"])
-            self._linear_bwd(ws["dy"], sv["att2"], lay["wo2T"], grads[p + "attn2.proj.weight"], grads[p + "attn2.proj.bias"], ws["datt"], ws)
+            self._linear_bwd(ws["dy"], sv["att2"], lay["wo2"], lay["wo2T"], grads[p + "attn2.proj.weight"], grads[p + "attn2.proj.bias"], ws["datt"], ws)
             dkv = dkv_all[:, li * 2 * D:(li + 1) * 2 * D]
             self._attn_bwd(ws["datt"], ws["dq2"], dkv[:, :D], dkv[:, D:], sv["qh2"], sv["kh2"], sv["vh2"], sv["P2"], ws, B, L, Lc)
-            self._linear_bwd(ws["dq2"], sv["h2"], lay["wq2T"], grads[p + "attn2.query.weight"], grads[p + "attn2.query.bias"], ws["dh"], ws)
+            self._linear_bwd(ws["dq2"], sv["h2"], lay["wq2"], lay["wq2T"], grads[p + "attn2.query.weight"], grads[p + "attn2.query.bias"], ws["dh"], ws)
             self._ada_bwd(blk.ln1_1, lay["lin2T"], sv["x2"], ws["dh"], sv["e2"], sv["s2"], sv["tab2"], grads, p + "ln1_1.", ws, B)
             # ---- self-attention: x2 = x1 + Wo1 attn(qkv)
             T.cast_scale(dx.view(M, D), ws["dy"])
-            self._linear_bwd(ws["dy"], sv["att1"], lay["wo1T"], grads[p + "attn1.proj.weight"], grads[p + "attn1.proj.bias"], ws["datt"], ws)
+            self._linear_bwd(ws["dy"], sv["att1"], lay["wo1"], lay["wo1T"], grads[p + "attn1.proj.weight"], grads[p + "attn1.proj.bias"], ws["datt"], ws)
             dqkv = ws["dqkv"]
             self._attn_bwd(ws["datt"], dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], sv["qh1"], sv["kh1"], sv["vh1"], sv["P1"], ws, B, L, L)
-            self._linear_bwd(dqkv, sv["h1"], lay["wqkvT"], grads[f"_qkv_w.{li}"], grads[f"_qkv_b.{li}"], ws["dh"], ws)
+            self._linear_bwd(dqkv, sv["h1"], lay["wqkv"], lay["wqkvT"], grads[f"_qkv_w.{li}"], grads[f"_qkv_b.{li}"], ws["dh"], ws)
             self._ada_bwd(blk.ln1, lay["lin1T"], sv["x1"], ws["dh"], sv["e1"], sv["s1"], sv["tab1"], grads, p + "ln1.", ws, B)
         # ---- cross-attention K/V projections of every layer in one wgrad: kv_all = cond Wkv^T + b
-        self._linear_bwd(dkv_all, ws["cond"], None, grads["_kv_w"], grads["_kv_b"], None, ws, yT=ws["ykvT"], xT=ws["condT"])
+        self._linear_bwd(dkv_all, ws["cond"], None, None, grads["_kv_w"], grads["_kv_b"], None, ws, yT=ws["ykvT"], xT=ws["condT"])
         # ---- embedding
         for n in ("content_emb.emb.weight", "content_emb.height_emb.weight", "content_emb.width_emb.weight"):
             grads[n].zero_()
