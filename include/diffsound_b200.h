@@ -243,6 +243,15 @@ int dsb_ada_layernorm_bwd(const float* x, const float* dy, float* dx_io, const f
 int dsb_softmax_fwd(const float* S, long long ld_s, void* P, long long ld_p, long long rows, int n, int dtype, void* stream);
 int dsb_softmax_bwd(const void* P, long long ld_p, const float* dP, long long ld_dp, void* dS, long long ld_ds, long long rows, int n,
                     float alpha, int dtype, void* stream);
+/* Fused attention for training (bf16, head_dim 64; FullAttention / CrossAttention, transformer_utils.py:43-58, :91-109): q/k/v/o/dout/dq/dk/dv
+ * are token-major with row strides (head h = columns [64h, 64h+64); batch b starts at row b*Lq resp. b*Lk), so they alias the QKV and
+ * gradient buffers of the surrounding GEMMs.  fwd also writes lse (B*H, Lq) = log2 sum_k exp(scale s_k); bwd rebuilds P from it and needs a
+ * (B*H, Lq) fp32 scratch `delta`. */
+int dsb_attention_train_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o, long long ldo,
+                            float* lse, int B, int H, int Lq, int Lk, float scale, void* stream);
+int dsb_attention_train_bwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, const void* o, long long ldo,
+                            const void* dout, long long lddo, const float* lse, float* delta, void* dq, long long lddq, void* dk, long long lddk,
+                            void* dv, long long lddv, int B, int H, int Lq, int Lk, float scale, void* stream);
 /* DalleMaskImageEmbedding backward (dalle_mask_image_embedding.py:36-58): demb / dheight / dwidth are ACCUMULATED. */
 int dsb_embed_bwd(const int64_t* ids, const float* dx, float* demb, float* dheight, float* dwidth, int B, int L, int D, int H, int W,
                   int num_embed, void* stream);

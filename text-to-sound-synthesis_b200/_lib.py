@@ -70,6 +70,8 @@ SIGNATURES = {
     "dsb_softmax_fwd": [c_vp, c_ll, c_vp, c_ll, c_ll, c_i, c_i, c_vp],
     "dsb_softmax_bwd": [c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_ll, c_i, c_f, c_i, c_vp],
     "dsb_embed_bwd": [c_vp] * 5 + [c_i] * 6 + [c_vp],
+    "dsb_attention_train_fwd": [c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_i, c_i, c_i, c_i, c_f, c_vp],
+    "dsb_attention_train_bwd": [c_vp, c_ll] * 5 + [c_vp, c_vp] + [c_vp, c_ll] * 3 + [c_i, c_i, c_i, c_i, c_f, c_vp],
 }
 
 _lib = None

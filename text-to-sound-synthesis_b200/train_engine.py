@@ -11,8 +11,10 @@ Layout notes
     live fp32 parameters (they change every optimizer step).
   * wgrad dW (N, K) = dY^T X contracts over the M = B*L tokens: dY^T (N, Mp) and X^T (K, Mp) are produced by dsb_transpose into scratch
     (Mp = M rounded up to 8 for the 16-byte TMA stride; the GEMM's reduction length is the exact M, TMA zero-fills the tail).
-  * attention runs head-major (B*H, L, 64): S = alpha Q K^T, P = softmax(S) (saved), O = P V, and backward
-    dV = P^T dO, dP = dO V^T, dS = alpha P (dP - rowsum(dP P)), dQ = dS K, dK = dS^T Q -- all batched tcgen05 GEMMs.
+  * attention, bf16 mode: fused kernels of csrc/attention_train.cu on the token-major QKV / gradient buffers in place (forward keeps only the
+    log-sum-exp rows; backward = a dQ kernel and a dK/dV kernel that rebuild P).  tf32 accuracy mode: composed head-major (B*H, L, 64):
+    S = alpha Q K^T, P = softmax(S) (saved), O = P V; dV = P^T dO, dP = dO V^T, dS = alpha P (dP - rowsum(dP P)), dQ = dS K, dK = dS^T Q
+    as batched tcgen05 GEMMs.
 """
 from __future__ import annotations
 
@@ -131,9 +133,12 @@ class DenoiserTrainEngine:
             per_layer.append(dict(
                 x1=f(B, L, D), x2=f(B, L, D), x3=f(B, L, D),
                 e1=f(B, D), s1=f(B, D), tab1=f(B, 2 * D), e2=f(B, D), s2=f(B, D), tab2=f(B, 2 * D),
-                h1=a(M, D), qkv=a(M, 3 * D), att1=a(M, D), h2=a(M, D), q2=a(M, D), att2=a(M, D), h3=a(M, D), u=a(M, Dh), act=a(M, Dh),
-                qh1=a(BH, L, 64), kh1=a(BH, L, 64), vh1=a(BH, L, 64), P1=a(BH, L, Lp),
-                qh2=a(BH, L, 64), kh2=a(BH, Lc, 64), vh2=a(BH, Lc, 64), P2=a(BH, L, Lcp)))
+                h1=a(M, D), qkv=a(M, 3 * D), att1=a(M, D), h2=a(M, D), q2=a(M, D), att2=a(M, D), h3=a(M, D), u=a(M, Dh), act=a(M, Dh)))
+            if self.mn:   # fused attention: only the log-sum-exp rows are kept
+                per_layer[-1].update(lse1=f(BH, L), lse2=f(BH, L))
+            else:         # composed attention (tf32 accuracy mode): head-major operands and the probabilities are kept
+                per_layer[-1].update(qh1=a(BH, L, 64), kh1=a(BH, L, 64), vh1=a(BH, L, 64), P1=a(BH, L, Lp),
+                                     qh2=a(BH, L, 64), kh2=a(BH, Lc, 64), vh2=a(BH, Lc, 64), P2=a(BH, L, Lcp))
         ws = dict(
             layers=per_layer, x_out=f(B, L, D), hf=a(M, D), logits=f(B, L, K), cond=a(Mc, self.Cd), kv_all=a(Mc, NL * 2 * D),
             arange=torch.arange(B, dtype=torch.int64, device=self.device),
@@ -142,13 +147,15 @@ class DenoiserTrainEngine:
             cond_in=f(Mc, self.Cd), dlogits=f(B, L, K), scale=torch.ones(1, dtype=torch.float32, device=self.device),
             grad_flat=torch.zeros(self._grad_layout()[1], dtype=torch.float32, device=self.device),
             # scratch shared by every layer
-            S=f(BH, L, Lp), vT=a(BH, 64, Lp), oh=a(BH, L, 64),
             dx=f(B, L, D), dy=a(M, D), dbig=a(M, Dh), dbig2=a(M, Dh), dh=f(M, D), dqkv=a(M, 3 * D), dq2=a(M, D), datt=a(M, D),
             dkv_all=a(Mc, NL * 2 * D), dlog=a(M, K),
-            yT=a(max(Dh, 3 * D, K), Mp), xT=a(max(Dh, D), Mp), ykvT=a(NL * 2 * D, Mcp), condT=a(self.Cd, Mcp),
-            doh=a(BH, L, 64), dP=f(BH, L, Lp), dS=a(BH, L, Lp), PT=a(BH, Lp, Lp), doT=a(BH, 64, Lp), kT=a(BH, 64, Lp), qT=a(BH, 64, Lp),
-            dST=a(BH, Lp, Lp), dqh=a(BH, L, 64), dkh=a(BH, L, 64), dvh=a(BH, L, 64),
+            delta=f(BH, L),
             dtab=f(B, 2 * D), dtabT=f(2 * D, Bp), sT=f(D, Bp), ds=f(B, D), de=f(B, D))
+        if not self.mn:  # composed-attention / explicit-transpose scratch of the tf32 accuracy mode
+            ws.update(S=f(BH, L, Lp), vT=a(BH, 64, Lp), oh=a(BH, L, 64),
+                      yT=a(max(Dh, 3 * D, K), Mp), xT=a(max(Dh, D), Mp), ykvT=a(NL * 2 * D, Mcp), condT=a(self.Cd, Mcp),
+                      doh=a(BH, L, 64), dP=f(BH, L, Lp), dS=a(BH, L, Lp), PT=a(BH, Lp, Lp), doT=a(BH, 64, Lp), kT=a(BH, 64, Lp), qT=a(BH, 64, Lp),
+                      dST=a(BH, Lp, Lp), dqh=a(BH, L, 64), dkh=a(BH, L, 64), dvh=a(BH, L, 64))
         ws["grads"] = self._grad_views(ws["grad_flat"])
         self._ws[key] = ws
         return ws
@@ -270,13 +277,19 @@ class DenoiserTrainEngine:
             ops.ada_layernorm(x1, sv["tab1"], ar, out=sv["h1"].view(B, L, D), eps=1e-5, round_out=rnd)
             self._lin(sv["h1"], lay["wqkv"], lay["bqkv"], sv["qkv"])
             qkv = sv["qkv"]
-            self._attn_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], sv["att1"], sv["qh1"], sv["kh1"], sv["vh1"], sv["P1"], ws, B, L, L)
+            if self.mn:
+                T.attention_train_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], sv["att1"], sv["lse1"], B, self.H, L, L, 0.125)
+            else:
+                self._attn_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], sv["att1"], sv["qh1"], sv["kh1"], sv["vh1"], sv["P1"], ws, B, L, L)
             self._lin(sv["att1"], lay["wo1"], blk.attn1.proj.bias.detach(), x2.view(B * L, D), residual=x1.view(B * L, D))
             self._ada_table(blk.ln1_1, self._t, sv["e2"], sv["s2"], sv["tab2"])
             ops.ada_layernorm(x2, sv["tab2"], ar, out=sv["h2"].view(B, L, D), eps=1e-5, round_out=rnd)
             self._lin(sv["h2"], lay["wq2"], blk.attn2.query.bias.detach(), sv["q2"])
             kv = ws["kv_all"][:, li * 2 * D:(li + 1) * 2 * D]
-            self._attn_fwd(sv["q2"], kv[:, :D], kv[:, D:], sv["att2"], sv["qh2"], sv["kh2"], sv["vh2"], sv["P2"], ws, B, L, Lc)
+            if self.mn:
+                T.attention_train_fwd(sv["q2"], kv[:, :D], kv[:, D:], sv["att2"], sv["lse2"], B, self.H, L, Lc, 0.125)
+            else:
+                self._attn_fwd(sv["q2"], kv[:, :D], kv[:, D:], sv["att2"], sv["qh2"], sv["kh2"], sv["vh2"], sv["P2"], ws, B, L, Lc)
             self._lin(sv["att2"], lay["wo2"], blk.attn2.proj.bias.detach(), x3.view(B * L, D), residual=x2.view(B * L, D))
             ops.layernorm(x3, blk.ln2.weight.detach(), blk.ln2.bias.detach(), out=sv["h3"].view(B, L, D), eps=blk.ln2.eps, round_out=rnd)
             self._lin(sv["h3"], lay["w1"], blk.mlp[0].bias.detach(), sv["u"])
@@ -415,14 +428,24 @@ class DenoiserTrainEngine:
             T.cast_scale(dx.view(M, D), ws["dy"])
             self._linear_bwd(ws["dy"], sv["att2"], lay["wo2"], lay["wo2T"], grads[p + "attn2.proj.weight"], grads[p + "attn2.proj.bias"], ws["datt"], ws)
             dkv = dkv_all[:, li * 2 * D:(li + 1) * 2 * D]
-            self._attn_bwd(ws["datt"], ws["dq2"], dkv[:, :D], dkv[:, D:], sv["qh2"], sv["kh2"], sv["vh2"], sv["P2"], ws, B, L, Lc)
+            if self.mn:
+                kv = ws["kv_all"][:, li * 2 * D:(li + 1) * 2 * D]
+                T.attention_train_bwd(sv["q2"], kv[:, :D], kv[:, D:], sv["att2"], ws["datt"], sv["lse2"], ws["delta"], ws["dq2"], dkv[:, :D], dkv[:, D:],
+                                      B, self.H, L, Lc, 0.125)
+            else:
+                self._attn_bwd(ws["datt"], ws["dq2"], dkv[:, :D], dkv[:, D:], sv["qh2"], sv["kh2"], sv["vh2"], sv["P2"], ws, B, L, Lc)
             self._linear_bwd(ws["dq2"], sv["h2"], lay["wq2"], lay["wq2T"], grads[p + "attn2.query.weight"], grads[p + "attn2.query.bias"], ws["dh"], ws)
             self._ada_bwd(blk.ln1_1, lay["lin2T"], sv["x2"], ws["dh"], sv["e2"], sv["s2"], sv["tab2"], grads, p + "ln1_1.", ws, B)
             # ---- self-attention: x2 = x1 + Wo1 attn(qkv)
             T.cast_scale(dx.view(M, D), ws["dy"])
             self._linear_bwd(ws["dy"], sv["att1"], lay["wo1"], lay["wo1T"], grads[p + "attn1.proj.weight"], grads[p + "attn1.proj.bias"], ws["datt"], ws)
             dqkv = ws["dqkv"]
-            self._attn_bwd(ws["datt"], dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], sv["qh1"], sv["kh1"], sv["vh1"], sv["P1"], ws, B, L, L)
+            if self.mn:
+                qkv = sv["qkv"]
+                T.attention_train_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], sv["att1"], ws["datt"], sv["lse1"], ws["delta"],
+                                      dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], B, self.H, L, L, 0.125)
+            else:
+                self._attn_bwd(ws["datt"], dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], sv["qh1"], sv["kh1"], sv["vh1"], sv["P1"], ws, B, L, L)
             self._linear_bwd(dqkv, sv["h1"], lay["wqkv"], lay["wqkvT"], grads[f"_qkv_w.{li}"], grads[f"_qkv_b.{li}"], ws["dh"], ws)
             self._ada_bwd(blk.ln1, lay["lin1T"], sv["x1"], ws["dh"], sv["e1"], sv["s1"], sv["tab1"], grads, p + "ln1.", ws, B)
         # ---- cross-attention K/V projections of every layer in one wgrad: kv_all = cond Wkv^T + b

@@ -148,3 +148,19 @@ def embed_bwd(ids, dx, demb, dheight, dwidth):
     D = dx.shape[-1]
     _lib.check(_lib.lib().dsb_embed_bwd(ids.data_ptr(), dx.data_ptr(), demb.data_ptr(), dheight.data_ptr(), dwidth.data_ptr(), B, L, D,
                                         dheight.shape[0], dwidth.shape[0], demb.shape[0], _stream()), "dsb_embed_bwd")
+
+
+def attention_train_fwd(q, k, v, o, lse, B: int, H: int, Lq: int, Lk: int, scale: float):
+    """Fused bf16 attention forward on token-major row-strided views (head h = columns [64h, 64h+64)); writes o and lse (B*H, Lq)."""
+    _need_cuda(q, k, v, o, lse)
+    _lib.check(_lib.lib().dsb_attention_train_fwd(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), o.data_ptr(), o.stride(0),
+                                                  lse.data_ptr(), B, H, Lq, Lk, scale, _stream()), "dsb_attention_train_fwd")
+    return o
+
+
+def attention_train_bwd(q, k, v, o, dout, lse, delta, dq, dk, dv, B: int, H: int, Lq: int, Lk: int, scale: float):
+    _need_cuda(q, k, v, o, dout, lse, delta, dq, dk, dv)
+    _lib.check(_lib.lib().dsb_attention_train_bwd(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), o.data_ptr(), o.stride(0),
+                                                  dout.data_ptr(), dout.stride(0), lse.data_ptr(), delta.data_ptr(), dq.data_ptr(), dq.stride(0),
+                                                  dk.data_ptr(), dk.stride(0), dv.data_ptr(), dv.stride(0), B, H, Lq, Lk, scale, _stream()),
+               "dsb_attention_train_bwd")
