@@ -323,3 +323,35 @@ def test_content_conditioned_sampling_runs(G, TO):
     x29 = m.q_sample(O.index_to_log_onehot(tok.cpu(), K + 1).cuda(), torch.full((B,), 29, device="cuda", dtype=torch.long), return_index=True)
     frac_masked = float((x29 == K).float().mean())
     assert 0.15 < frac_masked < 0.40 and float((x29[x29 != K] == tok[x29 != K]).float().mean()) > 0.9
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk", [(2, 4, 265, 265), (3, 2, 265, 77), (1, 1, 100, 64), (2, 3, 64, 130)])
+def test_fused_attention_forward_backward_match_autograd(G, TO, B, H, Lq, Lk):
+    """csrc/attention_train.cu on strided token-major views (as the engine calls it) vs torch autograd on the same bf16-rounded inputs."""
+    g = torch.Generator().manual_seed(B * 1000 + Lq + Lk)
+    D = H * 64
+    qkv = (torch.randn(B * Lq, 3 * D + 8, generator=g) * 1.5).bfloat16().cuda()       # q lives in a wider buffer, like the QKV GEMM output
+    kv = (torch.randn(B * Lk, 2 * D, generator=g) * 1.5).bfloat16().cuda()
+    dout = torch.randn(B * Lq, D, generator=g).bfloat16().cuda()
+    q, k, v = qkv[:, 8:8 + D], kv[:, :D], kv[:, D:]
+    o = torch.empty(B * Lq, D, dtype=torch.bfloat16, device="cuda")
+    lse = torch.empty(B * H, Lq, device="cuda")
+    TO.attention_train_fwd(q, k, v, o, lse, B, H, Lq, Lk, 0.125)
+    heads = lambda x, L: x.float().reshape(B, L, H, 64).permute(0, 2, 1, 3).detach().clone().requires_grad_(True)
+    qr, kr, vr = heads(q, Lq), heads(k, Lk), heads(v, Lk)
+    s = (qr @ kr.transpose(-1, -2)) * 0.125
+    oref = torch.softmax(s, -1) @ vr
+    unheads = lambda x, L: x.permute(0, 2, 1, 3).reshape(B * L, D)
+    assert G.relerr(o.float(), unheads(oref, Lq).detach()) < 1e-2
+    assert float((lse.reshape(B, H, Lq) - torch.logsumexp(s, -1).detach() * 1.4426950408889634).abs().max()) < 2e-3
+    oref.backward(heads(dout, Lq).detach())
+    dq = torch.zeros(B * Lq, 3 * D + 8, dtype=torch.bfloat16, device="cuda")
+    dkv = torch.zeros(B * Lk, 2 * D, dtype=torch.bfloat16, device="cuda")
+    delta = torch.empty(B * H, Lq, device="cuda")
+    TO.attention_train_bwd(q, k, v, o, dout, lse, delta, dq[:, 8:8 + D], dkv[:, :D], dkv[:, D:], B, H, Lq, Lk, 0.125)
+    e_q = G.relerr(dq[:, 8:8 + D].float(), unheads(qr.grad, Lq))
+    e_k = G.relerr(dkv[:, :D].float(), unheads(kr.grad, Lk))
+    e_v = G.relerr(dkv[:, D:].float(), unheads(vr.grad, Lk))
+    print(f"fused attention B={B} H={H} Lq={Lq} Lk={Lk}: dq {e_q:.2e} dk {e_k:.2e} dv {e_v:.2e}")
+    assert e_q < 1.5e-2 and e_k < 1.5e-2 and e_v < 1.5e-2
+    assert float(dq[:, :8].float().abs().max()) == 0.0 and float(dq[:, 8 + D:].float().abs().max()) == 0.0   # nothing outside the head columns
