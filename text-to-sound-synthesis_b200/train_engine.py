@@ -449,7 +449,7 @@ class DenoiserTrainEngine:
             self._linear_bwd(dqkv, sv["h1"], lay["wqkv"], lay["wqkvT"], grads[f"_qkv_w.{li}"], grads[f"_qkv_b.{li}"], ws["dh"], ws)
             self._ada_bwd(blk.ln1, lay["lin1T"], sv["x1"], ws["dh"], sv["e1"], sv["s1"], sv["tab1"], grads, p + "ln1.", ws, B)
         # ---- cross-attention K/V projections of every layer in one wgrad: kv_all = cond Wkv^T + b
-        self._linear_bwd(dkv_all, ws["cond"], None, None, grads["_kv_w"], grads["_kv_b"], None, ws, yT=ws["ykvT"], xT=ws["condT"])
+        self._linear_bwd(dkv_all, ws["cond"], None, None, grads["_kv_w"], grads["_kv_b"], None, ws, yT=ws.get("ykvT"), xT=ws.get("condT"))
         # ---- embedding
         for n in ("content_emb.emb.weight", "content_emb.height_emb.weight", "content_emb.width_emb.weight"):
             grads[n].zero_()
