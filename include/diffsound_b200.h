@@ -233,12 +233,13 @@ int dsb_gelu2_bwd(const void* u, const void* da, void* du, long long n, int dtyp
 int dsb_silu_bwd(const float* x, const float* dy, float* dx, long long n, void* stream);
 int dsb_gather_rows(const float* table, const int64_t* idx, float* out, int n, int D, void* stream);
 int dsb_scatter_add_rows(float* table, const int64_t* idx, const float* src, int n, int D, void* stream);
-/* LayerNorm backward: dx_io += dLN/dx (dx_io already holds the residual branch's gradient); dgamma / dbeta are ACCUMULATED. */
+/* LayerNorm backward: dx_io += dLN/dx (dx_io already holds the residual branch's gradient); dgamma / dbeta are ACCUMULATED.
+ * dx_act (optional): also write the updated dx_io in the activation dtype (the dY operand of the next Linear backward). */
 int dsb_layernorm_bwd(const float* x, const float* dy, float* dx_io, const float* gamma, float* dgamma, float* dbeta, long long rows, int D,
-                      float eps, void* stream);
+                      float eps, void* dx_act, int dtype, void* stream);
 /* AdaLayerNorm backward: table (n, 2D) = (scale | shift) rows selected by idx[b]; dtable (same shape) is ACCUMULATED. */
 int dsb_ada_layernorm_bwd(const float* x, const float* dy, float* dx_io, const float* table, const int64_t* idx, float* dtable, int B, int L,
-                          int D, float eps, void* stream);
+                          int D, float eps, void* dx_act, int dtype, void* stream);
 /* attention rows: P = softmax(S) and dS = alpha * P * (dP - sum(dP * P)) */
 int dsb_softmax_fwd(const float* S, long long ld_s, void* P, long long ld_p, long long rows, int n, int dtype, void* stream);
 int dsb_softmax_bwd(const void* P, long long ld_p, const float* dP, long long ld_dp, void* dS, long long ld_ds, long long rows, int n,

@@ -111,8 +111,10 @@ def test_layernorm_backward_plain_and_ada(G, TO, D):
     dx = torch.randn(B, L, D, device="cuda")
     dx0 = dx.clone()
     dg, db = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
-    TO.layernorm_bwd(x, dy, dx, gamma, dg, db)
+    dxa = torch.empty(B, L, D, device="cuda", dtype=torch.bfloat16)
+    TO.layernorm_bwd(x, dy, dx, gamma, dg, db, dx_act=dxa)
     assert G.relerr(dx - dx0, xr.grad) < 1e-4
+    assert torch.equal(dxa, dx.bfloat16())  # the fused activation-dtype copy of the updated stream gradient
     assert G.relerr(dg, gr.grad) < 1e-4 and G.relerr(db, br.grad) < 1e-4
     # AdaLN: y = LN(x) (1 + scale[idx[b]]) + shift[idx[b]]; rows of the table selected by idx, two batch elements share a row
     table = 0.2 * torch.randn(4, 2 * D, device="cuda")
@@ -122,8 +124,10 @@ def test_layernorm_backward_plain_and_ada(G, TO, D):
     (torch.nn.functional.layer_norm(xr, (D,)) * (1 + sel[:, None, :D]) + sel[:, None, D:]).backward(dy)
     dx = torch.zeros(B, L, D, device="cuda")
     dtab = torch.zeros_like(table)
-    TO.ada_layernorm_bwd(x, dy, dx, table, idx, dtab)
+    dxa = torch.empty(B, L, D, device="cuda")
+    TO.ada_layernorm_bwd(x, dy, dx, table, idx, dtab, dx_act=dxa)
     assert G.relerr(dx, xr.grad) < 1e-4
+    assert torch.equal(dxa, G.tf32_round_ref(dx.cpu()).cuda())
     assert G.relerr(dtab, tr.grad) < 1e-4
 
 

@@ -65,8 +65,8 @@ SIGNATURES = {
     "dsb_silu_bwd": [c_vp, c_vp, c_vp, c_ll, c_vp],
     "dsb_gather_rows": [c_vp, c_vp, c_vp, c_i, c_i, c_vp],
     "dsb_scatter_add_rows": [c_vp, c_vp, c_vp, c_i, c_i, c_vp],
-    "dsb_layernorm_bwd": [c_vp] * 6 + [c_ll, c_i, c_f, c_vp],
-    "dsb_ada_layernorm_bwd": [c_vp] * 6 + [c_i, c_i, c_i, c_f, c_vp],
+    "dsb_layernorm_bwd": [c_vp] * 6 + [c_ll, c_i, c_f, c_vp, c_i, c_vp],
+    "dsb_ada_layernorm_bwd": [c_vp] * 6 + [c_i, c_i, c_i, c_f, c_vp, c_i, c_vp],
     "dsb_softmax_fwd": [c_vp, c_ll, c_vp, c_ll, c_ll, c_i, c_i, c_vp],
     "dsb_softmax_bwd": [c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_ll, c_i, c_f, c_i, c_vp],
     "dsb_embed_bwd": [c_vp] * 5 + [c_i] * 6 + [c_vp],

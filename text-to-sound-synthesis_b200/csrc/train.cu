@@ -376,7 +376,8 @@ constexpr int LNB_ROWS = 32;
 template <int MODE, int NV>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dx_io, const float* __restrict__ p0,
-                     const int64_t* __restrict__ idx, float* __restrict__ dg_out, float* __restrict__ db_out, int L, int D, float eps) {
+                     const int64_t* __restrict__ idx, float* __restrict__ dg_out, float* __restrict__ db_out, int L, int D, float eps,
+                     void* __restrict__ dx_act, int act_mode /*0 none, 1 fp32 tf32-rounded, 2 bf16*/) {
   __shared__ float red[2][8][128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
@@ -427,6 +428,16 @@ layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, 
       o.x += rstd * (d[j].x - m1 - v[j].x * m2); o.y += rstd * (d[j].y - m1 - v[j].y * m2);
       o.z += rstd * (d[j].z - m1 - v[j].z * m2); o.w += rstd * (d[j].w - m1 - v[j].w * m2);
       dxr[lane + 32 * j] = o;
+      // the updated stream gradient is the next Linear backward's dY: emit its GEMM-operand copy here instead of a separate cast pass
+      if (act_mode == 2) {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(o.x, o.y), h1 = __floats2bfloat162_rn(o.z, o.w);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+        reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(dx_act) + row * D)[lane + 32 * j] = u;
+      } else if (act_mode == 1) {
+        reinterpret_cast<float4*>(reinterpret_cast<float*>(dx_act) + row * D)[lane + 32 * j] =
+            make_float4(round_tf32(o.x), round_tf32(o.y), round_tf32(o.z), round_tf32(o.w));
+      }
     }
   }
   // cross-warp reduction of the parameter gradients, 128 columns (one float4 slot j) at a time
@@ -636,7 +647,7 @@ extern "C" int dsb_colsum(const void* in, long long ld, float* out, long long ro
   cudaStream_t st = (cudaStream_t)stream;
   DSB_REQUIRE(rows > 0 && N > 0, "dsb_colsum: bad shape");
   DSB_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)N * sizeof(float), st));
-  DSB_ACT_CALL(dtype, run_colsum, in, ld, out, rows, N, 256, st);
+  DSB_ACT_CALL(dtype, run_colsum, in, ld, out, rows, N, 64, st);
   return 0;
 }
 
@@ -668,10 +679,12 @@ extern "C" int dsb_scatter_add_rows(float* table, const int64_t* idx, const floa
 
 template <int MODE>
 static int launch_ln_bwd(const float* x, const float* dy, float* dx_io, const float* p0, const int64_t* idx, float* dg, float* db, int B, int L, int D,
-                         float eps, cudaStream_t st) {
+                         float eps, void* dx_act, int dtype, cudaStream_t st) {
+  const int act_mode = dx_act ? (dtype == DSB_DTYPE_BF16 ? 2 : 1) : 0;
+  DSB_REQUIRE(!dx_act || dtype == DSB_DTYPE_BF16 || dtype == DSB_DTYPE_TF32, "layernorm_bwd: dx_act dtype must be DSB_DTYPE_TF32 or DSB_DTYPE_BF16");
   dim3 grid((L + LNB_ROWS - 1) / LNB_ROWS, B);
   switch (D / 128) {
-#define DSB_LNB_CASE(N) case N: layernorm_bwd_kernel<MODE, N><<<grid, 256, 0, st>>>(x, dy, dx_io, p0, idx, dg, db, L, D, eps); break;
+#define DSB_LNB_CASE(N) case N: layernorm_bwd_kernel<MODE, N><<<grid, 256, 0, st>>>(x, dy, dx_io, p0, idx, dg, db, L, D, eps, dx_act, act_mode); break;
     DSB_LNB_CASE(1) DSB_LNB_CASE(2) DSB_LNB_CASE(3) DSB_LNB_CASE(4) DSB_LNB_CASE(5) DSB_LNB_CASE(6) DSB_LNB_CASE(7) DSB_LNB_CASE(8)
 #undef DSB_LNB_CASE
     default: set_error("layernorm_bwd: D=%d unsupported (need D %% 128 == 0 and D <= 1024)", D); return 2;
@@ -680,14 +693,14 @@ static int launch_ln_bwd(const float* x, const float* dy, float* dx_io, const fl
   return 0;
 }
 extern "C" int dsb_layernorm_bwd(const float* x, const float* dy, float* dx_io, const float* gamma, float* dgamma, float* dbeta, long long rows, int D,
-                                 float eps, void* stream) {
+                                 float eps, void* dx_act, int dtype, void* stream) {
   DSB_REQUIRE(D % 128 == 0 && rows > 0 && rows < (1LL << 31), "dsb_layernorm_bwd: bad shape");
-  return launch_ln_bwd<0>(x, dy, dx_io, gamma, nullptr, dgamma, dbeta, 1, (int)rows, D, eps, (cudaStream_t)stream);
+  return launch_ln_bwd<0>(x, dy, dx_io, gamma, nullptr, dgamma, dbeta, 1, (int)rows, D, eps, dx_act, dtype, (cudaStream_t)stream);
 }
 extern "C" int dsb_ada_layernorm_bwd(const float* x, const float* dy, float* dx_io, const float* table, const int64_t* idx, float* dtable, int B, int L,
-                                     int D, float eps, void* stream) {
+                                     int D, float eps, void* dx_act, int dtype, void* stream) {
   DSB_REQUIRE(D % 128 == 0 && B > 0 && L > 0 && B <= 65535, "dsb_ada_layernorm_bwd: bad shape");
-  return launch_ln_bwd<1>(x, dy, dx_io, table, idx, dtable, nullptr, B, L, D, eps, (cudaStream_t)stream);
+  return launch_ln_bwd<1>(x, dy, dx_io, table, idx, dtable, nullptr, B, L, D, eps, dx_act, dtype, (cudaStream_t)stream);
 }
 
 extern "C" int dsb_softmax_fwd(const float* S, long long ld_s, void* P, long long ld_p, long long rows, int n, int dtype, void* stream) {

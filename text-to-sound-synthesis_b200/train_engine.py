@@ -362,7 +362,7 @@ class DenoiserTrainEngine:
         D = self.D
         dtab = ws["dtab"]
         dtab.zero_()
-        T.ada_layernorm_bwd(x, dh.view(x.shape), ws["dx"], tab, ws["arange"], dtab)
+        T.ada_layernorm_bwd(x, dh.view(x.shape), ws["dx"], tab, ws["arange"], dtab, dx_act=ws["dy"])
         Bp = _rup(B, 8)
         dtabT, sT = ws["dtabT"][:, :Bp], ws["sT"][:, :Bp]
         T.transpose(dtab, dtabT)
@@ -411,21 +411,20 @@ class DenoiserTrainEngine:
         dx.zero_()
         lnf = m.to_logits[0]
         grads["to_logits.0.weight"].zero_(); grads["to_logits.0.bias"].zero_()
-        T.layernorm_bwd(ws["x_out"], ws["dh"].view(B, L, D), dx, lnf.weight.detach(), grads["to_logits.0.weight"], grads["to_logits.0.bias"], lnf.eps)
+        T.layernorm_bwd(ws["x_out"], ws["dh"].view(B, L, D), dx, lnf.weight.detach(), grads["to_logits.0.weight"], grads["to_logits.0.bias"], lnf.eps,
+                        dx_act=ws["dy"])  # every LayerNorm backward also emits the stream gradient as the next Linear backward's dY operand
         dkv_all = ws["dkv_all"]
         for li in range(NL - 1, -1, -1):
             blk, lay, sv = m.blocks[li], self.layers[li], ws["layers"][li]
             p = f"blocks.{li}."
             Dh = lay["w1"].shape[0]
             # ---- MLP: x_next = x3 + W2 gelu2(W1 LN2(x3))
-            T.cast_scale(dx.view(M, D), ws["dy"])
             self._linear_bwd(ws["dy"], sv["act"], lay["w2"], lay["w2T"], grads[p + "mlp.2.weight"], grads[p + "mlp.2.bias"], ws["dbig"], ws)
             T.gelu2_bwd(sv["u"], ws["dbig"], ws["dbig2"])
             self._linear_bwd(ws["dbig2"], sv["h3"], lay["w1"], lay["w1T"], grads[p + "mlp.0.weight"], grads[p + "mlp.0.bias"], ws["dh"], ws)
             grads[p + "ln2.weight"].zero_(); grads[p + "ln2.bias"].zero_()
-            T.layernorm_bwd(sv["x3"], ws["dh"].view(B, L, D), dx, blk.ln2.weight.detach(), grads[p + "ln2.weight"], grads[p + "ln2.bias"], blk.ln2.eps)
+            T.layernorm_bwd(sv["x3"], ws["dh"].view(B, L, D), dx, blk.ln2.weight.detach(), grads[p + "ln2.weight"], grads[p + "ln2.bias"], blk.ln2.eps, dx_act=ws["dy"])
             # ---- cross-attention: x3 = x2 + Wo2 attn(q2, kv)
-            T.cast_scale(dx.view(M, D), ws["dy"])
             self._linear_bwd(ws["dy"], sv["att2"], lay["wo2"], lay["wo2T"], grads[p + "attn2.proj.weight"], grads[p + "attn2.proj.bias"], ws["datt"], ws)
             dkv = dkv_all[:, li * 2 * D:(li + 1) * 2 * D]
             if self.mn:
@@ -437,7 +436,6 @@ class DenoiserTrainEngine:
             self._linear_bwd(ws["dq2"], sv["h2"], lay["wq2"], lay["wq2T"], grads[p + "attn2.query.weight"], grads[p + "attn2.query.bias"], ws["dh"], ws)
             self._ada_bwd(blk.ln1_1, lay["lin2T"], sv["x2"], ws["dh"], sv["e2"], sv["s2"], sv["tab2"], grads, p + "ln1_1.", ws, B)
             # ---- self-attention: x2 = x1 + Wo1 attn(qkv)
-            T.cast_scale(dx.view(M, D), ws["dy"])
             self._linear_bwd(ws["dy"], sv["att1"], lay["wo1"], lay["wo1T"], grads[p + "attn1.proj.weight"], grads[p + "attn1.proj.bias"], ws["datt"], ws)
             dqkv = ws["dqkv"]
             if self.mn:

@@ -116,17 +116,20 @@ def scatter_add_rows(table, idx, src):
     return table
 
 
-def layernorm_bwd(x, dy, dx_io, gamma, dgamma, dbeta, eps=1e-5):
+def layernorm_bwd(x, dy, dx_io, gamma, dgamma, dbeta, eps=1e-5, dx_act=None):
+    """dx_act (optional, fp32 or bf16, same shape): also receives the updated dx_io in the activation dtype."""
     D = x.shape[-1]
     _lib.check(_lib.lib().dsb_layernorm_bwd(x.data_ptr(), dy.data_ptr(), dx_io.data_ptr(), gamma.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
-                                            x.numel() // D, D, eps, _stream()), "dsb_layernorm_bwd")
+                                            x.numel() // D, D, eps, _ptr(dx_act), act_code(dx_act) if dx_act is not None else 0, _stream()),
+               "dsb_layernorm_bwd")
     return dx_io
 
 
-def ada_layernorm_bwd(x, dy, dx_io, table, idx, dtable, eps=1e-5):
+def ada_layernorm_bwd(x, dy, dx_io, table, idx, dtable, eps=1e-5, dx_act=None):
     B, L, D = x.shape
     _lib.check(_lib.lib().dsb_ada_layernorm_bwd(x.data_ptr(), dy.data_ptr(), dx_io.data_ptr(), table.data_ptr(), idx.data_ptr(), dtable.data_ptr(),
-                                                B, L, D, eps, _stream()), "dsb_ada_layernorm_bwd")
+                                                B, L, D, eps, _ptr(dx_act), act_code(dx_act) if dx_act is not None else 0, _stream()),
+               "dsb_ada_layernorm_bwd")
     return dx_io
 
 
