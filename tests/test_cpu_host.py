@@ -206,3 +206,51 @@ def test_save_clip_writes_reference_layout(tmp_path):
     val = raw[:, 0] | (raw[:, 1] << 8) | (raw[:, 2] << 16)
     val = np.where(val >= 1 << 23, val - (1 << 24), val)
     assert np.allclose(val / 8388607.0, wav[0, :4].numpy(), atol=2e-7)
+
+
+def test_training_host_logic_without_gpu():
+    """A13 host side on the CPU: optimizer groups of parameters(name=...), sample_time policy, the flat gradient layout of the training engine
+    (every parameter a non-overlapping, correctly shaped view) -- no kernel is launched."""
+    import _pkg
+    _pkg.load()
+    from diffsound_b200.modeling.transformers.diffusion_transformer import DiffusionTransformer
+    K, D, NL = 32, 128, 2
+    m = DiffusionTransformer(
+        content_emb_config=dict(target="diffsound_b200.modeling.embeddings.dalle_mask_image_embedding.DalleMaskImageEmbedding",
+                                params=dict(num_embed=K, spatial_size=(5, 53), embed_dim=D, trainable=True, pos_emb_type="embedding")),
+        condition_emb_config=None,
+        transformer_config=dict(target="diffsound_b200.modeling.transformers.transformer_utils.Text2ImageTransformer",
+                                params=dict(attn_type="selfcross", n_layer=NL, condition_seq_len=77, content_seq_len=265, content_spatial_size=[5, 53],
+                                            n_embd=D, condition_dim=64, n_head=2, attn_pdrop=0.0, resid_pdrop=0.0, block_activate="GELU2",
+                                            timestep_type="adalayernorm", mlp_hidden_times=4)),
+        diffusion_step=100, alpha_init_type="alpha1", auxiliary_loss_weight=5.0e-4, adaptive_auxiliary_loss=True, mask_weight=[1, 1])
+    # optimizer groups (reference diffusion_transformer.py:483-537): Linear weights decayed, everything else not; every parameter exactly once
+    decay, no_decay = m.parameters(name="transformer")
+    assert decay["weight_decay"] == 0.01 and no_decay["weight_decay"] == 0.0
+    ids = [id(p) for p in decay["params"] + no_decay["params"]]
+    assert len(ids) == len(set(ids)) == len(list(m.transformer.parameters()))
+    assert all(p.dim() == 2 for p in decay["params"])
+    assert any(p.shape == (K + 1, D) for p in no_decay["params"])  # the token embedding is an nn.Embedding: not decayed
+    # sample_time (:379-406): uniform until every Lt_count > 10, then importance sampling proportional to sqrt(Lt_history) with entry 0 <- entry 1
+    torch.manual_seed(0)
+    t, pt = m.sample_time(64, "cpu", "importance")
+    assert t.shape == (64,) and torch.all(pt == 0.01) and int(t.max()) < 100
+    m.Lt_count.fill_(11.0)
+    m.Lt_history.copy_(torch.linspace(1.0, 4.0, 100))
+    t, pt = m.sample_time(64, "cpu", "importance")
+    w = torch.sqrt(m.Lt_history + 1e-10) + 0.0001
+    w[0] = w[1]
+    assert torch.allclose(pt, (w / w.sum())[t])
+    # flat gradient layout of the training engine
+    eng = m.transformer.train_engine
+    eng.D, eng.H, eng.n_layer, eng.Cd = D, 2, NL, 64
+    layout, total = eng._grad_layout()
+    views = eng._grad_views(torch.zeros(total))
+    spans = []
+    for n, p in m.transformer.named_parameters():
+        v = views[n]
+        assert v.shape == p.shape and v.is_contiguous(), n
+        spans.append((v.data_ptr(), v.data_ptr() + v.numel() * 4))
+    spans.sort()
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:])), "parameter gradient views overlap"
+    assert all(o % 64 == 0 for _, _, o in layout)

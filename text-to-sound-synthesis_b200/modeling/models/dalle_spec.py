@@ -1,4 +1,4 @@
-"""Drop-in for sound_synthesis/modeling/models/dalle_spec.py::DALLE (inference side): same constructor keys, the same
+"""Drop-in for sound_synthesis/modeling/models/dalle_spec.py::DALLE: same constructor keys, the same
 `generate_content` / `decode_to_img` / `get_ema_model` surface and the same state_dict prefixes (`transformer.*`,
 `content_codec.*`, `first_stage_permuter.*`), so `ckpt["model"]` loads with strict=False and `ckpt["ema"]` overlays
 `get_ema_model()` exactly as generate_samples_batch.py:78-85 does.
@@ -68,8 +68,8 @@ class DALLE(nn.Module):
                 if condition[k] is not None:
                     condition[k] = torch.cat([condition[k] for _ in range(replicate)], dim=0)
         parts = sample_type.split(",")
-        if len(parts) > 1 and parts[1][:1] == "q":
-            raise NotImplementedError("'q' re-sampling (p_sample_with_truncation, reference :135-143) is a 'next' row (SURVEY 8f N1)")
+        # 'top0.85r,q0.3': with probability 0.3 a step's p_sample is applied a second time at the same t (p_sample_with_truncation, reference :135-143)
+        self.transformer.resample_rate = float(parts[1][1:]) if (len(parts) > 1 and parts[1][:1] == "q") else 0.0
         self.transformer.truncation = parts[0] if parts[0][:3] == "top" else None
         emb = condition.get("condition_embed_token", None)
         bsz = (condition["condition_token"] if condition["condition_token"] is not None else emb).shape[0]
@@ -89,5 +89,37 @@ class DALLE(nn.Module):
         p = self.first_stage_permuter
         return (p.H, p.W)
 
+    def parameters(self, recurse=True, name=None):
+        """Reference override (dalle_spec.py:51-62): `name` selects sub-modules ('transformer') and forwards to their own parameters(name=...)."""
+        if name is None or name == "none":
+            return super().parameters(recurse=recurse)
+        params = []
+        for n in name.split("+"):
+            sub = getattr(self, n)
+            try:
+                params += sub.parameters(recurse=recurse, name=n)
+            except TypeError:  # plain nn.Module.parameters has no `name`
+                params += list(sub.parameters(recurse=recurse))
+        return params
+
+    @torch.no_grad()
+    def prepare_content(self, batch, with_mask=False):
+        """Reference :107-126.  Tokenising mels needs the SpecVQGAN encoder (`content_codec.get_tokens`), which is outside this library
+        (SURVEY.md section 8f N4): batches carry pre-tokenised grids under 'content_token' (B, 265) int64, in the transformer's
+        (column-major) order -- exactly what the reference's own prepare_content would hand to the transformer."""
+        if "content_token" in batch:
+            return {"content_token": batch["content_token"].to(self.device)}
+        if hasattr(self.content_codec, "get_tokens"):
+            quant_z, indices = self.content_codec.get_tokens(batch[self.content_info["key"]].to(self.device))
+            return {"content_token": indices, "content_quant": quant_z}
+        raise RuntimeError("DALLE.prepare_content: the content codec has no encoder here; put pre-tokenised 'content_token' (B, L) int64 in the batch")
+
+    @torch.no_grad()
+    def prepare_input(self, batch):
+        inp = self.prepare_condition(batch)
+        inp.update(self.prepare_content(batch))
+        return inp
+
     def forward(self, batch, name="none", **kwargs):
-        raise NotImplementedError("training forward (config 4) is SURVEY.md section 8 row A13 -- after the inference path")
+        """Training / validation step entry (reference :340-351): `Solver.step` calls model(batch=..., return_loss=True, step=...)."""
+        return self.transformer(self.prepare_input(batch), **kwargs)

@@ -95,6 +95,7 @@ class DiffusionTransformer(nn.Module):
         self.register_buffer("Lt_count", torch.zeros(self.num_timesteps))
         # knobs of the fused path (not in the reference): truncation applied inside the sampler kernel, CUDA-graph replay
         self.truncation = None
+        self.resample_rate = 0.0  # 'q' sample types: probability of repeating a step's p_sample at the same t
         self.use_cuda_graph = True
         self._sched_cache = None
         self._graphs = {}
@@ -286,6 +287,9 @@ class DiffusionTransformer(nn.Module):
             t0 = torch.full((batch_size,), start_step - 1, device=self.device, dtype=torch.long)
             x_init = self.q_sample(index_to_log_onehot(content_token, self.num_classes), t0, return_index=True)
         steps = list(range((start_step or self.num_timesteps) - 1, -1, -1))
+        if self.resample_rate > 0:  # host-side coin per step, like the reference's wrapper (python `random`, dalle_spec.py:139-141)
+            import random
+            steps = [s_ for t_ in steps for s_ in ([t_, t_] if random.random() < self.resample_rate else [t_])]
         if self._stages_overridden():
             content_token = self._sample_unfused(cond_emb, batch_size, steps, steps, x_init=x_init)
         else:
@@ -393,7 +397,7 @@ class _DenoiserLoss(torch.autograd.Function):
         res = train_ops.train_loss(logits, x0, x_t, t, pt, dt._sched(), dt.num_timesteps, aux_weight=aux, adaptive=bool(dt.adaptive_auxiliary_loss),
                                    mask_weight=dt.mask_weight, dlogits=dlogits, log_model_prob=prob, hits=hits, lt_history=dt.Lt_history,
                                    lt_count=dt.Lt_count, prob_as_exp=True)
-        ctx.eng, ctx.dlogits, ctx.names = eng, dlogits, names
+        ctx.eng, ctx.dlogits, ctx.names, ctx.forward_id = eng, dlogits, names, eng.forward_id
         loss = res["loss"].clone().reshape(())
         vb = res["vb_loss"].clone()
         if prob is None:
@@ -403,6 +407,9 @@ class _DenoiserLoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gloss, gprob, gvb, ghits):
+        if ctx.forward_id != ctx.eng.forward_id:
+            raise RuntimeError("DiffusionTransformer: backward() of a loss whose activations were overwritten by a later forward(); the training "
+                               "engine keeps one forward's activations (call loss.backward() before the next forward, as Solver.step does)")
         grads = ctx.eng.backward(ctx.dlogits, scale=gloss.detach().float().reshape(1).contiguous())
         return (None,) * 9 + tuple(grads[n] for n in ctx.names)
 

@@ -44,7 +44,8 @@ class DenoiserTrainEngine:
         self.mn = precision == "bf16"
         self._ws: Dict[tuple, dict] = {}
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
-        self.use_cuda_graph = True  # replay forward / backward as two CUDA graphs (~2.5k launches per step otherwise)
+        self.use_cuda_graph = True  # replay forward / backward as two CUDA graphs (~1.5k launches per step otherwise)
+        self.forward_id = 0         # activations live in engine-owned buffers: backward() must follow ITS forward (checked by the caller)
 
     # ------------------------------------------------------------------ small helpers
     @property
@@ -249,6 +250,7 @@ class DenoiserTrainEngine:
         Lc = cond_emb.shape[1]
         ws = self.workspace(B, L, Lc)
         self._shape = (B, L, Lc)
+        self.forward_id += 1
         ws["ids"].copy_(ids)
         ws["t"].copy_(t)
         ws["cond_in"].copy_(cond_emb.detach().reshape(B * Lc, -1))
