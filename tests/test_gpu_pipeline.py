@@ -67,3 +67,42 @@ def test_text_to_wav_pipeline_matches_oracle_stagewise():
     # the reference's skip-step sampler ('top0.85r,fast3': 25 denoiser calls) through the same entry point
     fast = dalle.generate_content(batch={"condition_embed": cond}, filter_ratio=0, sample_type="top0.85r,fast3")
     assert fast["content"].shape == (B, 1, 80, 848) and int(fast["content_token"].max()) < K
+
+
+def test_dalle_training_step_and_q_resampling_through_reference_config():
+    """Solver.step's call (solver_spec.py:286-320) on the drop-in DALLE built from a reference-style config: model(batch=..., return_loss=True)
+    -> loss.backward() -> optimizer over model.parameters(name='transformer'); plus the 'q' sample type (repeated p_sample at the same t)."""
+    import random
+    import _pkg
+    _pkg.load()
+    from diffsound_b200.utils.misc import instantiate_from_config, retarget_config
+    K, D, NL, NH, CD, B = 64, 128, 2, 2, 64, 3
+    torch.manual_seed(0)
+    dalle = instantiate_from_config(retarget_config(_config(K, D, NL, NH, CD))).cuda().train()
+    assert not dalle.content_codec.training  # the codec's .train is disabled, as in the reference (:17-20, :48)
+    groups = dalle.parameters(name="transformer")
+    opt = torch.optim.AdamW(groups, lr=1e-3, betas=(0.9, 0.96))
+    g = torch.Generator().manual_seed(1)
+    batch = {"content_token": torch.randint(0, K, (B, 265), generator=g), "condition_embed": torch.randn(B, 77, CD, generator=g)}
+    losses = []
+    for _ in range(6):
+        torch.manual_seed(5)
+        out = dalle(batch=batch, name="transformer", return_loss=True, step=0)
+        opt.zero_grad()
+        out["loss"].backward()
+        opt.step()
+        losses.append(float(out["loss"].detach()))
+    assert losses[-1] < losses[0], losses
+    stale = dalle(batch=batch, return_loss=True)["loss"]
+    dalle(batch=batch, return_loss=True)
+    with pytest.raises(RuntimeError, match="overwritten by a later forward"):
+        stale.backward()
+    # 'q' re-sampling: with rate 1 every step runs twice -> 200 denoiser calls; same seeds -> same tokens as calling it again
+    random.seed(3); torch.manual_seed(9)
+    a = dalle.generate_content(batch=batch, filter_ratio=0, sample_type="top0.85r,q1.0")["content_token"]
+    assert dalle.transformer.resample_rate == 1.0 and dalle.transformer.last_gpu_launches == 200 * (dalle.transformer.transformer.engine.launches_per_forward + 1)
+    random.seed(3); torch.manual_seed(9)
+    b = dalle.generate_content(batch=batch, filter_ratio=0, sample_type="top0.85r,q1.0")["content_token"]
+    assert torch.equal(a, b) and int(a.max()) < K
+    dalle.generate_content(batch=batch, filter_ratio=0, sample_type="top0.85r")
+    assert dalle.transformer.resample_rate == 0.0
