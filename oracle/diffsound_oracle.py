@@ -386,6 +386,40 @@ def decoder_forward(sd, z: Tensor, *, ch_mult=(1, 1, 2, 2, 4), num_res_blocks=2,
     return _conv(sd, p + "conv_out.", _swish(_gn(sd, p + "norm_out.", h)), 1)
 
 
+# --------------------------------------------------------------------------------------------
+# N4: SpecVQGAN encoder + nearest-codebook quantiser = DALLE.get_tokens (training-side tokeniser)
+# --------------------------------------------------------------------------------------------
+def encoder_forward(sd, x: Tensor, *, ch_mult=(1, 1, 2, 2, 4), num_res_blocks=2, prefix="content_codec.encoder.") -> Tensor:
+    """Encoder.forward (specvqgan/modules/diffusionmodules/model.py:476-500); Downsample = zero pad (0,1,0,1) + 3x3 stride-2 conv (:55-75)."""
+    p = prefix
+    h = _conv(sd, p + "conv_in.", x, 1)
+    for lvl in range(len(ch_mult)):
+        for blk in range(num_res_blocks):
+            h = dec_resnet_block(sd, f"{p}down.{lvl}.block.{blk}.", h)
+            if f"{p}down.{lvl}.attn.{blk}.norm.weight" in sd:
+                h = dec_attn_block(sd, f"{p}down.{lvl}.attn.{blk}.", h)
+        if lvl != len(ch_mult) - 1:
+            h = F.conv2d(F.pad(h, (0, 1, 0, 1)), sd[f"{p}down.{lvl}.downsample.conv.weight"], sd[f"{p}down.{lvl}.downsample.conv.bias"], stride=2)
+    h = dec_resnet_block(sd, p + "mid.block_1.", h)
+    h = dec_attn_block(sd, p + "mid.attn_1.", h)
+    h = dec_resnet_block(sd, p + "mid.block_2.", h)
+    return _conv(sd, p + "conv_out.", _swish(_gn(sd, p + "norm_out.", h)), 1)
+
+
+def encode_to_tokens(sd, mel: Tensor, *, ch_mult=(1, 1, 2, 2, 4), num_res_blocks=2, prefix="content_codec."):
+    """VQModel.encode (spec_codec/vqgan.py:48-54) + VectorQuantizer.forward's argmin (quantize.py:56-63) + DALLE.get_tokens' ColumnMajor
+    permutation (dalle_spec.py:71-78, permuter.py:41-49).  Returns (z after quant_conv (B,E,H,W), token ids (B, H*W) in the transformer's order)."""
+    h = encoder_forward(sd, mel, ch_mult=ch_mult, num_res_blocks=num_res_blocks, prefix=prefix + "encoder.")
+    z = _conv(sd, prefix + "quant_conv.", h, 0)
+    B, E, H, W = z.shape
+    zf = z.permute(0, 2, 3, 1).reshape(-1, E)
+    emb = sd[prefix + "quantize.embedding.weight"]
+    d = torch.sum(zf ** 2, dim=1, keepdim=True) + torch.sum(emb ** 2, dim=1) - 2 * torch.matmul(zf, emb.t())
+    idx = torch.argmin(d, dim=1).view(B, H * W)                         # row-major (h * W + w)
+    col_major = torch.arange(H * W).reshape(H, W).t().reshape(-1)       # ColumnMajor.forward: x[:, idx]
+    return z, idx[:, col_major]
+
+
 def decode_to_img(sd, ids: Tensor, *, grid=(5, 53), embed_dim=256, ch_mult=(1, 1, 2, 2, 4), num_res_blocks=2,
                   prefix="content_codec.") -> Tensor:
     """DALLE.decode_to_img (dalle_spec.py:80-91): ids (B,L) -> mel (B,1,16H,16W)."""

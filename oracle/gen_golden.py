@@ -162,6 +162,31 @@ def gen_decoder_tiny():
     print("decoder_tiny: mel", tuple(mel.shape), float(mel.abs().max()))
 
 
+def gen_encoder_tiny():
+    """N4: the reference tokeniser DALLE.get_tokens (SpecVQGAN Encoder + quant_conv + nearest code + ColumnMajor) on a tiny config."""
+    K = 32
+    model, _ = rh.build_dalle(K=K, overrides=dict(n_layer=1, n_embd=64, n_head=1, dec_ch=32, dec_ch_mult=[1, 1, 1, 1, 2],
+                                                  dec_z_channels=64, embed_dim=64, grid=(2, 7)), seed=3)
+    g = torch.Generator().manual_seed(21)
+    cc = model.content_codec
+    for n_, p_ in cc.encoder.named_parameters():
+        if n_.endswith("bias"):
+            p_.add_(torch.randn(p_.shape, generator=g) * 0.05)
+    mel = torch.rand(2, 1, 32, 112, generator=g) * 2 - 1
+    z0 = cc.quant_conv(cc.encoder(mel))
+    # a random-init codebook is U(-1/K, 1/K): every latent would map to the same code.  Give the codes the latents' own statistics
+    # (per-channel mean + spread) so that the argmin is exercised with realistic margins.
+    zf = z0.permute(0, 2, 3, 1).reshape(-1, 64)
+    cc.quantize.embedding.weight.copy_(zf.mean(0, keepdim=True) + torch.randn(K, 64, generator=g) * zf.std(0, keepdim=True))
+    quant_z, tokens = model.get_tokens(mel)
+    z = cc.quant_conv(cc.encoder(mel))
+    sd = {k: v for k, v in model.state_dict().items()
+          if k.startswith("content_codec.encoder.") or k.startswith("content_codec.quant_conv.") or k.startswith("content_codec.quantize.")}
+    np.savez_compressed(os.path.join(GOLD, "encoder_tiny.npz"), in_mel=mel.numpy(), out_z=z.numpy(), out_tokens=tokens.numpy().astype(np.int16),
+                        out_quant=quant_z.numpy(), __cfg=np.array([K, 64, 32, 2, 7]), **{"sd." + k: v.numpy() for k, v in sd.items()})
+    print("encoder_tiny: z", tuple(z.shape), "tokens", tokens[0].tolist())
+
+
 def gen_melgan():
     rh.install_shims()
     from vocoder.modules import Generator
@@ -202,6 +227,7 @@ if __name__ == "__main__":
     gen_train_tiny(gen_xf_tiny())
     gen_sampler_cases()
     gen_decoder_tiny()
+    gen_encoder_tiny()
     gen_melgan()
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)) // 1024, "KB")

@@ -120,3 +120,13 @@ def test_train_loss_and_gradients_match_reference():
         ref = torch.from_numpy(g["grad." + n])
         err = (leaf[n].grad - ref).abs().max() / ref.abs().max().clamp_min(1e-12)
         assert err < 5e-4, (n, float(err))
+
+
+def test_encoder_tokeniser_matches_reference():
+    """N4: oracle SpecVQGAN encoder + nearest-code quantiser + ColumnMajor permutation vs the reference's DALLE.get_tokens."""
+    sd, g = load_golden("encoder_tiny.npz")
+    z, tok = O.encode_to_tokens(sd, torch.from_numpy(g["in_mel"]), ch_mult=(1, 1, 1, 1, 2))
+    ref_z = torch.from_numpy(g["out_z"])
+    assert (z - ref_z).abs().max() <= 1e-5 * ref_z.abs().max()
+    assert torch.equal(tok, torch.from_numpy(g["out_tokens"]).long())
+    assert len(set(tok.flatten().tolist())) > 8  # the golden exercises many codes, not one
