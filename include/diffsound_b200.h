@@ -187,6 +187,14 @@ int dsb_groupnorm_apply(const float* x, const double* stats, const float* gamma,
 int dsb_upsample2x_padded(const float* in, float* out, int B, int H, int W, int C, int flags, void* stream);
 /* AttnBlock plumbing (model.py:202-226): in-place masked row softmax; scatter-add of (B, Lp, C) tokens into the padded image */
 int dsb_softmax_rows(float* x, long long rows, int n_valid, int ld, int flags, void* stream);
+/* Encoder side of the SpecVQGAN codec (training-time tokeniser):
+ * Downsample (specvqgan/modules/diffusionmodules/model.py:55-75: zero pad (0,1,0,1) + 3x3 stride-2 conv) = this phase rearrangement of the
+ * padded image (B,H+2,W+2,C) into (B,H/2+2,W/2+2,4C) [DSB_SPLIT_OUT: (hi | lo), 8C columns] followed by a 9-tap dsb_gemm_ex with row shifts
+ * (dy/2)(W/2+2) + dx/2 and A column offsets (2(dy%2) + dx%2) C. */
+int dsb_space_to_depth_padded(const float* in, float* out, int B, int H, int W, int C, int flags, void* stream);
+/* VectorQuantizer.forward's nearest code (specvqgan/modules/vqvae/quantize.py:56-63): out[r] = argmin_k x[r, k], first index on ties;
+ * x = |e|^2 - 2 z.e from a GEMM with alpha = -2 and bias = |e|^2. */
+int dsb_row_argmin(const float* x, long long ld, long long rows, int n, int64_t* out, void* stream);
 int dsb_tokens_add_to_padded(const float* tok, float* xpad, int B, int H, int W, int C, int Lp, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------

@@ -46,6 +46,8 @@ SIGNATURES = {
     "dsb_groupnorm_apply": [c_vp] * 5 + [c_i] * 5 + [c_f, c_i, c_i, c_vp],
     "dsb_upsample2x_padded": [c_vp, c_vp] + [c_i] * 5 + [c_vp],
     "dsb_softmax_rows": [c_vp, c_ll, c_i, c_i, c_i, c_vp],
+    "dsb_space_to_depth_padded": [c_vp, c_vp] + [c_i] * 5 + [c_vp],
+    "dsb_row_argmin": [c_vp, c_ll, c_ll, c_i, c_vp, c_vp],
     "dsb_tokens_add_to_padded": [c_vp, c_vp] + [c_i] * 5 + [c_vp],
     "dsb_lrelu_pad": [c_vp, c_vp] + [c_i] * 4 + [c_f, c_i, c_i, c_i, c_vp],
     "dsb_attention_f16": [c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_i, c_i, c_i, c_i, c_f, c_i, c_vp],

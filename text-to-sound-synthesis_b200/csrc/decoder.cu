@@ -160,6 +160,58 @@ __global__ void upsample2x_padded_kernel(const float* __restrict__ in, float* __
   }
 }
 
+// Downsample (model.py:55-75: zero pad (0,1,0,1) + 3x3 stride-2 conv) as a tap GEMM: the padded input (B, H+2, W+2, C) is rearranged into
+// its four stride-2 phases side by side, on the OUTPUT's padded grid (B, H/2+2, W/2+2, 4C):
+//   out[b, i+1, j+1, (2p+q) C + c] = in_unpadded[b, 2i+p, 2j+q, c]   (zero beyond the image: that is the reference's right / bottom pad)
+// so that tap (dy, dx) of the strided conv becomes the constant row shift (dy/2) (W/2+2) + dx/2 with A column offset (2 (dy%2) + dx%2) C.
+// DSB_SPLIT_OUT writes the split-TF32 operand [hi (4C) | lo (4C)].
+__global__ void space_to_depth_padded_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C, int flags) {
+  const int Hi = H + 2, Wi = W + 2, Ho = H / 2 + 2, Wo = W / 2 + 2, c4n = C / 4;
+  const long long total = (long long)B * Ho * Wo * 4 * c4n;
+  const int ocols = (flags & DSB_SPLIT_OUT) ? 8 * C : 4 * C;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c4 = idx % c4n;
+    const int ph = (idx / c4n) % 4;
+    const long long orow = idx / (4 * c4n);
+    const int b = orow / (Ho * Wo);
+    const int pp = orow % (Ho * Wo);
+    const int i = pp / Wo - 1, j = pp % Wo - 1;
+    const int r = 2 * i + (ph >> 1), s_ = 2 * j + (ph & 1);  // unpadded source pixel
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i >= 0 && j >= 0 && r < H && s_ < W) v = *reinterpret_cast<const float4*>(in + (((long long)b * Hi + r + 1) * Wi + s_ + 1) * C + c4 * 4);
+    float* o = out + orow * ocols + ph * C + c4 * 4;
+    if (flags & DSB_SPLIT_OUT) {
+      const float4 hi = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+      *reinterpret_cast<float4*>(o) = hi;
+      *reinterpret_cast<float4*>(o + 4 * C) = make_float4(round_tf32(v.x - hi.x), round_tf32(v.y - hi.y), round_tf32(v.z - hi.z), round_tf32(v.w - hi.w));
+    } else {
+      if (flags & DSB_GEMM_ROUND_TF32) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+      *reinterpret_cast<float4*>(o) = v;
+    }
+  }
+}
+
+// out[r] = argmin_k x[r, k] over the first n columns, first index on ties (VectorQuantizer.forward, quantize.py:56-63); one warp per row
+__global__ void row_argmin_kernel(const float* __restrict__ x, long long ld, long long rows, int n, int64_t* __restrict__ out) {
+  const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* r = x + row * ld;
+  float best = INFINITY;
+  int bi = 0x7fffffff;
+  for (int k = lane; k < n; k += 32) {
+    const float v = r[k];
+    if (v < best) { best = v; bi = k; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  if (lane == 0) out[row] = bi;
+}
+
 // in-place softmax over the first n_valid columns of each row (one warp per row); columns [n_valid, ld) are set to zero
 __global__ void softmax_rows_kernel(float* __restrict__ x, long long rows, int n_valid, int ld, int flags) {
   const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -240,6 +292,19 @@ extern "C" int dsb_upsample2x_padded(const float* in, float* out, int B, int H, 
   DSB_REQUIRE(C % 4 == 0, "dsb_upsample2x_padded: C must be a multiple of 4");
   const long long total = (long long)B * (2 * H + 2) * (2 * W + 2) * (C / 4);
   upsample2x_padded_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(in, out, B, H, W, C, flags);
+  DSB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int dsb_space_to_depth_padded(const float* in, float* out, int B, int H, int W, int C, int flags, void* stream) {
+  DSB_REQUIRE(C % 4 == 0 && H % 2 == 0 && W % 2 == 0, "dsb_space_to_depth_padded: C must be a multiple of 4 and H, W even (H=%d W=%d C=%d)", H, W, C);
+  const long long total = (long long)B * (H / 2 + 2) * (W / 2 + 2) * C;
+  space_to_depth_padded_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(in, out, B, H, W, C, flags);
+  DSB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int dsb_row_argmin(const float* x, long long ld, long long rows, int n, int64_t* out, void* stream) {
+  DSB_REQUIRE(rows > 0 && n > 0 && n <= ld, "dsb_row_argmin: bad shape");
+  row_argmin_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, ld, rows, n, out);
   DSB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -12,6 +12,7 @@ from torch import nn
 
 from .... import ops
 from ....decoder_engine import DecoderEngine
+from ....encoder_engine import EncoderEngine
 
 
 class ColumnMajor(nn.Module):
@@ -66,6 +67,52 @@ class Upsample(_Holder):
         self.with_conv = with_conv
         if with_conv:
             self.conv = nn.Conv2d(c, c, 3, 1, 1)
+
+
+class Downsample(_Holder):
+    def __init__(self, c, with_conv):
+        super().__init__()
+        assert with_conv
+        self.with_conv = with_conv
+        self.conv = nn.Conv2d(c, c, 3, 2, 0)  # applied after a (0,1,0,1) zero pad (model.py:55-75)
+
+
+class Encoder(nn.Module):
+    """Parameter holder with the reference's names (specvqgan/modules/diffusionmodules/model.py:410-475); compute runs in EncoderEngine."""
+
+    def __init__(self, *, ch, out_ch, ch_mult=(1, 2, 4, 8), num_res_blocks, attn_resolutions, dropout=0.0, resamp_with_conv=True, in_channels,
+                 resolution, z_channels, double_z=True, **ignore_kwargs):
+        super().__init__()
+        assert dropout == 0.0 and resamp_with_conv
+        self.ch, self.num_resolutions, self.num_res_blocks = ch, len(ch_mult), num_res_blocks
+        self.conv_in = nn.Conv2d(in_channels, ch, 3, 1, 1)
+        curr_res = resolution
+        in_ch_mult = (1,) + tuple(ch_mult)
+        self.down = nn.ModuleList()
+        block_in = ch
+        for i_level in range(self.num_resolutions):
+            block, attn = nn.ModuleList(), nn.ModuleList()
+            block_in, block_out = ch * in_ch_mult[i_level], ch * ch_mult[i_level]
+            for _ in range(num_res_blocks):
+                block.append(ResnetBlock(block_in, block_out))
+                block_in = block_out
+                if curr_res in attn_resolutions:
+                    attn.append(AttnBlock(block_in))
+            down = nn.Module()
+            down.block, down.attn = block, attn
+            if i_level != self.num_resolutions - 1:
+                down.downsample = Downsample(block_in, True)
+                curr_res = curr_res // 2
+            self.down.append(down)
+        self.mid = nn.Module()
+        self.mid.block_1 = ResnetBlock(block_in, block_in)
+        self.mid.attn_1 = AttnBlock(block_in)
+        self.mid.block_2 = ResnetBlock(block_in, block_in)
+        self.norm_out = Normalize(block_in)
+        self.conv_out = nn.Conv2d(block_in, 2 * z_channels if double_z else z_channels, 3, 1, 1)
+
+    def forward(self, x):
+        raise RuntimeError("call VQModel.encode (EncoderEngine); Encoder only stores parameters")
 
 
 class Decoder(nn.Module):
@@ -125,11 +172,18 @@ class VQModel(nn.Module):
         super().__init__()
         self.image_key = image_key
         self.ddconfig = dict(ddconfig)
+        self.encoder = Encoder(**ddconfig)
         self.decoder = Decoder(**ddconfig)
         self.quantize = VectorQuantizer(n_embed, embed_dim, beta=0.25)
+        self.quant_conv = nn.Conv2d(ddconfig["z_channels"], embed_dim, 1)
         self.post_quant_conv = nn.Conv2d(embed_dim, ddconfig["z_channels"], 1)
         self.engine = DecoderEngine(self, precision=precision)
-        self.register_load_state_dict_post_hook(lambda module, inc: module.engine.__setattr__("packed", False))
+        self.enc_engine = EncoderEngine(self)
+
+        def _stale(module, inc):
+            module.engine.packed = False
+            module.enc_engine.packed = False
+        self.register_load_state_dict_post_hook(_stale)
         if ckpt_path is not None:
             self.init_from_ckpt(ckpt_path, ignore_keys=ignore_keys)
 
@@ -145,10 +199,19 @@ class VQModel(nn.Module):
         out = super()._apply(fn, *a, **k)
         if hasattr(self, "engine"):
             self.engine.packed = False
+        if hasattr(self, "enc_engine"):
+            self.enc_engine.packed = False
         return out
 
+    @torch.no_grad()
     def encode(self, x):
-        raise NotImplementedError("the SpecVQGAN encoder is stage-1 / training-side (SURVEY.md section 8 'next' N4)")
+        """mel (B, 1, H, W) -> (quant (B, E, H/16, W/16), None, (None, None, indices (B*H/16*W/16, 1)))  (vqgan.py:48-54).  The tokeniser is
+        inference-only here (the frozen stage-1 codec of Diffsound training): no commitment loss / perplexity / one-hot encodings."""
+        z, ids = self.enc_engine.encode(x)
+        B, E, Hq, Wq = z.shape
+        quant = self.quantize.get_codebook_entry(ids.reshape(-1), (B, Hq, Wq, E))
+        self.last_latent = z  # pre-quantisation latent, kept for parity checks
+        return quant, None, (None, None, ids.reshape(-1, 1))
 
     @torch.no_grad()
     def decode(self, quant):

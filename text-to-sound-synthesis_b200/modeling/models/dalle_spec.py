@@ -103,16 +103,21 @@ class DALLE(nn.Module):
         return params
 
     @torch.no_grad()
+    def get_tokens(self, spec):
+        """mel (B, 1, 80, 848) -> (quant_z (B, E, 5, 53), token ids (B, 265) in the transformer's column-major order)  (reference :71-78)."""
+        quant_z, _, info = self.content_codec.encode(spec)
+        indices = self.first_stage_permuter(info[2].view(quant_z.shape[0], -1))
+        self.zshape = quant_z.shape
+        return quant_z, indices
+
+    @torch.no_grad()
     def prepare_content(self, batch, with_mask=False):
-        """Reference :107-126.  Tokenising mels needs the SpecVQGAN encoder (`content_codec.get_tokens`), which is outside this library
-        (SURVEY.md section 8f N4): batches carry pre-tokenised grids under 'content_token' (B, 265) int64, in the transformer's
-        (column-major) order -- exactly what the reference's own prepare_content would hand to the transformer."""
+        """Reference :107-126: mels under batch[content_info['key']] are tokenised by the frozen SpecVQGAN encoder (get_tokens); a batch may
+        instead carry pre-tokenised grids under 'content_token' (B, 265) int64 in the transformer's (column-major) order."""
         if "content_token" in batch:
             return {"content_token": batch["content_token"].to(self.device)}
-        if hasattr(self.content_codec, "get_tokens"):
-            quant_z, indices = self.content_codec.get_tokens(batch[self.content_info["key"]].to(self.device))
-            return {"content_token": indices, "content_quant": quant_z}
-        raise RuntimeError("DALLE.prepare_content: the content codec has no encoder here; put pre-tokenised 'content_token' (B, L) int64 in the batch")
+        quant_z, indices = self.get_tokens(batch[self.content_info["key"]].to(self.device))
+        return {"content_token": indices, "content_quant": quant_z}
 
     @torch.no_grad()
     def prepare_input(self, batch):

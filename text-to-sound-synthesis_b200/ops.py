@@ -312,6 +312,25 @@ def upsample2x_padded(x_pad, *, round_out=True, split=False):
     return out
 
 
+def space_to_depth_padded(x_pad, *, split=False, round_out=False):
+    """(B, H+2, W+2, C) zero-bordered image -> its four stride-2 phases on the half-resolution padded grid (B, H/2+2, W/2+2, 4C [8C if split])."""
+    _need_cuda(x_pad)
+    B, Hp, Wp, C = x_pad.shape
+    H, W = Hp - 2, Wp - 2
+    out = torch.empty(B, H // 2 + 2, W // 2 + 2, (8 if split else 4) * C, dtype=torch.float32, device=x_pad.device)
+    _lib.check(_lib.lib().dsb_space_to_depth_padded(x_pad.data_ptr(), out.data_ptr(), B, H, W, C, SPLIT_OUT if split else (ROUND_TF32 if round_out else 0),
+                                                    _stream()), "dsb_space_to_depth_padded")
+    return out
+
+
+def row_argmin(x, n: int):
+    """x: (rows, ld) fp32 -> int64 (rows,) index of the smallest of the first n columns (first on ties)."""
+    _need_cuda(x)
+    out = torch.empty(x.shape[0], dtype=torch.int64, device=x.device)
+    _lib.check(_lib.lib().dsb_row_argmin(x.data_ptr(), x.stride(0), x.shape[0], n, out.data_ptr(), _stream()), "dsb_row_argmin")
+    return out
+
+
 def softmax_rows_(x, n_valid, *, round_out=True):
     _need_cuda(x)
     assert x.is_contiguous()
