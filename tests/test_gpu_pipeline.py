@@ -93,6 +93,14 @@ def test_dalle_training_step_and_q_resampling_through_reference_config():
         opt.step()
         losses.append(float(out["loss"].detach()))
     assert losses[-1] < losses[0], losses
+    # the reference's real training batch: mels under content_info['key'], tokenised on the fly by the frozen SpecVQGAN encoder (get_tokens)
+    mel_batch = {"image": torch.rand(2, 1, 80, 848, generator=g) * 2 - 1, "condition_embed": torch.randn(2, 77, CD, generator=g)}
+    quant_z, toks = dalle.get_tokens(mel_batch["image"].cuda())
+    assert quant_z.shape == (2, 256, 5, 53) and toks.shape == (2, 265) and int(toks.max()) < K and dalle.zshape == quant_z.shape
+    assert dalle.decode_to_img(toks, quant_z.shape).shape == (2, 1, 80, 848)          # tokens round-trip through the decoder entry
+    out = dalle(batch=mel_batch, return_loss=True)
+    out["loss"].backward()
+    assert torch.isfinite(out["loss"]) and out["logits"].shape == (2, K + 1, 265)
     stale = dalle(batch=batch, return_loss=True)["loss"]
     dalle(batch=batch, return_loss=True)
     with pytest.raises(RuntimeError, match="overwritten by a later forward"):
