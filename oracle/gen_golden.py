@@ -187,6 +187,30 @@ def gen_encoder_tiny():
     print("encoder_tiny: z", tuple(z.shape), "tokens", tokens[0].tolist())
 
 
+CAPTIONS = ["A dog barks while a man is talking", "  Rain falls   on a tin roof, thunder in the distance!  ", "someone's typing on a keyboard & it's loud",
+            "Birds chirping; a car passes by (twice) at 60km/h", "A very long caption " + "with many many words " * 30, "", "caf\u00e9 na\u00efve \u00fcber 123 #tag @home",
+            "An engine revving and tires squealing &amp; a crowd cheering"]
+
+
+def gen_tokenizer_cases():
+    """N2 (host side): the reference's SimpleTokenizer + clip.tokenize on a few captions (ftfy is not installed here: a pass-through stub,
+    which is what ftfy.fix_text does on well-formed text)."""
+    import json
+    import types
+    if "ftfy" not in sys.modules:
+        sys.modules["ftfy"] = types.SimpleNamespace(fix_text=lambda t: t)
+    rh.install_shims()
+    from sound_synthesis.modeling.modules.clip.simple_tokenizer import SimpleTokenizer
+    from sound_synthesis.modeling.modules.clip.clip import tokenize
+    tk = SimpleTokenizer(end_idx=49152)
+    out = tokenize(CAPTIONS, context_length=77, add_start_and_end=True, with_mask=True, pad_value=0, tokenizer=tk)
+    raw = [tk.encode(c) for c in CAPTIONS]
+    with open(os.path.join(GOLD, "tokenizer_cases.json"), "w") as f:
+        json.dump({"captions": CAPTIONS, "token": out["token"].tolist(), "mask": out["mask"].int().tolist(), "encode": raw,
+                   "sot": tk.encoder["<|startoftext|>"], "eot": tk.encoder["<|endoftext|>"]}, f)
+    print("tokenizer_cases:", [len(r) for r in raw])
+
+
 def gen_melgan():
     rh.install_shims()
     from vocoder.modules import Generator
@@ -228,6 +252,7 @@ if __name__ == "__main__":
     gen_sampler_cases()
     gen_decoder_tiny()
     gen_encoder_tiny()
+    gen_tokenizer_cases()
     gen_melgan()
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)) // 1024, "KB")

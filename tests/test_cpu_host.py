@@ -254,3 +254,29 @@ def test_training_host_logic_without_gpu():
     spans.sort()
     assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:])), "parameter gradient views overlap"
     assert all(o % 64 == 0 for _, _, o in layout)
+
+
+def test_clip_tokenizer_matches_reference_cases():
+    """N2 host side: the re-implemented CLIP BPE tokenizer + Tokenize codec vs token ids produced by the reference's own SimpleTokenizer /
+    clip.tokenize (tests/golden/tokenizer_cases.json).  Needs the BPE merge table (data, not redistributed here): found in the reference checkout."""
+    import json
+    import _pkg
+    _pkg.load()
+    from diffsound_b200.modeling.modules.clip.simple_tokenizer import SimpleTokenizer, find_vocab
+    from diffsound_b200.modeling.codecs.text_codec.tokenize import Tokenize
+    try:
+        find_vocab()
+    except RuntimeError:
+        pytest.skip("CLIP BPE merge table not available on this machine")
+    with open(os.path.join(ROOT, "tests", "golden", "tokenizer_cases.json")) as f:
+        g = json.load(f)
+    tk = SimpleTokenizer(end_idx=49152)
+    assert tk.encoder["<|startoftext|>"] == g["sot"] and tk.encoder["<|endoftext|>"] == g["eot"] and len(tk.encoder) == 49408
+    for cap, ref in zip(g["captions"], g["encode"]):
+        assert tk.encode(cap) == ref, cap
+    assert tk.decode(tk.encode("A dog barks")).strip() == "a dog barks"
+    codec = Tokenize(context_length=77, add_start_and_end=True, with_mask=True, pad_value=0, clip_embedding=False,
+                     tokenizer_config={"target": "diffsound_b200.modeling.modules.clip.simple_tokenizer.SimpleTokenizer", "params": {"end_idx": 49152}})
+    out = codec.get_tokens(g["captions"])
+    assert out["token"].tolist() == g["token"] and out["mask"].int().tolist() == g["mask"]
+    assert int(out["token"][4, 76]) == g["eot"] and bool(out["mask"][4].all())  # the over-long caption is truncated but keeps <|endoftext|>
