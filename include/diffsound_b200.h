@@ -127,7 +127,9 @@ int dsb_silu(const float* in, float* out, long long n, void* stream);
 int dsb_attention(const float* q, long long ldq, const float* k, long long ldk, const float* v, long long ldv, float* o, long long ldo,
                   int B, int H, int Lq, int Lk, float scale, int flags, void* stream);
 
-/* Same attention core with fp16 q/k/v (row strides in halves, multiples of 8); o is fp16 (DSB_GEMM_OUT_F16) or fp32. */
+/* Same attention core with fp16 q/k/v (row strides in halves, multiples of 8); o is fp16 (DSB_GEMM_OUT_F16) or fp32.
+ * flags | DSB_ATTN_CAUSAL: key j is visible to query i only if j <= i (the CLIP text transformer's mask, clip/model.py build_attention_mask). */
+#define DSB_ATTN_CAUSAL 1024
 int dsb_attention_f16(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o, long long ldo,
                       int B, int H, int Lq, int Lk, float scale, int flags, void* stream);
 

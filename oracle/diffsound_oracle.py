@@ -466,6 +466,50 @@ def melgan_forward(sd, mel: Tensor, *, ratios=(8, 8, 2, 2), n_residual_layers=3,
 # --------------------------------------------------------------------------------------------
 # Deterministic synthetic weights with the reference's key names/shapes
 # --------------------------------------------------------------------------------------------
+# --------------------------------------------------------------------------------------------
+# N2: CLIP text tower as used by Diffsound (CLIPTextEmbedding with pick_last_embedding=False, embed_dim=512, normalize=True)
+# --------------------------------------------------------------------------------------------
+def clip_text_forward(sd, tokens: Tensor, *, n_layer: int, n_head: int = 8, normalize: bool = True, prefix: str = "") -> Tensor:
+    """CLIPTextEmbedding.forward for the Diffsound config (embeddings/clip_text_embedding.py:46-88 with modules/clip/model.py:166-199):
+    token + positional embedding, n_layer pre-LN residual blocks (causal multi-head attention, QuickGELU MLP), ln_final, per-token L2 norm."""
+    p = prefix
+    tok = tokens.clamp_min(0)                                                       # text[text < 0] = 0
+    x = F.embedding(tok, sd[p + "token_embedding.weight"]) + sd[p + "positional_embedding"]
+    B, L, D = x.shape
+    hs = D // n_head
+    mask = torch.full((L, L), float("-inf")).triu_(1)
+    for i in range(n_layer):
+        b = f"{p}transformer.resblocks.{i}."
+        h = F.layer_norm(x, (D,), sd[b + "ln_1.weight"], sd[b + "ln_1.bias"])
+        qkv = F.linear(h, sd[b + "attn.in_proj_weight"], sd[b + "attn.in_proj_bias"])
+        q, k, v = [t.view(B, L, n_head, hs).transpose(1, 2) for t in qkv.chunk(3, dim=-1)]
+        att = F.softmax((q @ k.transpose(-2, -1)) * (1.0 / math.sqrt(hs)) + mask, dim=-1)
+        y = (att @ v).transpose(1, 2).reshape(B, L, D)
+        x = x + F.linear(y, sd[b + "attn.out_proj.weight"], sd[b + "attn.out_proj.bias"])
+        h = F.layer_norm(x, (D,), sd[b + "ln_2.weight"], sd[b + "ln_2.bias"])
+        x = x + F.linear(gelu2(F.linear(h, sd[b + "mlp.c_fc.weight"], sd[b + "mlp.c_fc.bias"])), sd[b + "mlp.c_proj.weight"], sd[b + "mlp.c_proj.bias"])
+    x = F.layer_norm(x, (D,), sd[p + "ln_final.weight"], sd[p + "ln_final.bias"])
+    return x / x.norm(dim=-1, keepdim=True) if normalize else x
+
+
+def make_clip_text_state_dict(*, n_layer=12, width=512, vocab=49408, ctx=77, seed=0) -> Dict[str, Tensor]:
+    """Random text-tower weights under CLIP's parameter names (CLIP.initialize_parameters scales, modules/clip/model.py:300-321)."""
+    g = torch.Generator().manual_seed(seed)
+    n = lambda *s, std: torch.randn(*s, generator=g) * std
+    sd = {"token_embedding.weight": n(vocab, width, std=0.02), "positional_embedding": n(ctx, width, std=0.01),
+          "ln_final.weight": 1 + n(width, std=0.05), "ln_final.bias": n(width, std=0.05), "text_projection": n(width, width, std=width ** -0.5)}
+    proj_std, attn_std, fc_std = (width ** -0.5) * ((2 * n_layer) ** -0.5), width ** -0.5, (2 * width) ** -0.5
+    for i in range(n_layer):
+        b = f"transformer.resblocks.{i}."
+        sd[b + "attn.in_proj_weight"], sd[b + "attn.in_proj_bias"] = n(3 * width, width, std=attn_std), n(3 * width, std=0.02)
+        sd[b + "attn.out_proj.weight"], sd[b + "attn.out_proj.bias"] = n(width, width, std=proj_std), n(width, std=0.02)
+        sd[b + "ln_1.weight"], sd[b + "ln_1.bias"] = 1 + n(width, std=0.05), n(width, std=0.05)
+        sd[b + "ln_2.weight"], sd[b + "ln_2.bias"] = 1 + n(width, std=0.05), n(width, std=0.05)
+        sd[b + "mlp.c_fc.weight"], sd[b + "mlp.c_fc.bias"] = n(4 * width, width, std=fc_std), n(4 * width, std=0.02)
+        sd[b + "mlp.c_proj.weight"], sd[b + "mlp.c_proj.bias"] = n(width, 4 * width, std=proj_std), n(width, std=0.02)
+    return sd
+
+
 def make_transformer_state_dict(*, K=256, D=1024, n_layer=19, n_head=16, spatial=(5, 53), cond_dim=512, T=100,
                                 mlp_times=4, seed=0, std=0.02) -> Dict[str, Tensor]:
     """Random DiffusionTransformer state_dict: N(0,std) Linear/Embedding weights, zero biases, unit

@@ -211,6 +211,39 @@ def gen_tokenizer_cases():
     print("tokenizer_cases:", [len(r) for r in raw])
 
 
+def gen_clip_text():
+    """N2: the reference's CLIPTextEmbedding.forward (Diffsound flags) on seeded weights.  CLIPTextEmbedding.__init__ downloads CLIP, so the instance
+    is assembled by hand from the reference's own sub-modules (clip/model.py Transformer + LayerNorm) and driven through its unmodified forward()."""
+    import types
+    from oracle import diffsound_oracle as O
+    rh.install_shims()
+    if "ftfy" not in sys.modules:  # imported by the reference's tokenizer module, unused here
+        sys.modules["ftfy"] = types.SimpleNamespace(fix_text=lambda t: t)
+    from sound_synthesis.modeling.modules.clip import model as cm
+    from sound_synthesis.modeling.embeddings.clip_text_embedding import CLIPTextEmbedding
+    NL, V = 3, 2000
+    sd = O.make_clip_text_state_dict(n_layer=NL, vocab=V, seed=5)
+    emb = object.__new__(CLIPTextEmbedding)
+    torch.nn.Module.__init__(emb)
+    emb.num_embed, emb.clip_name, emb.normalize, emb.pick_last_embedding, emb.keep_seq_len_dim, emb.additional_last_embedding = V, "none", True, False, False, False
+    mask = torch.empty(77, 77).fill_(float("-inf")).triu_(1)
+    emb.token_embedding = torch.nn.Embedding(V, 512)
+    emb.positional_embedding = torch.nn.Parameter(torch.empty(77, 512))
+    emb.transformer = cm.Transformer(width=512, layers=NL, heads=8, attn_mask=mask)
+    emb.ln_final = cm.LayerNorm(512)
+    emb.text_projection = torch.nn.Parameter(torch.empty(512, 512))
+    emb.embed_dim, emb.trainable = 512, False
+    missing, unexpected = emb.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(6)
+    tok = torch.zeros(3, 77, dtype=torch.long)
+    for i, n_ in enumerate((9, 77, 30)):
+        tok[i, :n_] = torch.randint(1, V, (n_,), generator=g)
+    tok[2, 40] = -100   # padded ids may be negative (Tokenize pad_value=-100 configs): the reference clamps them to 0 in place
+    out = emb(tok.clone())
+    np.savez_compressed(os.path.join(GOLD, "clip_text.npz"), in_tokens=tok.numpy(), out_features=out.numpy(), __cfg=np.array([NL, V, 5]))
+    print("clip_text:", tuple(out.shape), float(out.norm(dim=-1).mean()))
+
+
 def gen_melgan():
     rh.install_shims()
     from vocoder.modules import Generator
@@ -253,6 +286,7 @@ if __name__ == "__main__":
     gen_decoder_tiny()
     gen_encoder_tiny()
     gen_tokenizer_cases()
+    gen_clip_text()
     gen_melgan()
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)) // 1024, "KB")

@@ -130,3 +130,14 @@ def test_encoder_tokeniser_matches_reference():
     assert (z - ref_z).abs().max() <= 1e-5 * ref_z.abs().max()
     assert torch.equal(tok, torch.from_numpy(g["out_tokens"]).long())
     assert len(set(tok.flatten().tolist())) > 8  # the golden exercises many codes, not one
+
+
+def test_clip_text_tower_matches_reference():
+    """N2: oracle CLIP text tower (causal pre-LN transformer + ln_final + per-token L2 norm) vs the reference's CLIPTextEmbedding.forward."""
+    _, g = load_golden("clip_text.npz")
+    NL, V, seed = [int(v) for v in g["__cfg"]]
+    sd = O.make_clip_text_state_dict(n_layer=NL, vocab=V, seed=seed)
+    out = O.clip_text_forward(sd, torch.from_numpy(g["in_tokens"]), n_layer=NL)
+    ref = torch.from_numpy(g["out_features"])
+    assert out.shape == ref.shape == (3, 77, 512)
+    assert (out - ref).abs().max() < 2e-6

@@ -56,6 +56,7 @@ attention_f16_kernel(const __half* __restrict__ q, long long ldq, const __half* 
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
+  const bool causal = (flags & DSB_ATTN_CAUSAL) != 0;
   const __half* qb = q + (long long)b * Lq * ldq + h * HD;
   const __half* kb = k + (long long)b * Lk * ldk + h * HD;
   const __half* vb = v + (long long)b * Lk * ldv + h * HD;
@@ -116,6 +117,13 @@ attention_f16_kernel(const __half* __restrict__ q, long long ldq, const __half* 
       const int key = kc * KT + nt * 8 + 2 * t;
       if (key >= Lk) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
       if (key + 1 >= Lk) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+      if (causal) {  // CLIP text tower: a query attends to keys at or before its own position (build_attention_mask, clip/model.py)
+        const int qa = qt * QT + warp * 16 + g, qb_ = qa + 8;
+        if (key > qa) s[nt][0] = -INFINITY;
+        if (key + 1 > qa) s[nt][1] = -INFINITY;
+        if (key > qb_) s[nt][2] = -INFINITY;
+        if (key + 1 > qb_) s[nt][3] = -INFINITY;
+      }
       mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
       mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
     }
