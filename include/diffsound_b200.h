@@ -118,6 +118,9 @@ int dsb_layernorm(const float* x, void* out, const float* gamma, const float* be
 int dsb_ada_layernorm(const float* x, void* out, const float* table, const int64_t* t, int B, int L, int D, int T, float eps, int flags,
                       void* stream);
 
+/* x[r, :] /= ||x[r, :]||_2 in place: the per-token normalisation of CLIPTextEmbedding.forward (embeddings/clip_text_embedding.py:78-79) */
+int dsb_l2_normalize_rows(float* x, long long rows, int D, void* stream);
+
 /* SiLU on a (rows, D) table (set-up of the AdaLN table) */
 int dsb_silu(const float* in, float* out, long long n, void* stream);
 

@@ -36,6 +36,7 @@ SIGNATURES = {
     "dsb_f32_to_bf16": [c_vp, c_vp, c_ll, c_vp],
     "dsb_f32_to_f16": [c_vp, c_vp, c_ll, c_vp],
     "dsb_silu": [c_vp, c_vp, c_ll, c_vp],
+    "dsb_l2_normalize_rows": [c_vp, c_ll, c_i, c_vp],
     "dsb_split_tf32": [c_vp, c_ll, c_vp, c_ll, c_ll, c_i, c_i, c_i, c_vp],
     "dsb_embed_tokens": [c_vp] * 5 + [c_i] * 6 + [c_vp, c_vp],
     "dsb_layernorm": [c_vp] * 4 + [c_i, c_i, c_f, c_i, c_vp],

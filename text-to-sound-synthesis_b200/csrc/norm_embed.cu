@@ -110,6 +110,19 @@ layernorm_kernel(const float* __restrict__ x, void* __restrict__ out, const floa
   }
 }
 
+// x[r, :] /= ||x[r, :]||_2  (CLIPTextEmbedding's per-token normalisation, clip_text_embedding.py:78-79); one warp per row, in place
+__global__ void __launch_bounds__(256)
+l2_normalize_rows_kernel(float* __restrict__ x, long long rows, int D) {
+  const long long row = blockIdx.x * 8LL + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float* r = x + row * D;
+  float ss = 0.f;
+  for (int i = lane; i < D; i += 32) ss += r[i] * r[i];
+  const float inv = 1.0f / sqrtf(warp_sum(ss));
+  for (int i = lane; i < D; i += 32) r[i] *= inv;
+}
+
 template <int MODE>
 static int launch_ln(const float* x, void* out, const float* p0, const float* p1, const int64_t* t, int rows, int L, int D, int T, float eps,
                      int flags, cudaStream_t st) {
@@ -134,6 +147,12 @@ extern "C" int dsb_embed_tokens(const int64_t* ids, const float* emb, const floa
   const int rows = B * L;
   DSB_CHECK_CUDA(launch_pdl(embed_tokens_kernel, dim3((rows + 7) / 8), dim3(256), 0, (cudaStream_t)stream, ids, emb, hemb, wemb, out, rows, L, D, W,
                             num_embed, err_flag));
+  return 0;
+}
+extern "C" int dsb_l2_normalize_rows(float* x, long long rows, int D, void* stream) {
+  DSB_REQUIRE(rows > 0 && D > 0, "dsb_l2_normalize_rows: bad shape");
+  l2_normalize_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, rows, D);
+  DSB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 extern "C" int dsb_layernorm(const float* x, void* out, const float* gamma, const float* beta, int rows, int D, float eps, int flags, void* stream) {

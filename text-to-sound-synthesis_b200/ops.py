@@ -213,8 +213,19 @@ def ada_layernorm(x, table, t, out=None, *, eps=1e-5, round_out=False, out_bf16=
     return out
 
 
-def attention(q, k, v, out, *, B, H, Lq, Lk, scale, round_out=False):
-    """q/out: row-strided views with (B*Lq) rows; k/v: (B*Lk) rows; head h = columns [64h, 64h+64)."""
+def l2_normalize_rows_(x):
+    """x (..., D) contiguous fp32: every row divided by its L2 norm, in place."""
+    _need_cuda(x)
+    D = x.shape[-1]
+    _lib.check(_lib.lib().dsb_l2_normalize_rows(x.data_ptr(), x.numel() // D, D, _stream()), "dsb_l2_normalize_rows")
+    return x
+
+
+ATTN_CAUSAL = 1024
+
+
+def attention(q, k, v, out, *, B, H, Lq, Lk, scale, round_out=False, causal=False):
+    """q/out: row-strided views with (B*Lq) rows; k/v: (B*Lk) rows; head h = columns [64h, 64h+64).  causal (fp16 path): key j visible to query i iff j <= i."""
     _need_cuda(q, k, v, out)
     for t_ in (q, k, v, out):
         if t_.stride(-1) != 1:
@@ -223,8 +234,11 @@ def attention(q, k, v, out, *, B, H, Lq, Lk, scale, round_out=False):
         if k.dtype != torch.float16 or v.dtype != torch.float16:
             raise RuntimeError("attention: q, k, v must share a dtype")
         _lib.check(_lib.lib().dsb_attention_f16(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), out.data_ptr(),
-                                                out.stride(0), B, H, Lq, Lk, scale, _out_flags(out, False), _stream()), "dsb_attention_f16")
+                                                out.stride(0), B, H, Lq, Lk, scale, _out_flags(out, False) | (ATTN_CAUSAL if causal else 0), _stream()),
+                   "dsb_attention_f16")
         return out
+    if causal:
+        raise RuntimeError("causal attention is implemented for fp16 operands")
     _lib.check(_lib.lib().dsb_attention(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), out.data_ptr(), out.stride(0),
                                         B, H, Lq, Lk, scale, _out_flags(out, round_out), _stream()), "dsb_attention")
     return out

@@ -26,6 +26,12 @@ TARGET_MAP = {
         "diffsound_b200.modeling.models.dalle_spec.DALLE",
     "specvqgan.modules.transformer.permuter.ColumnMajor":
         "diffsound_b200.modeling.codecs.spec_codec.vqgan.ColumnMajor",
+    "sound_synthesis.modeling.codecs.text_codec.tokenize.Tokenize":
+        "diffsound_b200.modeling.codecs.text_codec.tokenize.Tokenize",
+    "sound_synthesis.modeling.modules.clip.simple_tokenizer.SimpleTokenizer":
+        "diffsound_b200.modeling.modules.clip.simple_tokenizer.SimpleTokenizer",
+    "sound_synthesis.modeling.embeddings.clip_text_embedding.CLIPTextEmbedding":
+        "diffsound_b200.modeling.embeddings.clip_text_embedding.CLIPTextEmbedding",
 }
 
 
