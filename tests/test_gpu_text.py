@@ -95,7 +95,9 @@ def test_captions_condition_the_sampler_through_the_reference_config_path():
     m.truncation = "top0.85r"
     torch.manual_seed(3)
     a = m.sample(condition_token=tok, condition_mask=None, condition_embed=None, filter_ratio=0)["content_token"]
-    torch.manual_seed(3)
     emb = m.condition_emb(tok)
+    tower, m.condition_emb = m.condition_emb, None      # without a condition_emb the module takes pre-computed embeddings (:623-627)
+    torch.manual_seed(3)
     b = m.sample(condition_token=None, condition_mask=None, condition_embed=emb, filter_ratio=0, batch_size=2)["content_token"]
+    m.condition_emb = tower
     assert a.shape == (2, 265) and torch.equal(a, b)
