@@ -280,3 +280,39 @@ def test_clip_tokenizer_matches_reference_cases():
     out = codec.get_tokens(g["captions"])
     assert out["token"].tolist() == g["token"] and out["mask"].int().tolist() == g["mask"]
     assert int(out["token"][4, 76]) == g["eot"] and bool(out["mask"][4].all())  # the over-long caption is truncated but keeps <|endoftext|>
+
+
+def test_reference_yaml_retargets_to_dropins_including_text_front_end():
+    """The reference's own configs/caps.yaml (only present in the build container) -> retarget_config -> every `target:` of the hot path resolves to a
+    drop-in class, the model builds on the CPU (modules only hold parameters), and its state_dict carries the reference's key families."""
+    import yaml
+    path = "/root/reference/Diffsound/configs/caps.yaml"
+    if not os.path.exists(path):
+        pytest.skip("reference checkout not present on this machine")
+    from diffsound_b200.utils.misc import instantiate_from_config, retarget_config
+    from diffsound_b200.modeling.modules.clip.simple_tokenizer import find_vocab
+    with open(path) as f:
+        cfg = yaml.full_load(f)["model"]
+    cfg["params"]["content_codec_config"]["params"]["ckpt_path"] = None          # no checkpoints in the tree
+    new = retarget_config(cfg)
+
+    def targets(c):
+        if isinstance(c, dict):
+            return ([c["target"]] if isinstance(c.get("target"), str) else []) + [t for v in c.values() for t in targets(v)]
+        return [t for v in c for t in targets(v)] if isinstance(c, (list, tuple)) else []
+    left = [t for t in targets(new) if not t.startswith("diffsound_b200.")]
+    assert left == ["specvqgan.modules.losses.DummyLoss"], left                    # the (unused) stage-1 loss is the only reference class left
+    new["params"]["content_codec_config"]["params"]["lossconfig"] = None
+    new["params"]["condition_codec_config"]["params"]["tokenizer_config"]["params"]["bpe_path"] = find_vocab()
+    model = instantiate_from_config(new)
+    keys = set(model.state_dict().keys())
+    for k in ("transformer.condition_emb.transformer.resblocks.11.attn.in_proj_weight", "transformer.condition_emb.token_embedding.weight",
+              "transformer.transformer.blocks.18.mlp.2.weight", "transformer.transformer.to_logits.1.bias", "content_codec.encoder.down.4.attn.1.q.weight",
+              "content_codec.decoder.up.4.attn.2.proj_out.bias", "content_codec.quantize.embedding.weight", "transformer.Lt_history"):
+        assert k in keys, k
+    assert model.transformer.condition_emb.embed_dim == 512 and model.transformer.transformer.content_emb.num_embed == 257
+    cond = model.prepare_condition({"text": ["a dog barks", "rain on a tin roof"]})
+    tk = model.condition_codec.tokenizer
+    want = sum(len(tk.encode(t)) + 2 for t in ("a dog barks", "rain on a tin roof"))  # <|startoftext|> ... <|endoftext|>
+    assert cond["condition_token"].shape == (2, 77) and cond["condition_mask"].dtype == torch.bool and int(cond["condition_mask"].sum()) == want
+    assert int(cond["condition_token"][0, 0]) == tk.encoder["<|startoftext|>"]
