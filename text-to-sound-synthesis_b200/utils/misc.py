@@ -32,6 +32,8 @@ TARGET_MAP = {
         "diffsound_b200.modeling.modules.clip.simple_tokenizer.SimpleTokenizer",
     "sound_synthesis.modeling.embeddings.clip_text_embedding.CLIPTextEmbedding":
         "diffsound_b200.modeling.embeddings.clip_text_embedding.CLIPTextEmbedding",
+    "sound_synthesis.engine.ema.EMA":
+        "diffsound_b200.engine_utils.ema.EMA",
 }
 
 
