@@ -361,3 +361,22 @@ def test_device_resident_ema_matches_reference_ema():
     mine.modify_to_train()
     assert all(torch.equal(b.body.state_dict()[k], live[k]) for k in live)
     assert not any(p.requires_grad for p in mine.ema_model.parameters())
+
+
+def test_generate_samples_cli_dry_run_on_reference_yaml(tmp_path):
+    """tools/generate_samples.py (the generate_samples_batch.py flow on the drop-ins): config retargeting, caption grouping, sample_type string."""
+    cfgp = "/root/reference/Diffsound/evaluation/caps_text.yaml"
+    if not os.path.exists(cfgp):
+        pytest.skip("reference checkout not present on this machine")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("generate_samples", os.path.join(ROOT, "tools", "generate_samples.py"))
+    gs = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gs)
+    csvp = tmp_path / "val.csv"
+    csvp.write_text("file_name,caption\nY1.wav,a dog barks\nY1.wav,\"a dog barks, twice\"\nY2.wav,rain\n")
+    ck = os.path.join(ROOT, "oracle", "_ref", "best_netG.pt")
+    argv = ["--config", cfgp, "--captions", str(csvp), "--out", str(tmp_path / "o"), "--fast", "3", "--dry-run"] + (["--vocoder-ckpt", ck] if os.path.exists(ck) else [])
+    model, vocoder, caps, st = gs.main(argv)
+    assert caps == {"Y1.wav": ["a dog barks", "a dog barks, twice"], "Y2.wav": ["rain"]} and st == "top0.85r,fast2"
+    assert type(model).__module__.startswith("diffsound_b200.") and model.condition_codec is not None
+    assert model.transformer.condition_emb is not None and (vocoder is None or type(vocoder).__module__.startswith("diffsound_b200."))
