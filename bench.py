@@ -203,14 +203,14 @@ def full_pipeline_probe(model, cond_dev, B):
     _pkg.load()
     from diffsound_b200.modeling.codecs.spec_codec.vqgan import VQModel
     from diffsound_b200.vocoder.modules import Generator
-    from oracle import diffsound_oracle as O
     dd = dict(double_z=False, z_channels=256, resolution=848, in_channels=1, out_ch=1, ch=128, ch_mult=[1, 1, 2, 2, 4], num_res_blocks=2,
               attn_resolutions=[53], dropout=0.0)
     torch.manual_seed(0)
     vq = VQModel(dd, None, n_embed=256, embed_dim=256).cuda().eval()
     ck = os.path.join(ROOT, "oracle", "_ref", "best_netG.pt")
-    voc = Generator(80, 32, 3)
-    voc.load_state_dict(torch.load(ck, map_location="cpu") if os.path.exists(ck) else O.make_melgan_state_dict(seed=1), strict=True)
+    voc = Generator(80, 32, 3)  # the shipped MelGAN weights when build() staged them; otherwise the module's own random initialisation
+    if os.path.exists(ck):
+        voc.load_state_dict(torch.load(ck, map_location="cpu"), strict=True)
     voc = voc.cuda().eval()
 
     def run():
