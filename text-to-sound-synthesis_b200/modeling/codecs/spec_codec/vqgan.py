@@ -10,7 +10,6 @@ import numpy as np
 import torch
 from torch import nn
 
-from .... import ops
 from ....decoder_engine import DecoderEngine
 from ....encoder_engine import EncoderEngine
 
