@@ -147,7 +147,6 @@ def time_events(fn, iters, stream):
 def gemm_roofline(model, B, peaks, peaks_src):
     """Average device time of the dominant kernel (gemm_tcgen05_kernel) over the launches of one denoiser pass, CUDA events on
     the launching stream; every launch uses a different layer's weights so nothing is L2-warm."""
-    from diffsound_b200 import ops
     eng = model.transformer.engine
     L, D = 265, eng.D
     ws = eng.workspace(B, L)
