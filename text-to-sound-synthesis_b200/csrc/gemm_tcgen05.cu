@@ -693,6 +693,10 @@ extern "C" int dsb_gemm_ex(const dsb_gemm_desc* d, void* stream) {
   const int sms = sm_count();
   int block_n = d->block_n;
   if (block_n == 0) {
+    static const int forced = [] { const char* e = getenv("DSB_GEMM_BLOCK_N"); return e ? atoi(e) : 0; }();  // A/B switch for tuning runs
+    if (forced == 128 || forced == 256) block_n = forced;
+  }
+  if (block_n == 0) {
     if (d->N <= 128) block_n = 128;
     else {
       const long long t256 = (long long)p.tiles_m * ((d->N + 255) / 256) * d->batch;
