@@ -81,6 +81,7 @@ class DenoiserTrainEngine:
         if D % 128 or D // H != 64 or D > 1024:
             raise RuntimeError(f"training kernels need head_dim 64 and n_embd a multiple of 128, <= 1024 (n_embd={D}, n_head={H})")
         self.D, self.H, self.n_layer = D, H, len(m.blocks)
+        self.scale = 1.0 / math.sqrt(D // H)  # softmax(Q K^T / sqrt(head_dim)) (transformer_utils.py:50, :101)
         first = not hasattr(self, "layers")
         if first:
             self.layers = []
@@ -230,7 +231,7 @@ class DenoiserTrainEngine:
         T.heads_split(k_tok, kh, B, H, Lk)
         T.heads_split(v_tok, vh, B, H, Lk)
         S = ws["S"][:, :, :Lkp]
-        ops.gemm(qh, kh, None, None, S, dtype=self.gd, alpha=1.0 / math.sqrt(64))
+        ops.gemm(qh, kh, None, None, S, dtype=self.gd, alpha=self.scale)
         T.softmax_fwd(S, P, Lk)
         if self.mn:
             ops.gemm(P[:, :, :Lk], vh, None, None, ws["oh"], dtype=self.gd, w_mn=True)          # O = P V, V as stored (Lk, 64)
@@ -280,7 +281,7 @@ class DenoiserTrainEngine:
             self._lin(sv["h1"], lay["wqkv"], lay["bqkv"], sv["qkv"])
             qkv = sv["qkv"]
             if self.mn:
-                T.attention_train_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], sv["att1"], sv["lse1"], B, self.H, L, L, 0.125)
+                T.attention_train_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], sv["att1"], sv["lse1"], B, self.H, L, L, self.scale)
             else:
                 self._attn_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], sv["att1"], sv["qh1"], sv["kh1"], sv["vh1"], sv["P1"], ws, B, L, L)
             self._lin(sv["att1"], lay["wo1"], blk.attn1.proj.bias.detach(), x2.view(B * L, D), residual=x1.view(B * L, D))
@@ -289,7 +290,7 @@ class DenoiserTrainEngine:
             self._lin(sv["h2"], lay["wq2"], blk.attn2.query.bias.detach(), sv["q2"])
             kv = ws["kv_all"][:, li * 2 * D:(li + 1) * 2 * D]
             if self.mn:
-                T.attention_train_fwd(sv["q2"], kv[:, :D], kv[:, D:], sv["att2"], sv["lse2"], B, self.H, L, Lc, 0.125)
+                T.attention_train_fwd(sv["q2"], kv[:, :D], kv[:, D:], sv["att2"], sv["lse2"], B, self.H, L, Lc, self.scale)
             else:
                 self._attn_fwd(sv["q2"], kv[:, :D], kv[:, D:], sv["att2"], sv["qh2"], sv["kh2"], sv["vh2"], sv["P2"], ws, B, L, Lc)
             self._lin(sv["att2"], lay["wo2"], blk.attn2.proj.bias.detach(), x3.view(B * L, D), residual=x2.view(B * L, D))
@@ -328,7 +329,7 @@ class DenoiserTrainEngine:
     def _attn_bwd(self, datt_tok, dq_tok, dk_tok, dv_tok, qh, kh, vh, P, ws, B, Lq, Lk):
         H = self.H
         Lkp, Lqp = _rup(Lk, 8), _rup(Lq, 8)
-        scale = 1.0 / math.sqrt(64)
+        scale = self.scale
         rnd = self.adt == torch.float32
         doh = ws["doh"]
         T.heads_split(datt_tok, doh, B, H, Lq)
@@ -432,7 +433,7 @@ class DenoiserTrainEngine:
             if self.mn:
                 kv = ws["kv_all"][:, li * 2 * D:(li + 1) * 2 * D]
                 T.attention_train_bwd(sv["q2"], kv[:, :D], kv[:, D:], sv["att2"], ws["datt"], sv["lse2"], ws["delta"], ws["dq2"], dkv[:, :D], dkv[:, D:],
-                                      B, self.H, L, Lc, 0.125)
+                                      B, self.H, L, Lc, self.scale)
             else:
                 self._attn_bwd(ws["datt"], ws["dq2"], dkv[:, :D], dkv[:, D:], sv["qh2"], sv["kh2"], sv["vh2"], sv["P2"], ws, B, L, Lc)
             self._linear_bwd(ws["dq2"], sv["h2"], lay["wq2"], lay["wq2T"], grads[p + "attn2.query.weight"], grads[p + "attn2.query.bias"], ws["dh"], ws)
@@ -443,7 +444,7 @@ class DenoiserTrainEngine:
             if self.mn:
                 qkv = sv["qkv"]
                 T.attention_train_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], sv["att1"], ws["datt"], sv["lse1"], ws["delta"],
-                                      dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], B, self.H, L, L, 0.125)
+                                      dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], B, self.H, L, L, self.scale)
             else:
                 self._attn_bwd(ws["datt"], dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], sv["qh1"], sv["kh1"], sv["vh1"], sv["P1"], ws, B, L, L)
             self._linear_bwd(dqkv, sv["h1"], lay["wqkv"], lay["wqkvT"], grads[f"_qkv_w.{li}"], grads[f"_qkv_b.{li}"], ws["dh"], ws)
