@@ -45,6 +45,7 @@ class DenoiserTrainEngine:
         self._ws: Dict[tuple, dict] = {}
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self.use_cuda_graph = True  # replay forward / backward as two CUDA graphs (~1.5k launches per step otherwise)
+        self._kernel_device = "cuda"  # the kernels exist for CUDA only; tests/test_cpu_train_engine.py swaps in CPU stand-ins to check the orchestration
         self.forward_id = 0         # activations live in engine-owned buffers: backward() must follow ITS forward (checked by the caller)
 
     # ------------------------------------------------------------------ small helpers
@@ -75,7 +76,7 @@ class DenoiserTrainEngine:
     def pack(self) -> None:
         """Cast (and transpose) the live fp32 parameters into GEMM operands.  Called at the start of every forward()."""
         m = self.m
-        if self.device.type != "cuda":
+        if self.device.type != self._kernel_device:
             raise RuntimeError("DenoiserTrainEngine needs the module on a CUDA device (no CPU fallback)")
         D, H = m.n_embd, m.n_head
         if D % 128 or D // H != 64 or D > 1024:
