@@ -31,8 +31,8 @@ def gemm(a, w, bias=None, residual=None, out=None, *, dtype=TF32, gelu=False, ro
     return out
 
 
-def gemm_f32(a, w, bias=None, residual=None, out=None, **kw):
-    return gemm(a, w, bias, residual, out)
+def gemm_f32(a, w, bias=None, residual=None, out=None, *, gelu=False, round_out=False):
+    return gemm(a, w, bias, residual, out, gelu=gelu)
 
 
 def silu(x, out=None):
@@ -191,3 +191,29 @@ def attention_train_bwd(q, k, v, o, dout, lse, delta, dq, dk, dv, B, H, Lq, Lk, 
     dq[:, : H * 64].copy_(_unheads(dS @ K, B, H, Lq))
     dk[:, : H * 64].copy_(_unheads(dS.transpose(-1, -2) @ Q, B, H, Lk))
     dv[:, : H * 64].copy_(_unheads(dV, B, H, Lk))
+
+
+# ------------------------------------------------------------------------------------------------ inference-side stand-ins
+def to_f16(x):
+    return x.float().clone()      # storage stays fp32 on the CPU: the orchestration is under test, not the rounding
+
+
+def round_tf32(x, out=None):
+    return x.clone() if out is None else out.copy_(x)
+
+
+def attention(q, k, v, out, *, B, H, Lq, Lk, scale, round_out=False, causal=False):
+    Q, K, V = _heads(q, B, H, Lq), _heads(k, B, H, Lk), _heads(v, B, H, Lk)
+    s = (Q @ K.transpose(-1, -2)) * scale
+    if causal:
+        s = s + torch.full((Lq, Lk), float("-inf")).triu_(1)
+    out[:, : H * 64].copy_(_unheads(torch.softmax(s, -1) @ V, B, H, Lq))
+    return out
+
+
+def attention_tc(q, k, v, out, *, B, H, Lq, Lk, scale, pipelined=True):
+    return attention(q, k, v, out, B=B, H=H, Lq=Lq, Lk=Lk, scale=scale)
+
+
+def l2_normalize_rows_(x):
+    return x.div_(x.norm(dim=-1, keepdim=True))

@@ -70,3 +70,44 @@ def test_engine_orchestration_matches_oracle_autograd(engine_env, mode):
         err = float((gr - r).abs().max()) / max(float(r.abs().max()), 1e-4 * gmax)
         assert err < 2e-3, (mode, n, err)
     assert set(grads) == {n for n, _ in m.transformer.named_parameters()}
+
+
+def test_inference_engine_and_text_tower_orchestration(engine_env, monkeypatch):
+    """DenoiserEngine.forward (hoisted AdaLN tables, fused QKV, all-layer cross K/V GEMM, in-place residual GEMMs) and TextTowerEngine.forward
+    (embedding-as-grid trick, causal attention, final L2 norm) with the kernel stand-ins, against the oracle."""
+    ops = engine_env
+    for name in ("to_f16", "round_tf32", "attention", "attention_tc", "l2_normalize_rows_"):
+        monkeypatch.setattr(ops, name, getattr(emu, name))
+    K, D, NL, NH, CD, B, L = 32, 128, 2, 2, 64, 2, 265
+    sd = O.make_transformer_state_dict(K=K, D=D, n_layer=NL, n_head=NH, cond_dim=CD, seed=8)
+    m = _model(K, D, NL, NH, CD, sd)
+    eng = m.transformer.engine
+    monkeypatch.setattr(type(eng), "device", property(lambda self: torch.device("cuda")), raising=False)   # repack()'s device gate
+    g = torch.Generator().manual_seed(2)
+    cond = torch.randn(B, 77, CD, generator=g)
+    x_t = torch.randint(0, K + 1, (B, L), generator=g)
+    t = torch.tensor([99, 3])
+    import functools
+    real_empty, real_zeros = torch.empty, torch.zeros
+    strip = lambda fn: functools.wraps(fn)(lambda *a, **k: fn(*a, **{kk: vv for kk, vv in k.items() if kk != "device"}))
+    monkeypatch.setattr(torch, "empty", strip(real_empty))
+    monkeypatch.setattr(torch, "zeros", strip(real_zeros))
+    for prec in ("f16", "tf32", "fp32"):
+        eng.__init__(m.transformer, precision=prec)
+        kv = eng.encode_condition(cond)
+        logits = eng.forward(x_t, kv.float(), t, 77)
+        ref = O.transformer_forward(sd, x_t, cond, t, n_layer=NL, n_head=NH, spatial=(5, 53))
+        err = float((logits.permute(0, 2, 1) - ref).abs().max() / ref.abs().max())
+        assert err < (3e-3 if prec == "f16" else 5e-5), (prec, err)   # 'f16' keeps real fp16 activation buffers (storage rounding), the others are exact here
+        assert eng.launches_per_forward == 2 + 11 * NL + 1
+    # CLIP text tower
+    from diffsound_b200.modeling.embeddings.clip_text_embedding import CLIPTextEmbedding
+    tsd = O.make_clip_text_state_dict(n_layer=2, vocab=500, seed=3)
+    clip = CLIPTextEmbedding(num_embed=500, text_layers=2, pick_last_embedding=False, embed_dim=512)
+    clip.load_state_dict(tsd, strict=True)
+    teng = clip.engine
+    tok = torch.randint(1, 500, (2, 77), generator=g)
+    tok[1, 50:] = 0
+    monkeypatch.setattr(type(clip.token_embedding.weight), "device", property(lambda self: torch.device("cuda")), raising=False)
+    out = teng.forward(tok)
+    assert torch.allclose(out, O.clip_text_forward(tsd, tok, n_layer=2), rtol=1e-4, atol=2e-6)
