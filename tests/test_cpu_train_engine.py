@@ -110,4 +110,5 @@ def test_inference_engine_and_text_tower_orchestration(engine_env, monkeypatch):
     tok[1, 50:] = 0
     monkeypatch.setattr(type(clip.token_embedding.weight), "device", property(lambda self: torch.device("cuda")), raising=False)
     out = teng.forward(tok)
-    assert torch.allclose(out, O.clip_text_forward(tsd, tok, n_layer=2), rtol=1e-4, atol=2e-6)
+    ref = O.clip_text_forward(tsd, tok, n_layer=2)
+    assert float((out - ref).abs().max() / ref.abs().max()) < 3e-3   # real fp16 activation buffers on the way (storage rounding only)
