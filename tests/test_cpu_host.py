@@ -380,3 +380,21 @@ def test_generate_samples_cli_dry_run_on_reference_yaml(tmp_path):
     assert caps == {"Y1.wav": ["a dog barks", "a dog barks, twice"], "Y2.wav": ["rain"]} and st == "top0.85r,fast2"
     assert type(model).__module__.startswith("diffsound_b200.") and model.condition_codec is not None
     assert model.transformer.condition_emb is not None and (vocoder is None or type(vocoder).__module__.startswith("diffsound_b200."))
+
+
+def test_synthesize_captions_sharding_and_replication_logic():
+    """pipeline.synthesize_captions: single process (no group) keeps every caption; replicate repeats the whole caption block, as generate_content's
+    torch.cat does; the caption index list says which caption each clip belongs to."""
+    from diffsound_b200 import pipeline
+
+    class FakeDalle:
+        def generate_content(self, *, batch, filter_ratio, replicate, sample_type):
+            n = len(batch["text"]) * replicate
+            ids = torch.tensor([len(t) for t in batch["text"]] * replicate)
+            return {"content": ids.float().view(n, 1, 1, 1).expand(n, 1, 2, 4).contiguous(), "content_token": ids.view(n, 1)}
+
+    caps = ["a", "bb", "ccc"]
+    out = pipeline.synthesize_captions(FakeDalle(), lambda s: s.sum(-1, keepdim=True).unsqueeze(1), caps, replicate=2, seed=5)
+    assert out["caption_index"] == [0, 1, 2, 0, 1, 2]
+    assert out["tokens"].view(-1).tolist() == [1, 2, 3, 1, 2, 3] and out["mel"].shape == (6, 1, 2, 4) and out["wav"].shape == (6, 1, 1)
+    assert pipeline.synthesize_captions(FakeDalle(), None, caps)["wav"] is None

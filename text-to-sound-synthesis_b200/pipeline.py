@@ -44,6 +44,26 @@ def synthesize_sharded(dalle, vocoder, cond_emb_all: torch.Tensor, *, sample_typ
     return out
 
 
+@torch.no_grad()
+def synthesize_captions(dalle, vocoder, captions, *, sample_type: str = "top0.85r", replicate: int = 1, seed: Optional[int] = None, shard: bool = False):
+    """Captions (list of str) -> dict(tokens, mel, wav), through the model's own text front end (Tokenize + CLIPTextEmbedding, i.e. a DALLE built with
+    a condition_codec).  shard=True splits the caption list in contiguous blocks over the ranks of the default process group (seed + rank per
+    rank, as synthesize_sharded) and returns this rank's clips together with the caption indices they belong to."""
+    import torch.distributed as dist
+    world = dist.get_world_size() if (shard and dist.is_initialized()) else 1
+    rank = dist.get_rank() if (shard and dist.is_initialized()) else 0
+    per = (len(captions) + world - 1) // world
+    mine = list(range(rank * per, min(len(captions), (rank + 1) * per)))
+    if seed is not None:
+        torch.manual_seed(seed + rank)
+    if not mine:
+        return {"tokens": None, "mel": None, "wav": None, "caption_index": []}
+    out = dalle.generate_content(batch={"text": [captions[i] for i in mine], "image": None}, filter_ratio=0, replicate=replicate, sample_type=sample_type)
+    mel = out["content"]
+    wav = vocoder((mel[:, 0] + 1) / 2) if vocoder is not None else None
+    return {"tokens": out["content_token"], "mel": mel, "wav": wav, "caption_index": [i for _ in range(replicate) for i in mine]}
+
+
 def save_clip(save_root: str, base_name: str, index: int, mel: torch.Tensor, wav: Optional[torch.Tensor], sample_rate: int = 22050):
     """Write one clip the way Diffsound/evaluation/generate_samples_batch.py:173-187 does:
     ``{base}_mel_sample_{n}.npy`` = the (80, 848) mel scaled to [0,1] with (spec + 1) / 2 (the layout/range Codebook/evaluate.py and
