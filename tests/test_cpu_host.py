@@ -396,5 +396,5 @@ def test_synthesize_captions_sharding_and_replication_logic():
     caps = ["a", "bb", "ccc"]
     out = pipeline.synthesize_captions(FakeDalle(), lambda s: s.sum(-1, keepdim=True).unsqueeze(1), caps, replicate=2, seed=5)
     assert out["caption_index"] == [0, 1, 2, 0, 1, 2]
-    assert out["tokens"].view(-1).tolist() == [1, 2, 3, 1, 2, 3] and out["mel"].shape == (6, 1, 2, 4) and out["wav"].shape == (6, 1, 1)
+    assert out["tokens"].view(-1).tolist() == [1, 2, 3, 1, 2, 3] and out["mel"].shape == (6, 1, 2, 4) and out["wav"].shape == (6, 1, 2, 1)
     assert pipeline.synthesize_captions(FakeDalle(), None, caps)["wav"] is None
