@@ -297,7 +297,7 @@ def train_loss(sd, sched, x_start: Tensor, cond_emb: Tensor, t: Tensor, pt: Tens
 
 def sample(sd, cond_emb: Tensor, uniforms, *, n_layer: int, n_head: int, spatial, num_timesteps: int = 100,
            truncation: Optional[str] = "top0.85r", steps: Optional[Sequence[int]] = None, x_init: Optional[Tensor] = None,
-           return_trace: bool = False):
+           return_trace: bool = False, post_steps: Optional[Sequence[int]] = None):
     """DiffusionTransformer.sample, filter_ratio=0 branch (diffusion_transformer.py:628-654).
 
     ``uniforms`` is either a callable step_index -> (B,K+1,L) tensor or a torch.Generator (then
@@ -315,7 +315,8 @@ def sample(sd, cond_emb: Tensor, uniforms, *, n_layer: int, n_head: int, spatial
         t = torch.full((B,), ti, dtype=torch.long)
         out = transformer_forward(sd, x, cond_emb, t, n_layer=n_layer, n_head=n_head, spatial=spatial)
         u = uniforms(i) if callable(uniforms) else torch.rand((B, K + 1, L), generator=uniforms)
-        x_new, post, lp = posterior_sample_step(sched, out, x, t, u, T=num_timesteps, truncation=truncation)
+        tp = None if post_steps is None else torch.full((B,), post_steps[i], dtype=torch.long)   # sample_fast: q_posterior at t - skip_step (:799-802)
+        x_new, post, lp = posterior_sample_step(sched, out, x, t, u, T=num_timesteps, truncation=truncation, t_posterior=tp)
         if return_trace:
             trace.append({"t": ti, "x_in": x.clone(), "logits": out.clone(), "x_out": x_new.clone()})
         x = x_new
@@ -326,6 +327,14 @@ def sample(sd, cond_emb: Tensor, uniforms, *, n_layer: int, n_head: int, spatial
 # A10 + A11: ids -> mel   (dalle_spec.py:80-91, permuter.py:21-55, quantize.py:88-103,
 #                          spec_codec/vqgan.py:62-65, specvqgan/modules/diffusionmodules/model.py)
 # --------------------------------------------------------------------------------------------
+def fast_schedule(num_timesteps: int, skip_step: int):
+    """(denoiser steps, posterior steps) of sample_fast (diffusion_transformer.py:792-802)."""
+    steps = list(range(num_timesteps - 1, -1, -1 - skip_step))
+    if steps[-1] != 0:
+        steps.append(0)
+    return steps, [s - skip_step if s > skip_step else s for s in steps]
+
+
 def column_major_reverse(ids: Tensor, H: int, W: int) -> Tensor:
     idx = torch.arange(H * W).reshape(H, W).T.reshape(-1)  # permuter.py:51-55
     return ids[:, torch.argsort(idx)]                      # :46-49 reverse=True

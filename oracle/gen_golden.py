@@ -71,7 +71,14 @@ def gen_xf_tiny():
     out = dict(sd_np(tr.state_dict()))
     torch.manual_seed(1234)
     tok = tr.sample(condition_token=None, condition_mask=None, condition_embed=cond, filter_ratio=0, batch_size=B)["content_token"]
-    np.savez_compressed(os.path.join(GOLD, "xf_tiny.npz"), __cfg=np.array([K, D, NL, NH, CD, B, L]),
+    # N1 variants through the reference's own entry points (same truncating predict_start): skip-step sampler and content-conditioned start
+    torch.manual_seed(1235)
+    tok_fast = tr.sample_fast(condition_token=torch.zeros(B, 1), condition_mask=None, condition_embed=cond, filter_ratio=0, skip_step=3)["content_token"]
+    x0 = torch.randint(0, K, (B, L), generator=g)
+    torch.manual_seed(1236)
+    tok_cond = tr.sample(condition_token=None, condition_mask=None, condition_embed=cond, content_token=x0, filter_ratio=0.3, batch_size=B)["content_token"]
+    extra = dict(out_fast3_tokens=tok_fast.numpy().astype(np.int16), in_content=x0.numpy().astype(np.int16), out_cond_tokens=tok_cond.numpy().astype(np.int16))
+    np.savez_compressed(os.path.join(GOLD, "xf_tiny.npz"), __cfg=np.array([K, D, NL, NH, CD, B, L]), **extra,
                         in_cond=cond.numpy(), in_x_t=x_t.numpy().astype(np.int16), in_t=t.numpy(),
                         out_logits=logits.numpy(), out_lp=lp.numpy(), out_post=post.numpy(),
                         out_sample_tokens=tok.numpy().astype(np.int16), **{"sd." + k: v for k, v in out.items()})

@@ -141,3 +141,22 @@ def test_clip_text_tower_matches_reference():
     ref = torch.from_numpy(g["out_features"])
     assert out.shape == ref.shape == (3, 77, 512)
     assert (out - ref).abs().max() < 2e-6
+
+
+def test_skip_step_and_content_conditioned_samplers_match_reference_tokens():
+    """N1: oracle sample_fast schedule (denoiser at t, posterior at t - skip) and the content-conditioned start (q_sample to t = 29, then 30 steps)
+    against tokens produced by the reference's own sample_fast / sample(filter_ratio=0.3) with the same CPU generator stream."""
+    sd, g = load_golden("xf_tiny.npz")
+    K, D, NL, NH, CD, B, L = [int(v) for v in g["__cfg"]]
+    cond = torch.from_numpy(g["in_cond"])
+    steps, post = O.fast_schedule(100, 3)
+    assert steps[:3] == [99, 95, 91] and steps[-1] == 0 and post[:2] == [96, 92] and post[-1] == 0
+    gen = torch.Generator().manual_seed(1235)
+    tok = O.sample(sd, cond, gen, n_layer=NL, n_head=NH, spatial=(5, 53), steps=steps, post_steps=post)
+    assert torch.equal(tok, torch.from_numpy(g["out_fast3_tokens"]).long())
+    gen = torch.Generator().manual_seed(1236)
+    x0 = torch.from_numpy(g["in_content"]).long()
+    sched = {k: sd[k] for k in sd if k.startswith("log_")}
+    x29 = O.q_sample_ids(sched, x0, torch.full((B,), 29), torch.rand((B, K + 1, L), generator=gen), T=100, num_classes=K + 1)
+    tok = O.sample(sd, cond, gen, n_layer=NL, n_head=NH, spatial=(5, 53), steps=list(range(29, -1, -1)), x_init=x29)
+    assert torch.equal(tok, torch.from_numpy(g["out_cond_tokens"]).long())
