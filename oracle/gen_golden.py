@@ -130,7 +130,8 @@ def gen_sampler_cases():
         logits, x_t, t, u = sampler_case_inputs(case)
         # feed the case logits through the reference's predict_start tail by stubbing the denoiser
         tr.transformer.forward = lambda *_a, _l=logits, **_k: _l
-        for trunc in ("top0.85r", None):
+        model.this_save_path = None  # read (unused) by the 'p' branch of predict_start_with_truncation
+        for trunc in ("top0.85r", None, "top20p"):
             ps = type(tr).predict_start.__get__(tr)
             if trunc:
                 ps = model.predict_start_with_truncation(ps, trunc)
@@ -142,7 +143,7 @@ def gen_sampler_cases():
             post = tr.q_posterior(lp, log_x, t)
             g = -torch.log(-torch.log(u + 1e-30) + 1e-30)
             nxt = (g + post).argmax(1)
-            tag = f"c{case}_{'nuc' if trunc else 'raw'}"
+            tag = f"c{case}_{ {'top0.85r': 'nuc', None: 'raw', 'top20p': 'topk'}[trunc] }"
             res[tag + "_next"] = nxt.numpy().astype(np.int16)
             res[tag + "_post_head"] = post[:, :, :6].numpy()
             res[tag + "_lp_head"] = lp[:, :, :6].numpy()

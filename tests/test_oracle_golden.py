@@ -41,13 +41,13 @@ def test_free_running_sample_matches_reference_tokens():
 
 
 @pytest.mark.parametrize("case", range(5))
-@pytest.mark.parametrize("trunc", ["top0.85r", None])
+@pytest.mark.parametrize("trunc", ["top0.85r", None, "top20p"])
 def test_sampler_cases_match_reference(case, trunc):
     _, g = load_golden("sampler_cases.npz")
     logits, x_t, t, u = sampler_case_inputs(case)
     sched = O.schedule_buffers(100, 257)
     nxt, post, lp = O.posterior_sample_step(sched, logits, x_t, t, u, T=100, truncation=trunc, first_step_carrier=(case == 0))
-    tag = f"c{case}_{'nuc' if trunc else 'raw'}"
+    tag = f"c{case}_{ {'top0.85r': 'nuc', None: 'raw', 'top20p': 'topk'}[trunc] }"
     assert torch.equal(lp[:, :, :6], torch.from_numpy(g[tag + "_lp_head"]))
     assert torch.equal(post[:, :, :6], torch.from_numpy(g[tag + "_post_head"]))
     assert torch.equal(nxt, torch.from_numpy(g[tag + "_next"]).long())
