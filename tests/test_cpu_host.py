@@ -443,3 +443,23 @@ def test_host_policies_match_live_reference_module():
         torch.manual_seed(42)
         t_m, pt_m = mine.sample_time(16, torch.device("cpu"), "importance")
         assert torch.equal(t_r, t_m) and torch.equal(pt_r, pt_m)
+
+
+@pytest.mark.parametrize("ctx,sot_eot,pad", [(77, True, 0), (256, False, -100), (12, True, 0)])
+def test_tokenize_variants_match_live_reference(ctx, sot_eot, pad):
+    """Tokenize / clip.tokenize option space (DALL-E style 256 without start/end tokens and -100 padding, and a context short enough to truncate)
+    against the reference's own functions in this container."""
+    import types
+    from oracle import ref_harness as rh
+    if not rh.available():
+        pytest.skip("reference checkout not present on this machine")
+    rh.install_shims()
+    sys.modules.setdefault("ftfy", types.SimpleNamespace(fix_text=lambda t: t))
+    from sound_synthesis.modeling.modules.clip.simple_tokenizer import SimpleTokenizer as RefTok
+    from sound_synthesis.modeling.modules.clip.clip import tokenize as ref_tokenize
+    from diffsound_b200.modeling.codecs.text_codec.tokenize import Tokenize
+    caps = ["Two people talk while a dog barks and a car drives past on a wet road", "wind", "A B C d e f g h i j k l m n o p"]
+    ref = ref_tokenize(caps, context_length=ctx, add_start_and_end=sot_eot, with_mask=True, pad_value=pad, tokenizer=RefTok(end_idx=49152))
+    mine = Tokenize(context_length=ctx, add_start_and_end=sot_eot, with_mask=True, pad_value=pad,
+                    tokenizer_config={"target": "diffsound_b200.modeling.modules.clip.simple_tokenizer.SimpleTokenizer", "params": {"end_idx": 49152}}).get_tokens(caps)
+    assert torch.equal(mine["token"], ref["token"]) and torch.equal(mine["mask"], ref["mask"])
