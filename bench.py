@@ -307,7 +307,7 @@ def run_gpu_arm(args):
             cpu = {"value": v, "unit": "clips/s", "cores": cores, "kind": "port", "sample": sample}
         line = {"metric": "clips/sec (10s audio, 100 diffusion steps)", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": {"f16": "f16", "tf32": "tf32", "fp32": "f32"}[args.precision], "data": "synthetic",
+                "dtype": {"f16x3": "f16x3", "f16": "f16", "tf32": "tf32", "fp32": "f32"}[args.precision], "data": "synthetic",
                 "config": {"workload": f"Diffsound AudioCaps inference: batch {B}/GPU, 100 steps, K={K} codebook, 265-token grid, top0.85r "
                                        f"(BASELINE.json configs[1]); {args.layers}-layer D=1024 denoiser, random-init weights, synthetic caption embeddings",
                            "arithmetic": "GEMM operands fp16 (11-bit significand, = TF32), fp32 accumulation; residual stream / LayerNorm / softmax fp32; log_softmax fp64",
@@ -332,7 +332,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full-pipeline", action="store_true")
-    ap.add_argument("--precision", default="f16", choices=["f16", "tf32", "fp32"])
+    ap.add_argument("--precision", default="f16", choices=["f16x3", "f16", "tf32", "fp32"])
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -38,6 +38,8 @@ extern "C" {
 #define DSB_GEMM_TANH 16      /* tanh                           (reference vocoder/modules.py:123) */
 #define DSB_GEMM_OUT_F16 256   /* store fp16 instead of fp32 */
 #define DSB_GEMM_RES_BEFORE_ACT 128 /* add the residual before the activation (default: after) */
+#define DSB_GEMM_OUT_F16_SPLIT 2048 /* store the fp16 (hi | lo) pair of the fp32 result: hi = f16(x) at out[r*ldo + c], lo = f16(x - hi) at
+                                       out[r*ldo + split_off + c] -- the A operand of a split-fp16 ("f16x3") GEMM, see dsb_split_f16 */
 /* GroupNorm-apply flags (share the ROUND_TF32 bit) */
 #define DSB_GN_SWISH 32       /* x * sigmoid(x) after the affine (reference model.py:29-31) */
 #define DSB_GN_COMPACT 64     /* write (B, Lp, C) tokens instead of the zero-padded image */
@@ -83,6 +85,10 @@ typedef struct dsb_gemm_desc {
   int a_mn_major;        /* 1: A lies in memory as (K rows, M columns), lda = row stride: out[m, n] = sum_k A[k, m] W[n, k]; 2-byte dtypes, 1 tap */
   int b_mn_major;        /* 1: W lies in memory as (K rows, N columns), ldw = row stride (e.g. dW = dY^T X with both operands token-major,
                             dX = dY W with torch's (out, in) weight as stored) */
+  int use_tap_wcol;      /* 1: tap i reads W columns [tap_wcol[i], tap_wcol[i] + K) instead of [i*K, (i+1)*K) */
+  int tap_wcol[32];
+  long long w_cols;      /* columns of W that exist (0 -> num_taps*K) */
+  long long split_off;   /* DSB_GEMM_OUT_F16_SPLIT: element offset of the lo half inside an output row (0 -> N) */
 } dsb_gemm_desc;
 int dsb_gemm_ex(const dsb_gemm_desc* desc, void* stream);
 
@@ -95,6 +101,13 @@ int dsb_gemm_f32(const float* A, const float* W, const float* bias, const float*
 int dsb_round_tf32(const float* in, float* out, long long n, void* stream);
 int dsb_f32_to_bf16(const float* in, void* out_bf16, long long n, void* stream);
 int dsb_f32_to_f16(const float* in, void* out_f16, long long n, void* stream);
+/* Split-fp16 operand ("f16x3", the parity-grade tensor-core mode of the denoiser): hi = f16(scale * in), lo = f16(scale * in - hi);
+ * out[r, c] = hi, out[r, lo_off + c] = lo (fp16, ld_out elements per row).  A W^T ~ Ahi Whi^T + Alo Whi^T + Ahi Wlo^T with fp32
+ * accumulation carries 22 significand bits per operand: three kind::f16 passes replace the reference's fp32 nn.Linear
+ * (transformer_utils.py:45-57,95-108,248-253,345-348) at fp32-class accuracy.  scale is a power of two that lifts small weights
+ * out of fp16's subnormal range (undone exactly by the GEMM's alpha). */
+int dsb_split_f16(const float* in, long long ld_in, void* out_f16, long long ld_out, long long lo_off, long long rows, int C, float scale,
+                  void* stream);
 /* Split-TF32 operand: out[r, c] = hi = tf32(in[r, c]), out[r, Cp + c] = lo = tf32(in[r, c] - hi), zeros in the padding columns
  * [C, Cp); out has 2*Cp columns (ld_out elements per row).  A*W ~ hi*Whi + lo*Whi + hi*Wlo recovers fp32-class accuracy on
  * the TF32 tensor pipe (three K passes), used for the SpecVQGAN decoder / MelGAN convolutions.  w_format = 1 writes the
@@ -110,7 +123,8 @@ int dsb_split_tf32(const float* in, long long ld_in, float* out, long long ld_ou
 int dsb_embed_tokens(const int64_t* ids, const float* emb, const float* height_emb, const float* width_emb, float* out, int B, int L,
                      int D, int H, int W, int num_embed, int* err_flag, void* stream);
 
-/* nn.LayerNorm(D) with affine (transformer_utils.py:197 ln2, :345 to_logits.0): out = LN(x) * gamma + beta. flags: DSB_GEMM_ROUND_TF32 | DSB_GEMM_OUT_BF16 */
+/* nn.LayerNorm(D) with affine (transformer_utils.py:197 ln2, :345 to_logits.0): out = LN(x) * gamma + beta. flags: DSB_GEMM_ROUND_TF32 | DSB_GEMM_OUT_BF16 |
+ * DSB_GEMM_OUT_F16 | DSB_GEMM_OUT_F16_SPLIT (then out has 2*D fp16 columns per row: hi | lo) */
 int dsb_layernorm(const float* x, void* out, const float* gamma, const float* beta, int rows, int D, float eps, int flags, void* stream);
 
 /* AdaLayerNorm.forward (transformer_utils.py:145-149) with the timestep MLP hoisted into a table:
@@ -144,6 +158,12 @@ int dsb_attention_tc(const void* q, long long ldq, const void* k, long long ldk,
  * balanced slice of the (batch, head, query tile) list */
 int dsb_attention_tc2(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o, long long ldo,
                       int B, int H, int Lq, int Lk, float scale, void* stream);
+/* split-fp16 ("f16x3") version of the same core for the parity-grade mode: q / k / v / o are fp16 (hi | lo) pairs -- the lo half of a row
+ * lies *_lo_off elements after its hi half -- S = Qhi Khi^T + Qlo Khi^T + Qhi Klo^T and O = Phi Vhi + Plo Vhi + Phi Vlo on tcgen05 with fp32
+ * accumulation in TMEM; P = exp2(...) is split into (hi | lo) by the softmax warps and written IN PLACE over S.  Lk <= 288. */
+int dsb_attention_tc_split(const void* q, long long ldq, long long q_lo_off, const void* k, long long ldk, long long k_lo_off, const void* v,
+                           long long ldv, long long v_lo_off, void* o, long long ldo, long long o_lo_off, int B, int H, int Lq, int Lk,
+                           float scale, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Posterior + truncation + Gumbel-argmax sampler, one kernel (reference diffusion_transformer.py:285-289 predict_start tail,

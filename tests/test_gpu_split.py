@@ -1,0 +1,122 @@
+"""Split-fp16 ("f16x3") building blocks of the parity-grade denoiser mode: every kernel against an fp64 reference on the B200.
+
+The reference computes its nn.Linear / attention in fp32 (transformer_utils.py:43-58, :91-109, :248-253); these kernels reach
+fp32-class accuracy on the fp16 tensor pipe by carrying every operand as an fp16 (hi | lo) pair and running three MMA passes."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def G():
+    from tests import gpu_common
+    return gpu_common
+
+
+def _pair_value(p, C):
+    return p[:, :C].double() + p[:, C:2 * C].double()
+
+
+def test_split_f16_reconstructs_fp32(G):
+    x = torch.randn(300, 192, device="cuda") * torch.logspace(-3, 2, 192, device="cuda")
+    p = G.ops.split_f16(x)
+    assert p.shape == (300, 384) and p.dtype == torch.float16
+    rec = _pair_value(p, 192)
+    # 22 significand bits, with an absolute floor of half an fp16 subnormal quantum (2^-25) for the lo half of small values
+    assert bool(((rec - x.double()).abs() <= torch.maximum(3e-7 * x.double().abs(), torch.tensor(3.0e-8, dtype=torch.float64, device="cuda"))).all())
+    ps = G.ops.split_f16(x * 1e-4, 2.0 ** 12)  # power-of-two prescale keeps small values out of fp16's subnormals
+    assert float(((_pair_value(ps, 192) / 4096 - (x * 1e-4).double()).abs() / (x * 1e-4).double().abs().clamp_min(1e-7)).max()) < 3e-7
+
+
+@pytest.mark.parametrize("M,N,K", [(4240, 1024, 1024), (530, 3072, 1024), (265, 1024, 4096), (154, 2048, 512), (100, 256, 1024)])
+def test_gemm_f16x3_matches_fp64(G, M, N, K):
+    """out = A W^T + b (+ residual) at fp32-class accuracy; also the (hi | lo) pair output and the GELU2 epilogue."""
+    ops = G.ops
+    a = torch.randn(M, K, device="cuda")
+    w = torch.randn(N, K, device="cuda") * 0.02
+    b = torch.randn(N, device="cuda")
+    r = torch.randn(M, N, device="cuda")
+    ap, wp = ops.split_f16(a), ops.split_f16(w, 2.0 ** 17)
+    ref = _pair_value(ap, K) @ (_pair_value(wp, K) / 2.0 ** 17).T + b.double()
+    out = ops.gemm_f16x3(ap, wp, b, alpha=2.0 ** -17)
+    scale = float(ref.abs().max())
+    assert float((out.double() - ref).abs().max()) / scale < 2e-6
+    out_r = ops.gemm_f16x3(ap, wp, b, residual=r, alpha=2.0 ** -17)
+    assert float((out_r.double() - (ref + r.double())).abs().max()) / scale < 2e-6
+    pair = ops.gemm_f16x3(ap, wp, b, alpha=2.0 ** -17, split_out=True)
+    assert pair.shape == (M, 2 * N) and pair.dtype == torch.float16
+    assert float((_pair_value(pair, N) - ref).abs().max()) / scale < 2e-6
+    g = ops.gemm_f16x3(ap, wp, b, alpha=2.0 ** -17, gelu=True)
+    ref_g = ref * torch.sigmoid(1.702 * ref)
+    assert float((g.double() - ref_g).abs().max()) / scale < 1e-5  # __expf in the epilogue
+
+
+def test_layernorm_split_output(G):
+    ops = G.ops
+    x = torch.randn(2, 265, 1024, device="cuda") * 3
+    gam, bet = torch.randn(1024, device="cuda"), torch.randn(1024, device="cuda")
+    ref = ops.layernorm(x, gam, bet)
+    pr = ops.layernorm(x, gam, bet, split=True)
+    assert pr.shape == (2, 265, 2048)
+    assert float((_pair_value(pr.view(-1, 2048), 1024) - ref.view(-1, 1024).double()).abs().max()) < 2e-6
+    tab = torch.randn(100, 2048, device="cuda") * 0.1
+    t = torch.tensor([3, 77], device="cuda")
+    ref = ops.ada_layernorm(x, tab, t)
+    pr = ops.ada_layernorm(x, tab, t, split=True)
+    assert float((_pair_value(pr.view(-1, 2048), 1024) - ref.view(-1, 1024).double()).abs().max()) < 2e-6
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk", [(2, 3, 265, 265), (2, 16, 265, 77), (1, 2, 77, 77), (3, 1, 128, 288), (1, 1, 9, 33)])
+def test_attention_tc_split_matches_fp64(G, B, H, Lq, Lk):
+    ops = G.ops
+    D = H * 64
+    q = torch.randn(B * Lq, D, device="cuda") * 1.5
+    k = torch.randn(B * Lk, D, device="cuda") * 1.5
+    v = torch.randn(B * Lk, D, device="cuda")
+    qp, kp, vp = ops.split_f16(q), ops.split_f16(k), ops.split_f16(v)
+    out = torch.full((B * Lq, 2 * D), float("nan"), dtype=torch.float16, device="cuda")
+    ops.attention_tc_split(qp[:, :D], kp[:, :D], vp[:, :D], out[:, :D], q_lo=D, k_lo=D, v_lo=D, o_lo=D, B=B, H=H, Lq=Lq, Lk=Lk, scale=0.125)
+    qd = _pair_value(qp, D).view(B, Lq, H, 64).permute(0, 2, 1, 3)
+    kd = _pair_value(kp, D).view(B, Lk, H, 64).permute(0, 2, 1, 3)
+    vd = _pair_value(vp, D).view(B, Lk, H, 64).permute(0, 2, 1, 3)
+    ref = (torch.softmax(qd @ kd.transpose(-1, -2) * 0.125, -1) @ vd).permute(0, 2, 1, 3).reshape(B * Lq, D)
+    got = _pair_value(out, D)
+    assert torch.isfinite(got).all()
+    err = float((got - ref).abs().max() / ref.abs().max())
+    print(f"attention_tc_split B={B} H={H} Lq={Lq} Lk={Lk}: rel err {err:.2e}")
+    assert err < 3e-6
+
+
+def test_attention_tc_split_inside_packed_buffers(G):
+    """The engine's calling convention: hi halves are column views of wider buffers (qkv = [Qh Kh Vh | Ql Kl Vl])."""
+    ops = G.ops
+    B, H, L = 2, 16, 265
+    D = H * 64
+    x = torch.randn(B * L, 3 * D, device="cuda")
+    qkv = ops.split_f16(x)  # (M, 6D)
+    att = torch.zeros(B * L, 2 * D, dtype=torch.float16, device="cuda")
+    ops.attention_tc_split(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:3 * D], att[:, :D], q_lo=3 * D, k_lo=3 * D, v_lo=3 * D, o_lo=D, B=B, H=H, Lq=L, Lk=L,
+                           scale=0.125)
+    full = _pair_value(qkv, 3 * D)
+    sp = lambda m: m.view(B, L, H, 64).permute(0, 2, 1, 3)
+    ref = (torch.softmax(sp(full[:, :D]) @ sp(full[:, D:2 * D]).transpose(-1, -2) * 0.125, -1) @ sp(full[:, 2 * D:])).permute(0, 2, 1, 3).reshape(B * L, D)
+    assert float((_pair_value(att, D) - ref).abs().max() / ref.abs().max()) < 3e-6
+
+
+def test_split_mode_survives_large_dynamic_range(G):
+    """Range stress the fp16 containers: activations x64 and weights / 64 (and the reverse) must give the same fp32-class answer -- the
+    weight prescale and the fp32 accumulator carry the exponent, not the fp16 operands."""
+    ops = G.ops
+    M, N, K = 530, 1024, 1024
+    a = torch.randn(M, K, device="cuda")
+    w = torch.randn(N, K, device="cuda") * 0.02
+    ref = a.double() @ w.double().T
+    for sa, sw in ((64.0, 1 / 64.0), (1 / 64.0, 64.0), (512.0, 1.0)):
+        wq = w * sw
+        s = 13 - math.frexp(float(wq.abs().max()))[1]
+        out = ops.gemm_f16x3(ops.split_f16(a * sa), ops.split_f16(wq, 2.0 ** s), alpha=2.0 ** -s)
+        err = float((out.double() / (sa * sw) - ref).abs().max() / ref.abs().max())
+        assert err < 3e-6, (sa, sw, err)

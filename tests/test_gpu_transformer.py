@@ -90,7 +90,7 @@ def test_fused_graph_and_unfused_paths_agree(G):
     assert torch.equal(again, toks[0])
 
 
-@pytest.mark.parametrize("precision,tol", [("f16", 2e-3), ("tf32", 2e-3), ("fp32", 3e-4)])
+@pytest.mark.parametrize("precision,tol", [("f16x3", 3e-5), ("f16", 2e-3), ("tf32", 2e-3), ("fp32", 3e-4)])
 def test_teacher_forced_steps_match_oracle_full_width(G, precision, tol):
     """D=1024 / 16 heads / K=256 (4 layers to keep the CPU oracle fast): feed the oracle's x_t each step (SURVEY 7.2 ladder ii).
     Logit tolerance (max|err| / max|ref|): 2e-3 for 11-bit-significand tensor-core operands (f16 / tf32), 3e-4 with exact fp32
@@ -133,7 +133,7 @@ def test_free_running_full_size_tokens_vs_oracle(G):
     cond = cond / cond.norm(dim=-1, keepdim=True)
     us = [torch.rand(B, K + 1, L, generator=g) for _ in range(100)]
     ref = O.sample(sd, cond, lambda i: us[i], n_layer=NL, n_head=NH, spatial=(5, 53))
-    for prec, floor in (("fp32", 1.0), ("f16", 0.97)):
+    for prec, floor in (("f16x3", 1.0), ("fp32", 1.0), ("f16", 0.97)):
         m = build_dt(K, D, NL, NH, CD, sd, precision=prec)
         eng = m.transformer.engine
         kv = eng.encode_condition(cond.cuda())

@@ -80,6 +80,19 @@ __global__ void split_tf32_kernel(const float* __restrict__ in, long long ld_in,
     }
   }
 }
+// fp16 (hi | lo) split of scale * in: hi = f16(x), lo = f16(x - hi)  (x - hi is exact in fp32)
+__global__ void split_f16_kernel(const float* __restrict__ in, long long ld_in, __half* __restrict__ out, long long ld_out, long long lo_off,
+                                 long long rows, int C, float scale) {
+  const long long total = rows * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C;
+    const int c = (int)(i - r * C);
+    const float x = in[r * ld_in + c] * scale;
+    const __half h = __float2half_rn(x);
+    out[r * ld_out + c] = h;
+    out[r * ld_out + lo_off + c] = __float2half_rn(x - __half2float(h));
+  }
+}
 __global__ void silu_kernel(const float* __restrict__ in, float* __restrict__ out, long long n) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -128,6 +141,13 @@ extern "C" int dsb_split_tf32(const float* in, long long ld_in, float* out, long
   DSB_REQUIRE(rows > 0 && C > 0 && Cp >= C && ld_out >= (wfmt ? 3LL : 2LL) * Cp, "dsb_split_tf32: bad shape");
   DSB_REQUIRE(Cp % 4 == 0 && ld_out % 4 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "dsb_split_tf32: output must be 16-byte aligned with Cp %% 4 == 0");
   split_tf32_kernel<<<grid_for(rows * (Cp / 4), 256), 256, 0, (cudaStream_t)stream>>>(in, ld_in, out, ld_out, rows, C, Cp, wfmt);
+  DSB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+extern "C" int dsb_split_f16(const float* in, long long ld_in, void* out, long long ld_out, long long lo_off, long long rows, int C, float scale,
+                             void* stream) {
+  DSB_REQUIRE(rows > 0 && C > 0 && lo_off >= C && ld_out >= lo_off + C, "dsb_split_f16: bad shape (rows=%lld C=%d lo_off=%lld ld_out=%lld)", rows, C, lo_off, ld_out);
+  split_f16_kernel<<<grid_for(rows * C, 256), 256, 0, (cudaStream_t)stream>>>(in, ld_in, (__half*)out, ld_out, lo_off, rows, C, scale == 0.f ? 1.f : scale);
   DSB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -1,0 +1,302 @@
+// Split-fp16 ("f16x3") tcgen05 / TMEM attention core -- the parity-grade twin of attention_tc.cu
+// (reference transformer_utils.py:48-54 FullAttention, :99-105 CrossAttention: softmax(Q K^T / sqrt(64)) V, 16 heads x 64).
+//
+// Every operand is an fp16 (hi | lo) pair (x ~ hi + lo, 22 significand bits) produced by the split GEMM epilogue:
+//   S = Qlo Khi^T + Qhi Klo^T + Qhi Khi^T : 3 x tcgen05.mma kind::f16 passes into one fp32 TMEM accumulator (128 lanes x kpad columns);
+//   softmax: 8 warps (two per TMEM lane quadrant, each half of the 32-key chunks), one query row per thread; fp32 max / exp2 / sum;
+//            P is split into (hi | lo) and written IN PLACE over the S columns it came from (chunk of 32 keys = 32 fp32 columns
+//            -> 16 packed-fp16 hi columns + 16 lo columns), so S + P + O fit the 512 TMEM columns at 288 keys;
+//   O = Plo Vhi + Phi Vlo + Phi Vhi       : A operand from TMEM, B = V rows as TMA wrote them (MN-major SW128), fp32 accumulator in TMEM;
+//   epilogue: O / rowsum -> (hi | lo) fp16 pair -> HBM (the A operand of the output projection's split GEMM).
+// One CTA per (batch, head); K/V (hi and lo) are staged once by TMA, Q tiles are double-buffered.  fp32-class accuracy: measured
+// against an fp64 reference in tests/test_gpu_split.py.
+#include "common.cuh"
+#include "diffsound_b200.h"
+#include <cuda_fp16.h>
+
+namespace dsb {
+namespace {
+constexpr int SP_HD = 64;
+constexpr int SP_QM = 128;
+constexpr int SP_KMAX = 288;      // padded key capacity (multiple of 32)
+constexpr int SP_THREADS = 288;   // warps 0-7 softmax + epilogue, warp 8 control (TMA producer, MMA issuer, TMEM owner)
+constexpr int SP_QTILE = SP_QM * 128;  // bytes of one 128 x 64 fp16 SW128 tile
+
+struct SpParams {
+  int B, H, Lq, Lk, kpad, n_qt, box_rows, n_box;
+  int q_lo_col, k_lo_col, v_lo_col;  // column (element) offset of the lo halves inside the tensor maps
+  long long ldo, o_lo_off;
+  __half* o;
+  float scale_log2e;
+  uint32_t tmem_cols;
+};
+
+__device__ __forceinline__ void sp_tmem_st_x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+        "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void sp_tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void sp_umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+               ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ constexpr uint32_t sp_idesc(int M, int N, bool b_mn_major) {  // fp16 operands, fp32 accumulate
+  return (1u << 4) | (b_mn_major ? (1u << 16) : 0u) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+__device__ __forceinline__ float sp_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(SP_THREADS, 1)
+attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
+                          const __grid_constant__ SpParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int kv_bytes = p.kpad * 128;
+  uint8_t* sQ = smem;                         // [2 buffers][hi, lo] x 16 KB
+  uint8_t* sKh = sQ + 4 * SP_QTILE;
+  uint8_t* sKl = sKh + kv_bytes;
+  uint8_t* sVh = sKl + kv_bytes;
+  uint8_t* sVl = sVh + kv_bytes;
+  float* s_max = reinterpret_cast<float*>(sVl + kv_bytes);   // [2 tile parities][2 halves][128 rows]
+  float* s_sum = s_max + 512;                                // same shape
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_sum + 512);
+  uint64_t* kv_full = bars;
+  uint64_t* q_full = bars + 1;   // [2]
+  uint64_t* s_full = bars + 3;
+  uint64_t* p_full = bars + 4;
+  uint64_t* o_full = bars + 5;
+  uint64_t* o_empty = bars + 6;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    mbar_init(kv_full, 1);
+    mbar_init(&q_full[0], 1); mbar_init(&q_full[1], 1);
+    mbar_init(s_full, 1); mbar_init(p_full, 8); mbar_init(o_full, 1); mbar_init(o_empty, 8);
+    fence_barrier_init();
+    prefetch_tmap(&map_q); prefetch_tmap(&map_k); prefetch_tmap(&map_v);
+  }
+  if (warp == 8) {
+    tmem_alloc(tmem_ptr, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tS = tmem_base, tO = tmem_base + p.kpad;
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp == 8) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ control thread: TMA producer + MMA issuer
+      mbar_arrive_expect_tx(kv_full, 4 * kv_bytes);
+      for (int bx = 0; bx < p.n_box; ++bx) {
+        const int r = b * p.Lk + bx * p.box_rows, off = bx * p.box_rows * 128;
+        tma_load_3d(&map_k, kv_full, sKh + off, h * SP_HD, r, 0);
+        tma_load_3d(&map_k, kv_full, sKl + off, p.k_lo_col + h * SP_HD, r, 0);
+        tma_load_3d(&map_v, kv_full, sVh + off, h * SP_HD, r, 0);
+        tma_load_3d(&map_v, kv_full, sVl + off, p.v_lo_col + h * SP_HD, r, 0);
+      }
+      auto issue_q = [&](int qt) {
+        const int qb = qt & 1;
+        mbar_arrive_expect_tx(&q_full[qb], 2 * SP_QTILE);
+        tma_load_3d(&map_q, &q_full[qb], sQ + qb * 2 * SP_QTILE, h * SP_HD, b * p.Lq + qt * SP_QM, 0);
+        tma_load_3d(&map_q, &q_full[qb], sQ + qb * 2 * SP_QTILE + SP_QTILE, p.q_lo_col + h * SP_HD, b * p.Lq + qt * SP_QM, 0);
+      };
+      issue_q(0);
+      if (p.n_qt > 1) issue_q(1);
+      const int n_hi = p.kpad > 256 ? 256 : p.kpad, n_lo = p.kpad - n_hi;
+      const uint32_t id_hi = sp_idesc(SP_QM, n_hi, false), id_lo = sp_idesc(SP_QM, n_lo > 0 ? n_lo : 16, false);
+      const uint32_t id_pv = sp_idesc(SP_QM, SP_HD, true);
+      const int ksteps = p.kpad >> 4;
+      mbar_wait(kv_full, 0);
+      for (int qt = 0; qt < p.n_qt; ++qt) {
+        const int qb = qt & 1;
+        mbar_wait(&q_full[qb], (qt >> 1) & 1);
+        tc_fence_after();
+        // ---- S = Qlo Khi^T + Qhi Klo^T + Qhi Khi^T  (tcgen05.mma from one thread execute in issue order: this also follows P.V(qt-1))
+        const uint32_t qh = smem_u32(sQ + qb * 2 * SP_QTILE), ql = qh + SP_QTILE;
+        const uint32_t kh = smem_u32(sKh), kl = smem_u32(sKl);
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t qa = pass == 0 ? ql : qh, ka = pass == 1 ? kl : kh;
+          const uint64_t dq = make_sw128_kmajor_desc(qa), dk = make_sw128_kmajor_desc(ka), dk2 = make_sw128_kmajor_desc(ka + 256 * 128);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t acc = (pass | ks) != 0 ? 1u : 0u;
+            umma<false>(tS, dq + 2 * ks, dk + 2 * ks, id_hi, acc);
+            if (n_lo > 0) umma<false>(tS + 256, dq + 2 * ks, dk2 + 2 * ks, id_lo, acc);
+          }
+        }
+        umma_commit(s_full);
+        // the Q buffer is free once S has been computed: prefetch tile qt + 2 into it
+        if (qt + 2 < p.n_qt) {
+          mbar_wait(s_full, qt & 1);
+          issue_q(qt + 2);
+        }
+        mbar_wait(p_full, qt & 1);                       // P(qt) is in TMEM
+        if (qt > 0) mbar_wait(o_empty, (qt - 1) & 1);    // epilogue(qt-1) has read O
+        tc_fence_after();
+        // ---- O = Plo Vhi + Phi Vlo + Phi Vhi : per 16-key step, A = 8 packed-fp16 TMEM columns, B = 16 V rows (2048 B)
+        const uint64_t dvh = make_sw128_kmajor_desc(smem_u32(sVh)), dvl = make_sw128_kmajor_desc(smem_u32(sVl));
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint32_t a_hi = tS + (ks >> 1) * 32 + (ks & 1) * 8, a_lo = a_hi + 16;
+          sp_umma_ts(tO, a_lo, dvh + (uint64_t)(ks * 128), id_pv, ks != 0 ? 1u : 0u);
+          sp_umma_ts(tO, a_hi, dvl + (uint64_t)(ks * 128), id_pv, 1u);
+          sp_umma_ts(tO, a_hi, dvh + (uint64_t)(ks * 128), id_pv, 1u);
+        }
+        umma_commit(o_full);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax + epilogue warps
+    const int quad = warp & 3, half = warp >> 2;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const int row_in_tile = quad * 32 + lane;
+    const int n_chunks = p.kpad >> 5;
+    const int csplit = (n_chunks + 1) >> 1;
+    const int c_begin = (half == 0 ? 0 : csplit) * 32, c_end = (half == 0 ? csplit : n_chunks) * 32;
+    for (int qt = 0; qt < p.n_qt; ++qt) {
+      const bool live = qt * SP_QM + quad * 32 < p.Lq;  // a 32-row slab entirely beyond Lq does no exp work; its rows are never stored
+      mbar_wait(s_full, qt & 1);
+      tc_fence_after();
+      float mx = -INFINITY, sum = 0.f;
+      float* smx = s_max + (qt & 1) * 256;
+      if (live) {
+        for (int c = c_begin; c < c_end; c += 32) {
+          uint32_t sv[32];
+          tmem_ld_32x32(tS + lane_off + c, sv);
+          tmem_ld_wait();
+          if (c + 32 <= p.Lk) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(sv[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c + j < p.Lk) mx = fmaxf(mx, __uint_as_float(sv[j]));
+          }
+        }
+      }
+      smx[half * 128 + row_in_tile] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (live) {
+        mx = fmaxf(mx, smx[(half ^ 1) * 128 + row_in_tile]);
+        const float ms = mx * p.scale_log2e;
+        for (int c = c_begin; c < c_end; c += 32) {
+          uint32_t sv[32];
+          tmem_ld_32x32(tS + lane_off + c, sv);
+          tmem_ld_wait();
+          uint32_t ph[16], pl[16];
+          const bool full = c + 32 <= p.Lk;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float p0 = sp_ex2(fmaf(__uint_as_float(sv[2 * j]), p.scale_log2e, -ms));
+            float p1 = sp_ex2(fmaf(__uint_as_float(sv[2 * j + 1]), p.scale_log2e, -ms));
+            if (!full) {
+              if (c + 2 * j >= p.Lk) p0 = 0.f;
+              if (c + 2 * j + 1 >= p.Lk) p1 = 0.f;
+            }
+            sum += p0 + p1;
+            const __half2 hh = __floats2half2_rn(p0, p1);  // low half = even key
+            const __half2 ll = __floats2half2_rn(p0 - __low2float(hh), p1 - __high2float(hh));
+            ph[j] = *reinterpret_cast<const uint32_t*>(&hh);
+            pl[j] = *reinterpret_cast<const uint32_t*>(&ll);
+          }
+          sp_tmem_st_x16(tS + lane_off + c, ph);        // in place: this thread has consumed these 32 S columns
+          sp_tmem_st_x16(tS + lane_off + c + 16, pl);
+        }
+        sp_tmem_st_wait();
+      }
+      s_sum[((qt & 1) * 2 + half) * 128 + row_in_tile] = sum;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      // ---- epilogue: this warp's 32 rows x 32 of the 64 output columns
+      mbar_wait(o_full, qt & 1);
+      tc_fence_after();
+      const int row = qt * SP_QM + row_in_tile;
+      if (live) {
+        const float inv = 1.0f / (s_sum[((qt & 1) * 2) * 128 + row_in_tile] + s_sum[((qt & 1) * 2 + 1) * 128 + row_in_tile]);
+        uint32_t ov[32];
+        tmem_ld_32x32(tO + lane_off + half * 32, ov);
+        tmem_ld_wait();
+        if (row < p.Lq) {
+          __half* orow = p.o + ((long long)b * p.Lq + row) * p.ldo + h * SP_HD + half * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint32_t uh[4], ul[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float x0 = __uint_as_float(ov[j + 2 * e]) * inv, x1 = __uint_as_float(ov[j + 2 * e + 1]) * inv;
+              const __half2 hh = __floats2half2_rn(x0, x1);
+              const __half2 ll = __floats2half2_rn(x0 - __low2float(hh), x1 - __high2float(hh));
+              uh[e] = *reinterpret_cast<const uint32_t*>(&hh);
+              ul[e] = *reinterpret_cast<const uint32_t*>(&ll);
+            }
+            *reinterpret_cast<uint4*>(orow + j) = make_uint4(uh[0], uh[1], uh[2], uh[3]);
+            *reinterpret_cast<uint4*>(orow + p.o_lo_off + j) = make_uint4(ul[0], ul[1], ul[2], ul[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+}  // namespace
+}  // namespace dsb
+
+extern "C" int dsb_attention_tc_split(const void* q, long long ldq, long long q_lo_off, const void* k, long long ldk, long long k_lo_off, const void* v,
+                                      long long ldv, long long v_lo_off, void* o, long long ldo, long long o_lo_off, int B, int H, int Lq, int Lk,
+                                      float scale, void* stream) {
+  using namespace dsb;
+  DSB_REQUIRE(B > 0 && H > 0 && Lq > 0 && Lk > 0 && Lk <= SP_KMAX, "dsb_attention_tc_split: need 0 < Lk <= %d", SP_KMAX);
+  DSB_REQUIRE(ldo % 8 == 0 && o_lo_off % 8 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0, "dsb_attention_tc_split: o must be 16-byte aligned, ldo / o_lo_off %% 8 == 0");
+  DSB_REQUIRE(q_lo_off >= (long long)H * SP_HD && k_lo_off >= (long long)H * SP_HD && v_lo_off >= (long long)H * SP_HD && o_lo_off >= (long long)H * SP_HD,
+              "dsb_attention_tc_split: the lo halves must not overlap the hi halves");
+  DSB_REQUIRE(q_lo_off + (long long)H * SP_HD <= ldq && k_lo_off + (long long)H * SP_HD <= ldk && v_lo_off + (long long)H * SP_HD <= ldv,
+              "dsb_attention_tc_split: lo halves must lie inside a row (lo_off + H*64 <= ld)");
+  SpParams p{};
+  p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk;
+  p.kpad = (Lk + 31) & ~31;
+  p.n_qt = (Lq + SP_QM - 1) / SP_QM;
+  p.n_box = p.kpad > 256 ? 2 : 1;
+  p.box_rows = p.kpad / p.n_box;
+  DSB_REQUIRE(p.box_rows % 8 == 0, "dsb_attention_tc_split: internal box size");
+  p.q_lo_col = (int)q_lo_off; p.k_lo_col = (int)k_lo_off; p.v_lo_col = (int)v_lo_off;
+  p.ldo = ldo; p.o_lo_off = o_lo_off; p.o = (__half*)o;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  uint32_t cols = 32;
+  while ((int)cols < p.kpad + SP_HD) cols <<= 1;
+  p.tmem_cols = cols;
+  CUtensorMap mq, mk, mv;
+  if (make_operand_map(&mq, q, DSB_DTYPE_F16, q_lo_off + (long long)H * SP_HD, (long long)B * Lq, 1, ldq, 0, SP_QM)) return 3;
+  if (make_operand_map(&mk, k, DSB_DTYPE_F16, k_lo_off + (long long)H * SP_HD, (long long)B * Lk, 1, ldk, 0, p.box_rows)) return 3;
+  if (make_operand_map(&mv, v, DSB_DTYPE_F16, v_lo_off + (long long)H * SP_HD, (long long)B * Lk, 1, ldv, 0, p.box_rows)) return 3;
+  const int smem = 4 * SP_QTILE + 4 * p.kpad * 128 + (512 + 512) * 4 + 16 * 8 + 1024;
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    DSB_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
+  }
+  DSB_CHECK_CUDA(launch_pdl(attention_tc_split_kernel, dim3(H, B), dim3(SP_THREADS), smem, (cudaStream_t)stream, mq, mk, mv, p));
+  return 0;
+}

@@ -44,7 +44,9 @@ struct GemmParams {
   int num_taps;
   int tap_shift[MAX_TAPS];
   int tap_acol[MAX_TAPS];
-  int kc;          // channels per tap (B column offset per tap)
+  int tap_wcol[MAX_TAPS];  // W column offset per tap (default tap * Kc)
+  long long split_off;     // DSB_GEMM_OUT_F16_SPLIT: offset of the lo half inside an output row
+  int kc;          // channels per tap
   int b_batched;
   const float* bias;
   const float* residual;
@@ -77,12 +79,12 @@ template <int BLOCK_N>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, float* sw, uint32_t tmem_acc, uint64_t* tmem_full_bar, uint32_t aphase,
                                               int row_base, int n_blk, int b, int q, int half, int lane) {
   const bool has_geo = p.geo_P > 0;
-  const int out_mode = (p.flags & DSB_GEMM_OUT_F16) ? 1 : ((p.flags & DSB_GEMM_OUT_BF16) ? 2 : 0);
+  const int out_mode = (p.flags & DSB_GEMM_OUT_F16_SPLIT) ? 3 : ((p.flags & DSB_GEMM_OUT_F16) ? 1 : ((p.flags & DSB_GEMM_OUT_BF16) ? 2 : 0));
   const int act = (p.flags & DSB_GEMM_GELU2) ? 1 : ((p.flags & DSB_GEMM_LRELU) ? 2 : ((p.flags & DSB_GEMM_TANH) ? 3 : 0));
   const bool do_round = (p.flags & DSB_GEMM_ROUND_TF32) != 0;
   const bool res_first = (p.flags & DSB_GEMM_RES_BEFORE_ACT) != 0;
   const int out_es = out_mode ? 2 : 4;
-  const bool vec_ok = ((p.ldo & 3) == 0) && ((p.out_bstride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & (4 * out_es - 1)) == 0) &&
+  const bool vec_ok = ((p.ldo & 3) == 0) && ((p.out_bstride & 3) == 0) && ((p.split_off & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & (4 * out_es - 1)) == 0) &&
                       (!p.residual || (((p.ld_res & 3) == 0) && ((p.res_bstride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0))) &&
                       (!p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0));
   const int c4 = lane & 7;    // float4 column slot inside the 32-column chunk
@@ -195,6 +197,20 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, float* sw, ui
         u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
         *reinterpret_cast<uint2*>(op + (long long)i * 4 * p.ldo) = u;
       }
+      } else if (out_mode == 3) {  // fp16 (hi | lo) pair: the A operand of a split-fp16 GEMM / attention
+    __half* op = reinterpret_cast<__half*>(p.out) + out_boff + (long long)(row_base + rsub) * p.ldo + col;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if ((ok_mask >> i) & 1u) {
+        const __half2 h0 = __floats2half2_rn(x[4 * i], x[4 * i + 1]), h1 = __floats2half2_rn(x[4 * i + 2], x[4 * i + 3]);
+        const __half2 l0 = __floats2half2_rn(x[4 * i] - __low2float(h0), x[4 * i + 1] - __high2float(h0));
+        const __half2 l1 = __floats2half2_rn(x[4 * i + 2] - __low2float(h1), x[4 * i + 3] - __high2float(h1));
+        uint2 u, w;
+        u.x = *reinterpret_cast<const uint32_t*>(&h0); u.y = *reinterpret_cast<const uint32_t*>(&h1);
+        w.x = *reinterpret_cast<const uint32_t*>(&l0); w.y = *reinterpret_cast<const uint32_t*>(&l1);
+        *reinterpret_cast<uint2*>(op + (long long)i * 4 * p.ldo) = u;
+        *reinterpret_cast<uint2*>(op + (long long)i * 4 * p.ldo + p.split_off) = w;
+      }
       } else {
     __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + out_boff + (long long)(row_base + rsub) * p.ldo + col;
 #pragma unroll
@@ -231,6 +247,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, float* sw, ui
       const long long o = out_boff + row * p.ldo + col + k;
       if (out_mode == 0) reinterpret_cast<float*>(p.out)[o] = xv;
       else if (out_mode == 1) reinterpret_cast<__half*>(p.out)[o] = __float2half_rn(xv);
+      else if (out_mode == 3) {
+        const __half hv = __float2half_rn(xv);
+        reinterpret_cast<__half*>(p.out)[o] = hv;
+        reinterpret_cast<__half*>(p.out)[o + p.split_off] = __float2half_rn(xv - __half2float(hv));
+      }
       else reinterpret_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16(xv);
     }
       }
@@ -310,7 +331,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             for (int j = 0; j < BLOCK_N / 64; ++j)
               tma_load_3d(&tmap_b, &full_bar[stage], sa + S::A_BYTES + j * MN_BOX_BYTES, n_blk * BLOCK_N + j * 64, c0, p.b_batched ? b : 0);
           } else {
-            tma_load_3d(&tmap_b, &full_bar[stage], sa + S::A_BYTES, tap * p.kc + c0, n_blk * BLOCK_N, p.b_batched ? b : 0);
+            tma_load_3d(&tmap_b, &full_bar[stage], sa + S::A_BYTES, p.tap_wcol[tap] + c0, n_blk * BLOCK_N, p.b_batched ? b : 0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -496,7 +517,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           const uint32_t bar = map_to_cta(smem_u32(&full_bar[stage]), 0);
           uint8_t* sa = smem + stage * S::STAGE_BYTES;
           tma_load_3d_2sm(&tmap_a, bar, sa, c0 + p.tap_acol[tap], row0 + p.tap_shift[tap], b);
-          tma_load_3d_2sm(&tmap_b, bar, sa + S::A_BYTES, tap * p.kc + c0, nrow0, p.b_batched ? b : 0);
+          tma_load_3d_2sm(&tmap_b, bar, sa + S::A_BYTES, p.tap_wcol[tap] + c0, nrow0, p.b_batched ? b : 0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -675,7 +696,10 @@ extern "C" int dsb_gemm_ex(const dsb_gemm_desc* d, void* stream) {
   for (int i = 0; i < MAX_TAPS; ++i) {
     p.tap_shift[i] = i < d->num_taps ? d->tap_shift[i] : 0;
     p.tap_acol[i] = i < d->num_taps ? d->tap_acol[i] : 0;
+    p.tap_wcol[i] = i < d->num_taps ? (d->use_tap_wcol ? d->tap_wcol[i] : i * d->K) : 0;
   }
+  p.split_off = d->split_off > 0 ? d->split_off : d->N;
+  DSB_REQUIRE(!(d->flags & DSB_GEMM_OUT_F16_SPLIT) || d->batch == 1, "dsb_gemm_ex: DSB_GEMM_OUT_F16_SPLIT takes batch == 1");
   p.kc = d->K;
   p.b_batched = d->w_batch_stride != 0;
   p.bias = d->bias; p.residual = d->residual; p.ld_res = d->ld_res; p.res_bstride = d->res_batch_stride;
@@ -725,8 +749,8 @@ extern "C" int dsb_gemm_ex(const dsb_gemm_desc* d, void* stream) {
   } else if (make_operand_map(&ma, d->A, kind, d->a_cols > 0 ? d->a_cols : d->K, a_rows, d->batch, d->lda, d->a_batch_stride, BLOCK_M)) return 3;
   if (p.b_mn) {
     if (make_operand_map_mn(&mb, d->W, kind, d->N, d->K, p.b_batched ? d->batch : 1, d->ldw, d->w_batch_stride)) return 3;
-  } else if (make_operand_map(&mb, d->W, kind, (long long)d->K * d->num_taps, d->N, p.b_batched ? d->batch : 1, d->ldw, d->w_batch_stride,
-                              use_pair ? block_n / 2 : block_n)) return 3;
+  } else if (make_operand_map(&mb, d->W, kind, d->w_cols > 0 ? d->w_cols : (long long)d->K * d->num_taps, d->N, p.b_batched ? d->batch : 1, d->ldw,
+                              d->w_batch_stride, use_pair ? block_n / 2 : block_n)) return 3;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int max_ctas = d->max_ctas > 0 ? d->max_ctas : sms;
   if (use_pair) {

@@ -80,7 +80,7 @@ layernorm_kernel(const float* __restrict__ x, void* __restrict__ out, const floa
     b4 = reinterpret_cast<const float4*>(p0 + ti * 2LL * D + D);  // shift
   }
   const bool rnd = (flags & DSB_GEMM_ROUND_TF32) != 0;
-  const int omode = (flags & DSB_GEMM_OUT_F16) ? 1 : ((flags & DSB_GEMM_OUT_BF16) ? 2 : 0);
+  const int omode = (flags & DSB_GEMM_OUT_F16_SPLIT) ? 3 : ((flags & DSB_GEMM_OUT_F16) ? 1 : ((flags & DSB_GEMM_OUT_BF16) ? 2 : 0));
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
     const int i = lane + 32 * j;
@@ -98,6 +98,16 @@ layernorm_kernel(const float* __restrict__ x, void* __restrict__ out, const floa
       uint2 u;
       u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
       reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out) + (long long)row * D)[i] = u;
+    } else if (omode == 3) {  // fp16 (hi | lo) pair, 2*D columns per row: the A operand of a split-fp16 GEMM
+      const __half2 h0 = __floats2half2_rn(y.x, y.y), h1 = __floats2half2_rn(y.z, y.w);
+      const __half2 l0 = __floats2half2_rn(y.x - __low2float(h0), y.y - __high2float(h0));
+      const __half2 l1 = __floats2half2_rn(y.z - __low2float(h1), y.w - __high2float(h1));
+      uint2 u, w;
+      u.x = *reinterpret_cast<const uint32_t*>(&h0); u.y = *reinterpret_cast<const uint32_t*>(&h1);
+      w.x = *reinterpret_cast<const uint32_t*>(&l0); w.y = *reinterpret_cast<const uint32_t*>(&l1);
+      __half* orow = reinterpret_cast<__half*>(out) + (long long)row * 2 * D;
+      reinterpret_cast<uint2*>(orow)[i] = u;
+      reinterpret_cast<uint2*>(orow + D)[i] = w;
     } else if (omode == 2) {
       __nv_bfloat162 h0 = __floats2bfloat162_rn(y.x, y.y), h1 = __floats2bfloat162_rn(y.z, y.w);
       uint2 u;

@@ -19,13 +19,17 @@ from . import ops
 
 
 class DenoiserEngine:
-    def __init__(self, transformer, precision: str = "f16"):
-        """precision: 'f16'  -- fp16 GEMM operands on tcgen05 kind::f16 (11-bit significand = TF32's, at twice the rate), fp32
-                                accumulation, fp32 residual stream / LayerNorm statistics / softmax / logits;
-                      'tf32' -- fp32 containers rounded to TF32, tcgen05 kind::tf32;
-                      'fp32' -- exact FFMA GEMMs (slow; the fp32-exact mode of SURVEY.md section 7.2)."""
-        if precision not in ("f16", "tf32", "fp32"):
-            raise ValueError("precision must be 'f16', 'tf32' or 'fp32'")
+    def __init__(self, transformer, precision: str = "f16x3"):
+        """precision: 'f16x3' -- the parity-grade tensor-core mode (default): every GEMM / attention operand is an fp16 (hi | lo) pair
+                                (22 significand bits), products run as three tcgen05 kind::f16 passes (lo*hi + hi*lo + hi*hi) into one
+                                fp32 TMEM accumulator; fp32 residual stream / LayerNorm / softmax / logits.  fp32-class logits (the
+                                reference computes its nn.Linear layers in fp32): free-running token ids reproduce the fp32 oracle;
+                      'f16'   -- single-pass fp16 operands (11-bit significand = TF32's, at twice the TF32 rate): 3x fewer MMAs, logits
+                                within ~1e-3 of fp32, token agreement ~99.6 % -- the throughput mode;
+                      'tf32'  -- fp32 containers rounded to TF32, tcgen05 kind::tf32;
+                      'fp32'  -- exact FFMA GEMMs (slow; the fp32-exact mode of SURVEY.md section 7.2)."""
+        if precision not in ("f16x3", "f16", "tf32", "fp32"):
+            raise ValueError("precision must be 'f16x3', 'f16', 'tf32' or 'fp32'")
         self.m = transformer
         self.precision = precision
         self.packed = False
@@ -38,8 +42,14 @@ class DenoiserEngine:
     def device(self):
         return self.m.to_logits[1].weight.device
 
-    def _prep(self, w: torch.Tensor) -> torch.Tensor:
+    def _prep(self, w: torch.Tensor):
         w = w.detach().float().contiguous()
+        if self.precision == "f16x3":
+            # (hi | lo) fp16 pair of 2^s * W, s chosen so the largest weight sits near 2^13: the lo halves of ordinary weights stay
+            # clear of fp16's subnormal range; the GEMM epilogue multiplies by alpha = 2^-s (exact)
+            amax = float(w.abs().max())
+            s = 0 if amax == 0.0 or not math.isfinite(amax) else 13 - math.frexp(amax)[1]
+            return _SplitWeight(ops.split_f16(w, 2.0 ** s), 2.0 ** (-s))
         if self.precision == "f16":
             return ops.to_f16(w)
         return ops.round_tf32(w) if self.precision == "tf32" else w.clone()
@@ -54,6 +64,7 @@ class DenoiserEngine:
         self.H = m.n_head
         self.n_layer = len(m.blocks)
         self.T = m.diffusion_step
+        self.mlp_times = m.blocks[0].mlp[0].weight.shape[0] // m.n_embd
         D = self.D
         if D % 64 or D // self.H != 64:
             raise RuntimeError(f"kernels are specialised for head_dim 64 (n_embd={D}, n_head={self.H})")
@@ -82,7 +93,7 @@ class DenoiserEngine:
         self.wlog, self.blog = self._prep(m.to_logits[1].weight), f(m.to_logits[1].bias)
         ce = m.content_emb
         self.emb, self.hemb, self.wemb = f(ce.emb.weight), f(ce.height_emb.weight), f(ce.width_emb.weight)
-        self.K = self.wlog.shape[0]
+        self.K = m.to_logits[1].weight.shape[0]
         self.packed = True
         self.generation += 1
         self._ws.clear()
@@ -99,14 +110,19 @@ class DenoiserEngine:
         if ws is None:
             dev, M, D = self.device, B * L, self.D
             e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
-            a = (lambda *s: torch.empty(*s, dtype=torch.float16, device=dev)) if self.precision == "f16" else e  # GEMM A operands
-            ws = dict(x=e(B, L, D), h=a(B, L, D), qkv=a(M, 3 * D), att=a(M, D), q2=a(M, D), hid=a(M, self.layers[0]["w1"].shape[0]),
+            if self.precision == "f16x3":  # every GEMM A operand is an fp16 (hi | lo) pair: twice the columns
+                a = lambda *s: torch.zeros(*s[:-1], 2 * s[-1], dtype=torch.float16, device=dev)
+            else:
+                a = (lambda *s: torch.empty(*s, dtype=torch.float16, device=dev)) if self.precision == "f16" else e  # GEMM A operands
+            ws = dict(x=e(B, L, D), h=a(B, L, D), qkv=a(M, 3 * D), att=a(M, D), q2=a(M, D), hid=a(M, self.mlp_times * D),
                       logits=e(B, L, self.K), err=torch.zeros(1, dtype=torch.int32, device=dev))
             self._ws[key] = ws
         return ws
 
     # ------------------------------------------------------------------ compute
-    def _linear(self, a, w, bias, residual=None, out=None, gelu=False, round_out=False):
+    def _linear(self, a, w, bias, residual=None, out=None, gelu=False, round_out=False, split_out=False):
+        if self.precision == "f16x3":
+            return ops.gemm_f16x3(a, w.pair, bias, residual, out, alpha=w.alpha, gelu=gelu, split_out=split_out)
         if self.precision == "f16":
             return ops.gemm(a, w, bias, residual, out, dtype=ops.F16, gelu=gelu)
         if self.precision == "tf32":
@@ -120,11 +136,14 @@ class DenoiserEngine:
             self.repack()
         B, Lc, Cd = cond_emb.shape
         c = cond_emb.detach().float().reshape(B * Lc, Cd).contiguous()
+        if self.precision == "f16x3":
+            out = torch.empty(B * Lc, 2 * self.n_layer * 2 * self.D, dtype=torch.float16, device=c.device)  # (hi | lo) pair of every layer's K|V
+            return self._linear(ops.split_f16(c), self.wkv_all, self.bkv_all, out=out, split_out=True)
         if self.precision == "tf32":
             c = ops.round_tf32(c)
         elif self.precision == "f16":
             c = ops.to_f16(c)
-        out = torch.empty(B * Lc, self.wkv_all.shape[0], dtype=torch.float16 if self.precision == "f16" else torch.float32, device=c.device)
+        out = torch.empty(B * Lc, self.n_layer * 2 * self.D, dtype=torch.float16 if self.precision == "f16" else torch.float32, device=c.device)
         return self._linear(c, self.wkv_all, self.bkv_all, out=out)
 
     @torch.no_grad()
@@ -138,6 +157,8 @@ class DenoiserEngine:
         ws = self.workspace(B, L)
         x, h, qkv, att, q2, hid = ws["x"], ws["h"], ws["qkv"], ws["att"], ws["q2"], ws["hid"]
         rnd = self.precision == "tf32"
+        if self.precision == "f16x3":
+            return self._forward_split(ids, kv_all, t, Lc, out)
         x2 = x.view(B * L, D)
         h2 = h.view(B * L, D)
         scale = 1.0 / math.sqrt(64)
@@ -169,3 +190,51 @@ class DenoiserEngine:
         self._linear(h2, self.wlog, self.blog, out=logits.view(B * L, self.K))
         self.launches_per_forward = n + 2
         return logits
+
+    @torch.no_grad()
+    def _forward_split(self, ids, kv_all, t, Lc, out=None):
+        """The 'f16x3' pass: same launch sequence as forward(), every tensor-core operand an fp16 (hi | lo) pair.
+        qkv (M, 6D) = [Qh Kh Vh | Ql Kl Vl]; kv_all (B*Lc, 2 * n_layer*2D) = [hi of every layer's K|V | lo ...]."""
+        B, L = ids.shape
+        D, H = self.D, self.H
+        ws = self.workspace(B, L)
+        x, h, qkv, att, q2, hid = ws["x"], ws["h"], ws["qkv"], ws["att"], ws["q2"], ws["hid"]
+        M = B * L
+        x2, h2 = x.view(M, D), h.view(M, 2 * D)
+        scale = 1.0 / math.sqrt(64)
+        kv_lo = self.n_layer * 2 * D
+        n = 0
+        ops.embed_tokens(ids, self.emb, self.hemb, self.wemb, out=x, err_flag=ws["err"]); n += 1
+        for li, lay in enumerate(self.layers):
+            ops.ada_layernorm(x, lay["tab1"], t, out=h, split=True)
+            self._linear(h2, lay["wqkv"], lay["bqkv"], out=qkv, split_out=True)
+            ops.attention_tc_split(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:3 * D], att[:, :D], q_lo=3 * D, k_lo=3 * D, v_lo=3 * D, o_lo=D,
+                                   B=B, H=H, Lq=L, Lk=L, scale=scale)
+            self._linear(att, lay["wo1"], lay["bo1"], residual=x2, out=x2)
+            ops.ada_layernorm(x, lay["tab2"], t, out=h, split=True)
+            self._linear(h2, lay["wq2"], lay["bq2"], out=q2, split_out=True)
+            kv = kv_all[:, li * 2 * D:]
+            ops.attention_tc_split(q2[:, :D], kv[:, :D], kv[:, D:2 * D], att[:, :D], q_lo=D, k_lo=kv_lo, v_lo=kv_lo, o_lo=D,
+                                   B=B, H=H, Lq=L, Lk=Lc, scale=scale)
+            self._linear(att, lay["wo2"], lay["bo2"], residual=x2, out=x2)
+            ops.layernorm(x, lay["g2"], lay["b2"], out=h, eps=lay["eps2"], split=True)
+            self._linear(h2, lay["w1"], lay["b1"], out=hid, gelu=True, split_out=True)
+            self._linear(hid, lay["w2"], lay["bm2"], residual=x2, out=x2)
+            n += 11
+        ops.layernorm(x, self.gf, self.bf, out=h, eps=self.epsf, split=True)
+        logits = ws["logits"] if out is None else out
+        self._linear(h2, self.wlog, self.blog, out=logits.view(M, self.K))
+        self.launches_per_forward = n + 2
+        return logits
+
+
+class _SplitWeight:
+    """fp16 (hi | lo) pair of 2^s * W, (N, 2K), plus alpha = 2^-s for the GEMM epilogue."""
+    __slots__ = ("pair", "alpha")
+
+    def __init__(self, pair, alpha):
+        self.pair, self.alpha = pair, alpha
+
+    @property
+    def shape(self):
+        return (self.pair.shape[0], self.pair.shape[1] // 2)

@@ -13,6 +13,7 @@ from . import _lib
 
 TF32, BF16, F16 = 0, 1, 2
 GELU2, ROUND_TF32, OUT_BF16, LRELU, TANH, GN_SWISH, GN_COMPACT, RES_BEFORE_ACT, OUT_F16, SPLIT_OUT = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512
+OUT_F16_SPLIT = 2048
 
 
 def _stream() -> int:
@@ -100,6 +101,34 @@ def gemm_split(a_split: torch.Tensor, w_split: torch.Tensor, bias=None, residual
     return gemm(a_split, w_split, bias, residual, out, dtype=TF32, taps=t3, tap_acol=ac, k_per_tap=Cp, **kw)
 
 
+def split_f16(x: torch.Tensor, scale: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(rows, C) fp32 -> (rows, 2C) fp16 [hi | lo] with hi = f16(scale*x), lo = f16(scale*x - hi): one operand of a split-fp16 ("f16x3") GEMM."""
+    _need_cuda(x)
+    if x.dim() != 2 or x.stride(1) != 1:
+        raise RuntimeError("split_f16 needs a 2-D tensor contiguous in its last dimension")
+    rows, Cc = x.shape
+    if out is None:
+        out = torch.empty(rows, 2 * Cc, dtype=torch.float16, device=x.device)
+    _lib.check(_lib.lib().dsb_split_f16(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), Cc, rows, Cc, float(scale), _stream()), "dsb_split_f16")
+    return out
+
+
+def gemm_f16x3(a_pair: torch.Tensor, w_pair: torch.Tensor, bias=None, residual=None, out=None, *, alpha: float = 1.0, gelu: bool = False,
+               split_out: bool = False, **kw) -> torch.Tensor:
+    """Split-fp16 GEMM at fp32-class accuracy on tcgen05: a_pair (M, 2K) [Ahi | Alo], w_pair (N, 2K) [Whi | Wlo] (both from split_f16 or a
+    split_out producer); out = epi(alpha * (Alo Whi^T + Ahi Wlo^T + Ahi Whi^T) + bias) (+ residual), fp32 accumulation over all three passes.
+    split_out: write the result as an fp16 (hi | lo) pair (M, 2N) for the next split GEMM / attention instead of fp32."""
+    K = a_pair.shape[-1] // 2
+    if w_pair.shape[-1] != 2 * K:
+        raise RuntimeError(f"gemm_f16x3: W pair has {w_pair.shape[-1]} columns, expected {2 * K}")
+    N = w_pair.shape[0]
+    M = a_pair.shape[0]
+    if out is None:
+        out = torch.empty(M, 2 * N, dtype=torch.float16, device=a_pair.device) if split_out else torch.empty(M, N, dtype=torch.float32, device=a_pair.device)
+    return gemm(a_pair, w_pair, bias, residual, out, dtype=F16, taps=[0, 0, 0], tap_acol=[K, 0, 0], tap_wcol=[0, K, 0], k_per_tap=K, alpha=alpha,
+                gelu=gelu, split_out=split_out, **kw)
+
+
 def silu(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _need_cuda(x, out)
     x = x.contiguous()
@@ -112,7 +141,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
          out: Optional[torch.Tensor] = None, *, dtype: int = TF32, gelu: bool = False, round_out: bool = False, out_bf16: bool = False, out_f16: bool = False,
          lrelu: bool = False, tanh: bool = False, res_before_act: bool = False, taps: Optional[Sequence[int]] = None,
          tap_acol: Optional[Sequence[int]] = None, k_per_tap: Optional[int] = None, out_rows: Optional[int] = None, geo: Optional[Sequence[int]] = None, alpha: float = 1.0,
-         block_n: int = 0, max_ctas: int = 0, cta_pair: int = 0, a_mn: bool = False, w_mn: bool = False) -> torch.Tensor:
+         block_n: int = 0, max_ctas: int = 0, cta_pair: int = 0, a_mn: bool = False, w_mn: bool = False,
+         tap_wcol: Optional[Sequence[int]] = None, split_out: bool = False) -> torch.Tensor:
     """out = epi(alpha * A @ W^T + bias) (+ residual) on tcgen05.  a: (M,K) or (batch,M,K); w: (N, taps*K) or (batch,N,K).
     a_mn / w_mn: that operand is given MN-major, i.e. as it lies in memory with the reduction dimension as rows -- a: (K, M), w: (K, N)
     (2-byte dtypes): out = a^T @ w with no transposed copies."""
@@ -125,14 +155,16 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     a_rows, a_cols = (a.shape[-1], a.shape[-2]) if a_mn else (a.shape[-2], a.shape[-1])  # (M, K)
     K = a_cols if k_per_tap is None else k_per_tap  # reduction length per tap (A may hold several K blocks side by side)
     N = w.shape[-1] if w_mn else w.shape[-2]
-    if (w.shape[-2] if w_mn else w.shape[-1]) != K * ntaps:
+    if tap_wcol is None and (w.shape[-2] if w_mn else w.shape[-1]) != K * ntaps:
         raise RuntimeError(f"gemm: W has reduction length {w.shape[-2] if w_mn else w.shape[-1]}, expected {K}*{ntaps}")
     M = a_rows if out_rows is None else out_rows
     odt = torch.bfloat16 if out_bf16 else (torch.float16 if out_f16 else torch.float32)
     if out is None:
         out = torch.empty((batch, M, N) if batched else (M, N), dtype=odt, device=a.device)
-    out_f16 = out.dtype == torch.float16
+    out_f16 = out.dtype == torch.float16 and not split_out
     out_bf16 = out.dtype == torch.bfloat16
+    if split_out and (out.dtype != torch.float16 or batched):
+        raise RuntimeError("gemm: split_out writes an fp16 (hi | lo) pair and is not batched")
     d = _lib.GemmDesc()
     d.A, d.W, d.bias, d.residual, d.out = a.data_ptr(), w.data_ptr(), _ptr(bias), _ptr(residual), out.data_ptr()
     d.M, d.N, d.K, d.batch = M, N, K, batch
@@ -144,7 +176,14 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     d.out_batch_stride = out.stride(0) if batched else 0
     d.res_batch_stride = residual.stride(0) if (residual is not None and batched) else 0
     d.dtype = dtype
-    d.flags = (GELU2 if gelu else 0) | (ROUND_TF32 if round_out else 0) | (OUT_BF16 if out_bf16 else 0) | (LRELU if lrelu else 0) | (TANH if tanh else 0) | (RES_BEFORE_ACT if res_before_act else 0) | (OUT_F16 if out_f16 else 0)
+    d.flags = (GELU2 if gelu else 0) | (ROUND_TF32 if round_out else 0) | (OUT_BF16 if out_bf16 else 0) | (LRELU if lrelu else 0) | (TANH if tanh else 0) | (RES_BEFORE_ACT if res_before_act else 0) | (OUT_F16 if out_f16 else 0) | (OUT_F16_SPLIT if split_out else 0)
+    if split_out:
+        d.split_off = N
+    if tap_wcol is not None:
+        d.use_tap_wcol = 1
+        d.w_cols = w.shape[-1]
+        for i, c_ in enumerate(tap_wcol):
+            d.tap_wcol[i] = int(c_)
     d.num_taps = ntaps
     for i, s in enumerate(taps or [0]):
         d.tap_shift[i] = int(s)
@@ -182,7 +221,9 @@ def embed_tokens(ids, emb, height_emb, width_emb, out=None, err_flag=None):
     return out
 
 
-def _out_flags(out, round_out):
+def _out_flags(out, round_out, split=False):
+    if split:
+        return OUT_F16_SPLIT
     if out.dtype == torch.float16:
         return OUT_F16
     if out.dtype == torch.bfloat16:
@@ -190,24 +231,31 @@ def _out_flags(out, round_out):
     return ROUND_TF32 if round_out else 0
 
 
-def layernorm(x, gamma, beta, out=None, *, eps=1e-5, round_out=False, out_bf16=False):
+def layernorm(x, gamma, beta, out=None, *, eps=1e-5, round_out=False, out_bf16=False, split=False):
+    """split: out is the fp16 (hi | lo) pair (..., 2D) of the fp32 result (the A operand of gemm_f16x3)."""
     _need_cuda(x, gamma, beta)
     D = x.shape[-1]
     rows = x.numel() // D
     if out is None:
-        out = torch.empty(x.shape, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x.device)
-    flags = _out_flags(out, round_out)
+        out = torch.empty(*x.shape[:-1], 2 * D, dtype=torch.float16, device=x.device) if split else \
+            torch.empty(x.shape, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x.device)
+    if split and (out.dtype != torch.float16 or out.shape[-1] != 2 * D):
+        raise RuntimeError("layernorm(split=True) writes an fp16 (..., 2D) tensor")
+    flags = _out_flags(out, round_out, split)
     _lib.check(_lib.lib().dsb_layernorm(x.data_ptr(), out.data_ptr(), gamma.data_ptr(), beta.data_ptr(), rows, D, eps, flags, _stream()), "dsb_layernorm")
     return out
 
 
-def ada_layernorm(x, table, t, out=None, *, eps=1e-5, round_out=False, out_bf16=False):
-    """x (B,L,D), table (T,2D) = Linear(SiLU(emb)) rows, t (B,) int64."""
+def ada_layernorm(x, table, t, out=None, *, eps=1e-5, round_out=False, out_bf16=False, split=False):
+    """x (B,L,D), table (T,2D) = Linear(SiLU(emb)) rows, t (B,) int64.  split: as layernorm()."""
     _need_cuda(x, table, t)
     B, L, D = x.shape
     if out is None:
-        out = torch.empty(x.shape, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x.device)
-    flags = _out_flags(out, round_out)
+        out = torch.empty(B, L, 2 * D, dtype=torch.float16, device=x.device) if split else \
+            torch.empty(x.shape, dtype=torch.bfloat16 if out_bf16 else torch.float32, device=x.device)
+    if split and (out.dtype != torch.float16 or out.shape[-1] != 2 * D):
+        raise RuntimeError("ada_layernorm(split=True) writes an fp16 (..., 2D) tensor")
+    flags = _out_flags(out, round_out, split)
     _lib.check(_lib.lib().dsb_ada_layernorm(x.data_ptr(), out.data_ptr(), table.data_ptr(), t.data_ptr(), B, L, D, table.shape[0], eps, flags, _stream()),
                "dsb_ada_layernorm")
     return out
@@ -255,6 +303,17 @@ def attention_tc(q, k, v, out, *, B, H, Lq, Lk, scale, pipelined=True):
     fn = _lib.lib().dsb_attention_tc2 if pipelined else _lib.lib().dsb_attention_tc
     _lib.check(fn(q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), out.data_ptr(), out.stride(0),
                   B, H, Lq, Lk, scale, _stream()), "dsb_attention_tc")
+    return out
+
+
+def attention_tc_split(q, k, v, out, *, q_lo, k_lo, v_lo, o_lo, B, H, Lq, Lk, scale):
+    """Split-fp16 tcgen05 attention: q/k/v/out are the hi halves (row-strided fp16 views, head h = columns [64h, 64h+64)); the matching lo half
+    of every row lies *_lo elements further along the row."""
+    _need_cuda(q, k, v, out)
+    if not all(t_.dtype == torch.float16 and t_.stride(-1) == 1 for t_ in (q, k, v, out)):
+        raise RuntimeError("attention_tc_split needs fp16 tensors contiguous in the head dimension")
+    _lib.check(_lib.lib().dsb_attention_tc_split(q.data_ptr(), q.stride(0), q_lo, k.data_ptr(), k.stride(0), k_lo, v.data_ptr(), v.stride(0), v_lo,
+                                                 out.data_ptr(), out.stride(0), o_lo, B, H, Lq, Lk, scale, _stream()), "dsb_attention_tc_split")
     return out
 
 
