@@ -15,22 +15,8 @@ def G():
 
 
 def build_dt(K, D, NL, NH, CD, sd=None, spatial=(5, 53), T=100, precision="f16"):
-    from diffsound_b200.modeling.transformers.diffusion_transformer import DiffusionTransformer
-    cfg = dict(
-        content_emb_config=dict(target="diffsound_b200.modeling.embeddings.dalle_mask_image_embedding.DalleMaskImageEmbedding",
-                                params=dict(num_embed=K, spatial_size=spatial, embed_dim=D, trainable=True, pos_emb_type="embedding")),
-        condition_emb_config=None,
-        transformer_config=dict(target="diffsound_b200.modeling.transformers.transformer_utils.Text2ImageTransformer",
-                                params=dict(attn_type="selfcross", n_layer=NL, condition_seq_len=77, content_seq_len=spatial[0] * spatial[1],
-                                            content_spatial_size=list(spatial), n_embd=D, condition_dim=CD, n_head=NH, attn_pdrop=0.0,
-                                            resid_pdrop=0.0, block_activate="GELU2", timestep_type="adalayernorm", mlp_hidden_times=4, precision=precision)),
-        diffusion_step=T, alpha_init_type="alpha1", auxiliary_loss_weight=5.0e-4, adaptive_auxiliary_loss=True, mask_weight=[1, 1])
-    m = DiffusionTransformer(**cfg)
-    if sd is not None:
-        missing, unexpected = m.load_state_dict(sd, strict=False)
-        assert not unexpected, unexpected
-        assert all("attn2.mask" in k for k in missing), missing  # the golden drops the dead causal-mask buffers
-    return m.cuda().eval()
+    from diffsound_b200.utils.builders import build_diffusion_transformer
+    return build_diffusion_transformer(K, D, NL, NH, CD, sd, spatial=spatial, T=T, precision=precision)
 
 
 def test_state_dict_keys_match_reference_golden(G):

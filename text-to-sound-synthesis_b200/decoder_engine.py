@@ -26,6 +26,7 @@ class DecoderEngine:
         self.packed = False
         self.launches = 0
         self.use_cuda_graph = True
+        self.max_batch = 32  # clips per pass: bounds the activation memory (34.7 MB fp32 per clip per full-resolution tensor) at any caller batch
         self._graphs = GraphCache()
 
     def _pack_conv(self, conv) -> torch.Tensor:
@@ -164,6 +165,8 @@ class DecoderEngine:
             self.repack()
         H, W = grid
         ids = ids.contiguous()
+        if ids.shape[0] > self.max_batch:
+            return torch.cat([self.decode_tokens(ids[i:i + self.max_batch], grid) for i in range(0, ids.shape[0], self.max_batch)], 0)
 
         def body(ids_):
             self.launches = 1

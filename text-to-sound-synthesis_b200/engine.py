@@ -11,6 +11,7 @@ What is hoisted relative to the reference (all algebraically identical):
 from __future__ import annotations
 
 import math
+import copy
 from typing import Dict, Optional
 
 import torch
@@ -36,6 +37,21 @@ class DenoiserEngine:
         self._ws: Dict[int, dict] = {}
         self.launches_per_forward = 0
         self.generation = 0  # bumped by repack(): captured CUDA graphs that baked old pointers must be rebuilt
+        self._param_sig = None
+
+    def __deepcopy__(self, memo):
+        """copy.deepcopy(module) (the reference EMA's shadow model, engine/ema.py:19) gets a fresh, unpacked engine bound to the COPIED module:
+        packed weights, workspaces and anything captured in CUDA graphs are per-instance caches, not state."""
+        return DenoiserEngine(memo.get(id(self.m), self.m), precision=self.precision)
+
+    def _signature(self):
+        """(storage pointer, in-place version counter) of every parameter: changes on optimizer.step(), p.data.copy_(), EMA swaps, .to()."""
+        return tuple((p.data_ptr(), p._version) for p in self.m.parameters())
+
+    def ensure_current(self) -> None:
+        """Repack if the module's parameters changed since the packed copies were made (in-place updates do not go through load_state_dict)."""
+        if not self.packed or self._param_sig != self._signature():
+            self.repack()
 
     # ------------------------------------------------------------------ weights
     @property
@@ -94,6 +110,7 @@ class DenoiserEngine:
         ce = m.content_emb
         self.emb, self.hemb, self.wemb = f(ce.emb.weight), f(ce.height_emb.weight), f(ce.width_emb.weight)
         self.K = m.to_logits[1].weight.shape[0]
+        self._param_sig = self._signature()
         self.packed = True
         self.generation += 1
         self._ws.clear()
@@ -119,6 +136,14 @@ class DenoiserEngine:
             self._ws[key] = ws
         return ws
 
+    def check_token_range(self, B: int, L: int) -> None:
+        """Raise the reference's embedding error (dalle_mask_image_embedding.py:40-44 -> torch's index error) if a forward pass since the last check
+        saw a token id >= num_embed; one 4-byte D2H read, call it once per sample() / training forward, outside any graph capture."""
+        ws = self._ws.get((B, L))
+        if ws is not None and int(ws["err"].item()) != 0:
+            ws["err"].zero_()
+            raise IndexError(f"index out of range in self: a content token id >= num_embed ({self.emb.shape[0]}) reached DalleMaskImageEmbedding")
+
     # ------------------------------------------------------------------ compute
     def _linear(self, a, w, bias, residual=None, out=None, gelu=False, round_out=False, split_out=False):
         if self.precision == "f16x3":
@@ -132,8 +157,7 @@ class DenoiserEngine:
     @torch.no_grad()
     def encode_condition(self, cond_emb: torch.Tensor) -> torch.Tensor:
         """cond_emb (B, Lc, cond_dim) -> K/V of every layer's cross-attention, (B*Lc, n_layer*2D)."""
-        if not self.packed:
-            self.repack()
+        self.ensure_current()
         B, Lc, Cd = cond_emb.shape
         c = cond_emb.detach().float().reshape(B * Lc, Cd).contiguous()
         if self.precision == "f16x3":

@@ -89,6 +89,56 @@ class DALLE(nn.Module):
         p = self.first_stage_permuter
         return (p.H, p.W)
 
+    @torch.no_grad()
+    def reconstruct(self, input):
+        """mel (B,1,80,848) -> encoder -> nearest codes -> decoder (reference :250-262; the reference body calls a VQModel.get_tokens that
+        does not exist in its codec -- `sefl.encode`, spec_codec/vqgan.py:84-85 -- so this implements the evident intent with DALLE.get_tokens)."""
+        if torch.is_tensor(input):
+            input = input.to(self.device)
+        quant_z, indices = self.get_tokens(input)
+        return self.decode_to_img(indices, quant_z.shape)
+
+    @torch.no_grad()
+    def sample(self, batch, clip=None, temperature=1.0, return_rec=True, filter_ratio=[0, 0.5, 1.0], content_ratio=[1], return_att_weight=False,
+               return_logits=False, sample_type="normal", **kwargs):
+        """Training-time preview sampler (reference :264-338), the call `Solver.sample` makes every `sample_iterations`
+        (engine/solver_spec.py:209-213: `model.sample(batch=batch, step=self.last_iter)`).  For each filter_ratio fr the ground-truth tokens are
+        noised to t = 100*fr - 1 (fr = 0: all-[MASK] start) and denoised back; every grid is decoded to a mel.  Returns the reference's dict:
+        'condition', 'input_image', 'reconstruction_image', 'cond1_cont{cr}_fr{fr}_image' (+ 'logits')."""
+        if return_att_weight:
+            raise NotImplementedError("attention maps are never materialised by the fused attention kernels (the reference's own path reads "
+                                      "self.content.token_shape, which does not exist: dalle_spec.py:330)")
+        if sample_type == "debug":
+            raise NotImplementedError("sample_debug does not exist in the reference's DiffusionTransformer either")
+        self.eval()
+        condition = self.prepare_condition(batch)
+        content = self.prepare_content(batch)
+        content_samples = {"input_image": batch.get(self.content_info["key"])}
+        B = content["content_token"].shape[0]
+        zshape = content["content_quant"].shape if "content_quant" in content else (B, self.content_codec.quantize.e_dim, *self._grid())
+        if return_rec:
+            content_samples["reconstruction_image"] = self.decode_to_img(content["content_token"], zshape)
+        prev_trunc, prev_rate = self.transformer.truncation, self.transformer.resample_rate
+        self.transformer.truncation, self.transformer.resample_rate = None, 0.0  # the reference's sample() path does not wrap predict_start
+        for fr in filter_ratio:
+            for cr in content_ratio:
+                num_content_tokens = int(content["content_token"].shape[1] * cr)
+                if num_content_tokens < 0:
+                    continue
+                content_token = content["content_token"][:, :num_content_tokens]
+                trans_out = self.transformer.sample(condition_token=condition["condition_token"], condition_mask=condition.get("condition_mask", None),
+                                                    condition_embed=condition.get("condition_embed_token", None), content_token=content_token,
+                                                    filter_ratio=fr, temperature=temperature, return_att_weight=False, return_logits=return_logits,
+                                                    content_logits=content.get("content_logits", None), sample_type=sample_type, batch_size=B, **kwargs)
+                content_samples["cond1_cont{}_fr{}_image".format(cr, fr)] = self.decode_to_img(trans_out["content_token"], zshape)
+                if return_logits:
+                    content_samples["logits"] = trans_out["logits"]
+        self.transformer.truncation, self.transformer.resample_rate = prev_trunc, prev_rate
+        self.train()
+        output = {"condition": batch.get(self.condition_info["key"])}
+        output.update(content_samples)
+        return output
+
     def parameters(self, recurse=True, name=None):
         """Reference override (dalle_spec.py:51-62): `name` selects sub-modules ('transformer') and forwards to their own parameters(name=...)."""
         if name is None or name == "none":

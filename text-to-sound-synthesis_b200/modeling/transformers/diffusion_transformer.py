@@ -101,6 +101,16 @@ class DiffusionTransformer(nn.Module):
         self._graphs = {}
         self.last_gpu_launches = 0
 
+    def __deepcopy__(self, memo):
+        """EMA's shadow copy (reference engine/ema.py:19): captured CUDA graphs / schedule caches belong to this instance only."""
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = {} if k == "_graphs" else (None if k == "_sched_cache" else copy.deepcopy(v, memo))
+        return new
+
     # ------------------------------------------------------------------ helpers
     @property
     def device(self):
@@ -192,6 +202,7 @@ class DiffusionTransformer(nn.Module):
         assert self.loss_type == "vb_stochastic"
         B, L = x.shape
         x = x.contiguous()
+        oob = ((x < 0) | (x >= self.num_classes)).any()  # read together with the accuracy flags below (no extra sync point)
         t, pt = self.sample_time(B, x.device, "importance")
         uniform = torch.rand(B, self.num_classes, L, dtype=torch.float32, device=x.device)  # == rand_like(log_EV_qxt_x0), :360
         x_t = train_ops.q_sample(x, t.contiguous(), uniform, self._sched(), self.num_timesteps)
@@ -200,6 +211,8 @@ class DiffusionTransformer(nn.Module):
                                                    names, *params)
         # accuracy bookkeeping of :424-436 (one small D2H copy instead of 2B .item() calls)
         rate = hits.float().mean(dim=1).cpu()
+        if bool(oob):  # the reference asserts in index_to_log_onehot (diffusion_transformer.py:46-47)
+            raise AssertionError(f"Error: content token id outside [0, {self.num_classes})")
         for i, this_t in enumerate(t.tolist()):
             self.diffusion_acc_list[this_t] = float(rate[i, 0]) * 0.1 + self.diffusion_acc_list[this_t] * 0.9
             self.diffusion_keep_list[this_t] = float(rate[i, 1]) * 0.1 + self.diffusion_keep_list[this_t] * 0.9
@@ -266,7 +279,9 @@ class DiffusionTransformer(nn.Module):
             else:
                 self._fused_step(st)
         self.last_gpu_launches = len(steps) * (eng.launches_per_forward + 1)
-        return st["x"].clone()
+        out = st["x"].clone()
+        eng.check_token_range(B, L)  # a token id >= num_embed raises like the reference's embedding lookup (one 4-byte read after the loop)
+        return out
 
     def _cond(self, condition_token, condition_embed):
         if self.condition_emb is not None:
@@ -290,6 +305,30 @@ class DiffusionTransformer(nn.Module):
         if self.resample_rate > 0:  # host-side coin per step, like the reference's wrapper (python `random`, dalle_spec.py:139-141)
             import random
             steps = [s_ for t_ in steps for s_ in ([t_, t_] if random.random() < self.resample_rate else [t_])]
+        if self._stages_overridden():
+            content_token = self._sample_unfused(cond_emb, batch_size, steps, steps, x_init=x_init)
+        else:
+            content_token = self._run_steps(cond_emb, batch_size, steps, steps, x_init=x_init)
+        output = {"content_token": content_token}
+        if return_logits:
+            output["logits"] = torch.exp(index_to_log_onehot(content_token, self.num_classes))
+        return output
+
+    @torch.no_grad()
+    def sample_uniform_only(self, condition_token, condition_mask, condition_embed, content_token=None, filter_ratio=0.5, temperature=1.0,
+                            return_att_weight=False, return_logits=False, content_logits=None, print_log=True, **kwargs):
+        """Reference :661-746: as sample(), but filter_ratio = 0 starts from tokens drawn uniformly from [0, K-1) (the reference's
+        `torch.randint(0, self.num_classes-2, ...)` on the CPU generator) instead of all-[MASK]."""
+        batch_size = condition_token.shape[0] if condition_token is not None else kwargs["batch_size"]
+        start_step = int(self.num_timesteps * filter_ratio)
+        cond_emb = self._cond(condition_token, condition_embed)
+        if start_step == 0:
+            x_init = torch.randint(0, self.num_classes - 2, (batch_size, self.shape)).to(self.device)
+            start_step = self.num_timesteps
+        else:
+            t0 = torch.full((batch_size,), start_step - 1, device=self.device, dtype=torch.long)
+            x_init = self.q_sample(index_to_log_onehot(content_token, self.num_classes), t0, return_index=True)
+        steps = list(range(start_step - 1, -1, -1))
         if self._stages_overridden():
             content_token = self._sample_unfused(cond_emb, batch_size, steps, steps, x_init=x_init)
         else:

@@ -5,6 +5,7 @@ Same constructor arguments and the same state_dict keys, 
 training goes through ``DenoiserTrainEngine`` (called from DiffusionTransformer._train_loss).  The sub-modules
 below only HOLD parameters under the reference's names -- they have no torch forward (there is no fallback path).
 """
+import copy
 import math
 
 import torch
@@ -72,7 +73,7 @@ class Text2ImageTransformer(nn.Module):
     def __init__(self, condition_seq_len=77, n_layer=14, n_embd=1024, n_head=16, content_seq_len=1024, attn_pdrop=0, resid_pdrop=0,
                  mlp_hidden_times=4, block_activate=None, attn_type="selfcross", content_spatial_size=[32, 32], condition_dim=512,
                  diffusion_step=1000, timestep_type="adalayernorm", content_emb_config=None, mlp_type="fc", checkpoint=False,
-                 precision="f16", train_precision="bf16"):
+                 precision="f16x3", train_precision="bf16"):
         super().__init__()
         assert attn_type == "selfcross"
         assert mlp_type == "fc", "conv_mlp is not used by the Diffsound configs"
@@ -96,6 +97,20 @@ class Text2ImageTransformer(nn.Module):
         self.train_engine = DenoiserTrainEngine(self, precision=train_precision)  # forward-with-activations + backward (A13)
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.engine.__setattr__("packed", False))
 
+    def __deepcopy__(self, memo):
+        """EMA's copy.deepcopy (reference engine/ema.py:19): copy parameters / buffers / hooks, give the copy its own fresh engines (packed weights,
+        workspaces with saved activations and captured CUDA graphs are caches of THIS instance and cannot be deep-copied)."""
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k in ("engine", "train_engine"):
+                continue
+            new.__dict__[k] = copy.deepcopy(v, memo)
+        new.engine = DenoiserEngine(new, precision=self.engine.precision)
+        new.train_engine = DenoiserTrainEngine(new, precision=self.train_engine.precision)
+        return new
+
     def _init_weights(self, module):  # same distribution as the reference (:355-363)
         if isinstance(module, (nn.Linear, nn.Embedding)):
             module.weight.data.normal_(mean=0.0, std=0.02)
@@ -116,6 +131,7 @@ class Text2ImageTransformer(nn.Module):
     @torch.no_grad()
     def forward(self, input, cond_emb, t):
         """input (B,L) int64 ids, cond_emb (B,Lc,condition_dim) fp32, t (B,) int64 -> logits (B, K, L) (view, as the reference's rearrange)."""
-        kv = self.engine.encode_condition(cond_emb)
+        kv = self.engine.encode_condition(cond_emb)  # repacks first if the parameters changed (optimizer.step(), EMA swap, ...)
         logits = self.engine.forward(input.contiguous(), kv, t.to(input.device).contiguous(), cond_emb.shape[1])
+        self.engine.check_token_range(*input.shape)
         return logits.clone().permute(0, 2, 1)  # clone: the engine reuses its workspace on the next call

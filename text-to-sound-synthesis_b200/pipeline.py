@@ -12,10 +12,15 @@ import torch
 
 
 @torch.no_grad()
-def synthesize(dalle, vocoder, cond_emb: torch.Tensor, *, sample_type: str = "top0.85r", seed: Optional[int] = None):
-    """cond_emb (B,77,512) on the device -> dict(tokens (B,265) int64, mel (B,1,80,848) in ~[-1,1], wav (B,1,217088))."""
+def synthesize(dalle, vocoder, cond_emb: torch.Tensor, *, sample_type: str = "top0.85r", seed: Optional[int] = None, codec_batch: Optional[int] = None):
+    """cond_emb (B,77,512) on the device -> dict(tokens (B,265) int64, mel (B,1,80,848) in ~[-1,1], wav (B,1,217088)).
+    codec_batch: clips per SpecVQGAN-decoder / MelGAN pass (default: the engines' max_batch); the sampler always runs the whole batch."""
     if seed is not None:
         torch.manual_seed(seed)
+    if codec_batch:
+        dalle.content_codec.engine.max_batch = int(codec_batch)
+        if vocoder is not None:
+            vocoder.engine.max_batch = int(codec_batch)
     out = dalle.generate_content(batch={"condition_embed": cond_emb}, filter_ratio=0, replicate=1, sample_type=sample_type)
     mel = out["content"]
     spec01 = (mel[:, 0] + 1) / 2  # the script's (spec + 1) / 2 before saving / vocoding (generate_samples_batch.py:181)

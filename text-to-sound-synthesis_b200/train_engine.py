@@ -208,7 +208,7 @@ class DenoiserTrainEngine:
                 fn()
             cur.wait_stream(side)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):  # the backward graph is captured from autograd's worker thread; other threads (pin-memory) may touch CUDA
                 fn()
             ent = self._graphs[key] = (g, ptrs)
         ent[0].replay()

@@ -33,6 +33,7 @@ class VocoderEngine:
         self.packed = False
         self.launches = 0
         self.use_cuda_graph = True
+        self.max_batch = 32  # clips per pass (27.8 MB fp32 per clip for the widest activation)
         self._graphs = GraphCache()
 
     def _pack(self, w2d: torch.Tensor, ntaps: int) -> torch.Tensor:
@@ -91,6 +92,8 @@ class VocoderEngine:
         if not mel.is_cuda:
             raise RuntimeError("VocoderEngine.forward needs a CUDA tensor (no CPU fallback)")
         mel = mel.detach().float().contiguous()
+        if mel.shape[0] > self.max_batch:
+            return torch.cat([self.forward(mel[i:i + self.max_batch]) for i in range(0, mel.shape[0], self.max_batch)], 0)
         if self.use_cuda_graph:
             return self._graphs.run(tuple(mel.shape), self._forward, mel)
         return self._forward(mel)

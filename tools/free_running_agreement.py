@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import _pkg; _pkg.load()
 from diffsound_b200 import ops
 from oracle import diffsound_oracle as O
-from tests.test_gpu_transformer import build_dt
+from diffsound_b200.utils.builders import build_diffusion_transformer as build_dt
 NL = int(sys.argv[1]) if len(sys.argv) > 1 else 19
 K, D, NH, CD, B, L = 256, 1024, 16, 512, 1, 265
 torch.set_num_threads(16)

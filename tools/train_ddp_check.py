@@ -14,7 +14,7 @@ sys.path.insert(0, ROOT)
 import _pkg  # noqa: E402
 
 _pkg.load()
-from tests.test_gpu_transformer import build_dt  # noqa: E402
+from diffsound_b200.utils.builders import build_diffusion_transformer as build_dt  # noqa: E402
 
 
 def main():
