@@ -28,7 +28,8 @@ def test_split_f16_reconstructs_fp32(G):
     # 22 significand bits, with an absolute floor of half an fp16 subnormal quantum (2^-25) for the lo half of small values
     assert bool(((rec - x.double()).abs() <= torch.maximum(3e-7 * x.double().abs(), torch.tensor(3.0e-8, dtype=torch.float64, device="cuda"))).all())
     ps = G.ops.split_f16(x * 1e-4, 2.0 ** 12)  # power-of-two prescale keeps small values out of fp16's subnormals
-    assert float(((_pair_value(ps, 192) / 4096 - (x * 1e-4).double()).abs() / (x * 1e-4).double().abs().clamp_min(1e-7)).max()) < 3e-7
+    xs = (x * 1e-4).double()
+    assert bool(((_pair_value(ps, 192) / 4096 - xs).abs() <= torch.maximum(3e-7 * xs.abs(), torch.tensor(3.0e-8 / 4096, dtype=torch.float64, device="cuda"))).all())
 
 
 @pytest.mark.parametrize("M,N,K", [(4240, 1024, 1024), (530, 3072, 1024), (265, 1024, 4096), (154, 2048, 512), (100, 256, 1024)])

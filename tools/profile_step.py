@@ -10,16 +10,21 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from bench import build_model, synthetic_cond  # noqa: E402
+from bench import synthetic_cond  # noqa: E402
+import _pkg  # noqa: E402
+_pkg.load()
+from diffsound_b200.utils.builders import build_diffusion_transformer  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--batch", type=int, default=16)
-ap.add_argument("--precision", default="f16")
+ap.add_argument("--precision", default="f16x3")
 ap.add_argument("--layers", type=int, default=19)
 args = ap.parse_args()
 
-m = build_model(256, args.layers, args.precision)
+torch.manual_seed(0)
+m = build_diffusion_transformer(256, 1024, args.layers, 16, 512, precision=args.precision)
+m.truncation = "top0.85r"
 m.use_cuda_graph = False
 cond = synthetic_cond(args.batch, 1).cuda()
 torch.manual_seed(1234)
