@@ -38,11 +38,15 @@ extern "C" {
 #define DSB_GEMM_TANH 16      /* tanh                           (reference vocoder/modules.py:123) */
 #define DSB_GEMM_OUT_F16 256   /* store fp16 instead of fp32 */
 #define DSB_GEMM_RES_BEFORE_ACT 128 /* add the residual before the activation (default: after) */
+#define DSB_GEMM_DUAL_LRELU 4096 /* with OUT_F16_SPLIT: also store the pair of LeakyReLU(0.2)(x) at +dual_off (reference vocoder/modules.py:76: the
+                                   next ResnetBlock convolves the activated signal while its 1x1 shortcut reads the raw one) */
 #define DSB_GEMM_OUT_F16_SPLIT 2048 /* store the fp16 (hi | lo) pair of the fp32 result: hi = f16(x) at out[r*ldo + c], lo = f16(x - hi) at
                                        out[r*ldo + split_off + c] -- the A operand of a split-fp16 ("f16x3") GEMM, see dsb_split_f16 */
 /* GroupNorm-apply flags (share the ROUND_TF32 bit) */
 #define DSB_GN_SWISH 32       /* x * sigmoid(x) after the affine (reference model.py:29-31) */
 #define DSB_GN_COMPACT 64     /* write (B, Lp, C) tokens instead of the zero-padded image */
+#define DSB_SPLIT_OUT_F16 8192 /* elementwise producers: write the fp16 (hi | lo) pair, 2*C halves per row (out is then a __half buffer): the A
+                                  operand of a split-fp16 conv GEMM (codebook gather, GroupNorm apply, upsample) */
 #define DSB_SPLIT_OUT 512     /* elementwise producers: write the split-TF32 operand (hi | lo), 2*Cp floats per row (see dsb_split_tf32) */
 
 const char* dsb_last_error(void);
@@ -89,6 +93,14 @@ typedef struct dsb_gemm_desc {
   int tap_wcol[32];
   long long w_cols;      /* columns of W that exist (0 -> num_taps*K) */
   long long split_off;   /* DSB_GEMM_OUT_F16_SPLIT: element offset of the lo half inside an output row (0 -> N) */
+  long long dual_off;    /* DSB_GEMM_DUAL_LRELU: element offset of the LeakyReLU(0.2) copy of the output pair */
+  int out_col_group;     /* > 0: logical output column n is stored at (n / group) * out_col_group_stride + n % group -- lets the polyphase
+                            ConvTranspose1d GEMM (columns = phase * Cout + c) write straight into rows of [raw pair | activated pair] */
+  int out_col_group_stride;
+  const void* A2;        /* optional second A operand (same dtype, K-major): taps with tap_a2[i] != 0 read it instead of A -- one GEMM over two
+                            activation buffers, e.g. MelGAN's ResnetBlock tail  shortcut(x) + conv1x1(y)  (vocoder/modules.py:84-85) */
+  long long a2_rows, a2_cols, lda2, a2_batch_stride;
+  int tap_a2[32];
 } dsb_gemm_desc;
 int dsb_gemm_ex(const dsb_gemm_desc* desc, void* stream);
 
@@ -228,6 +240,17 @@ int dsb_tokens_add_to_padded(const float* tok, float* xpad, int B, int H, int W,
  * ------------------------------------------------------------------------------------------------------------- */
 int dsb_lrelu_pad(const float* in, float* out, int B, int T, int C, int pad, float slope, int reflect, int in_channel_major, int flags,
                   void* stream);
+/* Split-fp16 ("f16x3") MelGAN path.  Activations live in per-stage STATE buffers (B, P + T + P, 4C) fp16 whose rows are
+ * [raw_hi | raw_lo | act_hi | act_lo], act = LeakyReLU(0.2)(raw); every Conv1d / ConvTranspose1d / ResnetBlock tail is one dsb_gemm_ex over
+ * them (taps = row shifts into the P pad rows; DSB_GEMM_OUT_F16_SPLIT | DSB_GEMM_DUAL_LRELU writes the next state's rows).
+ * dsb_mel_pack_f16: mel (B, Cm, T) fp32 (Generator.forward's input, vocoder/modules.py:129) -> (B, T + 2 pad, 2 Kp) fp16 [hi | lo],
+ *   ReflectionPad1d(pad) applied in time (:96), channel columns [Cm, Kp) zero (Kp = K rounded up to the GEMM's 64-wide k-block).
+ * dsb_edge_pad_f16: fills pad rows P-j and P+T-1+j (j = 1..d) of columns [col0, col0 + ncols) of every clip with the reflection of rows
+ *   P+j / P+T-1-j (ReflectionPad1d(dilation), :77; ReflectionPad1d(3), :121) or with zeros (the zero-extended input of the polyphase
+ *   ConvTranspose1d taps). */
+int dsb_mel_pack_f16(const float* mel, void* out_f16, int B, int Cm, int T, int pad, int Kp, void* stream);
+int dsb_edge_pad_f16(void* state_f16, long long ld, long long batch_stride, int B, int T, int P, int d, int col0, int ncols, int reflect,
+                     void* stream);
 
 
 /* ---------------------------------------------------------------------------------------------------------------

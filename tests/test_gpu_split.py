@@ -44,12 +44,13 @@ def test_gemm_f16x3_matches_fp64(G, M, N, K):
     ref = _pair_value(ap, K) @ (_pair_value(wp, K) / 2.0 ** 17).T + b.double()
     out = ops.gemm_f16x3(ap, wp, b, alpha=2.0 ** -17)
     scale = float(ref.abs().max())
-    assert float((out.double() - ref).abs().max()) / scale < 2e-6
+    tol = 2e-6 * max(1.0, (K / 1024) ** 0.5)  # fp32 accumulation over 3K products: rounding noise grows like sqrt(K)
+    assert float((out.double() - ref).abs().max()) / scale < tol
     out_r = ops.gemm_f16x3(ap, wp, b, residual=r, alpha=2.0 ** -17)
-    assert float((out_r.double() - (ref + r.double())).abs().max()) / scale < 2e-6
+    assert float((out_r.double() - (ref + r.double())).abs().max()) / scale < tol
     pair = ops.gemm_f16x3(ap, wp, b, alpha=2.0 ** -17, split_out=True)
     assert pair.shape == (M, 2 * N) and pair.dtype == torch.float16
-    assert float((_pair_value(pair, N) - ref).abs().max()) / scale < 2e-6
+    assert float((_pair_value(pair, N) - ref).abs().max()) / scale < tol
     g = ops.gemm_f16x3(ap, wp, b, alpha=2.0 ** -17, gelu=True)
     ref_g = ref * torch.sigmoid(1.702 * ref)
     assert float((g.double() - ref_g).abs().max()) / scale < 1e-5  # __expf in the epilogue

@@ -24,6 +24,8 @@ class GemmDesc(C.Structure):
         ("geo_P", c_i), ("geo_Wp", c_i), ("geo_y0", c_i), ("geo_y1", c_i), ("geo_x0", c_i), ("geo_x1", c_i),
         ("alpha", c_f), ("block_n", c_i), ("max_ctas", c_i), ("cta_pair", c_i), ("a_mn_major", c_i), ("b_mn_major", c_i),
         ("use_tap_wcol", c_i), ("tap_wcol", c_i * 32), ("w_cols", c_ll), ("split_off", c_ll),
+        ("dual_off", c_ll), ("out_col_group", c_i), ("out_col_group_stride", c_i), ("A2", c_vp),
+        ("a2_rows", c_ll), ("a2_cols", c_ll), ("lda2", c_ll), ("a2_batch_stride", c_ll), ("tap_a2", c_i * 32),
     ]
 
 
@@ -54,6 +56,8 @@ SIGNATURES = {
     "dsb_row_argmin": [c_vp, c_ll, c_ll, c_i, c_vp, c_vp],
     "dsb_tokens_add_to_padded": [c_vp, c_vp] + [c_i] * 5 + [c_vp],
     "dsb_lrelu_pad": [c_vp, c_vp] + [c_i] * 4 + [c_f, c_i, c_i, c_i, c_vp],
+    "dsb_mel_pack_f16": [c_vp, c_vp] + [c_i] * 5 + [c_vp],
+    "dsb_edge_pad_f16": [c_vp, c_ll, c_ll] + [c_i] * 7 + [c_vp],
     "dsb_attention_f16": [c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_i, c_i, c_i, c_i, c_f, c_i, c_vp],
     "dsb_attention_tc2": [c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_i, c_i, c_i, c_i, c_f, c_vp],
     "dsb_attention_tc": [c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_i, c_i, c_i, c_i, c_f, c_vp],

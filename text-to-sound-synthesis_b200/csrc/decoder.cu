@@ -6,8 +6,21 @@
 // 3x3 tap a pure row shift of the flattened (b, y, x) index.  All kernels here are HBM-bound elementwise/reduction passes.
 #include "common.cuh"
 #include "diffsound_b200.h"
+#include <cuda_fp16.h>
 
 namespace dsb {
+
+// fp16 (hi | lo) pair of four fp32 values: hi at o[0..3], lo at o[lo_off..lo_off+3]  (8-byte stores)
+__device__ __forceinline__ void store_pair_f16(__half* o, long long lo_off, float4 v) {
+  const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+  const __half2 l0 = __floats2half2_rn(v.x - __low2float(h0), v.y - __high2float(h0));
+  const __half2 l1 = __floats2half2_rn(v.z - __low2float(h1), v.w - __high2float(h1));
+  uint2 u, w;
+  u.x = *reinterpret_cast<const uint32_t*>(&h0); u.y = *reinterpret_cast<const uint32_t*>(&h1);
+  w.x = *reinterpret_cast<const uint32_t*>(&l0); w.y = *reinterpret_cast<const uint32_t*>(&l1);
+  *reinterpret_cast<uint2*>(o) = u;
+  *reinterpret_cast<uint2*>(o + lo_off) = w;
+}
 
 __global__ void codebook_gather_padded_kernel(const int64_t* __restrict__ ids, const float* __restrict__ codebook, float* __restrict__ out,
                                               int B, int H, int W, int E, int n_codes, int flags, int* err_flag) {
@@ -19,6 +32,21 @@ __global__ void codebook_gather_padded_kernel(const int64_t* __restrict__ ids, c
   const int p = row % (Hp * Wp);
   const int y = p / Wp - 1, x = p % Wp - 1;
   const bool split = flags & DSB_SPLIT_OUT;
+  if (flags & DSB_SPLIT_OUT_F16) {  // rows of 2E halves: [hi | lo]
+    __half* oh = reinterpret_cast<__half*>(out) + row * 2 * E;
+    const bool inside = !(y < 0 || y >= H || x < 0 || x >= W);
+    long long id = 0;
+    if (inside) {
+      id = ids[(long long)b * H * W + (long long)x * H + y];
+      if (id < 0 || id >= n_codes) {
+        if (lane == 0 && err_flag) atomicExch(err_flag, 1);
+        id = 0;
+      }
+    }
+    const float4* c = reinterpret_cast<const float4*>(codebook + id * E);
+    for (int i = lane; i < E / 4; i += 32) store_pair_f16(oh + i * 4, E, inside ? __ldg(c + i) : make_float4(0.f, 0.f, 0.f, 0.f));
+    return;
+  }
   float4* o = reinterpret_cast<float4*>(out + row * (split ? 2 * E : E));
   if (y < 0 || y >= H || x < 0 || x >= W) {
     for (int i = lane; i < (split ? E / 2 : E / 4); i += 32) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -124,6 +152,10 @@ __global__ void groupnorm_apply_kernel(const float* __restrict__ x, const double
       }
       r = make_float4(o[0], o[1], o[2], o[3]);
     }
+    if (flags & DSB_SPLIT_OUT_F16) {  // rows of 2*C halves: [hi | lo]
+      store_pair_f16(reinterpret_cast<__half*>(out) + orow * 2 * C + c4 * 4, C, r);
+      continue;
+    }
     if (flags & DSB_SPLIT_OUT) {  // rows of 2*C floats: [hi | lo]
       const float4 hi = make_float4(round_tf32(r.x), round_tf32(r.y), round_tf32(r.z), round_tf32(r.w));
       *reinterpret_cast<float4*>(out + orow * 2 * C + c4 * 4) = hi;
@@ -148,6 +180,10 @@ __global__ void upsample2x_padded_kernel(const float* __restrict__ in, float* __
     if (y >= 0 && y < 2 * H && x >= 0 && x < 2 * W) {
       v = *reinterpret_cast<const float4*>(in + (((long long)b * Hi + (y >> 1) + 1) * Wi + (x >> 1) + 1) * C + c4 * 4);
       if (flags & DSB_GEMM_ROUND_TF32) { v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w); }
+    }
+    if (flags & DSB_SPLIT_OUT_F16) {
+      store_pair_f16(reinterpret_cast<__half*>(out) + orow * 2 * C + c4 * 4, C, v);
+      continue;
     }
     if (flags & DSB_SPLIT_OUT) {
       const float4 hi = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));

@@ -45,7 +45,10 @@ struct GemmParams {
   int tap_shift[MAX_TAPS];
   int tap_acol[MAX_TAPS];
   int tap_wcol[MAX_TAPS];  // W column offset per tap (default tap * Kc)
+  unsigned tap_a2_mask;    // bit i set: tap i reads the SECOND A tensor map (a fused GEMM over two activation buffers)
   long long split_off;     // DSB_GEMM_OUT_F16_SPLIT: offset of the lo half inside an output row
+  long long dual_off;      // DSB_GEMM_DUAL_LRELU: offset of the LeakyReLU(0.2) copy (hi at +dual_off, lo at +dual_off+split_off)
+  int ocg, ocg_stride;     // output column groups: logical column n lives at (n / ocg) * ocg_stride + n % ocg (0 = plain)
   int kc;          // channels per tap
   int b_batched;
   const float* bias;
@@ -82,9 +85,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, float* sw, ui
   const int out_mode = (p.flags & DSB_GEMM_OUT_F16_SPLIT) ? 3 : ((p.flags & DSB_GEMM_OUT_F16) ? 1 : ((p.flags & DSB_GEMM_OUT_BF16) ? 2 : 0));
   const int act = (p.flags & DSB_GEMM_GELU2) ? 1 : ((p.flags & DSB_GEMM_LRELU) ? 2 : ((p.flags & DSB_GEMM_TANH) ? 3 : 0));
   const bool do_round = (p.flags & DSB_GEMM_ROUND_TF32) != 0;
+  const bool dual = (p.flags & DSB_GEMM_DUAL_LRELU) != 0;
   const bool res_first = (p.flags & DSB_GEMM_RES_BEFORE_ACT) != 0;
   const int out_es = out_mode ? 2 : 4;
-  const bool vec_ok = ((p.ldo & 3) == 0) && ((p.out_bstride & 3) == 0) && ((p.split_off & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & (4 * out_es - 1)) == 0) &&
+  const bool vec_ok = ((p.ldo & 3) == 0) && ((p.out_bstride & 3) == 0) && ((p.split_off & 3) == 0) && ((p.dual_off & 3) == 0) && ((p.ocg & 3) == 0) &&
+                      ((p.ocg_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & (4 * out_es - 1)) == 0) &&
                       (!p.residual || (((p.ld_res & 3) == 0) && ((p.res_bstride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0))) &&
                       (!p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0));
   const int c4 = lane & 7;    // float4 column slot inside the 32-column chunk
@@ -198,19 +203,28 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, float* sw, ui
         *reinterpret_cast<uint2*>(op + (long long)i * 4 * p.ldo) = u;
       }
       } else if (out_mode == 3) {  // fp16 (hi | lo) pair: the A operand of a split-fp16 GEMM / attention
-    __half* op = reinterpret_cast<__half*>(p.out) + out_boff + (long long)(row_base + rsub) * p.ldo + col;
+    const int ocol = p.ocg > 0 ? (col / p.ocg) * p.ocg_stride + col % p.ocg : col;
+    __half* op = reinterpret_cast<__half*>(p.out) + out_boff + (long long)(row_base + rsub) * p.ldo + ocol;
+#pragma unroll 1
+    for (int pass = 0; pass < (dual ? 2 : 1); ++pass) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if ((ok_mask >> i) & 1u) {
-        const __half2 h0 = __floats2half2_rn(x[4 * i], x[4 * i + 1]), h1 = __floats2half2_rn(x[4 * i + 2], x[4 * i + 3]);
-        const __half2 l0 = __floats2half2_rn(x[4 * i] - __low2float(h0), x[4 * i + 1] - __high2float(h0));
-        const __half2 l1 = __floats2half2_rn(x[4 * i + 2] - __low2float(h1), x[4 * i + 3] - __high2float(h1));
-        uint2 u, w;
-        u.x = *reinterpret_cast<const uint32_t*>(&h0); u.y = *reinterpret_cast<const uint32_t*>(&h1);
-        w.x = *reinterpret_cast<const uint32_t*>(&l0); w.y = *reinterpret_cast<const uint32_t*>(&l1);
-        *reinterpret_cast<uint2*>(op + (long long)i * 4 * p.ldo) = u;
-        *reinterpret_cast<uint2*>(op + (long long)i * 4 * p.ldo + p.split_off) = w;
+      for (int i = 0; i < 8; ++i)
+        if ((ok_mask >> i) & 1u) {
+          const __half2 h0 = __floats2half2_rn(x[4 * i], x[4 * i + 1]), h1 = __floats2half2_rn(x[4 * i + 2], x[4 * i + 3]);
+          const __half2 l0 = __floats2half2_rn(x[4 * i] - __low2float(h0), x[4 * i + 1] - __high2float(h0));
+          const __half2 l1 = __floats2half2_rn(x[4 * i + 2] - __low2float(h1), x[4 * i + 3] - __high2float(h1));
+          uint2 u, w;
+          u.x = *reinterpret_cast<const uint32_t*>(&h0); u.y = *reinterpret_cast<const uint32_t*>(&h1);
+          w.x = *reinterpret_cast<const uint32_t*>(&l0); w.y = *reinterpret_cast<const uint32_t*>(&l1);
+          *reinterpret_cast<uint2*>(op + (long long)i * 4 * p.ldo) = u;
+          *reinterpret_cast<uint2*>(op + (long long)i * 4 * p.ldo + p.split_off) = w;
+        }
+      if (dual) {  // second copy: LeakyReLU(0.2) of the value just stored (the next conv's input; the raw copy feeds the 1x1 shortcut)
+#pragma unroll
+        for (int e = 0; e < 32; ++e) x[e] = x[e] > 0.f ? x[e] : 0.2f * x[e];
+        op += p.dual_off;
       }
+    }
       } else {
     __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + out_boff + (long long)(row_base + rsub) * p.ldo + col;
 #pragma unroll
@@ -248,9 +262,17 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, float* sw, ui
       if (out_mode == 0) reinterpret_cast<float*>(p.out)[o] = xv;
       else if (out_mode == 1) reinterpret_cast<__half*>(p.out)[o] = __float2half_rn(xv);
       else if (out_mode == 3) {
-        const __half hv = __float2half_rn(xv);
-        reinterpret_cast<__half*>(p.out)[o] = hv;
-        reinterpret_cast<__half*>(p.out)[o + p.split_off] = __float2half_rn(xv - __half2float(hv));
+        const int cc = col + k;
+        const long long o3 = out_boff + row * p.ldo + (p.ocg > 0 ? (cc / p.ocg) * p.ocg_stride + cc % p.ocg : cc);
+        __half hv = __float2half_rn(xv);
+        reinterpret_cast<__half*>(p.out)[o3] = hv;
+        reinterpret_cast<__half*>(p.out)[o3 + p.split_off] = __float2half_rn(xv - __half2float(hv));
+        if (dual) {
+          const float yv = xv > 0.f ? xv : 0.2f * xv;
+          hv = __float2half_rn(yv);
+          reinterpret_cast<__half*>(p.out)[o3 + p.dual_off] = hv;
+          reinterpret_cast<__half*>(p.out)[o3 + p.dual_off + p.split_off] = __float2half_rn(yv - __half2float(hv));
+        }
       }
       else reinterpret_cast<__nv_bfloat16*>(p.out)[o] = __float2bfloat16(xv);
     }
@@ -262,7 +284,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, float* sw, ui
 
 template <int BLOCK_N, int KIND>  // KIND = DSB_DTYPE_*
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ GemmParams p) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ GemmParams p) {
   using S = GemmSmem<BLOCK_N>;
   constexpr int STAGES = S::STAGES;
   constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;  // 2 accumulator stages; 256 or 512 (power of two)
@@ -282,6 +305,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_a2);
     prefetch_tmap(&tmap_b);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -324,7 +348,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
             for (int j = 0; j < BLOCK_M / 64; ++j) tma_load_3d(&tmap_a, &full_bar[stage], sa + j * MN_BOX_BYTES, m_blk * BLOCK_M + j * 64, c0, b);
           } else {
-            tma_load_3d(&tmap_a, &full_bar[stage], sa, c0 + p.tap_acol[tap], m_blk * BLOCK_M + p.tap_shift[tap], b);
+            tma_load_3d(((p.tap_a2_mask >> tap) & 1u) ? &tmap_a2 : &tmap_a, &full_bar[stage], sa, c0 + p.tap_acol[tap], m_blk * BLOCK_M + p.tap_shift[tap], b);
           }
           if (p.b_mn) {
 #pragma unroll
@@ -451,7 +475,8 @@ struct PairSmem {
 
 template <int KIND>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
-gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ GemmParams p) {
+gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ CUtensorMap tmap_b,
+                         const __grid_constant__ GemmParams p) {
   using S = PairSmem;
   constexpr int BLOCK_N = S::BLOCK_N;
   constexpr int STAGES = S::STAGES;
@@ -475,6 +500,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_a2);
     prefetch_tmap(&tmap_b);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);   // leader's copy is the one in use: its producer arms expect_tx for both CTAs' bytes
@@ -516,7 +542,7 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
           const uint32_t bar = map_to_cta(smem_u32(&full_bar[stage]), 0);
           uint8_t* sa = smem + stage * S::STAGE_BYTES;
-          tma_load_3d_2sm(&tmap_a, bar, sa, c0 + p.tap_acol[tap], row0 + p.tap_shift[tap], b);
+          tma_load_3d_2sm(((p.tap_a2_mask >> tap) & 1u) ? &tmap_a2 : &tmap_a, bar, sa, c0 + p.tap_acol[tap], row0 + p.tap_shift[tap], b);
           tma_load_3d_2sm(&tmap_b, bar, sa + S::A_BYTES, p.tap_wcol[tap] + c0, nrow0, p.b_batched ? b : 0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -636,7 +662,7 @@ int make_operand_map_mn(CUtensorMap* map, const void* ptr, int kind, long long m
 }
 
 template <int BLOCK_N, int KIND>
-static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int max_ctas, cudaStream_t st) {
+static int launch(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& mb, const GemmParams& p, int max_ctas, cudaStream_t st) {
   using S = GemmSmem<BLOCK_N>;
   auto kern = gemm_tcgen05_kernel<BLOCK_N, KIND>;
   static bool attr_done = false;
@@ -646,12 +672,12 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams
   }
   const int tiles = p.tiles_m * p.tiles_n * p.batch;
   int grid = tiles < max_ctas ? tiles : max_ctas;
-  DSB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), S::TOTAL, st, ma, mb, p));
+  DSB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), S::TOTAL, st, ma, ma2, mb, p));
   return 0;
 }
 
 template <int KIND>
-static int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int max_ctas, cudaStream_t st) {
+static int launch_pair(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& mb, const GemmParams& p, int max_ctas, cudaStream_t st) {
   auto kern = gemm_tcgen05_pair_kernel<KIND>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -662,7 +688,7 @@ static int launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, const GemmP
   int pairs = max_ctas / 2;
   if (pairs < 1) pairs = 1;
   if (tiles < pairs) pairs = tiles;
-  DSB_CHECK_CUDA(launch_pdl(kern, dim3(2 * pairs), dim3(GEMM_THREADS), PairSmem::TOTAL, st, ma, mb, p));
+  DSB_CHECK_CUDA(launch_pdl(kern, dim3(2 * pairs), dim3(GEMM_THREADS), PairSmem::TOTAL, st, ma, ma2, mb, p));
   return 0;
 }
 
@@ -699,7 +725,17 @@ extern "C" int dsb_gemm_ex(const dsb_gemm_desc* d, void* stream) {
     p.tap_wcol[i] = i < d->num_taps ? (d->use_tap_wcol ? d->tap_wcol[i] : i * d->K) : 0;
   }
   p.split_off = d->split_off > 0 ? d->split_off : d->N;
-  DSB_REQUIRE(!(d->flags & DSB_GEMM_OUT_F16_SPLIT) || d->batch == 1, "dsb_gemm_ex: DSB_GEMM_OUT_F16_SPLIT takes batch == 1");
+  p.dual_off = d->dual_off;
+  p.ocg = d->out_col_group; p.ocg_stride = d->out_col_group_stride;
+  p.tap_a2_mask = 0;
+  if (d->A2) {
+    for (int i = 0; i < d->num_taps; ++i)
+      if (d->tap_a2[i]) p.tap_a2_mask |= 1u << i;
+  }
+  DSB_REQUIRE(!(d->flags & DSB_GEMM_DUAL_LRELU) || ((d->flags & DSB_GEMM_OUT_F16_SPLIT) && d->dual_off > 0),
+              "dsb_gemm_ex: DSB_GEMM_DUAL_LRELU needs DSB_GEMM_OUT_F16_SPLIT and dual_off > 0");
+  DSB_REQUIRE(d->out_col_group == 0 || ((d->flags & DSB_GEMM_OUT_F16_SPLIT) && d->out_col_group % 4 == 0 && d->out_col_group_stride % 4 == 0 && !d->residual),
+              "dsb_gemm_ex: output column groups need the split-fp16 output, multiples of 4 and no residual");
   p.kc = d->K;
   p.b_batched = d->w_batch_stride != 0;
   p.bias = d->bias; p.residual = d->residual; p.ld_res = d->ld_res; p.res_bstride = d->res_batch_stride;
@@ -751,19 +787,24 @@ extern "C" int dsb_gemm_ex(const dsb_gemm_desc* d, void* stream) {
     if (make_operand_map_mn(&mb, d->W, kind, d->N, d->K, p.b_batched ? d->batch : 1, d->ldw, d->w_batch_stride)) return 3;
   } else if (make_operand_map(&mb, d->W, kind, d->w_cols > 0 ? d->w_cols : (long long)d->K * d->num_taps, d->N, p.b_batched ? d->batch : 1, d->ldw,
                               d->w_batch_stride, use_pair ? block_n / 2 : block_n)) return 3;
+  CUtensorMap ma2 = ma;
+  if (p.tap_a2_mask) {
+    DSB_REQUIRE(!any_mn, "dsb_gemm_ex: a second A operand is K-major only");
+    if (make_operand_map(&ma2, d->A2, kind, d->a2_cols > 0 ? d->a2_cols : d->K, d->a2_rows > 0 ? d->a2_rows : d->M, d->batch, d->lda2, d->a2_batch_stride, BLOCK_M)) return 3;
+  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int max_ctas = d->max_ctas > 0 ? d->max_ctas : sms;
   if (use_pair) {
-    if (kind == DSB_DTYPE_TF32) return launch_pair<DSB_DTYPE_TF32>(ma, mb, p, max_ctas, st);
-    if (kind == DSB_DTYPE_BF16) return launch_pair<DSB_DTYPE_BF16>(ma, mb, p, max_ctas, st);
-    return launch_pair<DSB_DTYPE_F16>(ma, mb, p, max_ctas, st);
+    if (kind == DSB_DTYPE_TF32) return launch_pair<DSB_DTYPE_TF32>(ma, ma2, mb, p, max_ctas, st);
+    if (kind == DSB_DTYPE_BF16) return launch_pair<DSB_DTYPE_BF16>(ma, ma2, mb, p, max_ctas, st);
+    return launch_pair<DSB_DTYPE_F16>(ma, ma2, mb, p, max_ctas, st);
   }
   if (block_n == 256) {
-    if (kind == DSB_DTYPE_TF32) return launch<256, DSB_DTYPE_TF32>(ma, mb, p, max_ctas, st);
-    if (kind == DSB_DTYPE_BF16) return launch<256, DSB_DTYPE_BF16>(ma, mb, p, max_ctas, st);
-    return launch<256, DSB_DTYPE_F16>(ma, mb, p, max_ctas, st);
+    if (kind == DSB_DTYPE_TF32) return launch<256, DSB_DTYPE_TF32>(ma, ma2, mb, p, max_ctas, st);
+    if (kind == DSB_DTYPE_BF16) return launch<256, DSB_DTYPE_BF16>(ma, ma2, mb, p, max_ctas, st);
+    return launch<256, DSB_DTYPE_F16>(ma, ma2, mb, p, max_ctas, st);
   }
-  if (kind == DSB_DTYPE_TF32) return launch<128, DSB_DTYPE_TF32>(ma, mb, p, max_ctas, st);
-  if (kind == DSB_DTYPE_BF16) return launch<128, DSB_DTYPE_BF16>(ma, mb, p, max_ctas, st);
-  return launch<128, DSB_DTYPE_F16>(ma, mb, p, max_ctas, st);
+  if (kind == DSB_DTYPE_TF32) return launch<128, DSB_DTYPE_TF32>(ma, ma2, mb, p, max_ctas, st);
+  if (kind == DSB_DTYPE_BF16) return launch<128, DSB_DTYPE_BF16>(ma, ma2, mb, p, max_ctas, st);
+  return launch<128, DSB_DTYPE_F16>(ma, ma2, mb, p, max_ctas, st);
 }

@@ -12,15 +12,19 @@ import torch
 
 from . import ops
 from .graphs import GraphCache
+from .packing import PackedConv
 
 
 class DecoderEngine:
-    def __init__(self, vq, precision: str = "tf32x3"):
-        """precision: 'tf32x3' -- split-TF32 operands (A = hi+lo, W = hi+lo; hi*Whi + lo*Whi + hi*Wlo on the tensor pipe): fp32-class
-                                   accuracy, needed for the 1e-3 mel tolerance through ~30 conv + GroupNorm layers;
+    def __init__(self, vq, precision: str = "f16x3"):
+        """precision: 'f16x3'  -- split-fp16 operands: conv inputs leave GroupNorm / upsample / the codebook gather as fp16 (hi | lo) pairs, weights are
+                                   (hi | lo) pairs of 2^s * W, every product is lo*hi + hi*lo + hi*hi on tcgen05 kind::f16 with fp32 accumulation:
+                                   fp32-class accuracy (1e-3 mel tolerance through ~30 conv + GroupNorm layers) at twice the TF32 MMA rate and half
+                                   the operand bytes of 'tf32x3';
+                      'tf32x3' -- split-TF32 operands (fp32 containers), the round-1 path; still used by the encoder and the AttnBlocks;
                       'tf32'   -- single-pass TF32 (3x fewer MMAs; mel error ~4e-3 relative)."""
-        if precision not in ("tf32x3", "tf32"):
-            raise ValueError("precision must be 'tf32x3' or 'tf32'")
+        if precision not in ("f16x3", "tf32x3", "tf32"):
+            raise ValueError("precision must be 'f16x3', 'tf32x3' or 'tf32'")
         self.vq = vq
         self.precision = precision
         self.packed = False
@@ -29,15 +33,18 @@ class DecoderEngine:
         self.max_batch = 32  # clips per pass: bounds the activation memory (34.7 MB fp32 per clip per full-resolution tensor) at any caller batch
         self._graphs = GraphCache()
 
-    def _pack_conv(self, conv) -> torch.Tensor:
+    def _pack_conv(self, conv, tf32x3: bool = False):
         w = conv.weight.detach().float()  # (Cout, Cin, kh, kw) -> (Cout, kh*kw*Cin), tap-major
         ntaps = w.shape[2] * w.shape[3]
+        if self.precision == "f16x3" and not tf32x3:
+            return PackedConv([w[:, :, ky, kx] for ky in range(w.shape[2]) for kx in range(w.shape[3])], conv.bias)
         w = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
-        return ops.pack_split_weight(w, ntaps) if self.precision == "tf32x3" else ops.round_tf32(w)
+        return ops.pack_split_weight(w, ntaps) if self.precision != "tf32" else ops.round_tf32(w)
 
     def _mm(self, a, w, bias=None, residual=None, out=None, presplit=False, **kw):
-        """a: fp32 activation (rows, C) or batched (already in (hi | lo) form when presplit); w: packed weight (split or rounded)."""
-        if self.precision == "tf32x3":
+        """a: fp32 activation (rows, C) or batched (already in (hi | lo) form when presplit); w: packed weight (split-TF32 or rounded).
+        (In 'f16x3' mode this serves the AttnBlocks only: 265 tokens x 512 channels, four small GEMMs kept on the split-TF32 path.)"""
+        if self.precision != "tf32":
             return ops.gemm_split(a if presplit else ops.split_tf32(a), w, bias, residual, out, **kw)
         return ops.gemm(a, w, bias, residual, out, **kw)
 
@@ -63,7 +70,8 @@ class DecoderEngine:
         def attn(name, m):
             gn(name + ".norm", m.norm)
             for n in ("q", "k", "v", "proj_out"):
-                conv(name + "." + n, getattr(m, n))
+                c_ = getattr(m, n)
+                self.w[name + "." + n] = (self._pack_conv(c_, tf32x3=True), f(c_.bias), 1)
 
         conv("post_quant", vq.post_quant_conv)
         conv("conv_in", d.conv_in)
@@ -82,11 +90,27 @@ class DecoderEngine:
         self._graphs.clear()
 
     # ------------------------------------------------------------------ building blocks (all on padded NHWC tensors)
-    def _conv(self, x, name, residual=None, round_out=False, presplit=False):
+    def _conv_f16(self, x, cv, k, residual=None, pair_out=False):
+        """x: fp16 pair image (B, Hp, Wp, 2*Cin) -> fp32 (B, Hp, Wp, Cout) (+ fp32 residual), or its fp16 pair when pair_out (no GroupNorm in between)."""
+        B, Hp, Wp, C2 = x.shape
+        Cin, R, N = C2 // 2, B * Hp * Wp, cv.N
+        shifts = [dy * Wp + dx for dy in (-1, 0, 1) for dx in (-1, 0, 1)] if k == 3 else [0]
+        out = torch.empty(B, Hp, Wp, 2 * N if pair_out else N, dtype=torch.float16 if pair_out else torch.float32, device=x.device)
+        ops.gemm_desc(A=x.data_ptr(), W=cv.w.data_ptr(), out=out.data_ptr(), M=R, N=N, K=cv.Kp, taps=cv.taps([(sh, 0, Cin, 0) for sh in shifts]),
+                      a_rows=R, a_cols=C2, lda=C2, ldw=cv.w.shape[1], w_cols=cv.w.shape[1], ldo=out.shape[-1], bias=cv.bias, alpha=cv.alpha,
+                      flags=ops.OUT_F16_SPLIT if pair_out else 0, split_off=N if pair_out else 0,
+                      residual=None if residual is None else residual.data_ptr(), ld_res=0 if residual is None else residual.shape[-1],
+                      geo=(Hp * Wp, Wp, 1, Hp - 1, 1, Wp - 1))
+        self.launches += 1
+        return out
+
+    def _conv(self, x, name, residual=None, round_out=False, presplit=False, pair_out=False):
         """x: padded image (B, Hp, Wp, C), or its split form (B, Hp, Wp, 2C) from a producer that fused the (hi | lo) split."""
         w, b, k = self.w[name]
         B, Hp, Wp, C = x.shape  # C counts the (hi | lo) columns when presplit; only used to flatten
         R = B * Hp * Wp
+        if isinstance(w, PackedConv):
+            return self._conv_f16(x, w, k, residual, pair_out)
         taps = [dy * Wp + dx for dy in (-1, 0, 1) for dx in (-1, 0, 1)] if k == 3 else [0]
         out = torch.empty(B, Hp, Wp, w.shape[0], dtype=torch.float32, device=x.device)
         self._mm(x.view(R, C), w, b, None if residual is None else residual.view(R, -1), out.view(R, -1), taps=taps, presplit=presplit,
@@ -99,14 +123,19 @@ class DecoderEngine:
         st = ops.groupnorm_stats(x)
         self.launches += 3  # memset + stats + apply
         split = self.precision == "tf32x3" and not compact_len  # conv inputs leave GroupNorm already in (hi | lo) form
-        return ops.groupnorm_apply(x, st, g, b, eps=eps, swish=swish, round_out=self.precision == "tf32", compact_len=compact_len, split=split)
+        return ops.groupnorm_apply(x, st, g, b, eps=eps, swish=swish, round_out=self.precision == "tf32", compact_len=compact_len, split=split,
+                                   split_f16=self.precision == "f16x3" and not compact_len)
 
     def _res(self, x, name):
-        sp = self.precision == "tf32x3"
+        sp = self.precision != "tf32"
         h = self._conv(self._gn(x, name + ".norm1"), name + ".conv1", presplit=sp)
         h = self._gn(h, name + ".norm2")
         if (name + ".nin") in self.w:
-            if self.precision == "tf32":
+            if self.precision == "f16x3":  # the 1x1 shortcut convolves the raw (un-normalised) input: one elementwise split pass, twice per decode
+                B_, Hp_, Wp_, C_ = x.shape
+                self.launches += 1
+                x = self._conv(ops.split_f16(x.view(-1, C_)).view(B_, Hp_, Wp_, 2 * C_), name + ".nin")
+            elif self.precision == "tf32":
                 self.launches += 1
                 x = self._conv(ops.round_tf32(x), name + ".nin")
             else:
@@ -125,7 +154,7 @@ class DecoderEngine:
         k = self._mm(h, wk, bk, round_out=rnd).view(B, Lp, C)
         v = self._mm(h, wv, bv, round_out=rnd).view(B, Lp, C)
         vT = v.transpose(1, 2).contiguous()  # (B, C, Lp): data movement only (token rows >= L are masked by the softmax below)
-        if self.precision == "tf32x3":
+        if self.precision != "tf32":
             s_ = ops.gemm_split(ops.split_tf32(q), ops.split_tf32(k, w_format=True), alpha=float(C) ** -0.5)  # (B, Lp, Lp)
             ops.softmax_rows_(s_, L, round_out=False)
             o = ops.gemm_split(ops.split_tf32(s_), ops.split_tf32(vT, w_format=True))  # (B, Lp, C)
@@ -142,8 +171,12 @@ class DecoderEngine:
     @torch.no_grad()
     def _decode_padded(self, z):
         d = self.vq.decoder
-        z = self._conv(z, "post_quant", round_out=True, presplit=self.precision == "tf32x3")
-        h = self._conv(z, "conv_in")
+        if self.precision == "f16x3":
+            z = self._conv(z, "post_quant", pair_out=True)  # 1x1 conv straight into the next conv's (hi | lo) operand: no GroupNorm between them
+            h = self._conv(z, "conv_in")
+        else:
+            z = self._conv(z, "post_quant", round_out=True, presplit=self.precision == "tf32x3")
+            h = self._conv(z, "conv_in")
         h = self._res(h, "mid.block_1")
         h = self._attn(h, "mid.attn_1")
         h = self._res(h, "mid.block_2")
@@ -154,7 +187,8 @@ class DecoderEngine:
                     h = self._attn(h, f"up.{lvl}.attn.{j}")
             if lvl != 0:
                 sp = self.precision == "tf32x3"
-                h = self._conv(ops.upsample2x_padded(h, round_out=not sp, split=sp), f"up.{lvl}.upsample", presplit=sp)
+                h = self._conv(ops.upsample2x_padded(h, round_out=self.precision == "tf32", split=sp, split_f16=self.precision == "f16x3"),
+                               f"up.{lvl}.upsample", presplit=sp)
                 self.launches += 1
         out = self._conv(self._gn(h, "norm_out"), "conv_out", presplit=self.precision == "tf32x3")  # (B, Hp, Wp, out_ch)
         return out[:, 1:-1, 1:-1, :].permute(0, 3, 1, 2).contiguous()
@@ -171,7 +205,8 @@ class DecoderEngine:
         def body(ids_):
             self.launches = 1
             err = torch.zeros(1, dtype=torch.int32, device=ids_.device)
-            z = ops.codebook_gather_padded(ids_, self.codebook, H, W, round_out=self.precision == "tf32", split=self.precision == "tf32x3", err_flag=err)
+            z = ops.codebook_gather_padded(ids_, self.codebook, H, W, round_out=self.precision == "tf32", split=self.precision == "tf32x3",
+                                           split_f16=self.precision == "f16x3", err_flag=err)
             return self._decode_padded(z), err
 
         if self.use_cuda_graph:
@@ -189,4 +224,7 @@ class DecoderEngine:
             self.repack()
         self.launches = 1
         z = torch.nn.functional.pad(quant.detach().float().permute(0, 2, 3, 1), (0, 0, 1, 1, 1, 1)).contiguous()
+        if self.precision == "f16x3":
+            B_, Hp_, Wp_, C_ = z.shape
+            return self._decode_padded(ops.split_f16(z.view(-1, C_)).view(B_, Hp_, Wp_, 2 * C_))
         return self._decode_padded(ops.round_tf32(z) if self.precision == "tf32" else ops.split_tf32(z))

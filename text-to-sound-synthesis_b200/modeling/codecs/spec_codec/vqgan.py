@@ -167,7 +167,7 @@ class VectorQuantizer(nn.Module):
 
 class VQModel(nn.Module):
     def __init__(self, ddconfig, lossconfig=None, n_embed=256, embed_dim=256, ckpt_path=None, ignore_keys=[], image_key="image",
-                 colorize_nlabels=None, monitor=None, precision="tf32x3"):
+                 colorize_nlabels=None, monitor=None, precision="f16x3"):
         super().__init__()
         self.image_key = image_key
         self.ddconfig = dict(ddconfig)

@@ -14,6 +14,8 @@ from . import _lib
 TF32, BF16, F16 = 0, 1, 2
 GELU2, ROUND_TF32, OUT_BF16, LRELU, TANH, GN_SWISH, GN_COMPACT, RES_BEFORE_ACT, OUT_F16, SPLIT_OUT = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512
 OUT_F16_SPLIT = 2048
+DUAL_LRELU = 4096
+SPLIT_OUT_F16 = 8192
 
 
 def _stream() -> int:
@@ -198,6 +200,46 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
     return out
 
 
+def gemm_desc(*, A, W, out, M, N, K, taps, lda, ldw, ldo, dtype=F16, batch=1, a_rows=0, a_cols=0, a_batch_stride=0, w_cols=0, out_batch_stride=0,
+              bias=None, flags=0, alpha=1.0, split_off=0, dual_off=0, out_col_group=0, out_col_group_stride=0, A2=None, lda2=0, a2_rows=0, a2_cols=0,
+              a2_batch_stride=0, block_n=0, cta_pair=0, residual=None, ld_res=0, geo=None):
+    """Thin front end of dsb_gemm_ex for callers that lay out their own buffers (the MelGAN / SpecVQGAN state buffers): A / W / out / A2 are
+    raw device addresses (ints: tensor.data_ptr() plus a byte offset), sizes and strides in elements; taps = [(row_shift, a_col, w_col, use_a2), ...]."""
+    d = _lib.GemmDesc()
+    d.A, d.W, d.out, d.bias, d.A2 = A, W, out, _ptr(bias), A2
+    d.M, d.N, d.K, d.batch = M, N, K, batch
+    d.a_rows, d.a_cols, d.lda, d.ldw, d.ldo = a_rows, a_cols, lda, ldw, ldo
+    d.a_batch_stride, d.out_batch_stride = a_batch_stride, out_batch_stride
+    d.dtype, d.flags, d.alpha = dtype, flags, alpha
+    d.num_taps = len(taps)
+    d.use_tap_wcol, d.w_cols = 1, w_cols
+    for i, (sh, ac, wc, a2) in enumerate(taps):
+        d.tap_shift[i], d.tap_acol[i], d.tap_wcol[i], d.tap_a2[i] = int(sh), int(ac), int(wc), int(a2)
+    d.split_off, d.dual_off, d.out_col_group, d.out_col_group_stride = split_off, dual_off, out_col_group, out_col_group_stride
+    d.lda2, d.a2_rows, d.a2_cols, d.a2_batch_stride = lda2, a2_rows, a2_cols, a2_batch_stride
+    d.block_n, d.cta_pair = block_n, cta_pair
+    d.residual, d.ld_res = residual, ld_res
+    if geo is not None:
+        d.geo_P, d.geo_Wp, d.geo_y0, d.geo_y1, d.geo_x0, d.geo_x1 = [int(v) for v in geo]
+    _lib.check(_lib.lib().dsb_gemm_ex(C.byref(d), _stream()), "dsb_gemm_ex")
+
+
+def mel_pack_f16(mel, pad, Kp):
+    """mel (B, Cm, T) fp32 -> (B, T + 2 pad, 2 Kp) fp16 (hi | lo), reflection-padded in time."""
+    _need_cuda(mel)
+    B, Cm, T = mel.shape
+    out = torch.empty(B, T + 2 * pad, 2 * Kp, dtype=torch.float16, device=mel.device)
+    _lib.check(_lib.lib().dsb_mel_pack_f16(mel.data_ptr(), out.data_ptr(), B, Cm, T, pad, Kp, _stream()), "dsb_mel_pack_f16")
+    return out
+
+
+def edge_pad_f16(state, T, P, d, col0, ncols, reflect=True):
+    """state (B, T + 2P, ld) fp16: fill pad rows P-j / P+T-1+j (j = 1..d) of columns [col0, col0+ncols) by reflection (or zeros)."""
+    _need_cuda(state)
+    B, Tp, ld = state.shape
+    _lib.check(_lib.lib().dsb_edge_pad_f16(state.data_ptr(), ld, Tp * ld, B, T, P, d, col0, ncols, 1 if reflect else 0, _stream()), "dsb_edge_pad_f16")
+
+
 def gemm_f32(a, w, bias=None, residual=None, out=None, *, gelu=False, round_out=False):
     """Exact fp32 FFMA GEMM (set-up tables, fp32-exact mode)."""
     _need_cuda(a, w, bias, residual, out)
@@ -342,13 +384,13 @@ def posterior_sample(inp, x_t, t, uniform, sched, *, T, trunc_mode=1, trunc_r=0.
 
 
 # ---------------------------------------------------------------------------------------------- decoder / vocoder support
-def codebook_gather_padded(ids, codebook, H, W, *, round_out=True, split=False, err_flag=None):
+def codebook_gather_padded(ids, codebook, H, W, *, round_out=True, split=False, split_f16=False, err_flag=None):
     _need_cuda(ids, codebook)
     B = ids.shape[0]
     E = codebook.shape[1]
-    out = torch.empty(B, H + 2, W + 2, 2 * E if split else E, dtype=torch.float32, device=ids.device)
+    out = torch.empty(B, H + 2, W + 2, 2 * E if (split or split_f16) else E, dtype=torch.float16 if split_f16 else torch.float32, device=ids.device)
     _lib.check(_lib.lib().dsb_codebook_gather_padded(ids.contiguous().data_ptr(), codebook.data_ptr(), out.data_ptr(), B, H, W, E, codebook.shape[0],
-                                                     SPLIT_OUT if split else (ROUND_TF32 if round_out else 0), _ptr(err_flag), _stream()),
+                                                     SPLIT_OUT_F16 if split_f16 else (SPLIT_OUT if split else (ROUND_TF32 if round_out else 0)), _ptr(err_flag), _stream()),
                "dsb_codebook_gather_padded")
     return out
 
@@ -362,25 +404,27 @@ def groupnorm_stats(x_pad, stats=None, groups=32):
     return stats
 
 
-def groupnorm_apply(x_pad, stats, gamma, beta, *, eps=1e-6, swish=True, round_out=True, compact_len=0, out=None, groups=32, split=False):
+def groupnorm_apply(x_pad, stats, gamma, beta, *, eps=1e-6, swish=True, round_out=True, compact_len=0, out=None, groups=32, split=False, split_f16=False):
     _need_cuda(x_pad, stats, gamma, beta)
     B, Hp, Wp, C = x_pad.shape
     H, W = Hp - 2, Wp - 2
-    flags = (GN_SWISH if swish else 0) | (ROUND_TF32 if round_out and not split else 0) | (GN_COMPACT if compact_len else 0) | (SPLIT_OUT if split else 0)
+    flags = (GN_SWISH if swish else 0) | (ROUND_TF32 if round_out and not (split or split_f16) else 0) | (GN_COMPACT if compact_len else 0) | \
+        (SPLIT_OUT_F16 if split_f16 else (SPLIT_OUT if split else 0))
     if out is None:
-        Co = 2 * C if split else C
-        out = torch.empty((B, compact_len, Co) if compact_len else (B, Hp, Wp, Co), dtype=torch.float32, device=x_pad.device)
+        Co = 2 * C if (split or split_f16) else C
+        out = torch.empty((B, compact_len, Co) if compact_len else (B, Hp, Wp, Co), dtype=torch.float16 if split_f16 else torch.float32, device=x_pad.device)
     _lib.check(_lib.lib().dsb_groupnorm_apply(x_pad.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), B, H, W, C, groups,
                                               eps, flags, compact_len, _stream()), "dsb_groupnorm_apply")
     return out
 
 
-def upsample2x_padded(x_pad, *, round_out=True, split=False):
+def upsample2x_padded(x_pad, *, round_out=True, split=False, split_f16=False):
     _need_cuda(x_pad)
     B, Hp, Wp, C = x_pad.shape
     H, W = Hp - 2, Wp - 2
-    out = torch.empty(B, 2 * H + 2, 2 * W + 2, 2 * C if split else C, dtype=torch.float32, device=x_pad.device)
-    _lib.check(_lib.lib().dsb_upsample2x_padded(x_pad.data_ptr(), out.data_ptr(), B, H, W, C, SPLIT_OUT if split else (ROUND_TF32 if round_out else 0), _stream()),
+    out = torch.empty(B, 2 * H + 2, 2 * W + 2, 2 * C if (split or split_f16) else C, dtype=torch.float16 if split_f16 else torch.float32, device=x_pad.device)
+    _lib.check(_lib.lib().dsb_upsample2x_padded(x_pad.data_ptr(), out.data_ptr(), B, H, W, C,
+                                                SPLIT_OUT_F16 if split_f16 else (SPLIT_OUT if split else (ROUND_TF32 if round_out else 0)), _stream()),
                "dsb_upsample2x_padded")
     return out
 

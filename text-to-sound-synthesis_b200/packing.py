@@ -1,0 +1,41 @@
+"""Weight packing for the split-fp16 ("f16x3") conv GEMMs of the SpecVQGAN decoder and the MelGAN generator."""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import ops
+
+
+def k64(c: int) -> int:
+    """Channels rounded up to the GEMM's 64-element fp16 k-block."""
+    return (c + 63) // 64 * 64
+
+
+class PackedConv:
+    """(N, n_blocks * 2 * Kp) fp16: per K-block j (one spatial tap of a conv, or one of several 1x1 operands), columns [j*2Kp, +Cin) hold the hi
+    half and [j*2Kp + Kp, +Cin) the lo half of 2^s * W_j; everything else is zero, so an A box that reads Kp columns where only Cin exist multiplies
+    the overhang by zeros.  alpha = 2^-s undoes the scale in the GEMM epilogue."""
+
+    def __init__(self, blocks, bias):
+        N, Cin = blocks[0].shape
+        Kp = k64(Cin)
+        amax = max(float(b.abs().max()) for b in blocks)
+        s = 0 if amax == 0.0 or not math.isfinite(amax) else 13 - math.frexp(amax)[1]
+        w = torch.zeros(N, len(blocks), 2, Kp, dtype=torch.float16, device=blocks[0].device)
+        for j, b in enumerate(blocks):
+            pr = ops.split_f16(b.detach().contiguous().float(), 2.0 ** s)  # (N, 2*Cin)
+            w[:, j, 0, :Cin] = pr[:, :Cin]
+            w[:, j, 1, :Cin] = pr[:, Cin:]
+        self.w = w.reshape(N, -1).contiguous()
+        self.alpha, self.Kp, self.N, self.nblk = 2.0 ** (-s), Kp, N, len(blocks)
+        self.bias = bias.detach().float().contiguous()
+
+    def taps(self, spatial):
+        """spatial: per K-block (row_shift, a_col_hi, a_col_lo, use_a2) -> the 3-pass tap list of dsb_gemm_ex (lo*hi, hi*lo, hi*hi)."""
+        out = []
+        for j, (sh, ah, al, a2) in enumerate(spatial):
+            wh, wl = j * 2 * self.Kp, j * 2 * self.Kp + self.Kp
+            out += [(sh, al, wh, a2), (sh, ah, wl, a2), (sh, ah, wh, a2)]
+        return out

@@ -28,7 +28,7 @@ class ResnetBlock(_Holder):
 
 
 class Generator(nn.Module):
-    def __init__(self, input_size, ngf, n_residual_layers, precision="tf32x3"):
+    def __init__(self, input_size, ngf, n_residual_layers, precision="f16x3"):
         super().__init__()
         ratios = [8, 8, 2, 2]
         self.ratios = ratios

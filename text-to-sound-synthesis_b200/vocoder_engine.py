@@ -1,12 +1,21 @@
-"""MelGAN generator on sm_100a: every Conv1d / ConvTranspose1d is a tcgen05 GEMM over channels-last (B, T, C) activations.
+"""MelGAN generator on sm_100a in split-fp16 ("f16x3") arithmetic: every Conv1d / ConvTranspose1d / ResnetBlock tail is ONE tcgen05 GEMM
+over per-stage state buffers, with all the elementwise work (bias, LeakyReLU, tanh, the (hi | lo) operand split, the residual sum) in GEMM
+epilogues.
 
-* weight_norm (w = g * v / ||v||, reference vocoder/modules.py:18-23) is folded once at pack time instead of every forward;
-* Conv1d(k, dilation d) = GEMM with k taps (row shifts 0, d, 2d, ...) over a reflection-padded copy of the input;
-* ConvTranspose1d(stride r, kernel 2r, padding r/2) is evaluated in polyphase form: output time q*r + ph only touches
-  inputs q-1, q (ph < r/2) or q, q+1 (ph >= r/2), so it is two GEMMs with 2 taps each whose (T, r*Cout) row-major output IS
-  the (r*T, Cout) channels-last result -- no zero-stuffing, no scatter;
-* LeakyReLU / tanh / bias / residual live in the GEMM epilogue; only the reflection pad of a ResnetBlock input needs its own
-  (HBM-bound) pass.
+Layout.  Stage i (C channels, T samples) keeps ONE state buffer S (B, P + T + P, 4C) fp16, P = 9 pad rows, whose rows are
+    [raw_hi | raw_lo | act_hi | act_lo],   raw ~ hi + lo (22 significand bits),   act = LeakyReLU(0.2)(raw),
+i.e. 8 bytes per element -- exactly the reference's fp32 activation plus its activated copy -- and a scratch Y (B, T, 2C) for a block's
+hidden tensor.  A ResnetBlock (reference vocoder/modules.py:72-85)
+    y = shortcut(x) + conv1x1(LeakyReLU(conv3_dilated(ReflectionPad(LeakyReLU(x)))))
+is:  edge_pad (reflect d rows of the act columns, a few KB)  ->  G1: 3 taps x 3 passes over S.act, LeakyReLU + split epilogue -> Y
+     ->  G2: ONE GEMM over two A operands (S.raw against the shortcut weights, Y against the 1x1 weights), epilogue writes the new raw pair AND
+     its LeakyReLU pair back into S in place (dsb_gemm_ex: A2 / DSB_GEMM_DUAL_LRELU).
+ConvTranspose1d(stride r, kernel 2r, padding r/2) runs in polyphase form (output time q*r + ph touches inputs q-1, q or q, q+1): two GEMMs
+with two taps each whose N = phase*Cout + c columns are scattered by the epilogue's column groups straight into the next stage's state rows.
+weight_norm (w = g * v / ||v||, :18-23) is folded once at pack time; weights are (hi | lo) fp16 pairs of 2^s * w (alpha = 2^-s in the epilogue).
+Every product is lo*hi + hi*lo + hi*hi on tcgen05 kind::f16 with fp32 accumulation: fp32-class accuracy (the shipped checkpoint's weights
+span a wide dynamic range; single-pass 11-bit operands give 2.6e-2 waveform error) at twice the TF32 MMA rate and half the operand bytes of
+the round-1 split-TF32 path, and 3 launches per ResnetBlock instead of 7.
 Reference: vocoder/modules.py:72-85 (ResnetBlock), :88-130 (Generator).
 """
 from __future__ import annotations
@@ -15,6 +24,9 @@ import torch
 
 from . import ops
 from .graphs import GraphCache
+from .packing import PackedConv as _PackedConv
+
+P = 9  # pad rows on either side of every clip in a state buffer (largest dilation / half kernel)
 
 
 def _fold(m) -> torch.Tensor:
@@ -23,40 +35,26 @@ def _fold(m) -> torch.Tensor:
 
 
 class VocoderEngine:
-    def __init__(self, gen, precision: str = "tf32x3"):
-        """precision 'tf32x3' (split-TF32, fp32-class accuracy: the shipped checkpoint's weights span a wide dynamic range and
-        single-pass TF32 gives 2.6e-2 waveform error) or 'tf32' (single pass)."""
-        if precision not in ("tf32x3", "tf32"):
-            raise ValueError("precision must be 'tf32x3' or 'tf32'")
+    def __init__(self, gen, precision: str = "f16x3"):
+        if precision != "f16x3":
+            raise ValueError("the MelGAN engine computes in split-fp16 ('f16x3': fp32-class accuracy on the fp16 tensor pipe)")
         self.gen = gen
         self.precision = precision
         self.packed = False
         self.launches = 0
         self.use_cuda_graph = True
-        self.max_batch = 32  # clips per pass (27.8 MB fp32 per clip for the widest activation)
+        self.max_batch = 32  # clips per pass (8 bytes per activation element: 55.6 MB per clip for the widest stage)
         self._graphs = GraphCache()
-
-    def _pack(self, w2d: torch.Tensor, ntaps: int) -> torch.Tensor:
-        """(N, ntaps*Cin) tap-major fp32 -> packed GEMM weight for the selected precision."""
-        w2d = w2d.contiguous().float()
-        return ops.pack_split_weight(w2d, ntaps) if self.precision == "tf32x3" else ops.round_tf32(w2d)
-
-    def _pack_conv1d(self, w) -> torch.Tensor:
-        return self._pack(w.permute(0, 2, 1).reshape(w.shape[0], -1), w.shape[2])  # (Cout, k*Cin), tap-major
-
-    def _mm(self, a, w, bias=None, residual=None, out=None, presplit=False, **kw):
-        if self.precision == "tf32x3":
-            kw.pop("round_out", None)
-            return ops.gemm_split(a if presplit else ops.split_tf32(a), w, bias, residual, out, **kw)
-        return ops.gemm(a, w, bias, residual, out, **kw)
+        self._bufs = {}
 
     @torch.no_grad()
     def repack(self):
         mods = list(self.gen.model)
         if mods[1].bias.device.type != "cuda":
             raise RuntimeError("VocoderEngine needs the module on a CUDA device (no CPU fallback)")
-        f = lambda p: p.detach().float().contiguous()
-        self.first = (self._pack_conv1d(_fold(mods[1])), f(mods[1].bias))
+        w0 = _fold(mods[1])  # (16*ngf, n_mel, 7)
+        self.n_mel = w0.shape[1]
+        self.first = _PackedConv([w0[:, :, j] for j in range(w0.shape[2])], mods[1].bias)
         self.stages = []
         i = 2
         for r in self.gen.ratios:
@@ -65,25 +63,40 @@ class VocoderEngine:
             p = r // 2 + r % 2
             assert r % 2 == 0, "polyphase split assumes even stride (the Diffsound ratios 8,8,2,2)"
             half = r - p
-            # phases [0, half): taps (q-1 -> k=ph+p+r, q -> k=ph+p); phases [half, r): taps (q -> k=ph+p, q+1 -> k=ph+p-r)
-            wa = torch.stack([torch.cat([w[:, :, ph + p + r].t(), w[:, :, ph + p].t()], dim=1) for ph in range(half)], 0)
-            wb = torch.stack([torch.cat([w[:, :, ph + p].t(), w[:, :, ph + p - r].t()], dim=1) for ph in range(half, r)], 0)
             cout = w.shape[1]
-            st = dict(r=r, cout=cout, half=half, wa=self._pack(wa.reshape(half * cout, -1), 2),
-                      wb=self._pack(wb.reshape((r - half) * cout, -1), 2),
-                      ba=f(ct.bias).repeat(half), bb=f(ct.bias).repeat(r - half), res=[])
+            # phases [0, half): taps (q-1 -> k=ph+p+r, q -> k=ph+p); phases [half, r): taps (q -> k=ph+p, q+1 -> k=ph+p-r); rows n = phase*Cout + c
+            wa = [torch.cat([w[:, :, ph + p + r].t() for ph in range(half)], 0), torch.cat([w[:, :, ph + p].t() for ph in range(half)], 0)]
+            wb = [torch.cat([w[:, :, ph + p].t() for ph in range(half, r)], 0), torch.cat([w[:, :, ph + p - r].t() for ph in range(half, r)], 0)]
+            st = dict(r=r, cin=w.shape[0], cout=cout, half=half, ca=_PackedConv(wa, ct.bias.detach().repeat(half)),
+                      cb=_PackedConv(wb, ct.bias.detach().repeat(r - half)), res=[])
             i += 2
             for _ in range(self.gen.n_residual_layers):
                 rb = mods[i]
-                st["res"].append(dict(d=rb.dilation, wd=self._pack_conv1d(_fold(rb.block[2])), bd=f(rb.block[2].bias),
-                                      w1=self._pack_conv1d(_fold(rb.block[4])), b1=f(rb.block[4].bias),
-                                      ws=self._pack_conv1d(_fold(rb.shortcut)), bs=f(rb.shortcut.bias)))
+                wd, w1, ws = _fold(rb.block[2]), _fold(rb.block[4]), _fold(rb.shortcut)
+                st["res"].append(dict(d=rb.dilation, g1=_PackedConv([wd[:, :, j] for j in range(3)], rb.block[2].bias),
+                                      g2=_PackedConv([ws[:, :, 0], w1[:, :, 0]], rb.shortcut.bias.detach() + rb.block[4].bias.detach())))
                 i += 1
             self.stages.append(st)
         last = mods[i + 2]
-        self.last = (self._pack_conv1d(_fold(last)), f(last.bias))
+        wl = _fold(last)  # (1, ngf, 7)
+        self.last = _PackedConv([wl[:, :, j] for j in range(wl.shape[2])], last.bias)
+        self.c0 = w0.shape[0]
         self.packed = True
         self._graphs.clear()
+        self._bufs.clear()
+
+    def _buffers(self, B, T0, dev):
+        key = (B, T0)
+        b = self._bufs.get(key)
+        if b is None:
+            z = lambda *s: torch.zeros(*s, dtype=torch.float16, device=dev)
+            states, ys, T = [z(B, T0 + 2 * P, 4 * self.c0)], [None], T0
+            for st in self.stages:
+                T *= st["r"]
+                states.append(z(B, T + 2 * P, 4 * st["cout"]))
+                ys.append(z(B, T, 2 * st["cout"]))
+            b = self._bufs[key] = (states, ys)
+        return b
 
     @torch.no_grad()
     def forward(self, mel: torch.Tensor) -> torch.Tensor:
@@ -100,33 +113,53 @@ class VocoderEngine:
 
     def _forward(self, mel: torch.Tensor) -> torch.Tensor:
         B, Cm, T = mel.shape
+        if Cm != self.n_mel:
+            raise RuntimeError(f"mel has {Cm} channels, the generator expects {self.n_mel}")
+        states, ys = self._buffers(B, T, mel.device)
+        SPLIT, DUAL, LRELU, TANH = ops.OUT_F16_SPLIT, ops.DUAL_LRELU, ops.LRELU, ops.TANH
         n = 0
-        rnd = self.precision == "tf32"
-        sp = not rnd
-        xl = ops.lrelu_pad(mel, 3, slope=1.0, reflect=True, channel_major=True, round_out=rnd, split=sp)          # ReflectionPad1d(3) of the mel, channels-last
-        w0, b0 = self.first
-        # conv k=7 -> LeakyReLU (the activation in front of the first ConvTranspose1d) fused in the epilogue
-        x = self._mm(xl, w0, b0, taps=list(range(7)), out_rows=T, lrelu=True, round_out=rnd, presplit=sp)   # (B, T, 16*ngf)
+        # ReflectionPad1d(3) + Conv1d(n_mel -> 16 ngf, k=7) + the LeakyReLU in front of the first ConvTranspose1d  ->  states[0].act
+        cv = self.first
+        mp = ops.mel_pack_f16(mel, 3, cv.Kp)
+        S, C = states[0], self.c0
+        ops.gemm_desc(A=mp.data_ptr(), W=cv.w.data_ptr(), out=S.data_ptr() + 2 * (P * 4 * C + 2 * C), M=T, N=C, K=cv.Kp, batch=B,
+                      taps=cv.taps([(j, 0, cv.Kp, 0) for j in range(7)]), a_rows=T + 6, a_cols=2 * cv.Kp, lda=2 * cv.Kp, a_batch_stride=(T + 6) * 2 * cv.Kp,
+                      ldw=cv.w.shape[1], w_cols=cv.w.shape[1], ldo=4 * C, out_batch_stride=(T + 2 * P) * 4 * C, bias=cv.bias, flags=SPLIT | LRELU,
+                      alpha=cv.alpha, split_off=C)
         n += 2
         for si, st in enumerate(self.stages):
-            r, cout, half = st["r"], st["cout"], st["half"]
-            y = torch.empty(B, T, r * cout, dtype=torch.float32, device=mel.device)
-            self._mm(x, st["wa"], st["ba"], out=y[:, :, : half * cout], taps=[-1, 0], round_out=rnd)
-            self._mm(x, st["wb"], st["bb"], out=y[:, :, half * cout:], taps=[0, 1], round_out=rnd)
-            T = T * r
-            x = y.view(B, T, cout)
+            r, Cin, Cout, half = st["r"], st["cin"], st["cout"], st["half"]
+            Sin, S, Y = states[si], states[si + 1], ys[si + 1]
+            Tin, T = T, T * r
+            ldin, ld = 4 * Cin, 4 * Cout
+            if si > 0:  # the blocks left reflected samples in the pad rows; the transposed conv's polyphase taps need zeros there
+                ops.edge_pad_f16(Sin, Tin, P, 1, 2 * Cin, 2 * Cin, reflect=False)
+                n += 1
+            for cv, shifts, col0 in ((st["ca"], (P - 1, P), 0), (st["cb"], (P, P + 1), half * ld)):
+                ops.gemm_desc(A=Sin.data_ptr(), W=cv.w.data_ptr(), out=S.data_ptr() + 2 * (P * ld + col0), M=Tin, N=cv.N, K=cv.Kp, batch=B,
+                              taps=cv.taps([(sh, 2 * Cin, 3 * Cin, 0) for sh in shifts]), a_rows=Tin + 2 * P, a_cols=ldin, lda=ldin,
+                              a_batch_stride=(Tin + 2 * P) * ldin, ldw=cv.w.shape[1], w_cols=cv.w.shape[1], ldo=r * ld, out_batch_stride=(T + 2 * P) * ld,
+                              bias=cv.bias, flags=SPLIT | DUAL, alpha=cv.alpha, split_off=Cout, dual_off=2 * Cout, out_col_group=Cout, out_col_group_stride=ld)
             n += 2
-            for ri, rb in enumerate(st["res"]):
-                d = rb["d"]
-                xl = ops.lrelu_pad(x, d, slope=0.2, reflect=True, round_out=rnd, split=sp)                          # LeakyReLU + ReflectionPad1d(d)
-                y1 = self._mm(xl, rb["wd"], rb["bd"], taps=[0, d, 2 * d], out_rows=T, lrelu=True, round_out=rnd, presplit=sp)
-                tmp = self._mm(y1, rb["w1"], rb["b1"])
-                last_of_stage = ri == len(st["res"]) - 1
-                # shortcut(x) + block(x); after the last block of a stage the next consumer is LeakyReLU -> ConvT / final conv
-                x = self._mm(x, rb["ws"], rb["bs"], residual=tmp, round_out=rnd, lrelu=last_of_stage, res_before_act=last_of_stage)
-                n += 4
-        xl = ops.lrelu_pad(x, 3, slope=1.0, reflect=True, round_out=rnd, split=sp)                                  # x already went through LeakyReLU
-        wl, bl = self.last
-        wav = self._mm(xl, wl, bl, taps=list(range(7)), out_rows=T, tanh=True, presplit=sp)             # (B, T, 1)
+            for rb in st["res"]:
+                d, g1, g2 = rb["d"], rb["g1"], rb["g2"]
+                ops.edge_pad_f16(S, T, P, d, 2 * Cout, 2 * Cout, reflect=True)
+                ops.gemm_desc(A=S.data_ptr(), W=g1.w.data_ptr(), out=Y.data_ptr(), M=T, N=Cout, K=g1.Kp, batch=B,
+                              taps=g1.taps([(P + (j - 1) * d, 2 * Cout, 3 * Cout, 0) for j in range(3)]), a_rows=T + 2 * P, a_cols=ld, lda=ld,
+                              a_batch_stride=(T + 2 * P) * ld, ldw=g1.w.shape[1], w_cols=g1.w.shape[1], ldo=2 * Cout, out_batch_stride=T * 2 * Cout,
+                              bias=g1.bias, flags=SPLIT | LRELU, alpha=g1.alpha, split_off=Cout)
+                ops.gemm_desc(A=S.data_ptr(), A2=Y.data_ptr(), W=g2.w.data_ptr(), out=S.data_ptr() + 2 * (P * ld), M=T, N=Cout, K=g2.Kp, batch=B,
+                              taps=g2.taps([(P, 0, Cout, 0), (0, 0, Cout, 1)]), a_rows=T + 2 * P, a_cols=ld, lda=ld, a_batch_stride=(T + 2 * P) * ld,
+                              lda2=2 * Cout, a2_rows=T, a2_cols=2 * Cout, a2_batch_stride=T * 2 * Cout, ldw=g2.w.shape[1], w_cols=g2.w.shape[1],
+                              ldo=ld, out_batch_stride=(T + 2 * P) * ld, bias=g2.bias, flags=SPLIT | DUAL, alpha=g2.alpha, split_off=Cout, dual_off=2 * Cout)
+                n += 3
+        # LeakyReLU (already in .act) + ReflectionPad1d(3) + Conv1d(ngf -> 1, k=7) + tanh
+        S, C = states[-1], self.stages[-1]["cout"]
+        cv = self.last
+        ops.edge_pad_f16(S, T, P, 3, 2 * C, 2 * C, reflect=True)
+        wav = torch.empty(B, T, 1, dtype=torch.float32, device=mel.device)
+        ops.gemm_desc(A=S.data_ptr(), W=cv.w.data_ptr(), out=wav.data_ptr(), M=T, N=1, K=cv.Kp, batch=B,
+                      taps=cv.taps([(P - 3 + j, 2 * C, 3 * C, 0) for j in range(7)]), a_rows=T + 2 * P, a_cols=4 * C, lda=4 * C, a_batch_stride=(T + 2 * P) * 4 * C,
+                      ldw=cv.w.shape[1], w_cols=cv.w.shape[1], ldo=1, out_batch_stride=T, bias=cv.bias, flags=TANH, alpha=cv.alpha)
         self.launches = n + 2
         return wav.view(B, 1, T)
