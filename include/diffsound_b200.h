@@ -40,6 +40,7 @@ extern "C" {
 #define DSB_GEMM_RES_BEFORE_ACT 128 /* add the residual before the activation (default: after) */
 #define DSB_GEMM_DUAL_LRELU 4096 /* with OUT_F16_SPLIT: also store the pair of LeakyReLU(0.2)(x) at +dual_off (reference vocoder/modules.py:76: the
                                    next ResnetBlock convolves the activated signal while its 1x1 shortcut reads the raw one) */
+#define DSB_GEMM_NO_STORE 16384 /* run the GEMM and its epilogue but store nothing (amax_out calibration pass) */
 #define DSB_GEMM_OUT_F16_SPLIT 2048 /* store the fp16 (hi | lo) pair of the fp32 result: hi = f16(x) at out[r*ldo + c], lo = f16(x - hi) at
                                        out[r*ldo + split_off + c] -- the A operand of a split-fp16 ("f16x3") GEMM, see dsb_split_f16 */
 /* GroupNorm-apply flags (share the ROUND_TF32 bit) */
@@ -101,6 +102,8 @@ typedef struct dsb_gemm_desc {
                             activation buffers, e.g. MelGAN's ResnetBlock tail  shortcut(x) + conv1x1(y)  (vocoder/modules.py:84-85) */
   long long a2_rows, a2_cols, lda2, a2_batch_stride;
   int tap_a2[32];
+  float* amax_out;       /* optional device float (caller zero-initialises): atomic max of |value| over everything this launch stores (or would store,
+                            with DSB_GEMM_NO_STORE) -- used once, at pack time, to calibrate the power-of-two activation scales of the fp16 MelGAN path */
 } dsb_gemm_desc;
 int dsb_gemm_ex(const dsb_gemm_desc* desc, void* stream);
 

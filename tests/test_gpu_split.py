@@ -122,3 +122,54 @@ def test_split_mode_survives_large_dynamic_range(G):
         out = ops.gemm_f16x3(ops.split_f16(a * sa), ops.split_f16(wq, 2.0 ** s), alpha=2.0 ** -s)
         err = float((out.double() / (sa * sw) - ref).abs().max() / ref.abs().max())
         assert err < 3e-6, (sa, sw, err)
+
+
+def test_gemm_two_operands_dual_output_and_column_groups(G):
+    """The epilogue / producer features the MelGAN state-buffer path relies on, each against fp64:
+    (1) A2: one GEMM over two activation buffers (shortcut(x) + conv1x1(y)), in place into rows of [raw pair | LeakyReLU pair];
+    (2) out_col_group: polyphase ConvTranspose1d columns (phase * Cout + c) scattered into (r*T, 4*Cout) state rows;  (3) batch + pad rows."""
+    import math
+    ops = G.ops
+    from diffsound_b200.packing import PackedConv
+    B, T, C, P = 2, 300, 64, 9
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(B, T, C, device="cuda", generator=g)
+    y = torch.randn(B, T, C, device="cuda", generator=g)
+    ws, w1 = torch.randn(C, C, device="cuda", generator=g) * 0.1, torch.randn(C, C, device="cuda", generator=g) * 0.1
+    bias = torch.randn(C, device="cuda", generator=g)
+    S = torch.zeros(B, T + 2 * P, 4 * C, dtype=torch.float16, device="cuda")
+    S[:, P:P + T, :2 * C] = ops.split_f16(x.view(-1, C)).view(B, T, 2 * C)
+    Y = ops.split_f16(y.view(-1, C)).view(B, T, 2 * C).contiguous()
+    cv = PackedConv([ws, w1], bias)
+    xv = (S[:, P:P + T, :C].double() + S[:, P:P + T, C:2 * C].double())
+    yv = (Y[..., :C].double() + Y[..., C:].double())
+    wsv = (cv.w[:, :C].double() + cv.w[:, cv.Kp:cv.Kp + C].double()) * cv.alpha
+    w1v = (cv.w[:, 2 * cv.Kp:2 * cv.Kp + C].double() + cv.w[:, 3 * cv.Kp:3 * cv.Kp + C].double()) * cv.alpha
+    ref = xv @ wsv.T + yv @ w1v.T + bias.double()
+    ld = 4 * C
+    ops.gemm_desc(A=S.data_ptr(), A2=Y.data_ptr(), W=cv.w.data_ptr(), out=S.data_ptr() + 2 * P * ld, M=T, N=C, K=cv.Kp, batch=B,
+                  taps=cv.taps([(P, 0, C, 0), (0, 0, C, 1)]), a_rows=T + 2 * P, a_cols=ld, lda=ld, a_batch_stride=(T + 2 * P) * ld, lda2=2 * C, a2_rows=T,
+                  a2_cols=2 * C, a2_batch_stride=T * 2 * C, ldw=cv.w.shape[1], w_cols=cv.w.shape[1], ldo=ld, out_batch_stride=(T + 2 * P) * ld, bias=cv.bias,
+                  flags=ops.OUT_F16_SPLIT | ops.DUAL_LRELU, alpha=cv.alpha, split_off=C, dual_off=2 * C)
+    raw = S[:, P:P + T, :C].double() + S[:, P:P + T, C:2 * C].double()
+    act = S[:, P:P + T, 2 * C:3 * C].double() + S[:, P:P + T, 3 * C:].double()
+    sc = float(ref.abs().max())
+    assert float((raw - ref).abs().max()) / sc < 3e-6
+    assert float((act - torch.nn.functional.leaky_relu(ref, 0.2)).abs().max()) / sc < 3e-6
+    assert float(S[:, :P].abs().max()) == 0.0 and float(S[:, P + T:].abs().max()) == 0.0  # pad rows untouched
+    # (2) column groups: N = r * Cout logical columns -> r consecutive state rows of 4*Cout halves
+    r_, Cout = 4, 32
+    wq = torch.randn(r_ * Cout, C, device="cuda", generator=g) * 0.1
+    cq = PackedConv([wq], torch.zeros(r_ * Cout, device="cuda"))
+    Sn = torch.zeros(B, r_ * T + 2 * P, 4 * Cout, dtype=torch.float16, device="cuda")
+    Ain = ops.split_f16(x.view(-1, C)).view(B, T, 2 * C).contiguous()
+    ops.gemm_desc(A=Ain.data_ptr(), W=cq.w.data_ptr(), out=Sn.data_ptr() + 2 * P * 4 * Cout, M=T, N=r_ * Cout, K=cq.Kp, batch=B, taps=cq.taps([(0, 0, C, 0)]),
+                  a_rows=T, a_cols=2 * C, lda=2 * C, a_batch_stride=T * 2 * C, ldw=cq.w.shape[1], w_cols=cq.w.shape[1], ldo=r_ * 4 * Cout,
+                  out_batch_stride=(r_ * T + 2 * P) * 4 * Cout, bias=cq.bias, flags=ops.OUT_F16_SPLIT | ops.DUAL_LRELU, alpha=cq.alpha, split_off=Cout,
+                  dual_off=2 * Cout, out_col_group=Cout, out_col_group_stride=4 * Cout)
+    wqv = (cq.w[:, :C].double() + cq.w[:, cq.Kp:cq.Kp + C].double()) * cq.alpha
+    refq = ((Ain[..., :C].double() + Ain[..., C:].double()) @ wqv.T).view(B, T, r_, Cout).reshape(B, r_ * T, Cout)
+    got = Sn[:, P:P + r_ * T, :Cout].double() + Sn[:, P:P + r_ * T, Cout:2 * Cout].double()
+    assert float((got - refq).abs().max()) / float(refq.abs().max()) < 3e-6
+    gact = Sn[:, P:P + r_ * T, 2 * Cout:3 * Cout].double() + Sn[:, P:P + r_ * T, 3 * Cout:].double()
+    assert float((gact - torch.nn.functional.leaky_relu(refq, 0.2)).abs().max()) / float(refq.abs().max()) < 3e-6

@@ -49,6 +49,7 @@ struct GemmParams {
   long long split_off;     // DSB_GEMM_OUT_F16_SPLIT: offset of the lo half inside an output row
   long long dual_off;      // DSB_GEMM_DUAL_LRELU: offset of the LeakyReLU(0.2) copy (hi at +dual_off, lo at +dual_off+split_off)
   int ocg, ocg_stride;     // output column groups: logical column n lives at (n / ocg) * ocg_stride + n % ocg (0 = plain)
+  float* amax_out;         // optional: atomic max of |value stored| over the whole output (calibration of fp16 activation scales)
   int kc;          // channels per tap
   int b_batched;
   const float* bias;
@@ -187,7 +188,18 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, float* sw, ui
     for (int i = 0; i < 8; ++i)
       if (!((in_mask >> i) & 1u)) { x[4 * i] = 0.f; x[4 * i + 1] = 0.f; x[4 * i + 2] = 0.f; x[4 * i + 3] = 0.f; }
       }
-      if (out_mode == 0) {
+      if (p.amax_out) {  // calibration runs only: largest magnitude this launch would store
+    float m = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if ((ok_mask >> i) & 1u) m = fmaxf(m, fmaxf(fmaxf(fabsf(x[4 * i]), fabsf(x[4 * i + 1])), fmaxf(fabsf(x[4 * i + 2]), fabsf(x[4 * i + 3]))));
+    int mi = __float_as_int(m);  // non-negative floats (and +inf, NaN payloads) order like their bit patterns
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mi = max(mi, __shfl_xor_sync(0xffffffffu, mi, o));
+    if (lane == 0) atomicMax(reinterpret_cast<int*>(p.amax_out), mi);
+      }
+      if (p.flags & DSB_GEMM_NO_STORE) {
+      } else if (out_mode == 0) {
     float* op = reinterpret_cast<float*>(p.out) + out_boff + (long long)(row_base + rsub) * p.ldo + col;
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -259,6 +271,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, float* sw, ui
       if (do_round) xv = round_tf32(xv);
       if (!((in_mask >> i) & 1u)) xv = 0.f;
       const long long o = out_boff + row * p.ldo + col + k;
+      if (p.amax_out) atomicMax(reinterpret_cast<int*>(p.amax_out), __float_as_int(fabsf(xv)));
+      if (p.flags & DSB_GEMM_NO_STORE) continue;
       if (out_mode == 0) reinterpret_cast<float*>(p.out)[o] = xv;
       else if (out_mode == 1) reinterpret_cast<__half*>(p.out)[o] = __float2half_rn(xv);
       else if (out_mode == 3) {
@@ -726,6 +740,7 @@ extern "C" int dsb_gemm_ex(const dsb_gemm_desc* d, void* stream) {
   }
   p.split_off = d->split_off > 0 ? d->split_off : d->N;
   p.dual_off = d->dual_off;
+  p.amax_out = d->amax_out;
   p.ocg = d->out_col_group; p.ocg_stride = d->out_col_group_stride;
   p.tap_a2_mask = 0;
   if (d->A2) {
