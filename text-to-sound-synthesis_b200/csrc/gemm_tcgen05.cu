@@ -738,6 +738,12 @@ extern "C" int dsb_gemm_ex(const dsb_gemm_desc* d, void* stream) {
     p.tap_acol[i] = i < d->num_taps ? d->tap_acol[i] : 0;
     p.tap_wcol[i] = i < d->num_taps ? (d->use_tap_wcol ? d->tap_wcol[i] : i * d->K) : 0;
   }
+  {
+    const int es_ = kind == DSB_DTYPE_TF32 ? 4 : 2;
+    for (int i = 0; i < d->num_taps; ++i)
+      DSB_REQUIRE((p.tap_acol[i] * es_) % 16 == 0 && (p.tap_wcol[i] * es_) % 16 == 0,
+                  "dsb_gemm_ex: tap %d starts at A column %d / W column %d: TMA box coordinates must be multiples of 16 bytes", i, p.tap_acol[i], p.tap_wcol[i]);
+  }
   p.split_off = d->split_off > 0 ? d->split_off : d->N;
   p.dual_off = d->dual_off;
   p.amax_out = d->amax_out;

@@ -38,6 +38,11 @@ from .packing import PackedConv as _PackedConv
 P = 9  # pad rows on either side of every clip in a state buffer (largest dilation / half kernel)
 
 
+def _c8(c: int) -> int:
+    """Column-block width of a state row: channels rounded up to 8 halves (TMA box coordinates must be 16-byte aligned)."""
+    return (c + 7) // 8 * 8
+
+
 def _fold(m) -> torch.Tensor:
     v, g = m.weight_v.detach().float(), m.weight_g.detach().float()
     return g * v / v.flatten(1).norm(dim=1).view(-1, *([1] * (v.dim() - 1)))
@@ -111,11 +116,11 @@ class VocoderEngine:
         b = self._bufs.get(key)
         if b is None:
             z = lambda *s: torch.zeros(*s, dtype=torch.float16, device=dev)
-            states, ys, T = [z(B, T0 + 2 * P, 4 * self.c0)], [None], T0
+            states, ys, T = [z(B, T0 + 2 * P, 4 * _c8(self.c0))], [None], T0
             for st in self.stages:
                 T *= st["r"]
-                states.append(z(B, T + 2 * P, 4 * st["cout"]))
-                ys.append(z(B, T, 2 * st["cout"]))
+                states.append(z(B, T + 2 * P, 4 * _c8(st["cout"])))
+                ys.append(z(B, T, 2 * _c8(st["cout"])))
             b = self._bufs[key] = (states, ys)
         return b
 
@@ -162,44 +167,46 @@ class VocoderEngine:
         cv = self.first
         mp = ops.mel_pack_f16(mel, 3, cv.Kp)
         S, C = states[0], self.c0
+        Cs = _c8(C)
         sig = self._scaled("first", 1.0, calibrate, [(cv, dict(
-            A=mp.data_ptr(), out=S.data_ptr() + 2 * (P * 4 * C + 2 * C), M=T, N=C, batch=B, taps=cv.taps([(j, 0, cv.Kp, 0) for j in range(7)]),
-            a_rows=T + 6, a_cols=2 * cv.Kp, lda=2 * cv.Kp, a_batch_stride=(T + 6) * 2 * cv.Kp, ldo=4 * C, out_batch_stride=(T + 2 * P) * 4 * C,
-            flags=SPLIT | LRELU, split_off=C))])
+            A=mp.data_ptr(), out=S.data_ptr() + 2 * (P * 4 * Cs + 2 * Cs), M=T, N=C, batch=B, taps=cv.taps([(j, 0, cv.Kp, 0) for j in range(7)]),
+            a_rows=T + 6, a_cols=2 * cv.Kp, lda=2 * cv.Kp, a_batch_stride=(T + 6) * 2 * cv.Kp, ldo=4 * Cs, out_batch_stride=(T + 2 * P) * 4 * Cs,
+            flags=SPLIT | LRELU, split_off=Cs))])
         n += 2
         for si, st in enumerate(self.stages):
             r, Cin, Cout, half = st["r"], st["cin"], st["cout"], st["half"]
             Sin, S, Y = states[si], states[si + 1], ys[si + 1]
             Tin, T = T, T * r
-            ldin, ld = 4 * Cin, 4 * Cout
+            Ci, Co = _c8(Cin), _c8(Cout)  # column-block widths of the input / output state rows
+            ldin, ld = 4 * Ci, 4 * Co
             if si > 0:  # the blocks left reflected samples in the pad rows; the transposed conv's polyphase taps need zeros there
-                ops.edge_pad_f16(Sin, Tin, P, 1, 2 * Cin, 2 * Cin, reflect=False)
+                ops.edge_pad_f16(Sin, Tin, P, 1, 2 * Ci, 2 * Ci, reflect=False)
                 n += 1
             sig = self._scaled(("convT", si), sig, calibrate, [(cv, dict(
-                A=Sin.data_ptr(), out=S.data_ptr() + 2 * (P * ld + col0), M=Tin, N=cv.N, batch=B, taps=cv.taps([(sh, 2 * Cin, 3 * Cin, 0) for sh in shifts]),
+                A=Sin.data_ptr(), out=S.data_ptr() + 2 * (P * ld + col0), M=Tin, N=cv.N, batch=B, taps=cv.taps([(sh, 2 * Ci, 3 * Ci, 0) for sh in shifts]),
                 a_rows=Tin + 2 * P, a_cols=ldin, lda=ldin, a_batch_stride=(Tin + 2 * P) * ldin, ldo=r * ld, out_batch_stride=(T + 2 * P) * ld,
-                flags=SPLIT | DUAL, split_off=Cout, dual_off=2 * Cout, out_col_group=Cout, out_col_group_stride=ld))
+                flags=SPLIT | DUAL, split_off=Co, dual_off=2 * Co, out_col_group=Cout, out_col_group_stride=ld))
                 for cv, shifts, col0 in ((st["ca"], (P - 1, P), 0), (st["cb"], (P, P + 1), half * ld))])
             n += 2
             for ri, rb in enumerate(st["res"]):
                 d, g1 = rb["d"], rb["g1"]
-                ops.edge_pad_f16(S, T, P, d, 2 * Cout, 2 * Cout, reflect=True)
+                ops.edge_pad_f16(S, T, P, d, 2 * Co, 2 * Co, reflect=True)
                 sig_y = self._scaled(("g1", si, ri), sig, calibrate, [(g1, dict(
-                    A=S.data_ptr(), out=Y.data_ptr(), M=T, N=Cout, batch=B, taps=g1.taps([(P + (j - 1) * d, 2 * Cout, 3 * Cout, 0) for j in range(3)]),
-                    a_rows=T + 2 * P, a_cols=ld, lda=ld, a_batch_stride=(T + 2 * P) * ld, ldo=2 * Cout, out_batch_stride=T * 2 * Cout,
-                    flags=SPLIT | LRELU, split_off=Cout))])
+                    A=S.data_ptr(), out=Y.data_ptr(), M=T, N=Cout, batch=B, taps=g1.taps([(P + (j - 1) * d, 2 * Co, 3 * Co, 0) for j in range(3)]),
+                    a_rows=T + 2 * P, a_cols=ld, lda=ld, a_batch_stride=(T + 2 * P) * ld, ldo=2 * Co, out_batch_stride=T * 2 * Co,
+                    flags=SPLIT | LRELU, split_off=Co))])
                 if calibrate:  # x is stored at sigma, y at sigma_y: the 1x1 half of the fused weight absorbs sigma / sigma_y (a power of two)
                     rb["g2"] = _PackedConv([rb["ws"], rb["w1"] * (sig / sig_y)], rb["b2"])
                 g2 = rb["g2"]
                 sig = self._scaled(("g2", si, ri), sig, calibrate, [(g2, dict(
-                    A=S.data_ptr(), A2=Y.data_ptr(), out=S.data_ptr() + 2 * (P * ld), M=T, N=Cout, batch=B, taps=g2.taps([(P, 0, Cout, 0), (0, 0, Cout, 1)]),
-                    a_rows=T + 2 * P, a_cols=ld, lda=ld, a_batch_stride=(T + 2 * P) * ld, lda2=2 * Cout, a2_rows=T, a2_cols=2 * Cout,
-                    a2_batch_stride=T * 2 * Cout, ldo=ld, out_batch_stride=(T + 2 * P) * ld, flags=SPLIT | DUAL, split_off=Cout, dual_off=2 * Cout,
+                    A=S.data_ptr(), A2=Y.data_ptr(), out=S.data_ptr() + 2 * (P * ld), M=T, N=Cout, batch=B, taps=g2.taps([(P, 0, Co, 0), (0, 0, Co, 1)]),
+                    a_rows=T + 2 * P, a_cols=ld, lda=ld, a_batch_stride=(T + 2 * P) * ld, lda2=2 * Co, a2_rows=T, a2_cols=2 * Co,
+                    a2_batch_stride=T * 2 * Co, ldo=ld, out_batch_stride=(T + 2 * P) * ld, flags=SPLIT | DUAL, split_off=Co, dual_off=2 * Co,
                     # in place: ONE N tile must cover all Cout columns (a second N tile would re-read rows the first one overwrote)
                     block_n=256 if Cout > 128 else 128))])
                 n += 3
         # LeakyReLU (already in .act) + ReflectionPad1d(3) + Conv1d(ngf -> 1, k=7) + tanh
-        S, C = states[-1], self.stages[-1]["cout"]
+        S, C = states[-1], _c8(self.stages[-1]["cout"])
         cv = self.last
         ops.edge_pad_f16(S, T, P, 3, 2 * C, 2 * C, reflect=True)
         wav = torch.empty(B, T, 1, dtype=torch.float32, device=mel.device)
