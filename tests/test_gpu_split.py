@@ -44,7 +44,8 @@ def test_gemm_f16x3_matches_fp64(G, M, N, K):
     ref = _pair_value(ap, K) @ (_pair_value(wp, K) / 2.0 ** 17).T + b.double()
     out = ops.gemm_f16x3(ap, wp, b, alpha=2.0 ** -17)
     scale = float(ref.abs().max())
-    tol = 2e-6 * max(1.0, (K / 1024) ** 0.5)  # fp32 accumulation over 3K products: rounding noise grows like sqrt(K)
+    tol = 3e-6 * max(1.0, K / 1024)  # fp32 accumulation of 3K products in the tensor core (not round-to-nearest per add): error grows with K
+    print(f"gemm_f16x3 M={M} N={N} K={K}: rel err {float((out.double() - ref).abs().max()) / scale:.2e} (tol {tol:.1e})")
     assert float((out.double() - ref).abs().max()) / scale < tol
     out_r = ops.gemm_f16x3(ap, wp, b, residual=r, alpha=2.0 ** -17)
     assert float((out_r.double() - (ref + r.double())).abs().max()) / scale < tol

@@ -19,11 +19,15 @@ namespace {
 constexpr int SP_HD = 64;
 constexpr int SP_QM = 128;
 constexpr int SP_KMAX = 288;      // padded key capacity (multiple of 32)
-constexpr int SP_THREADS = 288;   // warps 0-7 softmax + epilogue, warp 8 control (TMA producer, MMA issuer, TMEM owner)
+constexpr int SP_THREADS = 320;   // warps 0-7 softmax + epilogue, warp 8 control (TMA producer, MMA issuer, TMEM owner), warp 9 remainder rows
 constexpr int SP_QTILE = SP_QM * 128;  // bytes of one 128 x 64 fp16 SW128 tile
 
 struct SpParams {
   int B, H, Lq, Lk, kpad, n_qt, box_rows, n_box;
+  int q_bufs;           // Q tile buffers: 2 (prefetch one tile ahead) or 1 (short key sequences: leaves room for two CTAs per SM)
+  int rem_rows;         // > 0: the last (Lq % 128 <= 16) query rows are computed by the remainder warp with mma.sync, not by a third tensor tile
+  const __half* q;      // global Q (hi half; lo at + q_lo_col) for the remainder warp's register fragments
+  long long ldq;
   int q_lo_col, k_lo_col, v_lo_col;  // column (element) offset of the lo halves inside the tensor maps
   long long ldo, o_lo_off;
   __half* o;
@@ -53,14 +57,152 @@ __device__ __forceinline__ float sp_ex2(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(SP_THREADS, 1)
+// ---- remainder rows (265 = 2 x 128 + 9): one warp, legacy mma.sync m16n8k16, same split arithmetic (3 MMAs per product), straight from the
+// K / V tiles the TMA staged in shared memory, concurrently with the tensor tiles -- instead of a third latency-bound 128-row tile.
+__device__ __forceinline__ uint32_t sp_sw128(int r, int chunk) { return r * 128 + ((chunk ^ (r & 7)) << 4); }
+__device__ __forceinline__ void sp_ldsm_x4(uint32_t (&r)[4], const uint8_t* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void sp_ldsm_x4_t(uint32_t (&r)[4], const uint8_t* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void sp_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void sp_pack_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const __half2 l = __floats2half2_rn(a - __low2float(h), b - __high2float(h));
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void sp_remainder_rows(const SpParams& p, const uint8_t* sKh, const uint8_t* sKl, const uint8_t* sVh, const uint8_t* sVl, int b, int h,
+                                                  int row0, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  const __half* qb = p.q + (long long)b * p.Lq * p.ldq + h * SP_HD;
+  uint32_t ah[4][4], al[4][4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const int ra = row0 + g, rb = row0 + g + 8, c = ks * 16 + 2 * t;
+    const __half* pa = qb + (long long)ra * p.ldq + c;
+    const __half* pb = qb + (long long)rb * p.ldq + c;
+    ah[ks][0] = ra < p.Lq ? *reinterpret_cast<const uint32_t*>(pa) : 0u;
+    ah[ks][1] = rb < p.Lq ? *reinterpret_cast<const uint32_t*>(pb) : 0u;
+    ah[ks][2] = ra < p.Lq ? *reinterpret_cast<const uint32_t*>(pa + 8) : 0u;
+    ah[ks][3] = rb < p.Lq ? *reinterpret_cast<const uint32_t*>(pb + 8) : 0u;
+    al[ks][0] = ra < p.Lq ? *reinterpret_cast<const uint32_t*>(pa + p.q_lo_col) : 0u;
+    al[ks][1] = rb < p.Lq ? *reinterpret_cast<const uint32_t*>(pb + p.q_lo_col) : 0u;
+    al[ks][2] = ra < p.Lq ? *reinterpret_cast<const uint32_t*>(pa + p.q_lo_col + 8) : 0u;
+    al[ks][3] = rb < p.Lq ? *reinterpret_cast<const uint32_t*>(pb + p.q_lo_col + 8) : 0u;
+  }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  float oacc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.f;
+  for (int kc = 0; kc * 64 < p.kpad; ++kc) {
+    const int keys_left = p.Lk - kc * 64;
+    if (keys_left <= 0) break;
+    const int n_live = keys_left >= 64 ? 8 : (keys_left + 7) >> 3;
+    float s[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      if (nt >= n_live) continue;
+      const int row = kc * 64 + nt * 8 + (lane & 7);
+      uint32_t kh[4], kl[4];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {  // head-dim columns [0,32) then [32,64)
+        sp_ldsm_x4(kh, sKh + sp_sw128(row, 4 * half + (lane >> 3)));
+        sp_ldsm_x4(kl, sKl + sp_sw128(row, 4 * half + (lane >> 3)));
+        sp_mma(s[nt], al[2 * half], kh[0], kh[1]);
+        sp_mma(s[nt], al[2 * half + 1], kh[2], kh[3]);
+        sp_mma(s[nt], ah[2 * half], kl[0], kl[1]);
+        sp_mma(s[nt], ah[2 * half + 1], kl[2], kl[3]);
+        sp_mma(s[nt], ah[2 * half], kh[0], kh[1]);
+        sp_mma(s[nt], ah[2 * half + 1], kh[2], kh[3]);
+      }
+    }
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int key = kc * 64 + nt * 8 + 2 * t;
+      if (key >= p.Lk) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+      if (key + 1 >= p.Lk) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+    const float c0 = sp_ex2((m0 - mn0) * p.scale_log2e), c1 = sp_ex2((m1 - mn1) * p.scale_log2e);
+    const float ms0 = mn0 * p.scale_log2e, ms1 = mn1 * p.scale_log2e;
+    m0 = mn0; m1 = mn1;
+    l0 *= c0; l1 *= c1;
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd) { oacc[nd][0] *= c0; oacc[nd][1] *= c0; oacc[nd][2] *= c1; oacc[nd][3] *= c1; }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      s[nt][0] = sp_ex2(fmaf(s[nt][0], p.scale_log2e, -ms0)); s[nt][1] = sp_ex2(fmaf(s[nt][1], p.scale_log2e, -ms0));
+      s[nt][2] = sp_ex2(fmaf(s[nt][2], p.scale_log2e, -ms1)); s[nt][3] = sp_ex2(fmaf(s[nt][3], p.scale_log2e, -ms1));
+      l0 += s[nt][0] + s[nt][1];
+      l1 += s[nt][2] + s[nt][3];
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      if (kk * 2 >= n_live) continue;
+      uint32_t ph[4], pl[4];
+      sp_pack_pair(s[2 * kk][0], s[2 * kk][1], ph[0], pl[0]);
+      sp_pack_pair(s[2 * kk][2], s[2 * kk][3], ph[1], pl[1]);
+      sp_pack_pair(s[2 * kk + 1][0], s[2 * kk + 1][1], ph[2], pl[2]);
+      sp_pack_pair(s[2 * kk + 1][2], s[2 * kk + 1][3], ph[3], pl[3]);
+      const int row = kc * 64 + kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t vh[4], vl[4];
+        sp_ldsm_x4_t(vh, sVh + sp_sw128(row, 2 * np + (lane >> 4)));
+        sp_ldsm_x4_t(vl, sVl + sp_sw128(row, 2 * np + (lane >> 4)));
+        sp_mma(oacc[2 * np], pl, vh[0], vh[1]);
+        sp_mma(oacc[2 * np + 1], pl, vh[2], vh[3]);
+        sp_mma(oacc[2 * np], ph, vl[0], vl[1]);
+        sp_mma(oacc[2 * np + 1], ph, vl[2], vl[3]);
+        sp_mma(oacc[2 * np], ph, vh[0], vh[1]);
+        sp_mma(oacc[2 * np + 1], ph, vh[2], vh[3]);
+      }
+    }
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+  const int ra = row0 + g, rb = row0 + g + 8;
+  __half* ob = p.o + (long long)b * p.Lq * p.ldo + h * SP_HD;
+#pragma unroll
+  for (int nd = 0; nd < 8; ++nd) {
+    uint32_t hi, lo;
+    if (ra < p.Lq) {
+      sp_pack_pair(oacc[nd][0] * i0, oacc[nd][1] * i0, hi, lo);
+      *reinterpret_cast<uint32_t*>(ob + (long long)ra * p.ldo + nd * 8 + 2 * t) = hi;
+      *reinterpret_cast<uint32_t*>(ob + (long long)ra * p.ldo + p.o_lo_off + nd * 8 + 2 * t) = lo;
+    }
+    if (rb < p.Lq) {
+      sp_pack_pair(oacc[nd][2] * i1, oacc[nd][3] * i1, hi, lo);
+      *reinterpret_cast<uint32_t*>(ob + (long long)rb * p.ldo + nd * 8 + 2 * t) = hi;
+      *reinterpret_cast<uint32_t*>(ob + (long long)rb * p.ldo + p.o_lo_off + nd * 8 + 2 * t) = lo;
+    }
+  }
+}
+
+// MINB = CTAs per SM the register budget must allow: 2 for short key sequences (cross-attention, 96 keys: 113 KB of smem and 256 TMEM columns
+// per CTA, so two heads' softmax / MMA chains interleave on one SM), 1 for the 288-key self-attention tiles (208 KB of smem).
+template <int MINB>
+__global__ void __launch_bounds__(SP_THREADS, MINB)
 attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                           const __grid_constant__ SpParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int kv_bytes = p.kpad * 128;
-  uint8_t* sQ = smem;                         // [2 buffers][hi, lo] x 16 KB
-  uint8_t* sKh = sQ + 4 * SP_QTILE;
+  uint8_t* sQ = smem;                         // [q_bufs][hi, lo] x 16 KB
+  uint8_t* sKh = sQ + p.q_bufs * 2 * SP_QTILE;
   uint8_t* sKl = sKh + kv_bytes;
   uint8_t* sVh = sKl + kv_bytes;
   uint8_t* sVl = sVh + kv_bytes;
@@ -108,22 +250,23 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
         tma_load_3d(&map_v, kv_full, sVh + off, h * SP_HD, r, 0);
         tma_load_3d(&map_v, kv_full, sVl + off, p.v_lo_col + h * SP_HD, r, 0);
       }
+      const int nb = p.q_bufs;
       auto issue_q = [&](int qt) {
-        const int qb = qt & 1;
+        const int qb = qt % nb;
         mbar_arrive_expect_tx(&q_full[qb], 2 * SP_QTILE);
         tma_load_3d(&map_q, &q_full[qb], sQ + qb * 2 * SP_QTILE, h * SP_HD, b * p.Lq + qt * SP_QM, 0);
         tma_load_3d(&map_q, &q_full[qb], sQ + qb * 2 * SP_QTILE + SP_QTILE, p.q_lo_col + h * SP_HD, b * p.Lq + qt * SP_QM, 0);
       };
       issue_q(0);
-      if (p.n_qt > 1) issue_q(1);
+      if (nb > 1 && p.n_qt > 1) issue_q(1);
       const int n_hi = p.kpad > 256 ? 256 : p.kpad, n_lo = p.kpad - n_hi;
       const uint32_t id_hi = sp_idesc(SP_QM, n_hi, false), id_lo = sp_idesc(SP_QM, n_lo > 0 ? n_lo : 16, false);
       const uint32_t id_pv = sp_idesc(SP_QM, SP_HD, true);
       const int ksteps = p.kpad >> 4;
       mbar_wait(kv_full, 0);
       for (int qt = 0; qt < p.n_qt; ++qt) {
-        const int qb = qt & 1;
-        mbar_wait(&q_full[qb], (qt >> 1) & 1);
+        const int qb = qt % nb;
+        mbar_wait(&q_full[qb], (qt / nb) & 1);
         tc_fence_after();
         // ---- S = Qlo Khi^T + Qhi Klo^T + Qhi Khi^T  (tcgen05.mma from one thread execute in issue order: this also follows P.V(qt-1))
         const uint32_t qh = smem_u32(sQ + qb * 2 * SP_QTILE), ql = qh + SP_QTILE;
@@ -140,10 +283,10 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
           }
         }
         umma_commit(s_full);
-        // the Q buffer is free once S has been computed: prefetch tile qt + 2 into it
-        if (qt + 2 < p.n_qt) {
+        // the Q buffer is free once S has been computed: prefetch tile qt + q_bufs into it
+        if (qt + nb < p.n_qt) {
           mbar_wait(s_full, qt & 1);
-          issue_q(qt + 2);
+          issue_q(qt + nb);
         }
         mbar_wait(p_full, qt & 1);                       // P(qt) is in TMEM
         if (qt > 0) mbar_wait(o_empty, (qt - 1) & 1);    // epilogue(qt-1) has read O
@@ -158,6 +301,12 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
         }
         umma_commit(o_full);
       }
+    }
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ remainder rows (after the full 128-row tiles), concurrent with them
+    if (p.rem_rows > 0) {
+      mbar_wait(kv_full, 0);
+      sp_remainder_rows(p, sKh, sKl, sVh, sVl, b, h, p.n_qt * SP_QM, lane);
     }
   } else {
     // ------------------------------------------------------------------ softmax + epilogue warps
@@ -277,7 +426,15 @@ extern "C" int dsb_attention_tc_split(const void* q, long long ldq, long long q_
   SpParams p{};
   p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk;
   p.kpad = (Lk + 31) & ~31;
-  p.n_qt = (Lq + SP_QM - 1) / SP_QM;
+  const int rem = Lq % SP_QM;
+  if (Lq > SP_QM && rem > 0 && rem <= 16) {  // e.g. 265 = 2 x 128 + 9: the 9 rows go to the remainder warp, not to a third tensor tile
+    p.n_qt = Lq / SP_QM;
+    p.rem_rows = rem;
+  } else {
+    p.n_qt = (Lq + SP_QM - 1) / SP_QM;
+    p.rem_rows = 0;
+  }
+  p.q = (const __half*)q; p.ldq = ldq;
   p.n_box = p.kpad > 256 ? 2 : 1;
   p.box_rows = p.kpad / p.n_box;
   DSB_REQUIRE(p.box_rows % 8 == 0, "dsb_attention_tc_split: internal box size");
@@ -291,12 +448,16 @@ extern "C" int dsb_attention_tc_split(const void* q, long long ldq, long long q_
   if (make_operand_map(&mq, q, DSB_DTYPE_F16, q_lo_off + (long long)H * SP_HD, (long long)B * Lq, 1, ldq, 0, SP_QM)) return 3;
   if (make_operand_map(&mk, k, DSB_DTYPE_F16, k_lo_off + (long long)H * SP_HD, (long long)B * Lk, 1, ldk, 0, p.box_rows)) return 3;
   if (make_operand_map(&mv, v, DSB_DTYPE_F16, v_lo_off + (long long)H * SP_HD, (long long)B * Lk, 1, ldv, 0, p.box_rows)) return 3;
-  const int smem = 4 * SP_QTILE + 4 * p.kpad * 128 + (512 + 512) * 4 + 16 * 8 + 1024;
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
-    DSB_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_smem = smem;
+  const bool two = cols <= 256 && 2 * SP_QTILE + 4 * p.kpad * 128 + (512 + 512) * 4 + 16 * 8 + 1024 <= 112 * 1024;  // two CTAs per SM fit
+  p.q_bufs = two ? 1 : 2;
+  const int smem = p.q_bufs * 2 * SP_QTILE + 4 * p.kpad * 128 + (512 + 512) * 4 + 16 * 8 + 1024;
+  static int attr_smem[2] = {0, 0};
+  if (smem > attr_smem[two]) {
+    if (two) DSB_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_split_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    else DSB_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_split_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem[two] = smem;
   }
-  DSB_CHECK_CUDA(launch_pdl(attention_tc_split_kernel, dim3(H, B), dim3(SP_THREADS), smem, (cudaStream_t)stream, mq, mk, mv, p));
+  if (two) DSB_CHECK_CUDA(launch_pdl(attention_tc_split_kernel<2>, dim3(H, B), dim3(SP_THREADS), smem, (cudaStream_t)stream, mq, mk, mv, p));
+  else DSB_CHECK_CUDA(launch_pdl(attention_tc_split_kernel<1>, dim3(H, B), dim3(SP_THREADS), smem, (cudaStream_t)stream, mq, mk, mv, p));
   return 0;
 }
