@@ -207,6 +207,20 @@ int dsb_posterior_sample(const float* logits, const int64_t* x_t, const int64_t*
                          const float* sched, int64_t* x_next, float* log_prob_out, int B, int K, int L, int T, int trunc_mode,
                          float trunc_r, int trunc_k, int stage_flags, void* stream);
 
+/* Loop form of the same kernel for DiffusionTransformer.sample's 100-step loop (diffusion_transformer.py:638-641): no uniform tensor, no host
+ * update between steps.  The kernel draws the uniforms itself, replaying the CUDA stream of the reference's `torch.rand_like(logits)` (:360) bit for
+ * bit (Philox4x32-10, ATen's element -> (thread, call, component) mapping for a contiguous (B, K+1, L) float tensor), samples x IN PLACE (a column is
+ * read and written by the same warp), and its last CTA advances the philox offset and writes the next step's timesteps into t / t_post:
+ *   ctrl (device, 7 x uint64): [0] seed  [1] philox offset (multiple of 4)  [2] offset increment per step = ATen's counter_offset
+ *                              [3] ATen's thread count 256 * grid  [4] step index  [5] number of steps  [6] CTA ticket (0)
+ *   t_sched / t_post_sched (device, n_steps int64): denoiser / posterior timestep of every step; t, t_post (B,) hold step 0's values at entry. */
+int dsb_posterior_sample_loop(const float* logits, int64_t* x, int64_t* t, int64_t* t_post, const float* sched, unsigned long long* ctrl,
+                              const int64_t* t_sched, const int64_t* t_post_sched, int B, int K, int L, int T, int trunc_mode, float trunc_r,
+                              int trunc_k, void* stream);
+/* out[i] = the i-th element torch.rand(n, device='cuda') would hold for generator state (seed, philox offset) with ATen's launch geometry
+ * nthreads = 256 * min(SMs * (maxThreadsPerSM / 256), ceil(n / 256)); used by the tests to pin the replay against torch.rand itself. */
+int dsb_aten_uniform(float* out, long long n, unsigned long long seed, unsigned long long offset, unsigned long long nthreads, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * SpecVQGAN decoder support (reference Diffsound/specvqgan/modules/diffusionmodules/model.py:570-671 Decoder and its
  * blocks; sound_synthesis/modeling/models/dalle_spec.py:80-91 decode_to_img).  Activations are fp32 channels-last images

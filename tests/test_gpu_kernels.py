@@ -183,3 +183,63 @@ def test_attention_tcgen05_matches_fp64(G, B, H, Lq, Lk, pipelined):
         G.ops.attention_tc(qkv_d[:, :D], kv_d[:, :D], kv_d[:, D:], out, B=B, H=H, Lq=Lq, Lk=Lk, scale=0.125, pipelined=pipelined)
         assert torch.isfinite(out).all()
         assert G.relerr(out.float(), ref) < 1.5e-3
+
+
+def test_philox_replay_matches_torch_rand_bit_for_bit():
+    """The fused sampling loop draws its own uniforms; they must be the very numbers torch.rand_like would have produced from the default CUDA
+    generator (reference diffusion_transformer.py:360), for any tensor size (ATen's launch geometry changes with numel) and any offset."""
+    import _pkg
+    _pkg.load()
+    from diffsound_b200 import ops
+    gen = torch.cuda.default_generators[torch.cuda.current_device()]
+    for seed, n in ((1234, 16 * 257 * 265), (7, 257 * 265), (2 ** 40 + 3, 1000), (99, 512 * 513 * 265 // 4), (5, 3)):
+        torch.manual_seed(seed)
+        assert gen.initial_seed() == seed and gen.get_offset() == 0
+        a = torch.rand(n, device="cuda")
+        off1 = gen.get_offset()
+        nthreads, counter_offset = ops.aten_rand_geometry(n)
+        assert off1 == counter_offset, (off1, counter_offset)          # the offset bookkeeping the loop relies on
+        assert torch.equal(ops.aten_uniform(n, seed, 0), a), (seed, n)
+        b = torch.rand(n, device="cuda")                                # second draw: offset advanced by counter_offset
+        assert torch.equal(ops.aten_uniform(n, seed, off1), b), (seed, n)
+    x = torch.rand(2, 257, 265, device="cuda")                          # rand_like of a (B, K+1, L) tensor = the flat stream in memory order
+    torch.manual_seed(11)
+    y = torch.rand_like(x)
+    assert torch.equal(ops.aten_uniform(x.numel(), 11, 0).view_as(y), y)
+
+
+def test_sampling_loop_kernel_equals_explicit_uniforms():
+    """dsb_posterior_sample_loop (in-kernel RNG, in-place ids, device-side schedule) == dsb_posterior_sample fed torch.rand's tensor, step by step."""
+    import _pkg
+    _pkg.load()
+    from diffsound_b200 import ops
+    from oracle import diffsound_oracle as O
+    B, K, L, T = 3, 256, 265, 100
+    sb = O.schedule_buffers(T, K + 1)
+    sched = torch.zeros(8, T + 1)
+    for i, n in enumerate(["log_at", "log_bt", "log_ct", "log_1_min_ct", "log_cumprod_at", "log_cumprod_bt", "log_cumprod_ct", "log_1_min_cumprod_ct"]):
+        sched[i, :sb[n].numel()] = sb[n]
+    sched = sched.cuda()
+    g = torch.Generator().manual_seed(0)
+    steps, post = [99, 98, 60, 60, 3, 0], [99, 97, 60, 58, 3, 0]
+    logits = [(torch.randn(B, L, K, generator=g) * 3).cuda() for _ in steps]
+    x0 = torch.full((B, L), K, dtype=torch.long, device="cuda")
+    seed = 4242
+    torch.manual_seed(seed)
+    ref = x0.clone()
+    for lg, ti, tp in zip(logits, steps, post):
+        u = torch.rand(B, K + 1, L, device="cuda")
+        ref = ops.posterior_sample(lg, ref, torch.full((B,), ti, device="cuda"), u, sched, T=T, t_post=torch.full((B,), tp, device="cuda"))
+    nthreads, inc = ops.aten_rand_geometry(B * (K + 1) * L)
+    ctrl = torch.tensor([seed, 0, inc, nthreads, 0, len(steps), 0, 0], dtype=torch.int64, device="cuda")
+    t_s, tp_s = torch.tensor(steps, device="cuda"), torch.tensor(post, device="cuda")
+    t = torch.full((B,), steps[0], device="cuda")
+    tpb = torch.full((B,), post[0], device="cuda")
+    x = x0.clone()
+    for i, lg in enumerate(logits):
+        ops.posterior_sample_loop(lg, x, t, tpb, sched, ctrl, t_s, tp_s, T=T)
+        if i + 1 < len(steps):
+            torch.cuda.synchronize()
+            assert int(t[0]) == steps[i + 1] and int(t[-1]) == steps[i + 1] and int(tpb[0]) == post[i + 1]
+    assert torch.equal(x, ref)
+    assert ctrl.tolist()[:7] == [seed, inc * len(steps), inc, nthreads, len(steps), len(steps), 0]

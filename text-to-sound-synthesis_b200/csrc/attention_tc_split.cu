@@ -19,7 +19,8 @@ namespace {
 constexpr int SP_HD = 64;
 constexpr int SP_QM = 128;
 constexpr int SP_KMAX = 288;      // padded key capacity (multiple of 32)
-constexpr int SP_THREADS = 320;   // warps 0-7 softmax + epilogue, warp 8 control (TMA producer, MMA issuer, TMEM owner), warp 9 remainder rows
+// warps [0, 4*NSW): softmax + epilogue (NSW per TMEM lane quadrant), warp 4*NSW: control (TMA producer, MMA issuer, TMEM owner), warp 4*NSW+1: remainder rows
+constexpr int sp_threads(int nsw) { return (4 * nsw + 2) * 32; }
 constexpr int SP_QTILE = SP_QM * 128;  // bytes of one 128 x 64 fp16 SW128 tile
 
 struct SpParams {
@@ -194,8 +195,10 @@ __device__ __forceinline__ void sp_remainder_rows(const SpParams& p, const uint8
 
 // MINB = CTAs per SM the register budget must allow: 2 for short key sequences (cross-attention, 96 keys: 113 KB of smem and 256 TMEM columns
 // per CTA, so two heads' softmax / MMA chains interleave on one SM), 1 for the 288-key self-attention tiles (208 KB of smem).
-template <int MINB>
-__global__ void __launch_bounds__(SP_THREADS, MINB)
+// NSW = softmax warps per lane quadrant: 3 for the 288-key tiles (each warp owns three of the nine 32-key chunks and fetches them with ONE TMEM
+// round trip per pass -- the chain S -> softmax -> P.V is latency bound), 2 for short key sequences.
+template <int MINB, int NSW, int MAXC>
+__global__ void __launch_bounds__(sp_threads(NSW), MINB)
 attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                           const __grid_constant__ SpParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -206,9 +209,10 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
   uint8_t* sKl = sKh + kv_bytes;
   uint8_t* sVh = sKl + kv_bytes;
   uint8_t* sVl = sVh + kv_bytes;
-  float* s_max = reinterpret_cast<float*>(sVl + kv_bytes);   // [2 tile parities][2 halves][128 rows]
-  float* s_sum = s_max + 512;                                // same shape
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_sum + 512);
+  float* s_max = reinterpret_cast<float*>(sVl + kv_bytes);   // [2 tile parities][NSW][128 rows]
+  float* s_sum = s_max + 1024;                               // same shape
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_sum + 1024);
+  constexpr int CTRL = 4 * NSW;
   uint64_t* kv_full = bars;
   uint64_t* q_full = bars + 1;   // [2]
   uint64_t* s_full = bars + 3;
@@ -223,11 +227,11 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
   if (threadIdx.x == 0) {
     mbar_init(kv_full, 1);
     mbar_init(&q_full[0], 1); mbar_init(&q_full[1], 1);
-    mbar_init(s_full, 1); mbar_init(p_full, 8); mbar_init(o_full, 1); mbar_init(o_empty, 8);
+    mbar_init(s_full, 1); mbar_init(p_full, 4 * NSW); mbar_init(o_full, 1); mbar_init(o_empty, 8);
     fence_barrier_init();
     prefetch_tmap(&map_q); prefetch_tmap(&map_k); prefetch_tmap(&map_v);
   }
-  if (warp == 8) {
+  if (warp == CTRL) {
     tmem_alloc(tmem_ptr, p.tmem_cols);
     tmem_relinquish();
   }
@@ -239,7 +243,7 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
   pdl_wait();
   pdl_trigger();
 
-  if (warp == 8) {
+  if (warp == CTRL) {
     if (lane == 0) {
       // ------------------------------------------------------------------ control thread: TMA producer + MMA issuer
       mbar_arrive_expect_tx(kv_full, 4 * kv_bytes);
@@ -302,7 +306,7 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
         umma_commit(o_full);
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == CTRL + 1) {
     // ------------------------------------------------------------------ remainder rows (after the full 128-row tiles), concurrent with them
     if (p.rem_rows > 0) {
       mbar_wait(kv_full, 0);
@@ -310,42 +314,47 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
     }
   } else {
     // ------------------------------------------------------------------ softmax + epilogue warps
-    const int quad = warp & 3, half = warp >> 2;
+    const int quad = warp & 3, half = warp >> 2;  // half = which of the NSW column slices of this quadrant
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const int row_in_tile = quad * 32 + lane;
     const int n_chunks = p.kpad >> 5;
-    const int csplit = (n_chunks + 1) >> 1;
-    const int c_begin = (half == 0 ? 0 : csplit) * 32, c_end = (half == 0 ? csplit : n_chunks) * 32;
+    // slice j owns chunks [j * n / NSW, (j + 1) * n / NSW): 9 chunks -> 3,3,3 with NSW = 3
+    const int c_begin = (half * n_chunks / NSW) * 32, c_end = ((half + 1) * n_chunks / NSW) * 32;
+    // MAXC = chunks held in registers at once: one TMEM round trip per pass covers up to MAXC chunks; longer slices go in groups
     for (int qt = 0; qt < p.n_qt; ++qt) {
       const bool live = qt * SP_QM + quad * 32 < p.Lq;  // a 32-row slab entirely beyond Lq does no exp work; its rows are never stored
       mbar_wait(s_full, qt & 1);
       tc_fence_after();
       float mx = -INFINITY, sum = 0.f;
-      float* smx = s_max + (qt & 1) * 256;
+      float* smx = s_max + (qt & 1) * (NSW * 128);
+      auto chunk_max = [&](const uint32_t (&sv)[32], int c) {
+        if (c + 32 <= p.Lk) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(sv[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (c + j < p.Lk) mx = fmaxf(mx, __uint_as_float(sv[j]));
+        }
+      };
       if (live) {
-        for (int c = c_begin; c < c_end; c += 32) {
-          uint32_t sv[32];
-          tmem_ld_32x32(tS + lane_off + c, sv);
+        for (int c = c_begin; c < c_end; c += 32 * MAXC) {
+          uint32_t sa[32], sb[32];
+          const bool two = MAXC > 1 && c + 32 < c_end;
+          tmem_ld_32x32(tS + lane_off + c, sa);
+          if (two) tmem_ld_32x32(tS + lane_off + c + 32, sb);
           tmem_ld_wait();
-          if (c + 32 <= p.Lk) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(sv[j]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c + j < p.Lk) mx = fmaxf(mx, __uint_as_float(sv[j]));
-          }
+          chunk_max(sa, c);
+          if (two) chunk_max(sb, c + 32);
         }
       }
       smx[half * 128 + row_in_tile] = mx;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * 4 * NSW) : "memory");
       if (live) {
-        mx = fmaxf(mx, smx[(half ^ 1) * 128 + row_in_tile]);
+#pragma unroll
+        for (int j = 0; j < NSW; ++j) mx = fmaxf(mx, smx[j * 128 + row_in_tile]);
         const float ms = mx * p.scale_log2e;
-        for (int c = c_begin; c < c_end; c += 32) {
-          uint32_t sv[32];
-          tmem_ld_32x32(tS + lane_off + c, sv);
-          tmem_ld_wait();
+        auto chunk_p = [&](const uint32_t (&sv)[32], int c) {
           uint32_t ph[16], pl[16];
           const bool full = c + 32 <= p.Lk;
 #pragma unroll
@@ -364,19 +373,32 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
           }
           sp_tmem_st_x16(tS + lane_off + c, ph);        // in place: this thread has consumed these 32 S columns
           sp_tmem_st_x16(tS + lane_off + c + 16, pl);
+        };
+        for (int c = c_begin; c < c_end; c += 32 * MAXC) {
+          uint32_t sa[32], sb[32];
+          const bool two = MAXC > 1 && c + 32 < c_end;
+          tmem_ld_32x32(tS + lane_off + c, sa);
+          if (two) tmem_ld_32x32(tS + lane_off + c + 32, sb);
+          tmem_ld_wait();
+          chunk_p(sa, c);
+          if (two) chunk_p(sb, c + 32);
         }
         sp_tmem_st_wait();
       }
-      s_sum[((qt & 1) * 2 + half) * 128 + row_in_tile] = sum;
+      s_sum[((qt & 1) * NSW + half) * 128 + row_in_tile] = sum;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
-      // ---- epilogue: this warp's 32 rows x 32 of the 64 output columns
+      // ---- epilogue (slices 0 and 1 of every quadrant): 32 rows x 32 of the 64 output columns
+      if (half >= 2) continue;
       mbar_wait(o_full, qt & 1);
       tc_fence_after();
       const int row = qt * SP_QM + row_in_tile;
       if (live) {
-        const float inv = 1.0f / (s_sum[((qt & 1) * 2) * 128 + row_in_tile] + s_sum[((qt & 1) * 2 + 1) * 128 + row_in_tile]);
+        float tot = 0.f;
+#pragma unroll
+        for (int j = 0; j < NSW; ++j) tot += s_sum[((qt & 1) * NSW + j) * 128 + row_in_tile];
+        const float inv = 1.0f / tot;
         uint32_t ov[32];
         tmem_ld_32x32(tO + lane_off + half * 32, ov);
         tmem_ld_wait();
@@ -405,7 +427,7 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == CTRL) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
@@ -448,16 +470,16 @@ extern "C" int dsb_attention_tc_split(const void* q, long long ldq, long long q_
   if (make_operand_map(&mq, q, DSB_DTYPE_F16, q_lo_off + (long long)H * SP_HD, (long long)B * Lq, 1, ldq, 0, SP_QM)) return 3;
   if (make_operand_map(&mk, k, DSB_DTYPE_F16, k_lo_off + (long long)H * SP_HD, (long long)B * Lk, 1, ldk, 0, p.box_rows)) return 3;
   if (make_operand_map(&mv, v, DSB_DTYPE_F16, v_lo_off + (long long)H * SP_HD, (long long)B * Lk, 1, ldv, 0, p.box_rows)) return 3;
-  const bool two = cols <= 256 && 2 * SP_QTILE + 4 * p.kpad * 128 + (512 + 512) * 4 + 16 * 8 + 1024 <= 112 * 1024;  // two CTAs per SM fit
+  const bool two = cols <= 256 && 2 * SP_QTILE + 4 * p.kpad * 128 + (1024 + 1024) * 4 + 16 * 8 + 1024 <= 112 * 1024;  // two CTAs per SM fit
   p.q_bufs = two ? 1 : 2;
-  const int smem = p.q_bufs * 2 * SP_QTILE + 4 * p.kpad * 128 + (512 + 512) * 4 + 16 * 8 + 1024;
+  const int smem = p.q_bufs * 2 * SP_QTILE + 4 * p.kpad * 128 + (1024 + 1024) * 4 + 16 * 8 + 1024;
   static int attr_smem[2] = {0, 0};
   if (smem > attr_smem[two]) {
-    if (two) DSB_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_split_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    else DSB_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_split_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (two) DSB_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_split_kernel<2, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    else DSB_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_split_kernel<1, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_smem[two] = smem;
   }
-  if (two) DSB_CHECK_CUDA(launch_pdl(attention_tc_split_kernel<2>, dim3(H, B), dim3(SP_THREADS), smem, (cudaStream_t)stream, mq, mk, mv, p));
-  else DSB_CHECK_CUDA(launch_pdl(attention_tc_split_kernel<1>, dim3(H, B), dim3(SP_THREADS), smem, (cudaStream_t)stream, mq, mk, mv, p));
+  if (two) DSB_CHECK_CUDA(launch_pdl(attention_tc_split_kernel<2, 2, 1>, dim3(H, B), dim3(sp_threads(2)), smem, (cudaStream_t)stream, mq, mk, mv, p));
+  else DSB_CHECK_CUDA(launch_pdl(attention_tc_split_kernel<1, 3, 2>, dim3(H, B), dim3(sp_threads(3)), smem, (cudaStream_t)stream, mq, mk, mv, p));
   return 0;
 }

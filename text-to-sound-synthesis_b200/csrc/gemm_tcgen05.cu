@@ -619,6 +619,150 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   }
 }
 
+// ------------------------------------------------------------------------------------------ fused split-fp16 ("f16x3") CTA-pair kernel
+// out = epi(alpha * (Alo Whi^T + Ahi Wlo^T + Ahi Whi^T) + bias) with A = (M, 2K) [hi | lo] and W = (N, 2K) [hi | lo].  The tap form of the same
+// product streams every operand tile once PER PASS (3 x (32 KB in + 32 KB out of shared memory per SM and 64-deep k-block): exactly the MMA time,
+// no slack).  Here one pipeline stage holds the four tiles of a k-block (A hi, A lo, W hi half, W lo half: 64 KB per CTA) and the issuer runs the
+// three passes off them: 64 KB in + 96 KB out per 1536 MMA cycles, so the shared-memory port is no longer co-critical and L2 traffic drops by a third.
+struct PairSplitSmem {
+  static constexpr int BLOCK_N = 256;
+  static constexpr int TILE = BLOCK_M * ROW_BYTES;  // 16 KB: 128 rows x 64 halves (this CTA's A rows, or its half of the W tile)
+  static constexpr int STAGE_BYTES = 4 * TILE;      // A hi | A lo | W hi | W lo
+  static constexpr int STAGES = 3;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + 256 + 8 * 32 * 32 * 4;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_f16x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ GemmParams p) {
+  using S = PairSplitSmem;
+  constexpr int BLOCK_N = S::BLOCK_N;
+  constexpr int STAGES = S::STAGES;
+  constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* epi_smem = reinterpret_cast<float*>(smem + STAGES * S::STAGE_BYTES + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int num_tiles = p.tiles_m * p.tiles_n * p.batch;  // tiles_m counts 256-row pair tiles
+  const int num_kb = p.kb_per_tap;                        // k-blocks of the ORIGINAL reduction length K
+  const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int lo_a = p.tap_acol[0], lo_w = p.tap_wcol[0];   // column of the lo halves (= K)
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 16);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp == 0) {
+    if (lane == 0) {  // ------------------------------------------------------------ TMA producer (both CTAs): four boxes per k-block
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+        const int m_blk = tile % p.tiles_m;
+        const int n_blk = (tile / p.tiles_m) % p.tiles_n;
+        const int b = tile / (p.tiles_m * p.tiles_n);
+        const int row0 = m_blk * (2 * BLOCK_M) + (int)rank * BLOCK_M;
+        const int nrow0 = n_blk * BLOCK_N + (int)rank * (BLOCK_N / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int c0 = kb * 64;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
+          const uint32_t bar = map_to_cta(smem_u32(&full_bar[stage]), 0);
+          uint8_t* sa = smem + stage * S::STAGE_BYTES;
+          tma_load_3d_2sm(&tmap_a, bar, sa, c0, row0, b);
+          tma_load_3d_2sm(&tmap_a, bar, sa + S::TILE, lo_a + c0, row0, b);
+          tma_load_3d_2sm(&tmap_b, bar, sa + 2 * S::TILE, c0, nrow0, 0);
+          tma_load_3d_2sm(&tmap_b, bar, sa + 3 * S::TILE, lo_w + c0, nrow0, 0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {  // ---------------------------------------------------- MMA issuer: lo*hi, hi*lo, hi*hi per 16-element K slice
+      constexpr uint32_t idesc = make_idesc(DSB_DTYPE_F16, 2 * BLOCK_M, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint64_t dah = make_sw128_kmajor_desc(sa), dal = make_sw128_kmajor_desc(sa + S::TILE);
+          const uint64_t dbh = make_sw128_kmajor_desc(sa + 2 * S::TILE), dbl = make_sw128_kmajor_desc(sa + 3 * S::TILE);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_2sm<false>(d_tmem, dal + 2 * k, dbh + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_2sm<false>(d_tmem, dah + 2 * k, dbl + 2 * k, idesc, 1u);
+            umma_2sm<false>(d_tmem, dah + 2 * k, dbh + 2 * k, idesc, 1u);
+          }
+          umma_commit_2sm(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&tmem_full[as]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    float* sw = epi_smem + (warp - 2) * (32 * 32);
+    int it = 0;
+    for (int tile = pair_id; tile < num_tiles; tile += num_pairs, ++it) {
+      const int m_blk = tile % p.tiles_m;
+      const int n_blk = (tile / p.tiles_m) % p.tiles_n;
+      const int b = tile / (p.tiles_m * p.tiles_n);
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      epilogue_tile<BLOCK_N>(p, sw, tmem_base + as * BLOCK_N, &tmem_full[as], aphase, m_blk * (2 * BLOCK_M) + (int)rank * BLOCK_M + q * 32, n_blk, b, q,
+                             half, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(&tmem_empty[as]), 0));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -793,6 +937,11 @@ extern "C" int dsb_gemm_ex(const dsb_gemm_desc* d, void* stream) {
   DSB_REQUIRE(!(any_mn && d->cta_pair > 0), "dsb_gemm_ex: the cta_group::2 kernel takes K-major operands only");
   const bool use_pair = !any_mn && (d->cta_pair > 0 || (d->cta_pair == 0 && d->block_n == 0 && block_n == 256 && d->M > BLOCK_M &&
                                                         (long long)d->K * d->num_taps >= 2048 && pair_default()));
+  // split-fp16 tap list (lo*hi, hi*lo, hi*hi of one unshifted operand pair): run the three passes off ONE staged copy of the four tiles
+  static const bool fuse_ok = [] { const char* e = getenv("DSB_GEMM_F16X3_FUSED"); return !(e && e[0] == '0'); }();
+  const bool fused3 = use_pair && fuse_ok && kind == DSB_DTYPE_F16 && d->num_taps == 3 && !p.tap_a2_mask && d->batch == 1 && !p.b_batched &&
+                      p.tap_shift[0] == 0 && p.tap_shift[1] == 0 && p.tap_shift[2] == 0 && p.tap_acol[0] == d->K && p.tap_acol[1] == 0 && p.tap_acol[2] == 0 &&
+                      p.tap_wcol[0] == 0 && p.tap_wcol[1] == d->K && p.tap_wcol[2] == 0 && d->K % 64 == 0;
   if (use_pair) {
     block_n = 256;
     p.tiles_m = (d->M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
@@ -815,6 +964,21 @@ extern "C" int dsb_gemm_ex(const dsb_gemm_desc* d, void* stream) {
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int max_ctas = d->max_ctas > 0 ? d->max_ctas : sms;
+  if (fused3) {
+    p.tap_wcol[0] = (int)d->K;  // the fused kernel reads the lo-half columns from tap_acol[0] / tap_wcol[0]
+    auto kern = gemm_f16x3_pair_kernel;
+    static bool attr_done = false;
+    if (!attr_done) {
+      DSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PairSplitSmem::TOTAL));
+      attr_done = true;
+    }
+    const int tiles = p.tiles_m * p.tiles_n;
+    int pairs = max_ctas / 2;
+    if (pairs < 1) pairs = 1;
+    if (tiles < pairs) pairs = tiles;
+    DSB_CHECK_CUDA(launch_pdl(kern, dim3(2 * pairs), dim3(GEMM_THREADS), PairSplitSmem::TOTAL, st, ma, mb, p));
+    return 0;
+  }
   if (use_pair) {
     if (kind == DSB_DTYPE_TF32) return launch_pair<DSB_DTYPE_TF32>(ma, ma2, mb, p, max_ctas, st);
     if (kind == DSB_DTYPE_BF16) return launch_pair<DSB_DTYPE_BF16>(ma, ma2, mb, p, max_ctas, st);

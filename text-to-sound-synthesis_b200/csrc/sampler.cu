@@ -33,13 +33,48 @@ __device__ __forceinline__ double wsumd(double v) {
   return v;
 }
 
+// ---- in-kernel replay of torch.rand_like's CUDA stream (diffusion_transformer.py:360 draws uniform = torch.rand_like(logits)).
+// ATen fills a contiguous float tensor with distribution_elementwise_grid_stride_kernel (ATen/native/cuda/DistributionTemplates.h): thread
+// tid of `nthreads` = 256 * grid runs curand_init(seed, tid, offset) and its c-th curand_uniform4 call yields elements
+// tid + nthreads * (4 c + ii), ii = 0..3.  With offset a multiple of 4 (always, for ATen) that is Philox4x32-10 on counter
+// (offset / 4 + c, tid) under key = seed, component ii, mapped by curand's _curand_uniform and ATen's (0, 1] -> [0, 1) flip.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+__device__ __forceinline__ float aten_uniform(unsigned long long seed, unsigned long long offset, unsigned long long nthreads, unsigned long long li) {
+  const unsigned long long tid = li % nthreads, q = li / nthreads;
+  const unsigned long long ctr = (offset >> 2) + (q >> 2);
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)tid, (uint32_t)(tid >> 32)),
+                                make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const uint32_t ii = (uint32_t)(q & 3ull);
+  const uint32_t x = ii == 0 ? r.x : (ii == 1 ? r.y : (ii == 2 ? r.z : r.w));
+  const float u = x * 2.3283064e-10f + (2.3283064e-10f / 2.0f);  // _curand_uniform (curand_uniform.h:69-72), same expression / same contraction
+  return u == 1.0f ? 0.0f : u;                                    // uniform_kernel's reverse_bound_value (DistributionTemplates.h:494-502)
+}
+__global__ void aten_uniform_fill_kernel(float* out, long long n, unsigned long long seed, unsigned long long offset, unsigned long long nthreads) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = aten_uniform(seed, offset, nthreads, (unsigned long long)i);
+}
+
+// Loop control block (device memory, 64-bit words) of the fused sampling loop: the kernel draws its own uniforms and, when its last CTA retires,
+// advances the RNG offset and writes the NEXT step's timesteps, so a whole diffusion step is a fixed launch sequence with no host-side updates.
+//   [0] seed  [1] philox offset  [2] offset increment per step  [3] ATen's thread count (256 * grid)  [4] step index  [5] number of steps  [6] CTA ticket
+constexpr int CTRL_SEED = 0, CTRL_OFFSET = 1, CTRL_OFFSET_INC = 2, CTRL_NTHREADS = 3, CTRL_STEP = 4, CTRL_NSTEPS = 5, CTRL_TICKET = 6;
+
 // NJ = ceil((K+1)/32): elements per lane; element index k = lane + 32*j
 template <int NJ>
 __global__ void __launch_bounds__(SW * 32)
-posterior_sample_kernel(const float* __restrict__ logits, const int64_t* __restrict__ x_t, const int64_t* __restrict__ t,
-                        const int64_t* __restrict__ t_post, const float* __restrict__ uniform, const float* __restrict__ sched,
-                        int64_t* __restrict__ x_next, float* __restrict__ log_prob_out, int K, int L, int T, int trunc_mode, float trunc_r,
-                        int trunc_k, int stage) {
+posterior_sample_kernel(const float* __restrict__ logits, const int64_t* x_t, int64_t* t,
+                        int64_t* t_post, const float* __restrict__ uniform, const float* __restrict__ sched,
+                        int64_t* x_next, float* __restrict__ log_prob_out, int K, int L, int T, int trunc_mode, float trunc_r,
+                        int trunc_k, int stage, unsigned long long* ctrl, const int64_t* __restrict__ t_sched, const int64_t* __restrict__ tp_sched, int B) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int C = K + 1;
   float* u_s = reinterpret_cast<float*>(smem_raw);                    // [C][SW]  uniforms, later reused for log_prob_out
@@ -57,8 +92,10 @@ posterior_sample_kernel(const float* __restrict__ logits, const int64_t* __restr
   pdl_wait();
   pdl_trigger();
 
+  unsigned long long rng_seed = 0ull, rng_off = 0ull, rng_n = 1ull;
+  if (ctrl) { rng_seed = ctrl[CTRL_SEED]; rng_off = ctrl[CTRL_OFFSET]; rng_n = ctrl[CTRL_NTHREADS]; }
   // stage the (C x SW) tile of uniforms: u[b, k, l0 + j]
-  if (do_sample) {
+  if (do_sample && !ctrl) {
     const float* ub = uniform + (long long)b * C * L;
     for (int idx = threadIdx.x; idx < C * SW; idx += SW * 32) {
       const int k = idx / SW, j = idx - k * SW;
@@ -216,7 +253,7 @@ posterior_sample_kernel(const float* __restrict__ logits, const int64_t* __restr
           outv = fminf(fmaxf(r + lq1[j] + slse, -70.f), 0.f);
           lp[j] = outv;
         }
-        const float u = do_sample ? u_s[k * SW + warp] : 0.5f;
+        const float u = !do_sample ? 0.5f : (ctrl ? aten_uniform(rng_seed, rng_off, rng_n, ((unsigned long long)b * C + k) * L + l) : u_s[k * SW + warp]);
         const float gmb = -logf(-logf(u + 1e-30f) + 1e-30f);
         const float val = gmb + outv;
         if (val > best) { best = val; besti = k; }  // ascending k per lane -> keeps the first maximum
@@ -247,17 +284,37 @@ posterior_sample_kernel(const float* __restrict__ logits, const int64_t* __restr
       if (l0 + j < L) ob[(long long)k * L + l0 + j] = u_s[idx];
     }
   }
+  if (ctrl) {  // the last CTA to retire (every CTA has read offset / t by then) prepares the next step
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned long long n_cta = (unsigned long long)gridDim.x * gridDim.y;
+      if (atomicAdd(&ctrl[CTRL_TICKET], 1ull) == n_cta - 1ull) {
+        ctrl[CTRL_TICKET] = 0ull;
+        ctrl[CTRL_OFFSET] = rng_off + ctrl[CTRL_OFFSET_INC];
+        const unsigned long long step = ctrl[CTRL_STEP] + 1ull;
+        ctrl[CTRL_STEP] = step;
+        if (step < ctrl[CTRL_NSTEPS]) {
+          const int64_t tn = t_sched[step], tpn = tp_sched[step];
+          for (int i = 0; i < B; ++i) { t[i] = tn; if (t_post) t_post[i] = tpn; }
+        }
+        __threadfence();
+      }
+    }
+  }
 }
 
 template <int NJ>
-static int launch_sampler(const float* logits, const int64_t* x_t, const int64_t* t, const int64_t* t_post, const float* uniform,
-                          const float* sched, int64_t* x_next, float* lpo, int B, int K, int L, int T, int mode, float r, int kk, int stage, cudaStream_t st) {
+static int launch_sampler(const float* logits, const int64_t* x_t, int64_t* t, int64_t* t_post, const float* uniform,
+                          const float* sched, int64_t* x_next, float* lpo, int B, int K, int L, int T, int mode, float r, int kk, int stage, cudaStream_t st,
+                          unsigned long long* ctrl = nullptr, const int64_t* t_sched = nullptr, const int64_t* tp_sched = nullptr) {
   const int C = K + 1;
   const size_t smem = (size_t)C * SW * 4 + (((size_t)SW * C + 1) & ~(size_t)1) * 4 + (size_t)SW * C * 8 + (size_t)C * SW * 4;
   auto kern = posterior_sample_kernel<NJ>;
   if (smem > 48 * 1024) DSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((L + SW - 1) / SW, B);
-  DSB_CHECK_CUDA(launch_pdl(kern, grid, dim3(SW * 32), smem, st, logits, x_t, t, t_post, uniform, sched, x_next, lpo, K, L, T, mode, r, kk, stage));
+  DSB_CHECK_CUDA(launch_pdl(kern, grid, dim3(SW * 32), smem, st, logits, x_t, t, t_post, uniform, sched, x_next, lpo, K, L, T, mode, r, kk, stage, ctrl, t_sched,
+                            tp_sched, B));
   return 0;
 }
 }  // namespace dsb
@@ -274,7 +331,7 @@ extern "C" int dsb_posterior_sample(const float* logits, const int64_t* x_t, con
   cudaStream_t st = (cudaStream_t)stream;
   const int nj = (K + 1 + 31) / 32;
 #define DSB_SAMPLER_CASE(N) \
-  if (nj <= N) return launch_sampler<N>(logits, x_t, t, t_post, uniform, sched, x_next, log_prob_out, B, K, L, T, trunc_mode, trunc_r, trunc_k, stage_flags, st)
+  if (nj <= N) return launch_sampler<N>(logits, x_t, const_cast<int64_t*>(t), const_cast<int64_t*>(t_post), uniform, sched, x_next, log_prob_out, B, K, L, T, trunc_mode, trunc_r, trunc_k, stage_flags, st)
   DSB_SAMPLER_CASE(2);
   DSB_SAMPLER_CASE(5);
   DSB_SAMPLER_CASE(9);
@@ -282,4 +339,31 @@ extern "C" int dsb_posterior_sample(const float* logits, const int64_t* x_t, con
   DSB_SAMPLER_CASE(33);
 #undef DSB_SAMPLER_CASE
   return 2;
+}
+
+extern "C" int dsb_posterior_sample_loop(const float* logits, int64_t* x, int64_t* t, int64_t* t_post, const float* sched, unsigned long long* ctrl,
+                                         const int64_t* t_sched, const int64_t* t_post_sched, int B, int K, int L, int T, int trunc_mode, float trunc_r,
+                                         int trunc_k, void* stream) {
+  DSB_REQUIRE(B > 0 && K > 0 && L > 0 && T > 0 && K + 1 <= 32 * 33, "dsb_posterior_sample_loop: bad shape");
+  DSB_REQUIRE(logits && x && t && t_post && sched && ctrl && t_sched && t_post_sched, "dsb_posterior_sample_loop: null argument");
+  DSB_REQUIRE(trunc_mode >= 0 && trunc_mode <= 2, "dsb_posterior_sample_loop: trunc_mode must be 0, 1 or 2");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nj = (K + 1 + 31) / 32;
+#define DSB_SAMPLER_CASE(N) \
+  if (nj <= N) return launch_sampler<N>(logits, x, t, t_post, nullptr, sched, x, nullptr, B, K, L, T, trunc_mode, trunc_r, trunc_k, 0, st, ctrl, t_sched, t_post_sched)
+  DSB_SAMPLER_CASE(2);
+  DSB_SAMPLER_CASE(5);
+  DSB_SAMPLER_CASE(9);
+  DSB_SAMPLER_CASE(17);
+  DSB_SAMPLER_CASE(33);
+#undef DSB_SAMPLER_CASE
+  return 2;
+}
+extern "C" int dsb_aten_uniform(float* out, long long n, unsigned long long seed, unsigned long long offset, unsigned long long nthreads, void* stream) {
+  DSB_REQUIRE(n > 0 && nthreads > 0 && offset % 4 == 0, "dsb_aten_uniform: need n > 0, nthreads > 0 and a philox offset that is a multiple of 4");
+  long long g = (n + 255) / 256;
+  const long long cap = (long long)sm_count() * 8;
+  aten_uniform_fill_kernel<<<(unsigned)(g > cap ? cap : g), 256, 0, (cudaStream_t)stream>>>(out, n, seed, offset, nthreads);
+  DSB_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }

@@ -225,14 +225,29 @@ class DiffusionTransformer(nn.Module):
 
     @torch.no_grad()
     def _fused_step(self, st):
-        """One p_sample on ids: denoiser -> fused sampler (reads st['x'], st['t'], st['t_post']; writes st['x'])."""
+        """One p_sample on ids: denoiser -> fused sampler.  Every launch is a kernel of this library: the sampler draws its own uniforms (bit-for-bit
+        the stream torch.rand_like(model_log_prob) would produce, diffusion_transformer.py:360), writes x in place and advances t / t_post / the RNG
+        offset on the device, so the captured step needs no host-side update between replays."""
         eng = self.transformer.engine
         logits = eng.forward(st["x"], st["kv"], st["t"], st["Lc"])
-        u = torch.rand(st["ushape"], dtype=torch.float32, device=logits.device)  # == torch.rand_like(model_log_prob) in the reference
         mode, r, k = st["trunc"]
-        ops.posterior_sample(logits, st["x"], st["t"], u, self._sched(), T=self.num_timesteps, trunc_mode=mode, trunc_r=r, trunc_k=k,
-                             t_post=st["t_post"], x_next=st["x_next"])
-        st["x"].copy_(st["x_next"])
+        ops.posterior_sample_loop(logits, st["x"], st["t"], st["t_post"], self._sched(), st["ctrl"], st["t_sched"], st["tp_sched"], T=self.num_timesteps,
+                                  trunc_mode=mode, trunc_r=r, trunc_k=k)
+
+    def _arm_loop(self, st, steps, post_steps, seed, offset, counter_offset, nthreads):
+        """(Re)load the device-side loop state: RNG (seed, offset), the timestep schedule, step 0's t / t_post.  One small H2D copy per sample()."""
+        n = len(steps)
+        if n > st["t_sched"].numel():
+            raise RuntimeError(f"sampling schedule of {n} steps exceeds the captured capacity {st['t_sched'].numel()}")
+        host = st["host"]
+        host[:n] = torch.tensor(steps, dtype=torch.int64)
+        host[st["cap"]:st["cap"] + n] = torch.tensor(post_steps, dtype=torch.int64)
+        c = host[2 * st["cap"]:]
+        c[0] = np.array([seed & (2 ** 64 - 1)], dtype=np.uint64).view(np.int64)[0].item()
+        c[1], c[2], c[3], c[4], c[5], c[6] = offset, counter_offset, nthreads, 0, n, 0
+        st["dev"].copy_(host)  # blocking: the pinned staging buffer is rewritten by the next call
+        st["t"].fill_(steps[0])
+        st["t_post"].fill_(post_steps[0])
 
     def _run_steps(self, cond_emb, batch_size, steps, post_steps, x_init=None):
         dev = self.device
@@ -246,19 +261,22 @@ class DiffusionTransformer(nn.Module):
         if st is not None and st["generation"] != eng.generation:
             st = None  # weights were repacked: the captured graph holds stale pointers
         if st is None:
-            st = dict(x=torch.empty(B, L, dtype=torch.int64, device=dev), x_next=torch.empty(B, L, dtype=torch.int64, device=dev),
-                      t=torch.zeros(B, dtype=torch.int64, device=dev), t_post=torch.zeros(B, dtype=torch.int64, device=dev),
-                      kv=torch.empty_like(kv), Lc=cond_emb.shape[1], ushape=(B, K + 1, L), trunc=self._trunc(), graph=None, generation=eng.generation)
+            cap = max(4 * self.num_timesteps, len(steps))  # schedule capacity ('q' re-sampling can double the step count)
+            devbuf = torch.zeros(2 * cap + 8, dtype=torch.int64, device=dev)
+            st = dict(x=torch.empty(B, L, dtype=torch.int64, device=dev), t=torch.zeros(B, dtype=torch.int64, device=dev),
+                      t_post=torch.zeros(B, dtype=torch.int64, device=dev), kv=torch.empty_like(kv), Lc=cond_emb.shape[1], trunc=self._trunc(),
+                      graph=None, generation=eng.generation, cap=cap, dev=devbuf, host=torch.zeros(2 * cap + 8, dtype=torch.int64).pin_memory(),
+                      t_sched=devbuf[:cap], tp_sched=devbuf[cap:2 * cap], ctrl=devbuf[2 * cap:])
         st["kv"].copy_(kv)
-        if x_init is None:
-            st["x"].fill_(K)  # all-[MASK] start state (diffusion_transformer.py:633-636)
-        else:
-            st["x"].copy_(x_init)
+        # the reference draws torch.rand_like(logits) once per step from the default CUDA generator: replay exactly that stream, then leave the
+        # generator where the reference would have left it
+        gen = torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()]
+        seed, offset = gen.initial_seed(), gen.get_offset()
+        nthreads, counter_offset = ops.aten_rand_geometry(B * (K + 1) * L, dev)
         if self.use_cuda_graph and st["graph"] is None:
-            # warm-up on a side stream (lazy inits: cudaFuncSetAttribute, workspaces), then capture one step.  The warm-up
-            # must not disturb the sampling RNG stream or the token state, so both are restored.
-            rng = torch.cuda.get_rng_state(dev)
-            x_save = st["x"].clone()
+            # warm-up on a side stream (lazy inits: cudaFuncSetAttribute, workspaces), then capture one step; the loop state is re-armed afterwards
+            self._arm_loop(st, steps, post_steps, seed, offset, counter_offset, nthreads)
+            st["x"].fill_(K)
             s = torch.cuda.Stream(device=dev)
             s.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(s):
@@ -268,16 +286,18 @@ class DiffusionTransformer(nn.Module):
             with torch.cuda.graph(g):
                 self._fused_step(st)
             st["graph"] = g
-            st["x"].copy_(x_save)
-            torch.cuda.set_rng_state(rng, dev)
             self._graphs[key] = st
-        for ti, tp in zip(steps, post_steps):
-            st["t"].fill_(ti)
-            st["t_post"].fill_(tp)
+        self._arm_loop(st, steps, post_steps, seed, offset, counter_offset, nthreads)
+        if x_init is None:
+            st["x"].fill_(K)  # all-[MASK] start state (diffusion_transformer.py:633-636)
+        else:
+            st["x"].copy_(x_init)
+        for _ in steps:
             if st["graph"] is not None:
                 st["graph"].replay()
             else:
                 self._fused_step(st)
+        gen.set_offset(offset + len(steps) * counter_offset)
         self.last_gpu_launches = len(steps) * (eng.launches_per_forward + 1)
         out = st["x"].clone()
         eng.check_token_range(B, L)  # a token id >= num_embed raises like the reference's embedding lookup (one 4-byte read after the loop)

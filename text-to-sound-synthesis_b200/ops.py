@@ -385,6 +385,34 @@ def posterior_sample(inp, x_t, t, uniform, sched, *, T, trunc_mode=1, trunc_r=0.
     return x_next
 
 
+def aten_rand_geometry(numel: int, device=None):
+    """(nthreads, counter_offset) of the kernel ATen launches for torch.rand / rand_like on a contiguous float tensor of `numel` elements
+    (ATen/native/cuda/DistributionTemplates.h calc_execution_policy: block 256, grid = min(SMs * (maxThreadsPerSM // 256), ceil(numel / 256)),
+    four values per curand call)."""
+    pr = torch.cuda.get_device_properties(device if device is not None else torch.cuda.current_device())
+    grid = min(pr.multi_processor_count * (pr.max_threads_per_multi_processor // 256), (numel + 255) // 256)
+    return 256 * grid, ((numel - 1) // (256 * grid * 4) + 1) * 4
+
+
+def aten_uniform(numel: int, seed: int, offset: int, device=None) -> torch.Tensor:
+    """The tensor torch.rand(numel, device='cuda') would return for generator state (seed, philox offset), computed by this library's Philox."""
+    out = torch.empty(numel, dtype=torch.float32, device=device if device is not None else "cuda")
+    nthreads, _ = aten_rand_geometry(numel, out.device)
+    _lib.check(_lib.lib().dsb_aten_uniform(out.data_ptr(), numel, seed & (2 ** 64 - 1), offset, nthreads, _stream()), "dsb_aten_uniform")
+    return out
+
+
+def posterior_sample_loop(logits, x, t, t_post, sched, ctrl, t_sched, t_post_sched, *, T, trunc_mode=1, trunc_r=0.85, trunc_k=0):
+    """One step of the fused sampling loop (see dsb_posterior_sample_loop): in-kernel uniforms, x updated in place, t / t_post / RNG offset advanced on
+    the device by the kernel itself."""
+    _need_cuda(logits, x, t, t_post, sched, ctrl, t_sched, t_post_sched)
+    B, L, K = logits.shape
+    _lib.check(_lib.lib().dsb_posterior_sample_loop(logits.data_ptr(), x.data_ptr(), t.data_ptr(), t_post.data_ptr(), sched.data_ptr(), ctrl.data_ptr(),
+                                                    t_sched.data_ptr(), t_post_sched.data_ptr(), B, K, L, T, trunc_mode, trunc_r, trunc_k, _stream()),
+               "dsb_posterior_sample_loop")
+    return x
+
+
 # ---------------------------------------------------------------------------------------------- decoder / vocoder support
 def codebook_gather_padded(ids, codebook, H, W, *, round_out=True, split=False, split_f16=False, err_flag=None):
     _need_cuda(ids, codebook)
