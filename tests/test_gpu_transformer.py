@@ -205,3 +205,62 @@ def test_k512_codebook_config_runs(G):
     m.truncation = "top0.85r"
     tok = m.sample(None, None, cond.cuda(), filter_ratio=0, batch_size=B)["content_token"]
     assert int(tok.max()) < K
+
+
+def _chain_vs_oracle(K, B, steps, seed=3, precision="f16x3"):
+    """Free-running chain at the real denoiser size (19 layers, D=1024) against the fp32 CPU oracle on the same weights / caption embeddings / uniforms."""
+    D, NL, NH, CD, L = 1024, 19, 16, 512, 265
+    torch.set_num_threads(min(16, torch.get_num_threads()))
+    sd = O.make_transformer_state_dict(K=K, D=D, n_layer=NL, n_head=NH, cond_dim=CD, seed=0)
+    g = torch.Generator().manual_seed(seed)
+    cond = torch.randn(B, 77, CD, generator=g)
+    cond = cond / cond.norm(dim=-1, keepdim=True)
+    us = [torch.rand(B, K + 1, L, generator=g) for _ in range(steps)]
+    ts = list(range(99, 99 - steps, -1))
+    ref = O.sample(sd, cond, lambda i: us[i], n_layer=NL, n_head=NH, spatial=(5, 53), steps=ts)
+    m = build_dt(K, D, NL, NH, CD, sd, precision=precision)
+    m.truncation = "top0.85r"
+    got = _run_chain(m, cond.cuda(), [u.cuda() for u in us], steps).cpu()
+    return ref, got
+
+
+def test_configs1_batch16_short_chain_token_ids_equal_oracle(G):
+    """BASELINE configs[1] shape (B=16, K=256, 19 layers), 10 free-running steps from all-[MASK]: every token id of every clip equals the oracle's
+    in the parity-grade 'f16x3' mode (42 400 Gumbel-argmax decisions)."""
+    ref, got = _chain_vs_oracle(K=256, B=16, steps=10)
+    assert int((ref != 256).sum()) > 0  # some positions have been unmasked: the comparison is not vacuous
+    assert torch.equal(got, ref), f"{int((got != ref).sum())} of {ref.numel()} token ids differ"
+
+
+def test_configs4_k512_codebook_19_layers_token_ids_equal_oracle(G):
+    """BASELINE configs[4]'s codebook (K=512, 513-class sampler) at full depth: B=4, 10 free-running steps, token ids equal the oracle's."""
+    ref, got = _chain_vs_oracle(K=512, B=4, steps=10, seed=8)
+    assert int((ref != 512).sum()) > 0
+    assert torch.equal(got, ref), f"{int((got != ref).sum())} of {ref.numel()} token ids differ"
+
+
+def test_f16_modes_under_activation_range_stress(G):
+    """Exponent-range stress for the fp16 containers: the same network with its weights rescaled so that intermediate activations are
+    64x larger (LayerNorm affine / MLP / value / projection weights x4 each way) -- mathematically a different but equally valid model.  The
+    parity-grade 'f16x3' mode must keep fp32-class logits against the oracle run on the SAME rescaled weights; the single-pass 'f16' mode is
+    measured too (its error is relative to the 11-bit operands, not the range, as long as nothing overflows)."""
+    K, D, NL, NH, CD, B, L = 256, 1024, 4, 16, 512, 2, 265
+    sd = O.make_transformer_state_dict(K=K, D=D, n_layer=NL, n_head=NH, cond_dim=CD, seed=0)
+    for k in list(sd.keys()):
+        if k.endswith("mlp.0.weight") or k.endswith("attn1.value.weight") or k.endswith("attn2.value.weight"):
+            sd[k] = sd[k] * 64.0          # hidden / value activations 64x larger
+        if k.endswith("mlp.2.weight") or k.endswith("attn1.proj.weight") or k.endswith("attn2.proj.weight"):
+            sd[k] = sd[k] / 64.0          # ... folded back so the residual stream keeps its scale (GELU2 is not homogeneous: a different model)
+    g = torch.Generator().manual_seed(5)
+    cond = torch.randn(B, 77, CD, generator=g)
+    cond = cond / cond.norm(dim=-1, keepdim=True)
+    x = torch.where(torch.rand(B, L, generator=g) < 0.5, torch.full((B, L), K), torch.randint(0, K, (B, L), generator=g))
+    t = torch.tensor([70, 20])
+    ref = O.transformer_forward(sd, x, cond, t, n_layer=NL, n_head=NH, spatial=(5, 53))
+    for prec, tol in (("f16x3", 3e-5), ("f16", 4e-3)):
+        m = build_dt(K, D, NL, NH, CD, sd, precision=prec)
+        eng = m.transformer.engine
+        logits = eng.forward(x.cuda(), eng.encode_condition(cond.cuda()), t.cuda(), 77)
+        err = rel_err(logits.permute(0, 2, 1).cpu(), ref)
+        print(f"[{prec}] range-stressed logits rel err {err:.2e}")
+        assert torch.isfinite(logits).all() and err < tol, (prec, err)

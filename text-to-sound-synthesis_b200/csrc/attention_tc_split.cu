@@ -195,8 +195,9 @@ __device__ __forceinline__ void sp_remainder_rows(const SpParams& p, const uint8
 
 // MINB = CTAs per SM the register budget must allow: 2 for short key sequences (cross-attention, 96 keys: 113 KB of smem and 256 TMEM columns
 // per CTA, so two heads' softmax / MMA chains interleave on one SM), 1 for the 288-key self-attention tiles (208 KB of smem).
-// NSW = softmax warps per lane quadrant: 3 for the 288-key tiles (each warp owns three of the nine 32-key chunks and fetches them with ONE TMEM
-// round trip per pass -- the chain S -> softmax -> P.V is latency bound), 2 for short key sequences.
+// NSW = softmax warps per lane quadrant, MAXC = 32-key chunks fetched per TMEM round trip.  Measured at B=16 (tools/attn_split_bench.py): the softmax
+// is bound by the MUFU / conversion pipe (288 exp2 + fp16 pair conversions per row), not by TMEM latency -- <1,3,2> (12 warps, two chunks per
+// round trip) ran 47.5 us against 45.2 us for <1,2,1>, so the simplest configuration is used.
 template <int MINB, int NSW, int MAXC>
 __global__ void __launch_bounds__(sp_threads(NSW), MINB)
 attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
@@ -476,10 +477,10 @@ extern "C" int dsb_attention_tc_split(const void* q, long long ldq, long long q_
   static int attr_smem[2] = {0, 0};
   if (smem > attr_smem[two]) {
     if (two) DSB_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_split_kernel<2, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    else DSB_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_split_kernel<1, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    else DSB_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_split_kernel<1, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_smem[two] = smem;
   }
   if (two) DSB_CHECK_CUDA(launch_pdl(attention_tc_split_kernel<2, 2, 1>, dim3(H, B), dim3(sp_threads(2)), smem, (cudaStream_t)stream, mq, mk, mv, p));
-  else DSB_CHECK_CUDA(launch_pdl(attention_tc_split_kernel<1, 3, 2>, dim3(H, B), dim3(sp_threads(3)), smem, (cudaStream_t)stream, mq, mk, mv, p));
+  else DSB_CHECK_CUDA(launch_pdl(attention_tc_split_kernel<1, 2, 1>, dim3(H, B), dim3(sp_threads(2)), smem, (cudaStream_t)stream, mq, mk, mv, p));
   return 0;
 }

@@ -624,17 +624,23 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 // product streams every operand tile once PER PASS (3 x (32 KB in + 32 KB out of shared memory per SM and 64-deep k-block): exactly the MMA time,
 // no slack).  Here one pipeline stage holds the four tiles of a k-block (A hi, A lo, W hi half, W lo half: 64 KB per CTA) and the issuer runs the
 // three passes off them: 64 KB in + 96 KB out per 1536 MMA cycles, so the shared-memory port is no longer co-critical and L2 traffic drops by a third.
+// BN = 256: 256 x 256 pair tiles (best MMA shape).  BN = 128: 256 x 128 pair tiles for problems with fewer 256-wide tiles than CTA pairs (the
+// N = 1024 projections at M = 4240: 68 tiles on 74 pairs) -- twice the tiles, so every pair runs two and the first tile's epilogue (a 128 KB residual
+// read-modify-write per CTA, several microseconds) hides under the second tile's mainloop instead of being fully exposed.
+template <int BN>
 struct PairSplitSmem {
-  static constexpr int BLOCK_N = 256;
-  static constexpr int TILE = BLOCK_M * ROW_BYTES;  // 16 KB: 128 rows x 64 halves (this CTA's A rows, or its half of the W tile)
-  static constexpr int STAGE_BYTES = 4 * TILE;      // A hi | A lo | W hi | W lo
-  static constexpr int STAGES = 3;
+  static constexpr int BLOCK_N = BN;
+  static constexpr int TILE_A = BLOCK_M * ROW_BYTES;     // 16 KB: this CTA's 128 rows x 64 halves of A (hi or lo)
+  static constexpr int TILE_B = (BN / 2) * ROW_BYTES;    // this CTA's half of the W tile (hi or lo)
+  static constexpr int STAGE_BYTES = 2 * TILE_A + 2 * TILE_B;  // A hi | A lo | W hi | W lo
+  static constexpr int STAGES = BN == 256 ? 3 : 4;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + 256 + 8 * 32 * 32 * 4;
 };
 
+template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_f16x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ GemmParams p) {
-  using S = PairSplitSmem;
+  using S = PairSplitSmem<BN>;
   constexpr int BLOCK_N = S::BLOCK_N;
   constexpr int STAGES = S::STAGES;
   constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
@@ -698,9 +704,9 @@ gemm_f16x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
           const uint32_t bar = map_to_cta(smem_u32(&full_bar[stage]), 0);
           uint8_t* sa = smem + stage * S::STAGE_BYTES;
           tma_load_3d_2sm(&tmap_a, bar, sa, c0, row0, b);
-          tma_load_3d_2sm(&tmap_a, bar, sa + S::TILE, lo_a + c0, row0, b);
-          tma_load_3d_2sm(&tmap_b, bar, sa + 2 * S::TILE, c0, nrow0, 0);
-          tma_load_3d_2sm(&tmap_b, bar, sa + 3 * S::TILE, lo_w + c0, nrow0, 0);
+          tma_load_3d_2sm(&tmap_a, bar, sa + S::TILE_A, lo_a + c0, row0, b);
+          tma_load_3d_2sm(&tmap_b, bar, sa + 2 * S::TILE_A, c0, nrow0, 0);
+          tma_load_3d_2sm(&tmap_b, bar, sa + 2 * S::TILE_A + S::TILE_B, lo_w + c0, nrow0, 0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -721,8 +727,8 @@ gemm_f16x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
-          const uint64_t dah = make_sw128_kmajor_desc(sa), dal = make_sw128_kmajor_desc(sa + S::TILE);
-          const uint64_t dbh = make_sw128_kmajor_desc(sa + 2 * S::TILE), dbl = make_sw128_kmajor_desc(sa + 3 * S::TILE);
+          const uint64_t dah = make_sw128_kmajor_desc(sa), dal = make_sw128_kmajor_desc(sa + S::TILE_A);
+          const uint64_t dbh = make_sw128_kmajor_desc(sa + 2 * S::TILE_A), dbl = make_sw128_kmajor_desc(sa + 2 * S::TILE_A + S::TILE_B);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             umma_2sm<false>(d_tmem, dal + 2 * k, dbh + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
@@ -942,9 +948,16 @@ extern "C" int dsb_gemm_ex(const dsb_gemm_desc* d, void* stream) {
   const bool fused3 = use_pair && fuse_ok && kind == DSB_DTYPE_F16 && d->num_taps == 3 && !p.tap_a2_mask && d->batch == 1 && !p.b_batched &&
                       p.tap_shift[0] == 0 && p.tap_shift[1] == 0 && p.tap_shift[2] == 0 && p.tap_acol[0] == d->K && p.tap_acol[1] == 0 && p.tap_acol[2] == 0 &&
                       p.tap_wcol[0] == 0 && p.tap_wcol[1] == d->K && p.tap_wcol[2] == 0 && d->K % 64 == 0;
+  bool fused_n128 = false;
   if (use_pair) {
     block_n = 256;
     p.tiles_m = (d->M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+    // fewer 256-wide tiles than CTA pairs: halve the tile width so that every pair runs two tiles and overlaps an epilogue with a mainloop
+    static const bool n128_ok = [] { const char* e = getenv("DSB_GEMM_F16X3_N128"); return !(e && e[0] == '0'); }();
+    if (fused3 && n128_ok && d->N >= 256 && (long long)p.tiles_m * ((d->N + 255) / 256) <= (d->max_ctas > 0 ? d->max_ctas : sms) / 2) {
+      fused_n128 = true;
+      block_n = 128;
+    }
   }
   p.tiles_n = (d->N + block_n - 1) / block_n;
 
@@ -957,6 +970,7 @@ extern "C" int dsb_gemm_ex(const dsb_gemm_desc* d, void* stream) {
     if (make_operand_map_mn(&mb, d->W, kind, d->N, d->K, p.b_batched ? d->batch : 1, d->ldw, d->w_batch_stride)) return 3;
   } else if (make_operand_map(&mb, d->W, kind, d->w_cols > 0 ? d->w_cols : (long long)d->K * d->num_taps, d->N, p.b_batched ? d->batch : 1, d->ldw,
                               d->w_batch_stride, use_pair ? block_n / 2 : block_n)) return 3;
+  (void)fused_n128;
   CUtensorMap ma2 = ma;
   if (p.tap_a2_mask) {
     DSB_REQUIRE(!any_mn, "dsb_gemm_ex: a second A operand is K-major only");
@@ -966,17 +980,18 @@ extern "C" int dsb_gemm_ex(const dsb_gemm_desc* d, void* stream) {
   const int max_ctas = d->max_ctas > 0 ? d->max_ctas : sms;
   if (fused3) {
     p.tap_wcol[0] = (int)d->K;  // the fused kernel reads the lo-half columns from tap_acol[0] / tap_wcol[0]
-    auto kern = gemm_f16x3_pair_kernel;
-    static bool attr_done = false;
-    if (!attr_done) {
-      DSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PairSplitSmem::TOTAL));
-      attr_done = true;
-    }
     const int tiles = p.tiles_m * p.tiles_n;
     int pairs = max_ctas / 2;
     if (pairs < 1) pairs = 1;
     if (tiles < pairs) pairs = tiles;
-    DSB_CHECK_CUDA(launch_pdl(kern, dim3(2 * pairs), dim3(GEMM_THREADS), PairSplitSmem::TOTAL, st, ma, mb, p));
+    static bool attr_done[2] = {false, false};
+    if (fused_n128) {
+      if (!attr_done[0]) { DSB_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16x3_pair_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairSplitSmem<128>::TOTAL)); attr_done[0] = true; }
+      DSB_CHECK_CUDA(launch_pdl(gemm_f16x3_pair_kernel<128>, dim3(2 * pairs), dim3(GEMM_THREADS), PairSplitSmem<128>::TOTAL, st, ma, mb, p));
+    } else {
+      if (!attr_done[1]) { DSB_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16x3_pair_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairSplitSmem<256>::TOTAL)); attr_done[1] = true; }
+      DSB_CHECK_CUDA(launch_pdl(gemm_f16x3_pair_kernel<256>, dim3(2 * pairs), dim3(GEMM_THREADS), PairSplitSmem<256>::TOTAL, st, ma, mb, p));
+    }
     return 0;
   }
   if (use_pair) {
