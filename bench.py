@@ -475,11 +475,61 @@ def run_extras(args, rank, world, dev, dist, voc):
         del model
         torch.cuda.empty_cache()
 
+    out["configs3_train_ddp"] = train_extra(args, rank, world, dev, dist)
     one("configs2_b64_text_to_wav", 256, 64, 64 * world, "BASELINE.json configs[2]: batch 64 per GPU, full pipeline (weak scaling over ranks)")
     if 512 % world == 0:
         one("configs4_b512_k512_sharded", 512, 512 // world, 512, "BASELINE.json configs[4]: 512 clips TOTAL sharded over the ranks (strong scaling), K=512 codebook, "
             "full pipeline, NCCL all_gather of the waveforms inside the timed pass")
     return out
+
+
+def train_extra(args, rank, world, dev, dist, per_gpu_batch=20, warm=3, steps=8):
+    """BASELINE.json configs[3]: diffusion-transformer training step on synthetic tokens, bf16 GEMM operands, per-GPU batch 20 (configs/audioset.yaml:140),
+    stock torch DistributedDataParallel over NCCL when N > 1 (the reference's own wrapper, engine/solver_spec.py:109) + fused AdamW; whole-job samples/s."""
+    import _pkg
+    _pkg.load()
+    from diffsound_b200.utils import builders
+    K, L = 256, L_TOK
+    torch.manual_seed(0)
+    m = builders.build_diffusion_transformer(K, 1024, args.layers, 16, 512).train()
+    for p in m.parameters():
+        p.requires_grad_(True)
+    g = torch.Generator().manual_seed(100 + rank)
+    batch = {"content_token": torch.randint(0, K, (per_gpu_batch, L), generator=g).to(dev),
+             "condition_embed_token": torch.nn.functional.normalize(torch.randn(per_gpu_batch, 77, 512, generator=g), dim=-1).to(dev)}
+    net = torch.nn.parallel.DistributedDataParallel(m, device_ids=[dev.index]) if world > 1 else m
+    opt = torch.optim.AdamW(m.parameters(name="transformer"), lr=3e-6, betas=(0.9, 0.96), fused=True)
+
+    def step():
+        out = net(batch, return_loss=True, return_logits=False)
+        opt.zero_grad(set_to_none=True)
+        out["loss"].backward()
+        opt.step()
+        return out["loss"]
+    for _ in range(warm):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    st = torch.cuda.current_stream()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record(st)
+    for _ in range(steps):
+        loss = step()
+    e.record(st)
+    torch.cuda.synchronize()
+    ms = torch.tensor([s.elapsed_time(e)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = float(ms.item()) / steps
+    res = {"samples_per_s": world * per_gpu_batch / ms_step * 1e3, "ms_per_step": round(ms_step, 2), "per_gpu_batch": per_gpu_batch, "n_gpus": world,
+           "steps": steps, "loss": float(loss.detach()), "dtype": "bf16 GEMM operands, fp32 master weights / residual stream / loss",
+           "algorithmic_tflops": round(3 * 158.25e9 * per_gpu_batch * (args.layers / 19.0) / (ms_step * 1e-3) / 1e12, 1),
+           "note": "BASELINE.json configs[3]: forward + fused loss + hand-written backward + AdamW" + (", torch DDP gradient all-reduce (not overlapped with "
+                   "the backward graph)" if world > 1 else "")}
+    del net, m, opt
+    torch.cuda.empty_cache()
+    return res
 
 
 def main():

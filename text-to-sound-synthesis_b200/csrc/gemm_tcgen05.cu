@@ -953,7 +953,7 @@ extern "C" int dsb_gemm_ex(const dsb_gemm_desc* d, void* stream) {
     block_n = 256;
     p.tiles_m = (d->M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
     // fewer 256-wide tiles than CTA pairs: halve the tile width so that every pair runs two tiles and overlaps an epilogue with a mainloop
-    static const bool n128_ok = [] { const char* e = getenv("DSB_GEMM_F16X3_N128"); return !(e && e[0] == '0'); }();
+    static const bool n128_ok = [] { const char* e = getenv("DSB_GEMM_F16X3_N128"); return e && e[0] == '1'; }();  // opt-in: measured SLOWER at B=16 (proj 25.2 -> 26.4 us, MLP2 76.4 -> 93.9 us): the narrower tile is shared-memory bound
     if (fused3 && n128_ok && d->N >= 256 && (long long)p.tiles_m * ((d->N + 255) / 256) <= (d->max_ctas > 0 ? d->max_ctas : sms) / 2) {
       fused_n128 = true;
       block_n = 128;
