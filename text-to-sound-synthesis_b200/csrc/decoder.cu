@@ -116,6 +116,19 @@ __global__ void groupnorm_apply_kernel(const float* __restrict__ x, const double
   const long long total = (compact ? (long long)B * Lp : (long long)B * Hp * Wp) * c4n;
   const int cg = C / groups;
   const double cnt = (double)H * W * cg;
+  // per-(image, group) mean / rstd once per CTA (fp64 -> fp32), not per element: the element loop below is pure fp32 and HBM-bound
+  extern __shared__ float gn_ms[];  // [B * groups][2]
+  const bool cached = B * groups <= 2048;
+  if (cached) {
+    for (int i = threadIdx.x; i < B * groups; i += blockDim.x) {
+      const double mean = stats[(long long)i * 2] / cnt;
+      double var = stats[(long long)i * 2 + 1] / cnt - mean * mean;
+      var = var < 0.0 ? 0.0 : var;
+      gn_ms[2 * i] = (float)mean;
+      gn_ms[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+  }
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c4 = i % c4n;
     const long long orow = i / c4n;
@@ -141,12 +154,19 @@ __global__ void groupnorm_apply_kernel(const float* __restrict__ x, const double
       for (int j = 0; j < 4; ++j) {
         const int c = c4 * 4 + j;
         const int g = c / cg;
-        const double mean = stats[((long long)b * groups + g) * 2] / cnt;
-        double var = stats[((long long)b * groups + g) * 2 + 1] / cnt - mean * mean;
-        var = var < 0.0 ? 0.0 : var;
-        const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-        float t = (vv[j] - (float)mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
-        if (flags & DSB_GN_SWISH) t = t / (1.0f + expf(-t));
+        float meanf, rstd;
+        if (cached) {
+          meanf = gn_ms[2 * (b * groups + g)];
+          rstd = gn_ms[2 * (b * groups + g) + 1];
+        } else {
+          const double mean = stats[((long long)b * groups + g) * 2] / cnt;
+          double var = stats[((long long)b * groups + g) * 2 + 1] / cnt - mean * mean;
+          var = var < 0.0 ? 0.0 : var;
+          meanf = (float)mean;
+          rstd = (float)(1.0 / sqrt(var + (double)eps));
+        }
+        float t = (vv[j] - meanf) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+        if (flags & DSB_GN_SWISH) t = __fdividef(t, 1.0f + __expf(-t));
         if (flags & DSB_GEMM_ROUND_TF32) t = round_tf32(t);
         o[j] = t;
       }
@@ -320,7 +340,8 @@ extern "C" int dsb_groupnorm_apply(const float* x, const double* stats, const fl
   DSB_REQUIRE(!(flags & DSB_SPLIT_OUT) || C % 32 == 0, "dsb_groupnorm_apply: split output needs C %% 32 == 0");
   DSB_REQUIRE(!(flags & DSB_GN_COMPACT) || Lp >= H * W, "dsb_groupnorm_apply: Lp too small");
   const long long total = ((flags & DSB_GN_COMPACT) ? (long long)B * Lp : (long long)B * (H + 2) * (W + 2)) * (C / 4);
-  groupnorm_apply_kernel<<<ew_grid(total), 256, 0, (cudaStream_t)stream>>>(x, stats, gamma, beta, out, B, H, W, C, groups, eps, flags, Lp);
+  const size_t gn_smem = B * groups <= 2048 ? sizeof(float) * 2 * B * groups : 0;
+  groupnorm_apply_kernel<<<ew_grid(total), 256, gn_smem, (cudaStream_t)stream>>>(x, stats, gamma, beta, out, B, H, W, C, groups, eps, flags, Lp);
   DSB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -72,7 +72,8 @@ if a.json:
         j = json.load(open(a.json))
     except Exception:
         j = {}
-    gem = next((v for k, v in out.items() if "gemm_tcgen05_pair" in k), None) or next((v for k, v in out.items() if "gemm_tcgen05" in k), None)
+    gem = (next((v for k, v in out.items() if "gemm_f16x3_pair" in k), None) or next((v for k, v in out.items() if "gemm_tcgen05_pair" in k), None)
+           or next((v for k, v in out.items() if "gemm_tcgen05" in k), None))
     if gem:
         j[f"gemm_{a.precision}_B{a.batch}"] = {"dram_bytes_per_launch": gem["dram_bytes_per_launch"], "mean_us_under_ncu": gem["mean_us"], "launches": gem["launches"],
                                                  "tensor_pipe_pct": gem["tensor_pipe_pct"],
