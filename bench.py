@@ -452,12 +452,18 @@ def run_extras(args, rank, world, dev, dist, voc):
         cond = synthetic_cond(B_local, 100 + rank).to(dev)
         gathered = torch.empty(world * B_local, 1, WAV_LEN, dtype=torch.float32, device=dev) if world > 1 else None
 
+        mid = torch.cuda.Event(enable_timing=True)
+
         def go(sample_type):
             o = pipeline.synthesize(model, voc, cond, sample_type=sample_type, codec_batch=args.codec_batch)
+            mid.record(torch.cuda.current_stream())
             if world > 1:
                 dist.all_gather_into_tensor(gathered, o["wav"])
         go("top0.85r,fast24")  # warm-up: 5 denoiser calls (graph capture, workspaces, NCCL buffers)
         torch.manual_seed(4321 + rank)
+        clk = ClockSampler(dev.index) if rank == 0 else None
+        if clk is not None:
+            clk.start()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -468,10 +474,16 @@ def run_extras(args, rank, world, dev, dist, voc):
         e.record(st)
         torch.cuda.synchronize()
         ms = torch.tensor([s.elapsed_time(e)], device=dev)
+        ms_gather = round(mid.elapsed_time(e), 2)  # this rank: end of its own synthesis -> gather complete (includes waiting for slower ranks)
+        per_rank = [round(float(ms.item()), 1)]
         if world > 1:
+            allms = [torch.zeros_like(ms) for _ in range(world)]
+            dist.all_gather(allms, ms)
+            per_rank = [round(float(v.item()), 1) for v in allms]
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        out[tag] = {"clips_per_s": total / (float(ms.item()) * 1e-3), "ms": round(float(ms.item()), 1), "clips_total": total, "clips_per_gpu": B_local, "K": K,
-                    "n_gpus": world, "timed_passes": 1, "note": note}
+        out[tag] = {"clips_per_s": total / (float(ms.item()) * 1e-3), "ms": round(float(ms.item()), 1), "ms_per_rank": per_rank, "ms_gather_rank0": ms_gather, "clips_total": total,
+                    "clips_per_gpu": B_local, "K": K, "n_gpus": world, "timed_passes": 1, "note": note,
+                    "clocks": clk.stop() if clk is not None else None}
         del model
         torch.cuda.empty_cache()
 
