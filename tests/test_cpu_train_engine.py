@@ -70,6 +70,17 @@ def test_engine_orchestration_matches_oracle_autograd(engine_env, mode):
         err = float((gr - r).abs().max()) / max(float(r.abs().max()), 1e-4 * gmax)
         assert err < 2e-3, (mode, n, err)
     assert set(grads) == {n for n, _ in m.transformer.named_parameters()}
+    # the segmented form (one autograd node per segment, so DDP can all-reduce a layer's gradients while earlier layers still run) produces the same
+    # numbers as the monolithic pass, covers every parameter exactly once, and returns buffers the engine does not overwrite afterwards
+    eng.backward_begin(lg.grad.permute(0, 2, 1).contiguous(), scale=torch.tensor([2.0]))
+    seg_grads, order = {}, ["head"] + [("layer", li) for li in range(NL - 1, -1, -1)] + ["tail"]
+    for seg in order:
+        part = eng.backward_segment(seg)
+        assert set(part) == set(eng.segment_names(seg)) and not (set(part) & set(seg_grads)), seg
+        seg_grads.update(part)
+    assert set(seg_grads) == set(grads)
+    for n in grads:
+        assert torch.equal(seg_grads[n], grads[n]), n
 
 
 def test_inference_engine_and_text_tower_orchestration(engine_env, monkeypatch):

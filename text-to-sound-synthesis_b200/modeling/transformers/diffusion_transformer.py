@@ -206,9 +206,18 @@ class DiffusionTransformer(nn.Module):
         t, pt = self.sample_time(B, x.device, "importance")
         uniform = torch.rand(B, self.num_classes, L, dtype=torch.float32, device=x.device)  # == rand_like(log_EV_qxt_x0), :360
         x_t = train_ops.q_sample(x, t.contiguous(), uniform, self._sched(), self.num_timesteps)
-        names, params = zip(*self.transformer.named_parameters())
+        # One autograd node per backward segment (tail <- layer 0 <- ... <- layer NL-1 <- head/loss): a layer's parameter gradients reach autograd --
+        # and DistributedDataParallel's bucketed all-reduce (solver_spec.py:109) -- as soon as that layer's backward graph has been launched, so the
+        # NCCL traffic of layer l overlaps the backward of layers l-1 ... 0 instead of starting after the whole backward pass.
+        eng = self.transformer.train_engine
+        named = dict(self.transformer.named_parameters())
+        carrier = None
+        for seg in ["tail"] + [("layer", li) for li in range(len(self.transformer.blocks))]:
+            names = tuple(eng.segment_names(seg))
+            carrier = _SegmentGrad.apply(eng, seg, names, carrier, *[named[n] for n in names])
+        names = tuple(eng.segment_names("head"))
         loss, prob, vb, hits = _DenoiserLoss.apply(self, x, x_t, cond_emb, t.contiguous(), pt.float().contiguous(), bool(is_train), bool(want_prob),
-                                                   names, *params)
+                                                   names, carrier, *[named[n] for n in names])
         # accuracy bookkeeping of :424-436 (one small D2H copy instead of 2B .item() calls)
         rate = hits.float().mean(dim=1).cpu()
         if bool(oob):  # the reference asserts in index_to_log_onehot (diffusion_transformer.py:46-47)
@@ -443,13 +452,13 @@ class _DenoiserLoss(torch.autograd.Function):
     kernel (which also emits d loss / d logits); backward runs DenoiserTrainEngine.backward and hands every parameter its gradient."""
 
     @staticmethod
-    def forward(ctx, dt, x0, x_t, cond_emb, t, pt, is_train, want_prob, names, *params):
+    def forward(ctx, dt, x0, x_t, cond_emb, t, pt, is_train, want_prob, names, carrier, *params):
         eng = dt.transformer.train_engine
         B, L = x0.shape
         K = dt.num_classes - 1
         dev = x0.device
         logits = eng.forward(x_t, cond_emb, t)
-        need_grad = any(ctx.needs_input_grad[9:])
+        need_grad = any(ctx.needs_input_grad[9:])  # the carrier (-> earlier segments' parameters) or a head parameter
         dlogits = eng.dlogits_buffer() if need_grad else None  # engine-owned: the static input of its backward graph
         prob = torch.empty(B, K + 1, L, dtype=torch.float32, device=dev) if want_prob else None
         hits = torch.empty(B, L, 2, dtype=torch.int32, device=dev)
@@ -470,8 +479,25 @@ class _DenoiserLoss(torch.autograd.Function):
         if ctx.forward_id != ctx.eng.forward_id:
             raise RuntimeError("DiffusionTransformer: backward() of a loss whose activations were overwritten by a later forward(); the training "
                                "engine keeps one forward's activations (call loss.backward() before the next forward, as Solver.step does)")
-        grads = ctx.eng.backward(ctx.dlogits, scale=gloss.detach().float().reshape(1).contiguous())
-        return (None,) * 9 + tuple(grads[n] for n in ctx.names)
+        ctx.eng.backward_begin(ctx.dlogits, scale=gloss.detach().float().reshape(1).contiguous())
+        grads = ctx.eng.backward_segment("head")
+        return (None,) * 9 + (torch.zeros((), device=gloss.device),) + tuple(grads[n] for n in ctx.names)
+
+
+class _SegmentGrad(torch.autograd.Function):
+    """Autograd node of one backward segment ('tail' or ('layer', li)): forward only threads a scalar carrier through the chain (the actual forward
+    pass runs inside _DenoiserLoss.forward, the last node); backward launches that segment of DenoiserTrainEngine's backward and returns its
+    parameters' gradients."""
+
+    @staticmethod
+    def forward(ctx, eng, seg, names, carrier, *params):
+        ctx.eng, ctx.seg, ctx.names, ctx.has_carrier = eng, seg, names, carrier is not None
+        return params[0].new_zeros(()) if len(params) else torch.zeros(())
+
+    @staticmethod
+    def backward(ctx, g):
+        grads = ctx.eng.backward_segment(ctx.seg)
+        return (None, None, None, torch.zeros((), device=g.device) if ctx.has_carrier else None) + tuple(grads[n] for n in ctx.names)
 
 
 def index_to_log_onehot(x, num_classes):

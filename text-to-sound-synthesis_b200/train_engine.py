@@ -194,12 +194,21 @@ class DenoiserTrainEngine:
             v[f"blocks.{li}.attn2.key.bias"], v[f"blocks.{li}.attn2.value.bias"] = v["_kv_b"][o:o + D], v["_kv_b"][o + D:o + 2 * D]
         return v
 
-    def _replay(self, key, fn):
-        """Run fn() through a CUDA graph captured on first use (after one eager warm-up for lazy initialisation)."""
+    def _replay(self, key, fn, first_run_executes=False):
+        """Run fn() through a CUDA graph captured on first use (after one eager warm-up for lazy initialisation).
+        first_run_executes: fn is NOT idempotent (a backward segment accumulates into the stream gradient), so the first call runs it eagerly exactly
+        once -- that run is the execution -- and only records the graph for later calls."""
         ptrs = tuple(p.data_ptr() for p in self.m.parameters())
         ent = self._graphs.get(key)
         if ent is not None and ent[1] != ptrs:
             ent = None  # a parameter was re-allocated (EMA swap, .data assignment): the captured pointers are stale
+        if ent is None and first_run_executes:
+            fn()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                fn()
+            self._graphs[key] = (g, ptrs)
+            return
         if ent is None:
             cur = torch.cuda.current_stream()
             side = torch.cuda.Stream()
@@ -403,10 +412,94 @@ class DenoiserTrainEngine:
         out = self._grad_views(ws["grad_flat"].clone())
         return {n: out[n] for n, _ in self.m.named_parameters()}
 
+    # ---- segmented backward: head -> layer NL-1 ... layer 0 -> tail, one CUDA graph each.  DiffusionTransformer chains one autograd node per
+    # segment, so a layer's parameter gradients reach autograd (and DistributedDataParallel's bucketed NCCL all-reduce, solver_spec.py:109) as soon
+    # as that layer's backward has been launched, and the all-reduce of layer l overlaps the backward of layers l-1 ... 0.
+    def segment_names(self, seg):
+        """Parameter names (relative to the Text2ImageTransformer) whose gradients segment `seg` = 'head' | ('layer', li) | 'tail' produces."""
+        names = [n for n, _ in self.m.named_parameters()]
+        late = (".attn2.key.", ".attn2.value.")  # every layer's cross-attention K/V weight gradient comes out of ONE wgrad GEMM in the tail
+        if seg == "head":
+            return [n for n in names if n.startswith("to_logits.")]
+        if seg == "tail":
+            return [n for n in names if n.startswith("content_emb.") or any(k in n for k in late)]
+        pre = f"blocks.{seg[1]}."
+        return [n for n in names if n.startswith(pre) and not any(k in n for k in late)]
+
+    def backward_begin(self, dlogits: torch.Tensor, scale: Optional[torch.Tensor] = None) -> None:
+        B, L, Lc = self._shape
+        ws = self.workspace(B, L, Lc)
+        if dlogits.data_ptr() != ws["dlogits"].data_ptr():
+            ws["dlogits"].copy_(dlogits)
+        if scale is None:
+            ws["scale"].fill_(1.0)
+        else:
+            ws["scale"].copy_(scale.reshape(1))
+
+    def backward_segment(self, seg) -> Dict[str, torch.Tensor]:
+        """Run one segment of the backward pass (call them in order after backward_begin) and return fresh copies of the gradients it produced."""
+        B, L, Lc = self._shape
+        ws = self.workspace(B, L, Lc)
+        fn = {"head": lambda: self._bwd_head(ws, B, L, Lc), "tail": lambda: self._bwd_tail(ws, B, L, Lc)}.get(seg) if isinstance(seg, str) else \
+            (lambda: self._bwd_layer(ws, B, L, Lc, seg[1]))
+        if self.use_cuda_graph:
+            self._replay(("bwd_seg", seg, B, L, Lc), fn, first_run_executes=True)
+        else:
+            fn()
+        names = self.segment_names(seg)
+        # copy out with one clone per contiguous run of the flat gradient buffer (a layer = its own parameters + its fused QKV region)
+        layout = {k: (o, math.prod(shp)) for k, shp, o in self._grad_layout()[0]}
+        keys = set()
+        for n in names:
+            if n in layout:
+                keys.add(n)
+            elif ".attn1." in n:
+                li = int(n.split(".")[1])
+                keys.update((f"_qkv_w.{li}", f"_qkv_b.{li}"))
+            else:
+                keys.update(("_kv_w", "_kv_b"))
+        spans = sorted((layout[k][0], layout[k][0] + _rup(layout[k][1], 64)) for k in keys)
+        runs = []
+        for a, b in spans:
+            if runs and a == runs[-1][1]:
+                runs[-1][1] = b
+            else:
+                runs.append([a, b])
+        flat = ws["grad_flat"]
+        copies = [(a, flat[a:b].clone()) for a, b in runs]
+
+        def view(key):
+            o, n = layout[key]
+            a, buf = next((a, buf) for a, buf in reversed(copies) if a <= o)
+            shp = next(shp for k, shp, _ in self._grad_layout()[0] if k == key)
+            return buf[o - a:o - a + n].view(shp)
+        D = self.D
+        out = {}
+        for n in names:
+            if n in layout:
+                out[n] = view(n)
+            elif ".attn1." in n:
+                li = int(n.split(".")[1])
+                j = ("query", "key", "value").index(n.split(".")[3])
+                src = view(f"_qkv_w.{li}") if n.endswith("weight") else view(f"_qkv_b.{li}")
+                out[n] = src[j * D:(j + 1) * D]
+            else:
+                li = int(n.split(".")[1])
+                o = li * 2 * D + (0 if ".key." in n else D)
+                src = view("_kv_w") if n.endswith("weight") else view("_kv_b")
+                out[n] = src[o:o + D]
+        return out
+
     def _backward_impl(self, ws, B, L, Lc):
+        self._bwd_head(ws, B, L, Lc)
+        for li in range(self.n_layer - 1, -1, -1):
+            self._bwd_layer(ws, B, L, Lc, li)
+        self._bwd_tail(ws, B, L, Lc)
+
+    def _bwd_head(self, ws, B, L, Lc):
         m = self.m
-        D, K, NL = self.D, self.K, self.n_layer
-        M, Mc = B * L, B * Lc
+        D, K = self.D, self.K
+        M = B * L
         grads = ws["grads"]
         dx = ws["dx"]
         # ---- head: logits = LN_f(x) Wlog^T + b
@@ -417,8 +510,12 @@ class DenoiserTrainEngine:
         grads["to_logits.0.weight"].zero_(); grads["to_logits.0.bias"].zero_()
         T.layernorm_bwd(ws["x_out"], ws["dh"].view(B, L, D), dx, lnf.weight.detach(), grads["to_logits.0.weight"], grads["to_logits.0.bias"], lnf.eps,
                         dx_act=ws["dy"])  # every LayerNorm backward also emits the stream gradient as the next Linear backward's dY operand
-        dkv_all = ws["dkv_all"]
-        for li in range(NL - 1, -1, -1):
+
+    def _bwd_layer(self, ws, B, L, Lc, li):
+        m = self.m
+        D = self.D
+        grads, dx, dkv_all = ws["grads"], ws["dx"], ws["dkv_all"]
+        if True:
             blk, lay, sv = m.blocks[li], self.layers[li], ws["layers"][li]
             p = f"blocks.{li}."
             Dh = lay["w1"].shape[0]
@@ -450,6 +547,9 @@ class DenoiserTrainEngine:
                 self._attn_bwd(ws["datt"], dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], sv["qh1"], sv["kh1"], sv["vh1"], sv["P1"], ws, B, L, L)
             self._linear_bwd(dqkv, sv["h1"], lay["wqkv"], lay["wqkvT"], grads[f"_qkv_w.{li}"], grads[f"_qkv_b.{li}"], ws["dh"], ws)
             self._ada_bwd(blk.ln1, lay["lin1T"], sv["x1"], ws["dh"], sv["e1"], sv["s1"], sv["tab1"], grads, p + "ln1.", ws, B)
+
+    def _bwd_tail(self, ws, B, L, Lc):
+        grads, dx, dkv_all = ws["grads"], ws["dx"], ws["dkv_all"]
         # ---- cross-attention K/V projections of every layer in one wgrad: kv_all = cond Wkv^T + b
         self._linear_bwd(dkv_all, ws["cond"], None, None, grads["_kv_w"], grads["_kv_b"], None, ws, yT=ws.get("ykvT"), xT=ws.get("condT"))
         # ---- embedding
