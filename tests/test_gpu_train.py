@@ -217,12 +217,12 @@ def _grad_report(tag, grads, ref_of, tol):
 
 
 def _run_loss_and_grads(m, x0, x_t, cond, t, pt):
-    from diffsound_b200.modeling.transformers.diffusion_transformer import _DenoiserLoss
+    from diffsound_b200.modeling.transformers.diffusion_transformer import denoiser_loss
     for p in m.parameters():
         p.requires_grad_(True)
         p.grad = None
     names, params = zip(*m.transformer.named_parameters())
-    loss, prob, vb, hits = _DenoiserLoss.apply(m, x0, x_t, cond, t, pt, True, True, names, *params)
+    loss, prob, vb, hits = denoiser_loss(m, x0, x_t, cond, t, pt, True, True)
     loss.backward()
     return loss.detach(), prob, {n: p.grad for n, p in zip(names, params)}
 

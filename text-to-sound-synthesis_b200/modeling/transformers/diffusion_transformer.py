@@ -206,18 +206,7 @@ class DiffusionTransformer(nn.Module):
         t, pt = self.sample_time(B, x.device, "importance")
         uniform = torch.rand(B, self.num_classes, L, dtype=torch.float32, device=x.device)  # == rand_like(log_EV_qxt_x0), :360
         x_t = train_ops.q_sample(x, t.contiguous(), uniform, self._sched(), self.num_timesteps)
-        # One autograd node per backward segment (tail <- layer 0 <- ... <- layer NL-1 <- head/loss): a layer's parameter gradients reach autograd --
-        # and DistributedDataParallel's bucketed all-reduce (solver_spec.py:109) -- as soon as that layer's backward graph has been launched, so the
-        # NCCL traffic of layer l overlaps the backward of layers l-1 ... 0 instead of starting after the whole backward pass.
-        eng = self.transformer.train_engine
-        named = dict(self.transformer.named_parameters())
-        carrier = None
-        for seg in ["tail"] + [("layer", li) for li in range(len(self.transformer.blocks))]:
-            names = tuple(eng.segment_names(seg))
-            carrier = _SegmentGrad.apply(eng, seg, names, carrier, *[named[n] for n in names])
-        names = tuple(eng.segment_names("head"))
-        loss, prob, vb, hits = _DenoiserLoss.apply(self, x, x_t, cond_emb, t.contiguous(), pt.float().contiguous(), bool(is_train), bool(want_prob),
-                                                   names, carrier, *[named[n] for n in names])
+        loss, prob, vb, hits = denoiser_loss(self, x, x_t, cond_emb, t.contiguous(), pt.float().contiguous(), bool(is_train), bool(want_prob))
         # accuracy bookkeeping of :424-436 (one small D2H copy instead of 2B .item() calls)
         rate = hits.float().mean(dim=1).cpu()
         if bool(oob):  # the reference asserts in index_to_log_onehot (diffusion_transformer.py:46-47)
@@ -445,6 +434,21 @@ class DiffusionTransformer(nn.Module):
                 out["loss"] = loss
         self.amp = False
         return out
+
+
+def denoiser_loss(dt, x0, x_t, cond_emb, t, pt, is_train=True, want_prob=True):
+    """(loss, exp(log_model_prob) or empty, vb_loss, accuracy flags) with the hand-written backward attached.
+    One autograd node per backward segment (tail <- layer 0 <- ... <- layer NL-1 <- head/loss): a layer's parameter gradients reach autograd -- and
+    DistributedDataParallel's bucketed all-reduce (solver_spec.py:109) -- as soon as that layer's backward graph has been launched, so the NCCL traffic
+    of layer l overlaps the backward of layers l-1 ... 0 instead of starting after the whole backward pass."""
+    eng = dt.transformer.train_engine
+    named = dict(dt.transformer.named_parameters())
+    carrier = None
+    for seg in ["tail"] + [("layer", li) for li in range(len(dt.transformer.blocks))]:
+        names = tuple(eng.segment_names(seg))
+        carrier = _SegmentGrad.apply(eng, seg, names, carrier, *[named[n] for n in names])
+    names = tuple(eng.segment_names("head"))
+    return _DenoiserLoss.apply(dt, x0, x_t, cond_emb, t, pt, is_train, want_prob, names, carrier, *[named[n] for n in names])
 
 
 class _DenoiserLoss(torch.autograd.Function):

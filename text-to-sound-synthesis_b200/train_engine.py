@@ -67,7 +67,7 @@ class DenoiserTrainEngine:
         """Drop packed operands and workspaces (the module moved to another device / dtype)."""
         self._ws.clear()
         self._graphs.clear()
-        for attr in ("layers", "_layout"):
+        for attr in ("layers", "_layout", "_seg_plans", "_seg_names"):
             if hasattr(self, attr):
                 delattr(self, attr)
 
@@ -417,6 +417,13 @@ class DenoiserTrainEngine:
     # as that layer's backward has been launched, and the all-reduce of layer l overlaps the backward of layers l-1 ... 0.
     def segment_names(self, seg):
         """Parameter names (relative to the Text2ImageTransformer) whose gradients segment `seg` = 'head' | ('layer', li) | 'tail' produces."""
+        cache = self.__dict__.setdefault("_seg_names", {})
+        if seg in cache:
+            return cache[seg]
+        cache[seg] = self._segment_names(seg)
+        return cache[seg]
+
+    def _segment_names(self, seg):
         names = [n for n, _ in self.m.named_parameters()]
         late = (".attn2.key.", ".attn2.value.")  # every layer's cross-attention K/V weight gradient comes out of ONE wgrad GEMM in the tail
         if seg == "head":
@@ -446,49 +453,46 @@ class DenoiserTrainEngine:
             self._replay(("bwd_seg", seg, B, L, Lc), fn, first_run_executes=True)
         else:
             fn()
+        runs, items = self._segment_plan(seg)
+        flat = ws["grad_flat"]
+        copies = [flat[a:b].clone() for a, b in runs]   # one clone per contiguous run of the flat buffer (a layer: its parameters + its fused QKV region)
+        return {n: copies[r][o:o + numel].view(shp)[s0:s1] if s0 is not None else copies[r][o:o + numel].view(shp) for n, r, o, numel, shp, s0, s1 in items}
+
+    def _segment_plan(self, seg):
+        """(contiguous [start, end) runs of the flat gradient buffer, [(name, run index, offset in run, numel, shape, row slice or None)]), cached."""
+        cache = self.__dict__.setdefault("_seg_plans", {})
+        if seg in cache:
+            return cache[seg]
+        D = self.D
         names = self.segment_names(seg)
-        # copy out with one clone per contiguous run of the flat gradient buffer (a layer = its own parameters + its fused QKV region)
-        layout = {k: (o, math.prod(shp)) for k, shp, o in self._grad_layout()[0]}
-        keys = set()
+        layout = {k: (o, math.prod(shp), shp) for k, shp, o in self._grad_layout()[0]}
+        src = {}
         for n in names:
             if n in layout:
-                keys.add(n)
+                src[n] = (n, None, None)
             elif ".attn1." in n:
                 li = int(n.split(".")[1])
-                keys.update((f"_qkv_w.{li}", f"_qkv_b.{li}"))
+                j = ("query", "key", "value").index(n.split(".")[3])
+                src[n] = (f"_qkv_w.{li}" if n.endswith("weight") else f"_qkv_b.{li}", j * D, (j + 1) * D)
             else:
-                keys.update(("_kv_w", "_kv_b"))
-        spans = sorted((layout[k][0], layout[k][0] + _rup(layout[k][1], 64)) for k in keys)
+                li = int(n.split(".")[1])
+                o = li * 2 * D + (0 if ".key." in n else D)
+                src[n] = ("_kv_w" if n.endswith("weight") else "_kv_b", o, o + D)
+        spans = sorted({(layout[k][0], layout[k][0] + _rup(layout[k][1], 64)) for k, _, _ in src.values()})
         runs = []
         for a, b in spans:
             if runs and a == runs[-1][1]:
                 runs[-1][1] = b
             else:
                 runs.append([a, b])
-        flat = ws["grad_flat"]
-        copies = [(a, flat[a:b].clone()) for a, b in runs]
-
-        def view(key):
-            o, n = layout[key]
-            a, buf = next((a, buf) for a, buf in reversed(copies) if a <= o)
-            shp = next(shp for k, shp, _ in self._grad_layout()[0] if k == key)
-            return buf[o - a:o - a + n].view(shp)
-        D = self.D
-        out = {}
+        items = []
         for n in names:
-            if n in layout:
-                out[n] = view(n)
-            elif ".attn1." in n:
-                li = int(n.split(".")[1])
-                j = ("query", "key", "value").index(n.split(".")[3])
-                src = view(f"_qkv_w.{li}") if n.endswith("weight") else view(f"_qkv_b.{li}")
-                out[n] = src[j * D:(j + 1) * D]
-            else:
-                li = int(n.split(".")[1])
-                o = li * 2 * D + (0 if ".key." in n else D)
-                src = view("_kv_w") if n.endswith("weight") else view("_kv_b")
-                out[n] = src[o:o + D]
-        return out
+            key, s0, s1 = src[n]
+            o, numel, shp = layout[key]
+            r = max(i for i, (a, _) in enumerate(runs) if a <= o)
+            items.append((n, r, o - runs[r][0], numel, shp, s0, s1))
+        cache[seg] = ([tuple(r) for r in runs], items)
+        return cache[seg]
 
     def _backward_impl(self, ws, B, L, Lc):
         self._bwd_head(ws, B, L, Lc)
