@@ -487,9 +487,12 @@ def run_extras(args, rank, world, dev, dist, voc):
         del model
         torch.cuda.empty_cache()
 
-    out["configs3_train_ddp"] = train_extra(args, rank, world, dev, dist)
-    one("configs2_b64_text_to_wav", 256, 64, 64 * world, "BASELINE.json configs[2]: batch 64 per GPU, full pipeline (weak scaling over ranks)")
-    if 512 % world == 0:
+    sel = set(args.extras.split(","))
+    if "train" in sel:
+        out["configs3_train_ddp"] = train_extra(args, rank, world, dev, dist)
+    if "configs2" in sel:
+        one("configs2_b64_text_to_wav", 256, 64, 64 * world, "BASELINE.json configs[2]: batch 64 per GPU, full pipeline (weak scaling over ranks)")
+    if "configs4" in sel and 512 % world == 0:
         one("configs4_b512_k512_sharded", 512, 512 // world, 512, "BASELINE.json configs[4]: 512 clips TOTAL sharded over the ranks (strong scaling), K=512 codebook, "
             "full pipeline, NCCL all_gather of the waveforms inside the timed pass")
     return out
@@ -559,6 +562,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-modes", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--extras", default="train,configs2,configs4", help="which of the other BASELINE configs to measure in the same run")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
