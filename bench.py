@@ -540,8 +540,8 @@ def train_extra(args, rank, world, dev, dist, per_gpu_batch=20, warm=3, steps=8)
     res = {"samples_per_s": world * per_gpu_batch / ms_step * 1e3, "ms_per_step": round(ms_step, 2), "per_gpu_batch": per_gpu_batch, "n_gpus": world,
            "steps": steps, "loss": float(loss.detach()), "dtype": "bf16 GEMM operands, fp32 master weights / residual stream / loss",
            "algorithmic_tflops": round(3 * 158.25e9 * per_gpu_batch * (args.layers / 19.0) / (ms_step * 1e-3) / 1e12, 1),
-           "note": "BASELINE.json configs[3]: forward + fused loss + hand-written backward + AdamW" + (", torch DDP gradient all-reduce (not overlapped with "
-                   "the backward graph)" if world > 1 else "")}
+           "note": "BASELINE.json configs[3]: forward + fused loss + hand-written backward + AdamW" + (", torch DDP bucketed gradient all-reduce overlapped with the "
+                   "remaining backward segments (one autograd node per layer)" if world > 1 else "")}
     del net, m, opt
     torch.cuda.empty_cache()
     return res

@@ -425,13 +425,12 @@ class DenoiserTrainEngine:
 
     def _segment_names(self, seg):
         names = [n for n, _ in self.m.named_parameters()]
-        late = (".attn2.key.", ".attn2.value.")  # every layer's cross-attention K/V weight gradient comes out of ONE wgrad GEMM in the tail
         if seg == "head":
             return [n for n in names if n.startswith("to_logits.")]
         if seg == "tail":
-            return [n for n in names if n.startswith("content_emb.") or any(k in n for k in late)]
+            return [n for n in names if n.startswith("content_emb.")]
         pre = f"blocks.{seg[1]}."
-        return [n for n in names if n.startswith(pre) and not any(k in n for k in late)]
+        return [n for n in names if n.startswith(pre)]
 
     def backward_begin(self, dlogits: torch.Tensor, scale: Optional[torch.Tensor] = None) -> None:
         B, L, Lc = self._shape
@@ -456,41 +455,38 @@ class DenoiserTrainEngine:
         runs, items = self._segment_plan(seg)
         flat = ws["grad_flat"]
         copies = [flat[a:b].clone() for a, b in runs]   # one clone per contiguous run of the flat buffer (a layer: its parameters + its fused QKV region)
-        return {n: copies[r][o:o + numel].view(shp)[s0:s1] if s0 is not None else copies[r][o:o + numel].view(shp) for n, r, o, numel, shp, s0, s1 in items}
+        return {n: copies[r][o:o + numel].view(shp) for n, r, o, numel, shp in items}
 
     def _segment_plan(self, seg):
-        """(contiguous [start, end) runs of the flat gradient buffer, [(name, run index, offset in run, numel, shape, row slice or None)]), cached."""
+        """(contiguous [start, end) runs of the flat gradient buffer, [(name, run index, offset in run, numel, shape)]), cached."""
         cache = self.__dict__.setdefault("_seg_plans", {})
         if seg in cache:
             return cache[seg]
-        D = self.D
-        names = self.segment_names(seg)
-        layout = {k: (o, math.prod(shp), shp) for k, shp, o in self._grad_layout()[0]}
+        D, Cd = self.D, self.Cd
+        layout = {k: (o, shp) for k, shp, o in self._grad_layout()[0]}
         src = {}
-        for n in names:
+        for n in self.segment_names(seg):
             if n in layout:
-                src[n] = (n, None, None)
-            elif ".attn1." in n:
-                li = int(n.split(".")[1])
-                j = ("query", "key", "value").index(n.split(".")[3])
-                src[n] = (f"_qkv_w.{li}" if n.endswith("weight") else f"_qkv_b.{li}", j * D, (j + 1) * D)
-            else:
-                li = int(n.split(".")[1])
-                o = li * 2 * D + (0 if ".key." in n else D)
-                src[n] = ("_kv_w" if n.endswith("weight") else "_kv_b", o, o + D)
-        spans = sorted({(layout[k][0], layout[k][0] + _rup(layout[k][1], 64)) for k, _, _ in src.values()})
+                o, shp = layout[n]
+            elif ".attn1." in n:  # a third of the layer's fused QKV wgrad / bias-gradient region
+                li, j = int(n.split(".")[1]), ("query", "key", "value").index(n.split(".")[3])
+                w = n.endswith("weight")
+                o, shp = layout[f"_qkv_w.{li}" if w else f"_qkv_b.{li}"][0] + j * D * (D if w else 1), ((D, D) if w else (D,))
+            else:                 # rows [li*2D (+D for value), +D) of the all-layer cross-attention K/V region
+                li, w = int(n.split(".")[1]), n.endswith("weight")
+                r0 = li * 2 * D + (0 if ".key." in n else D)
+                o, shp = layout["_kv_w" if w else "_kv_b"][0] + r0 * (Cd if w else 1), ((D, Cd) if w else (D,))
+            src[n] = (o, math.prod(shp), shp)
         runs = []
-        for a, b in spans:
-            if runs and a == runs[-1][1]:
-                runs[-1][1] = b
+        for a, b in sorted((o, o + n_) for o, n_, _ in src.values()):
+            if runs and a <= runs[-1][1] + 64:  # adjacent up to the 64-element alignment gaps of the layout
+                runs[-1][1] = max(runs[-1][1], b)
             else:
                 runs.append([a, b])
         items = []
-        for n in names:
-            key, s0, s1 = src[n]
-            o, numel, shp = layout[key]
+        for n, (o, numel, shp) in src.items():
             r = max(i for i, (a, _) in enumerate(runs) if a <= o)
-            items.append((n, r, o - runs[r][0], numel, shp, s0, s1))
+            items.append((n, r, o - runs[r][0], numel, shp))
         cache[seg] = ([tuple(r) for r in runs], items)
         return cache[seg]
 
@@ -538,6 +534,11 @@ class DenoiserTrainEngine:
                                       B, self.H, L, Lc, self.scale)
             else:
                 self._attn_bwd(ws["datt"], ws["dq2"], dkv[:, :D], dkv[:, D:], sv["qh2"], sv["kh2"], sv["vh2"], sv["P2"], ws, B, L, Lc)
+            # this layer's cross-attention K/V projections: kv = cond Wkv^T + b (its rows of the all-layer region; per layer, so that every parameter
+            # of the layer has its gradient when the segment ends and DDP can start the layer's all-reduce)
+            o_kv = li * 2 * D
+            self._linear_bwd(dkv, ws["cond"], None, None, grads["_kv_w"][o_kv:o_kv + 2 * D], grads["_kv_b"][o_kv:o_kv + 2 * D], None, ws,
+                             yT=ws.get("ykvT"), xT=ws.get("condT"))
             self._linear_bwd(ws["dq2"], sv["h2"], lay["wq2"], lay["wq2T"], grads[p + "attn2.query.weight"], grads[p + "attn2.query.bias"], ws["dh"], ws)
             self._ada_bwd(blk.ln1_1, lay["lin2T"], sv["x2"], ws["dh"], sv["e2"], sv["s2"], sv["tab2"], grads, p + "ln1_1.", ws, B)
             # ---- self-attention: x2 = x1 + Wo1 attn(qkv)
@@ -553,9 +554,7 @@ class DenoiserTrainEngine:
             self._ada_bwd(blk.ln1, lay["lin1T"], sv["x1"], ws["dh"], sv["e1"], sv["s1"], sv["tab1"], grads, p + "ln1.", ws, B)
 
     def _bwd_tail(self, ws, B, L, Lc):
-        grads, dx, dkv_all = ws["grads"], ws["dx"], ws["dkv_all"]
-        # ---- cross-attention K/V projections of every layer in one wgrad: kv_all = cond Wkv^T + b
-        self._linear_bwd(dkv_all, ws["cond"], None, None, grads["_kv_w"], grads["_kv_b"], None, ws, yT=ws.get("ykvT"), xT=ws.get("condT"))
+        grads, dx = ws["grads"], ws["dx"]
         # ---- embedding
         for n in ("content_emb.emb.weight", "content_emb.height_emb.weight", "content_emb.width_emb.weight"):
             grads[n].zero_()
