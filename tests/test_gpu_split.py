@@ -72,7 +72,8 @@ def test_layernorm_split_output(G):
     assert float((_pair_value(pr.view(-1, 2048), 1024) - ref.view(-1, 1024).double()).abs().max()) < 2e-6
 
 
-@pytest.mark.parametrize("B,H,Lq,Lk", [(2, 3, 265, 265), (2, 16, 265, 77), (1, 2, 77, 77), (3, 1, 128, 288), (1, 1, 9, 33)])
+@pytest.mark.parametrize("B,H,Lq,Lk", [(2, 3, 265, 265), (2, 16, 265, 77), (1, 2, 77, 77), (3, 1, 128, 288), (1, 1, 9, 33),
+                                       (10, 16, 265, 265), (19, 16, 265, 77), (37, 5, 140, 265)])  # more (batch, head) units than CTAs: multi-head slices
 def test_attention_tc_split_matches_fp64(G, B, H, Lq, Lk):
     ops = G.ops
     D = H * 64

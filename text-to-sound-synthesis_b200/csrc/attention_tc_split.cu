@@ -25,6 +25,7 @@ constexpr int SP_QTILE = SP_QM * 128;  // bytes of one 128 x 64 fp16 SW128 tile
 
 struct SpParams {
   int B, H, Lq, Lk, kpad, n_qt, box_rows, n_box;
+  int n_heads;          // B * H (batch, head) units; CTA c owns the contiguous slice [c * n / grid, (c + 1) * n / grid)
   int q_bufs;           // Q tile buffers: 2 (prefetch one tile ahead) or 1 (short key sequences: leaves room for two CTAs per SM)
   int rem_rows;         // > 0: the last (Lq % 128 <= 16) query rows are computed by the remainder warp with mma.sync, not by a third tensor tile
   const __half* q;      // global Q (hi half; lo at + q_lo_col) for the remainder warp's register fragments
@@ -214,19 +215,23 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
   float* s_sum = s_max + 1024;                               // same shape
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_sum + 1024);
   constexpr int CTRL = 4 * NSW;
-  uint64_t* kv_full = bars;
+  uint64_t* k_full = bars;
   uint64_t* q_full = bars + 1;   // [2]
   uint64_t* s_full = bars + 3;
   uint64_t* p_full = bars + 4;
   uint64_t* o_full = bars + 5;
   uint64_t* o_empty = bars + 6;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* v_full = bars + 7;
+  uint64_t* rem_done = bars + 8;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
 
-  const int h = blockIdx.x, b = blockIdx.y;
+  // persistent over a contiguous slice of (batch, head) units: the next head's K is fetched as soon as the last S of the current head has been
+  // computed, its V as soon as the last P.V has, so that only the first head's loads are exposed
+  const int u0 = (int)((long long)p.n_heads * blockIdx.x / gridDim.x), u1 = (int)((long long)p.n_heads * (blockIdx.x + 1) / gridDim.x);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    mbar_init(kv_full, 1);
+    mbar_init(k_full, 1); mbar_init(v_full, 1); mbar_init(rem_done, 1);
     mbar_init(&q_full[0], 1); mbar_init(&q_full[1], 1);
     mbar_init(s_full, 1); mbar_init(p_full, 4 * NSW); mbar_init(o_full, 1); mbar_init(o_empty, 8);
     fence_barrier_init();
@@ -247,33 +252,52 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
   if (warp == CTRL) {
     if (lane == 0) {
       // ------------------------------------------------------------------ control thread: TMA producer + MMA issuer
-      mbar_arrive_expect_tx(kv_full, 4 * kv_bytes);
-      for (int bx = 0; bx < p.n_box; ++bx) {
-        const int r = b * p.Lk + bx * p.box_rows, off = bx * p.box_rows * 128;
-        tma_load_3d(&map_k, kv_full, sKh + off, h * SP_HD, r, 0);
-        tma_load_3d(&map_k, kv_full, sKl + off, p.k_lo_col + h * SP_HD, r, 0);
-        tma_load_3d(&map_v, kv_full, sVh + off, h * SP_HD, r, 0);
-        tma_load_3d(&map_v, kv_full, sVl + off, p.v_lo_col + h * SP_HD, r, 0);
-      }
+      auto load_k = [&](int u) {
+        const int b = u / p.H, h = u - b * p.H;
+        mbar_arrive_expect_tx(k_full, 2 * kv_bytes);
+        for (int bx = 0; bx < p.n_box; ++bx) {
+          const int r = b * p.Lk + bx * p.box_rows, off = bx * p.box_rows * 128;
+          tma_load_3d(&map_k, k_full, sKh + off, h * SP_HD, r, 0);
+          tma_load_3d(&map_k, k_full, sKl + off, p.k_lo_col + h * SP_HD, r, 0);
+        }
+      };
+      auto load_v = [&](int u) {
+        const int b = u / p.H, h = u - b * p.H;
+        mbar_arrive_expect_tx(v_full, 2 * kv_bytes);
+        for (int bx = 0; bx < p.n_box; ++bx) {
+          const int r = b * p.Lk + bx * p.box_rows, off = bx * p.box_rows * 128;
+          tma_load_3d(&map_v, v_full, sVh + off, h * SP_HD, r, 0);
+          tma_load_3d(&map_v, v_full, sVl + off, p.v_lo_col + h * SP_HD, r, 0);
+        }
+      };
       const int nb = p.q_bufs;
-      auto issue_q = [&](int qt) {
-        const int qb = qt % nb;
+      const int n_tiles = (u1 - u0) * p.n_qt;
+      auto issue_q = [&](int tg) {  // tg = tile index inside this CTA's slice
+        const int u = u0 + tg / p.n_qt, qt = tg % p.n_qt;
+        const int b = u / p.H, h = u - b * p.H;
+        const int qb = tg % nb;
         mbar_arrive_expect_tx(&q_full[qb], 2 * SP_QTILE);
         tma_load_3d(&map_q, &q_full[qb], sQ + qb * 2 * SP_QTILE, h * SP_HD, b * p.Lq + qt * SP_QM, 0);
         tma_load_3d(&map_q, &q_full[qb], sQ + qb * 2 * SP_QTILE + SP_QTILE, p.q_lo_col + h * SP_HD, b * p.Lq + qt * SP_QM, 0);
       };
-      issue_q(0);
-      if (nb > 1 && p.n_qt > 1) issue_q(1);
+      if (u0 < u1) {
+        load_k(u0);
+        load_v(u0);
+        issue_q(0);
+        if (nb > 1 && n_tiles > 1) issue_q(1);
+      }
       const int n_hi = p.kpad > 256 ? 256 : p.kpad, n_lo = p.kpad - n_hi;
       const uint32_t id_hi = sp_idesc(SP_QM, n_hi, false), id_lo = sp_idesc(SP_QM, n_lo > 0 ? n_lo : 16, false);
       const uint32_t id_pv = sp_idesc(SP_QM, SP_HD, true);
       const int ksteps = p.kpad >> 4;
-      mbar_wait(kv_full, 0);
-      for (int qt = 0; qt < p.n_qt; ++qt) {
-        const int qb = qt % nb;
-        mbar_wait(&q_full[qb], (qt / nb) & 1);
+      for (int tg = 0; tg < n_tiles; ++tg) {
+        const int hu = tg / p.n_qt, qt = tg - hu * p.n_qt;     // head index inside the slice, query tile inside the head
+        const bool last_of_head = qt == p.n_qt - 1, more_heads = u0 + hu + 1 < u1;
+        const int qb = tg % nb;
+        if (qt == 0) mbar_wait(k_full, hu & 1);
+        mbar_wait(&q_full[qb], (tg / nb) & 1);
         tc_fence_after();
-        // ---- S = Qlo Khi^T + Qhi Klo^T + Qhi Khi^T  (tcgen05.mma from one thread execute in issue order: this also follows P.V(qt-1))
+        // ---- S = Qlo Khi^T + Qhi Klo^T + Qhi Khi^T  (tcgen05.mma from one thread execute in issue order: this also follows P.V(tg-1))
         const uint32_t qh = smem_u32(sQ + qb * 2 * SP_QTILE), ql = qh + SP_QTILE;
         const uint32_t kh = smem_u32(sKh), kl = smem_u32(sKl);
 #pragma unroll
@@ -288,13 +312,17 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
           }
         }
         umma_commit(s_full);
-        // the Q buffer is free once S has been computed: prefetch tile qt + q_bufs into it
-        if (qt + nb < p.n_qt) {
-          mbar_wait(s_full, qt & 1);
-          issue_q(qt + nb);
+        // the Q buffer (and, after a head's last tile, the K tiles) are free once S has been computed
+        const bool refill_q = tg + nb < n_tiles, refill_k = last_of_head && more_heads;
+        if (refill_q || refill_k) mbar_wait(s_full, tg & 1);
+        if (refill_q) issue_q(tg + nb);
+        if (refill_k) {
+          if (p.rem_rows > 0) mbar_wait(rem_done, hu & 1);   // the remainder warp reads K / V of this head through ldmatrix
+          load_k(u0 + hu + 1);
         }
-        mbar_wait(p_full, qt & 1);                       // P(qt) is in TMEM
-        if (qt > 0) mbar_wait(o_empty, (qt - 1) & 1);    // epilogue(qt-1) has read O
+        mbar_wait(p_full, tg & 1);                       // P(tg) is in TMEM
+        if (tg > 0) mbar_wait(o_empty, (tg - 1) & 1);    // epilogue(tg-1) has read O
+        if (qt == 0) mbar_wait(v_full, hu & 1);
         tc_fence_after();
         // ---- O = Plo Vhi + Phi Vlo + Phi Vhi : per 16-key step, A = 8 packed-fp16 TMEM columns, B = 16 V rows (2048 B)
         const uint64_t dvh = make_sw128_kmajor_desc(smem_u32(sVh)), dvl = make_sw128_kmajor_desc(smem_u32(sVl));
@@ -305,13 +333,23 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
           sp_umma_ts(tO, a_hi, dvh + (uint64_t)(ks * 128), id_pv, 1u);
         }
         umma_commit(o_full);
+        if (refill_k) {  // V is free once this head's last P.V has completed
+          mbar_wait(o_full, tg & 1);
+          load_v(u0 + hu + 1);
+        }
       }
     }
   } else if (warp == CTRL + 1) {
     // ------------------------------------------------------------------ remainder rows (after the full 128-row tiles), concurrent with them
     if (p.rem_rows > 0) {
-      mbar_wait(kv_full, 0);
-      sp_remainder_rows(p, sKh, sKl, sVh, sVl, b, h, p.n_qt * SP_QM, lane);
+      for (int u = u0; u < u1; ++u) {
+        const int hu = u - u0;
+        mbar_wait(k_full, hu & 1);
+        mbar_wait(v_full, hu & 1);
+        sp_remainder_rows(p, sKh, sKl, sVh, sVl, u / p.H, u % p.H, p.n_qt * SP_QM, lane);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(rem_done);
+      }
     }
   } else {
     // ------------------------------------------------------------------ softmax + epilogue warps
@@ -322,12 +360,15 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
     // slice j owns chunks [j * n / NSW, (j + 1) * n / NSW): 9 chunks -> 3,3,3 with NSW = 3
     const int c_begin = (half * n_chunks / NSW) * 32, c_end = ((half + 1) * n_chunks / NSW) * 32;
     // MAXC = chunks held in registers at once: one TMEM round trip per pass covers up to MAXC chunks; longer slices go in groups
-    for (int qt = 0; qt < p.n_qt; ++qt) {
+    const int n_tiles = (u1 - u0) * p.n_qt;
+    for (int tg = 0; tg < n_tiles; ++tg) {
+      const int hu = tg / p.n_qt, qt = tg - hu * p.n_qt;
+      const int b = (u0 + hu) / p.H, h = (u0 + hu) - b * p.H;
       const bool live = qt * SP_QM + quad * 32 < p.Lq;  // a 32-row slab entirely beyond Lq does no exp work; its rows are never stored
-      mbar_wait(s_full, qt & 1);
+      mbar_wait(s_full, tg & 1);
       tc_fence_after();
       float mx = -INFINITY, sum = 0.f;
-      float* smx = s_max + (qt & 1) * (NSW * 128);
+      float* smx = s_max + (tg & 1) * (NSW * 128);
       auto chunk_max = [&](const uint32_t (&sv)[32], int c) {
         if (c + 32 <= p.Lk) {
 #pragma unroll
@@ -386,19 +427,19 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
         }
         sp_tmem_st_wait();
       }
-      s_sum[((qt & 1) * NSW + half) * 128 + row_in_tile] = sum;
+      s_sum[((tg & 1) * NSW + half) * 128 + row_in_tile] = sum;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
       // ---- epilogue (slices 0 and 1 of every quadrant): 32 rows x 32 of the 64 output columns
       if (half >= 2) continue;
-      mbar_wait(o_full, qt & 1);
+      mbar_wait(o_full, tg & 1);
       tc_fence_after();
       const int row = qt * SP_QM + row_in_tile;
       if (live) {
         float tot = 0.f;
 #pragma unroll
-        for (int j = 0; j < NSW; ++j) tot += s_sum[((qt & 1) * NSW + j) * 128 + row_in_tile];
+        for (int j = 0; j < NSW; ++j) tot += s_sum[((tg & 1) * NSW + j) * 128 + row_in_tile];
         const float inv = 1.0f / tot;
         uint32_t ov[32];
         tmem_ld_32x32(tO + lane_off + half * 32, ov);
@@ -473,14 +514,17 @@ extern "C" int dsb_attention_tc_split(const void* q, long long ldq, long long q_
   if (make_operand_map(&mv, v, DSB_DTYPE_F16, v_lo_off + (long long)H * SP_HD, (long long)B * Lk, 1, ldv, 0, p.box_rows)) return 3;
   const bool two = cols <= 256 && 2 * SP_QTILE + 4 * p.kpad * 128 + (1024 + 1024) * 4 + 16 * 8 + 1024 <= 112 * 1024;  // two CTAs per SM fit
   p.q_bufs = two ? 1 : 2;
-  const int smem = p.q_bufs * 2 * SP_QTILE + 4 * p.kpad * 128 + (1024 + 1024) * 4 + 16 * 8 + 1024;
+  const int smem = p.q_bufs * 2 * SP_QTILE + 4 * p.kpad * 128 + (1024 + 1024) * 4 + 16 * 8 + 1024;  // 16 words: 9 barriers + the TMEM address
   static int attr_smem[2] = {0, 0};
   if (smem > attr_smem[two]) {
     if (two) DSB_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_split_kernel<2, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     else DSB_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_split_kernel<1, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_smem[two] = smem;
   }
-  if (two) DSB_CHECK_CUDA(launch_pdl(attention_tc_split_kernel<2, 2, 1>, dim3(H, B), dim3(sp_threads(2)), smem, (cudaStream_t)stream, mq, mk, mv, p));
-  else DSB_CHECK_CUDA(launch_pdl(attention_tc_split_kernel<1, 2, 1>, dim3(H, B), dim3(sp_threads(2)), smem, (cudaStream_t)stream, mq, mk, mv, p));
+  p.n_heads = B * H;
+  int grid = sm_count() * (two ? 2 : 1);
+  if (grid > p.n_heads) grid = p.n_heads;
+  if (two) DSB_CHECK_CUDA(launch_pdl(attention_tc_split_kernel<2, 2, 1>, dim3(grid), dim3(sp_threads(2)), smem, (cudaStream_t)stream, mq, mk, mv, p));
+  else DSB_CHECK_CUDA(launch_pdl(attention_tc_split_kernel<1, 2, 1>, dim3(grid), dim3(sp_threads(2)), smem, (cudaStream_t)stream, mq, mk, mv, p));
   return 0;
 }
