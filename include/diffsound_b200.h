@@ -180,6 +180,10 @@ int dsb_attention_tc_split(const void* q, long long ldq, long long q_lo_off, con
                            long long ldv, long long v_lo_off, void* o, long long ldo, long long o_lo_off, int B, int H, int Lq, int Lk,
                            float scale, void* stream);
 
+/* debug aid (tools/attn_split_timing.py): enable = 1 makes CTA 0 of dsb_attention_tc_split record SM-clock timestamps of its phases;
+ * host_out_128 (host pointer, 128 x int64, may be NULL) receives them: [tile 0..7][slot 0..15]. */
+int dsb_attention_split_timing(int enable, long long* host_out_128);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Posterior + truncation + Gumbel-argmax sampler, one kernel (reference diffusion_transformer.py:285-289 predict_start tail,
  * models/dalle_spec.py:146-174 top-k / nucleus truncation, diffusion_transformer.py:293-339 q_posterior,

@@ -56,6 +56,7 @@ SIGNATURES = {
     "dsb_row_argmin": [c_vp, c_ll, c_ll, c_i, c_vp, c_vp],
     "dsb_tokens_add_to_padded": [c_vp, c_vp] + [c_i] * 5 + [c_vp],
     "dsb_lrelu_pad": [c_vp, c_vp] + [c_i] * 4 + [c_f, c_i, c_i, c_i, c_vp],
+    "dsb_attention_split_timing": [c_i, c_vp],
     "dsb_mel_pack_f16": [c_vp, c_vp] + [c_i] * 5 + [c_vp],
     "dsb_edge_pad_f16": [c_vp, c_ll, c_ll] + [c_i] * 7 + [c_vp],
     "dsb_attention_f16": [c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_i, c_i, c_i, c_i, c_f, c_i, c_vp],

@@ -53,6 +53,12 @@ __device__ __forceinline__ void sp_umma_ts(uint32_t tmem_d, uint32_t tmem_a, uin
 __device__ __forceinline__ constexpr uint32_t sp_idesc(int M, int N, bool b_mn_major) {  // fp16 operands, fp32 accumulate
   return (1u << 4) | (b_mn_major ? (1u << 16) : 0u) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
+// optional phase timestamps of CTA 0 (tools/attn_split_timing.py): [tile][0..7] softmax warp 0, [tile][8..15] control thread; SM clock cycles
+__device__ long long sp_dbg_times[8 * 16];
+__device__ int sp_dbg_on = 0;
+__device__ __forceinline__ void sp_stamp(int tile, int slot) {
+  if (sp_dbg_on && blockIdx.x == 0 && tile < 8) sp_dbg_times[tile * 16 + slot] = clock64();
+}
 __device__ __forceinline__ float sp_ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -312,6 +318,7 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
           }
         }
         umma_commit(s_full);
+        sp_stamp(tg, 8);
         // the Q buffer (and, after a head's last tile, the K tiles) are free once S has been computed
         const bool refill_q = tg + nb < n_tiles, refill_k = last_of_head && more_heads;
         if (refill_q || refill_k) mbar_wait(s_full, tg & 1);
@@ -320,7 +327,9 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
           if (p.rem_rows > 0) mbar_wait(rem_done, hu & 1);   // the remainder warp reads K / V of this head through ldmatrix
           load_k(u0 + hu + 1);
         }
+        sp_stamp(tg, 9);
         mbar_wait(p_full, tg & 1);                       // P(tg) is in TMEM
+        sp_stamp(tg, 10);
         if (tg > 0) mbar_wait(o_empty, (tg - 1) & 1);    // epilogue(tg-1) has read O
         if (qt == 0) mbar_wait(v_full, hu & 1);
         tc_fence_after();
@@ -333,6 +342,7 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
           sp_umma_ts(tO, a_hi, dvh + (uint64_t)(ks * 128), id_pv, 1u);
         }
         umma_commit(o_full);
+        sp_stamp(tg, 11);
         if (refill_k) {  // V is free once this head's last P.V has completed
           mbar_wait(o_full, tg & 1);
           load_v(u0 + hu + 1);
@@ -367,6 +377,7 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
       const bool live = qt * SP_QM + quad * 32 < p.Lq;  // a 32-row slab entirely beyond Lq does no exp work; its rows are never stored
       mbar_wait(s_full, tg & 1);
       tc_fence_after();
+      if (threadIdx.x == 0) sp_stamp(tg, 0);
       float mx = -INFINITY, sum = 0.f;
       float* smx = s_max + (tg & 1) * (NSW * 128);
       auto chunk_max = [&](const uint32_t (&sv)[32], int c) {
@@ -391,7 +402,9 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
         }
       }
       smx[half * 128 + row_in_tile] = mx;
+      if (threadIdx.x == 0) sp_stamp(tg, 1);
       asm volatile("bar.sync 1, %0;" ::"n"(32 * 4 * NSW) : "memory");
+      if (threadIdx.x == 0) sp_stamp(tg, 2);
       if (live) {
 #pragma unroll
         for (int j = 0; j < NSW; ++j) mx = fmaxf(mx, smx[j * 128 + row_in_tile]);
@@ -430,11 +443,13 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
       s_sum[((tg & 1) * NSW + half) * 128 + row_in_tile] = sum;
       tc_fence_before();
       __syncwarp();
+      if (threadIdx.x == 0) sp_stamp(tg, 3);
       if (lane == 0) mbar_arrive(p_full);
       // ---- epilogue (slices 0 and 1 of every quadrant): 32 rows x 32 of the 64 output columns
       if (half >= 2) continue;
       mbar_wait(o_full, tg & 1);
       tc_fence_after();
+      if (threadIdx.x == 0) sp_stamp(tg, 4);
       const int row = qt * SP_QM + row_in_tile;
       if (live) {
         float tot = 0.f;
@@ -464,6 +479,7 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
       }
       tc_fence_before();
       __syncwarp();
+      if (threadIdx.x == 0) sp_stamp(tg, 5);
       if (lane == 0) mbar_arrive(o_empty);
     }
   }
@@ -526,5 +542,14 @@ extern "C" int dsb_attention_tc_split(const void* q, long long ldq, long long q_
   if (grid > p.n_heads) grid = p.n_heads;
   if (two) DSB_CHECK_CUDA(launch_pdl(attention_tc_split_kernel<2, 2, 1>, dim3(grid), dim3(sp_threads(2)), smem, (cudaStream_t)stream, mq, mk, mv, p));
   else DSB_CHECK_CUDA(launch_pdl(attention_tc_split_kernel<1, 2, 1>, dim3(grid), dim3(sp_threads(2)), smem, (cudaStream_t)stream, mq, mk, mv, p));
+  return 0;
+}
+
+/* debug: enable / read the phase timestamps of CTA 0 (not part of the product path) */
+extern "C" int dsb_attention_split_timing(int enable, long long* host_out_128) {
+  using namespace dsb;
+  int v = enable;
+  DSB_CHECK_CUDA(cudaMemcpyToSymbol(sp_dbg_on, &v, sizeof(int)));
+  if (host_out_128) DSB_CHECK_CUDA(cudaMemcpyFromSymbol(host_out_128, sp_dbg_times, sizeof(long long) * 128));
   return 0;
 }
