@@ -19,8 +19,10 @@ namespace {
 constexpr int SP_HD = 64;
 constexpr int SP_QM = 128;
 constexpr int SP_KMAX = 288;      // padded key capacity (multiple of 32)
-// warps [0, 4*NSW): softmax + epilogue (NSW per TMEM lane quadrant), warp 4*NSW: control (TMA producer, MMA issuer, TMEM owner), warp 4*NSW+1: remainder rows
-constexpr int sp_threads(int nsw) { return (4 * nsw + 2) * 32; }
+// warps [0, 4*NSW): softmax (NSW per TMEM lane quadrant; they also run the epilogue when EPIW == 0), warp 4*NSW: control (TMA producer, MMA issuer,
+// TMEM owner), warp 4*NSW+1: remainder rows, then EPIW (0 or 4) dedicated epilogue warps, one per lane quadrant
+constexpr int sp_threads(int nsw, int epiw) { return (4 * nsw + 2 + epiw) * 32; }
+constexpr int SP_STG = 16 * 33;  // floats of one epilogue staging tile: 16 rows x 32 columns, padded (bank-conflict free both ways)
 constexpr int SP_QTILE = SP_QM * 128;  // bytes of one 128 x 64 fp16 SW128 tile
 
 struct SpParams {
@@ -58,6 +60,43 @@ __device__ long long sp_dbg_times[8 * 16];
 __device__ int sp_dbg_on = 0;
 __device__ __forceinline__ void sp_stamp(int tile, int slot) {
   if (sp_dbg_on && blockIdx.x == 0 && tile < 8) sp_dbg_times[tile * 16 + slot] = clock64();
+}
+// wait used by the many softmax / epilogue threads: back off between polls so that they do not take issue slots from the one control thread
+__device__ __forceinline__ void sp_wait_backoff(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(40);
+    if (++spins > (1u << 24)) { printf("dsb: attention mbarrier wait timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+  }
+}
+// epilogue of one 32-row x 32-column block of O (ov = this thread's row): scale, stage 16 rows at a time through padded shared memory, and store
+// (hi | lo) pairs with lanes 0-15 / 16-31 each covering one row's 32 columns = 64 contiguous bytes
+__device__ __forceinline__ void sp_store_block(const SpParams& p, float* stg, const uint32_t (&ov)[32], float inv, __half* obase, int row0, int lane) {
+#pragma unroll
+  for (int hr = 0; hr < 2; ++hr) {
+    if ((lane >> 4) == hr) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) stg[(lane & 15) * 33 + j] = __uint_as_float(ov[j]) * inv;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int r = it + 8 * (lane >> 4), c = 2 * (lane & 15);
+      const float x0 = stg[r * 33 + c], x1 = stg[r * 33 + c + 1];
+      const int row = row0 + hr * 16 + r;
+      if (row < p.Lq) {
+        uint32_t hi, lo;
+        const __half2 hh = __floats2half2_rn(x0, x1);
+        const __half2 ll = __floats2half2_rn(x0 - __low2float(hh), x1 - __high2float(hh));
+        hi = *reinterpret_cast<const uint32_t*>(&hh);
+        lo = *reinterpret_cast<const uint32_t*>(&ll);
+        __half* o = obase + (long long)row * p.ldo + c;
+        *reinterpret_cast<uint32_t*>(o) = hi;
+        *reinterpret_cast<uint32_t*>(o + p.o_lo_off) = lo;
+      }
+    }
+    __syncwarp();
+  }
 }
 __device__ __forceinline__ float sp_ex2(float x) {
   float y;
@@ -205,8 +244,13 @@ __device__ __forceinline__ void sp_remainder_rows(const SpParams& p, const uint8
 // NSW = softmax warps per lane quadrant, MAXC = 32-key chunks fetched per TMEM round trip.  Measured at B=16 (tools/attn_split_bench.py): the softmax
 // is bound by the MUFU / conversion pipe (288 exp2 + fp16 pair conversions per row), not by TMEM latency -- <1,3,2> (12 warps, two chunks per
 // round trip) ran 47.5 us against 45.2 us for <1,2,1>, so the simplest configuration is used.
-template <int MINB, int NSW, int MAXC>
-__global__ void __launch_bounds__(sp_threads(NSW), MINB)
+// EPIW = 4: dedicated epilogue warps, so the softmax warps go straight on to the next tile (self-attention: the chain is what bounds a head).
+// Measured with the phase timestamps (tools/attn_split_timing.py, B=16): one thread-per-row epilogue store pass cost 4 160 cycles per tile (every
+// warp-level store touched 32 different 128-byte lines) and ran on the softmax warps, serialised with the next tile; spinning waiters starved the
+// single MMA-issuing thread (65 cycles per tcgen05.mma issued).  Now: stores go through a padded shared-memory transpose (two rows = 2 x 64
+// contiguous bytes per warp-level store), waiting warps back off with nanosleep, and the epilogue has its own warps where registers allow.
+template <int MINB, int NSW, int MAXC, int EPIW>
+__global__ void __launch_bounds__(sp_threads(NSW, EPIW), MINB)
 attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_v,
                           const __grid_constant__ SpParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -218,8 +262,9 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
   uint8_t* sVh = sKl + kv_bytes;
   uint8_t* sVl = sVh + kv_bytes;
   float* s_max = reinterpret_cast<float*>(sVl + kv_bytes);   // [2 tile parities][NSW][128 rows]
-  float* s_sum = s_max + 1024;                               // same shape
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_sum + 1024);
+  float* s_sum = s_max + 2 * NSW * 128;                      // same shape
+  float* s_stage = s_sum + 2 * NSW * 128;                    // [8 epilogue slots][SP_STG]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + 8 * SP_STG);
   constexpr int CTRL = 4 * NSW;
   uint64_t* k_full = bars;
   uint64_t* q_full = bars + 1;   // [2]
@@ -239,7 +284,7 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
   if (threadIdx.x == 0) {
     mbar_init(k_full, 1); mbar_init(v_full, 1); mbar_init(rem_done, 1);
     mbar_init(&q_full[0], 1); mbar_init(&q_full[1], 1);
-    mbar_init(s_full, 1); mbar_init(p_full, 4 * NSW); mbar_init(o_full, 1); mbar_init(o_empty, 8);
+    mbar_init(s_full, 1); mbar_init(p_full, 4 * NSW); mbar_init(o_full, 1); mbar_init(o_empty, EPIW > 0 ? EPIW : 8);
     fence_barrier_init();
     prefetch_tmap(&map_q); prefetch_tmap(&map_k); prefetch_tmap(&map_v);
   }
@@ -361,8 +406,8 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
         if (lane == 0) mbar_arrive(rem_done);
       }
     }
-  } else {
-    // ------------------------------------------------------------------ softmax + epilogue warps
+  } else if (warp < CTRL) {
+    // ------------------------------------------------------------------ softmax (+ epilogue when EPIW == 0) warps
     const int quad = warp & 3, half = warp >> 2;  // half = which of the NSW column slices of this quadrant
     const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
     const int row_in_tile = quad * 32 + lane;
@@ -375,7 +420,7 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
       const int hu = tg / p.n_qt, qt = tg - hu * p.n_qt;
       const int b = (u0 + hu) / p.H, h = (u0 + hu) - b * p.H;
       const bool live = qt * SP_QM + quad * 32 < p.Lq;  // a 32-row slab entirely beyond Lq does no exp work; its rows are never stored
-      mbar_wait(s_full, tg & 1);
+      sp_wait_backoff(s_full, tg & 1);
       tc_fence_after();
       if (threadIdx.x == 0) sp_stamp(tg, 0);
       float mx = -INFINITY, sum = 0.f;
@@ -445,42 +490,61 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
       __syncwarp();
       if (threadIdx.x == 0) sp_stamp(tg, 3);
       if (lane == 0) mbar_arrive(p_full);
-      // ---- epilogue (slices 0 and 1 of every quadrant): 32 rows x 32 of the 64 output columns
+      if (EPIW > 0) continue;  // dedicated epilogue warps take it from here
+      // ---- epilogue on the softmax warps (slices 0 and 1 of every quadrant): 32 rows x 32 of the 64 output columns
       if (half >= 2) continue;
-      mbar_wait(o_full, tg & 1);
+      sp_wait_backoff(o_full, tg & 1);
       tc_fence_after();
       if (threadIdx.x == 0) sp_stamp(tg, 4);
-      const int row = qt * SP_QM + row_in_tile;
       if (live) {
         float tot = 0.f;
 #pragma unroll
         for (int j = 0; j < NSW; ++j) tot += s_sum[((tg & 1) * NSW + j) * 128 + row_in_tile];
-        const float inv = 1.0f / tot;
         uint32_t ov[32];
         tmem_ld_32x32(tO + lane_off + half * 32, ov);
         tmem_ld_wait();
-        if (row < p.Lq) {
-          __half* orow = p.o + ((long long)b * p.Lq + row) * p.ldo + h * SP_HD + half * 32;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint32_t uh[4], ul[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float x0 = __uint_as_float(ov[j + 2 * e]) * inv, x1 = __uint_as_float(ov[j + 2 * e + 1]) * inv;
-              const __half2 hh = __floats2half2_rn(x0, x1);
-              const __half2 ll = __floats2half2_rn(x0 - __low2float(hh), x1 - __high2float(hh));
-              uh[e] = *reinterpret_cast<const uint32_t*>(&hh);
-              ul[e] = *reinterpret_cast<const uint32_t*>(&ll);
-            }
-            *reinterpret_cast<uint4*>(orow + j) = make_uint4(uh[0], uh[1], uh[2], uh[3]);
-            *reinterpret_cast<uint4*>(orow + p.o_lo_off + j) = make_uint4(ul[0], ul[1], ul[2], ul[3]);
-          }
-        }
+        sp_store_block(p, s_stage + warp * SP_STG, ov, 1.0f / tot, p.o + (long long)b * p.Lq * p.ldo + h * SP_HD + half * 32, qt * SP_QM + quad * 32, lane);
       }
       tc_fence_before();
       __syncwarp();
       if (threadIdx.x == 0) sp_stamp(tg, 5);
       if (lane == 0) mbar_arrive(o_empty);
+    }
+  }
+  if (EPIW > 0 && warp >= CTRL + 2) {
+    // ------------------------------------------------------------------ dedicated epilogue warps: quadrant = warp % 4, all 64 output columns
+    const int quad = warp & 3;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    const int row_in_tile = quad * 32 + lane;
+    const int n_tiles = (u1 - u0) * p.n_qt;
+    float* stg = s_stage + (warp - (CTRL + 2)) * SP_STG;
+    for (int tg = 0; tg < n_tiles; ++tg) {
+      const int hu = tg / p.n_qt, qt = tg - hu * p.n_qt;
+      const int b = (u0 + hu) / p.H, h = (u0 + hu) - b * p.H;
+      sp_wait_backoff(o_full, tg & 1);
+      tc_fence_after();
+      if (qt * SP_QM + quad * 32 < p.Lq) {
+        float tot = 0.f;
+#pragma unroll
+        for (int j = 0; j < NSW; ++j) tot += s_sum[((tg & 1) * NSW + j) * 128 + row_in_tile];
+        const float inv = 1.0f / tot;
+        __half* obase = p.o + (long long)b * p.Lq * p.ldo + h * SP_HD;
+#pragma unroll
+        for (int cb = 0; cb < 2; ++cb) {
+          uint32_t ov[32];
+          tmem_ld_32x32(tO + lane_off + cb * 32, ov);
+          tmem_ld_wait();
+          if (cb == 1) {  // O has been read completely: the MMA thread may start the next P.V
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(o_empty);
+          }
+          sp_store_block(p, stg, ov, inv, obase + cb * 32, qt * SP_QM + quad * 32, lane);
+        }
+      } else {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_empty);
+      }
     }
   }
   tc_fence_before();
@@ -528,20 +592,21 @@ extern "C" int dsb_attention_tc_split(const void* q, long long ldq, long long q_
   if (make_operand_map(&mq, q, DSB_DTYPE_F16, q_lo_off + (long long)H * SP_HD, (long long)B * Lq, 1, ldq, 0, SP_QM)) return 3;
   if (make_operand_map(&mk, k, DSB_DTYPE_F16, k_lo_off + (long long)H * SP_HD, (long long)B * Lk, 1, ldk, 0, p.box_rows)) return 3;
   if (make_operand_map(&mv, v, DSB_DTYPE_F16, v_lo_off + (long long)H * SP_HD, (long long)B * Lk, 1, ldv, 0, p.box_rows)) return 3;
-  const bool two = cols <= 256 && 2 * SP_QTILE + 4 * p.kpad * 128 + (1024 + 1024) * 4 + 16 * 8 + 1024 <= 112 * 1024;  // two CTAs per SM fit
-  p.q_bufs = two ? 1 : 2;
-  const int smem = p.q_bufs * 2 * SP_QTILE + 4 * p.kpad * 128 + (1024 + 1024) * 4 + 16 * 8 + 1024;  // 16 words: 9 barriers + the TMEM address
+  const int fixed = (2 * 2 * 2 * 128 + 8 * SP_STG) * 4 + 16 * 8 + 1024;  // s_max + s_sum (NSW = 2), epilogue staging, 9 barriers + TMEM address, alignment
+  const bool two = cols <= 256 && 2 * SP_QTILE + 4 * p.kpad * 128 + fixed <= 112 * 1024;  // two CTAs per SM fit
+  p.q_bufs = 1;  // the next Q tile is requested as soon as S has been computed and lands long before the chain needs it
+  const int smem = p.q_bufs * 2 * SP_QTILE + 4 * p.kpad * 128 + fixed;
   static int attr_smem[2] = {0, 0};
   if (smem > attr_smem[two]) {
-    if (two) DSB_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_split_kernel<2, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    else DSB_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_split_kernel<1, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (two) DSB_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_split_kernel<2, 2, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    else DSB_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_split_kernel<1, 2, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_smem[two] = smem;
   }
   p.n_heads = B * H;
   int grid = sm_count() * (two ? 2 : 1);
   if (grid > p.n_heads) grid = p.n_heads;
-  if (two) DSB_CHECK_CUDA(launch_pdl(attention_tc_split_kernel<2, 2, 1>, dim3(grid), dim3(sp_threads(2)), smem, (cudaStream_t)stream, mq, mk, mv, p));
-  else DSB_CHECK_CUDA(launch_pdl(attention_tc_split_kernel<1, 2, 1>, dim3(grid), dim3(sp_threads(2)), smem, (cudaStream_t)stream, mq, mk, mv, p));
+  if (two) DSB_CHECK_CUDA(launch_pdl(attention_tc_split_kernel<2, 2, 1, 0>, dim3(grid), dim3(sp_threads(2, 0)), smem, (cudaStream_t)stream, mq, mk, mv, p));
+  else DSB_CHECK_CUDA(launch_pdl(attention_tc_split_kernel<1, 2, 1, 4>, dim3(grid), dim3(sp_threads(2, 4)), smem, (cudaStream_t)stream, mq, mk, mv, p));
   return 0;
 }
 
