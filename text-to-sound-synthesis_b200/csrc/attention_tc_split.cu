@@ -345,9 +345,12 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
         const int hu = tg / p.n_qt, qt = tg - hu * p.n_qt;     // head index inside the slice, query tile inside the head
         const bool last_of_head = qt == p.n_qt - 1, more_heads = u0 + hu + 1 < u1;
         const int qb = tg % nb;
+        sp_stamp(tg, 12);
         if (qt == 0) mbar_wait(k_full, hu & 1);
         mbar_wait(&q_full[qb], (tg / nb) & 1);
+        sp_stamp(tg, 13);
         tc_fence_after();
+        sp_stamp(tg, 14);
         // ---- S = Qlo Khi^T + Qhi Klo^T + Qhi Khi^T  (tcgen05.mma from one thread execute in issue order: this also follows P.V(tg-1))
         const uint32_t qh = smem_u32(sQ + qb * 2 * SP_QTILE), ql = qh + SP_QTILE;
         const uint32_t kh = smem_u32(sKh), kl = smem_u32(sKl);
@@ -523,6 +526,7 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
       const int b = (u0 + hu) / p.H, h = (u0 + hu) - b * p.H;
       sp_wait_backoff(o_full, tg & 1);
       tc_fence_after();
+      if (warp == CTRL + 2 && lane == 0) sp_stamp(tg, 6);
       if (qt * SP_QM + quad * 32 < p.Lq) {
         float tot = 0.f;
 #pragma unroll
@@ -541,6 +545,7 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
           }
           sp_store_block(p, stg, ov, inv, obase + cb * 32, qt * SP_QM + quad * 32, lane);
         }
+        if (warp == CTRL + 2 && lane == 0) sp_stamp(tg, 7);
       } else {
         __syncwarp();
         if (lane == 0) mbar_arrive(o_empty);

@@ -26,6 +26,6 @@ _lib.check(_lib.lib().dsb_attention_split_timing(0, ctypes.cast(buf, ctypes.c_vo
 t = [list(buf[i * 16:(i + 1) * 16]) for i in range(8)]
 base = min(v for row in t for v in row if v > 0)
 names = {0: "S ready (softmax w0)", 1: "pass1 max done", 2: "after bar", 3: "P written", 4: "O ready", 5: "epilogue done", 8: "ctrl: S issued", 9: "ctrl: S done/Q,K refill",
-         10: "ctrl: P ready", 11: "ctrl: PV issued"}
+         10: "ctrl: P ready", 11: "ctrl: PV issued", 12: "ctrl: loop top", 13: "ctrl: Q ready", 14: "ctrl: fenced", 6: "epiW: O ready", 7: "epiW: stored"}
 for i, row in enumerate(t[:4]):
     print(f"tile {i}: " + "  ".join(f"{names[k]}={row[k] - base}" for k in sorted(names) if row[k] > 0))
