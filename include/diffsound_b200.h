@@ -104,6 +104,9 @@ typedef struct dsb_gemm_desc {
   int tap_a2[32];
   float* amax_out;       /* optional device float (caller zero-initialises): atomic max of |value| over everything this launch stores (or would store,
                             with DSB_GEMM_NO_STORE) -- used once, at pack time, to calibrate the power-of-two activation scales of the fp16 MelGAN path */
+  int resident_w;        /* 1: narrow-channel conv form (MelGAN's 64- and 32-channel stages, vocoder/modules.py:104-126): every tap is ONE 64-deep
+                            k-block (K == 64), N <= 128; all taps' W boxes are loaded into shared memory once per CTA and stay there, consecutive taps
+                            with the same (shift, A column, operand) share one staged A box.  2-byte dtypes, K-major operands, W not batched */
 } dsb_gemm_desc;
 int dsb_gemm_ex(const dsb_gemm_desc* desc, void* stream);
 

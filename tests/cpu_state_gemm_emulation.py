@@ -54,7 +54,8 @@ def edge_pad_f16(state, T, P, d, col0, ncols, reflect=True):
 
 def gemm_desc(*, A, W, out, M, N, K, taps, lda, ldw, ldo, dtype=F16, batch=1, a_rows=0, a_cols=0, a_batch_stride=0, w_cols=0, out_batch_stride=0,
               bias=None, flags=0, alpha=1.0, split_off=0, dual_off=0, out_col_group=0, out_col_group_stride=0, A2=None, lda2=0, a2_rows=0, a2_cols=0,
-              a2_batch_stride=0, block_n=0, cta_pair=0, residual=None, ld_res=0, geo=None, amax_out=None):
+              a2_batch_stride=0, block_n=0, cta_pair=0, residual=None, ld_res=0, geo=None, amax_out=None, resident_w=0):
+    assert not resident_w or (K == 64 and N <= 128 and len(taps) <= 32 and len(taps) * ((N + 15) // 16 * 16) * 128 <= 96 * 1024), "resident_w contract"
     assert dtype == F16
     a_rows, a_cols = a_rows or M, a_cols or K
     Wm = _flat(W, torch.float16)

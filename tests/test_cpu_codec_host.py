@@ -31,8 +31,8 @@ def emulated_ops(monkeypatch):
     monkeypatch.setattr(packing.torch, "zeros", zeros)
     real_init = packing.PackedConv.__init__
 
-    def init(self, blocks, bias):
-        real_init(self, blocks, bias)
+    def init(self, blocks, bias, **kw):
+        real_init(self, blocks, bias, **kw)
         E.track(self.w)
 
     monkeypatch.setattr(packing.PackedConv, "__init__", init)

@@ -175,3 +175,82 @@ def test_gemm_two_operands_dual_output_and_column_groups(G):
     assert float((got - refq).abs().max()) / float(refq.abs().max()) < 3e-6
     gact = Sn[:, P:P + r_ * T, 2 * Cout:3 * Cout].double() + Sn[:, P:P + r_ * T, 3 * Cout:].double()
     assert float((gact - torch.nn.functional.leaky_relu(refq, 0.2)).abs().max()) / float(refq.abs().max()) < 3e-6
+
+
+@pytest.mark.parametrize("C,T,B", [(64, 30000, 2), (32, 1500, 2), (32, 40000, 3), (24, 333, 1)])
+def test_resident_w_conv_kernel_matches_generic_and_fp64(G, C, T, B):
+    """dsb_gemm_ex(resident_w=1): the narrow-channel MelGAN form (all W boxes resident in shared memory, shared A boxes, N <= 128) must give the
+    SAME bits as the generic kernel on the same tap list, and fp32-class agreement with fp64 -- for a dilated 3-tap conv (LeakyReLU + pair output,
+    32-channel rows folded to [hi | lo] . [Wh | Wh], [Wl | 0]), the in-place two-operand ResnetBlock tail (dual output), and a 7-tap N = 1 conv
+    with tanh into fp32 (reference vocoder/modules.py:72-85, :121-126)."""
+    ops = G.ops
+    from diffsound_b200.packing import PackedConv
+    P, d = 9, 3
+    Cs = (C + 7) // 8 * 8
+    ld = 4 * Cs
+    fold = Cs == 32
+    g = torch.Generator(device="cuda").manual_seed(C + T)
+    x = torch.randn(B, T + 2 * P, C, device="cuda", generator=g)
+    S0 = torch.zeros(B, T + 2 * P, ld, dtype=torch.float16, device="cuda")
+    pr = ops.split_f16(x.view(-1, C)).view(B, T + 2 * P, 2 * C)
+    S0[..., 2 * Cs:2 * Cs + C], S0[..., 3 * Cs:3 * Cs + C] = pr[..., :C], pr[..., C:]  # act pair (pad rows filled too: the "reflected" halo)
+    S0[..., :C], S0[..., Cs:Cs + C] = pr[..., :C], pr[..., C:]                          # raw pair
+    xv = pr[..., :C].double() + pr[..., C:].double()
+    wd = [torch.randn(C, C, device="cuda", generator=g) * 0.1 for _ in range(3)]
+    bias = torch.randn(C, device="cuda", generator=g)
+    g1 = PackedConv(wd, bias, fold=fold)
+
+    def wval(cv, j, cin):
+        return (cv.w[:, j * 2 * cv.Kp:j * 2 * cv.Kp + cin].double() + cv.w[:, j * 2 * cv.Kp + cv.Kp:j * 2 * cv.Kp + cv.Kp + cin].double()) * cv.alpha
+
+    spatial = [(P + (j - 1) * d, 2 * Cs, 3 * Cs, 0) for j in range(3)]
+    t64 = g1.taps64(spatial)
+    assert g1.resident_ok(len(t64))
+    outs = []
+    for res in (0, 1):
+        Y = torch.zeros(B, T, 2 * Cs, dtype=torch.float16, device="cuda")
+        ops.gemm_desc(A=S0.data_ptr(), W=g1.w.data_ptr(), out=Y.data_ptr(), M=T, N=C, K=64, batch=B, taps=t64, a_rows=T + 2 * P, a_cols=ld, lda=ld,
+                      a_batch_stride=(T + 2 * P) * ld, ldw=g1.w.shape[1], w_cols=g1.w.shape[1], ldo=2 * Cs, out_batch_stride=T * 2 * Cs, bias=g1.bias,
+                      flags=ops.OUT_F16_SPLIT | ops.LRELU, alpha=g1.alpha, split_off=Cs, resident_w=res)
+        outs.append(Y)
+    assert torch.equal(outs[0], outs[1])
+    ref = sum(xv[:, P + (j - 1) * d:P + (j - 1) * d + T] @ wval(g1, j, C).T for j in range(3)) + bias.double()
+    ref = torch.nn.functional.leaky_relu(ref, 0.2)
+    got = outs[1][..., :C].double() + outs[1][..., Cs:Cs + C].double()
+    assert float((got - ref).abs().max()) / float(ref.abs().max()) < 3e-6
+    # in-place two-operand tail with dual output
+    ws, w1 = torch.randn(C, C, device="cuda", generator=g) * 0.1, torch.randn(C, C, device="cuda", generator=g) * 0.1
+    g2 = PackedConv([ws, w1], bias, fold=fold)
+    t2 = g2.taps64([(P, 0, Cs, 0), (0, 0, Cs, 1)])
+    Yin = outs[1]
+    res_states = []
+    for res in (0, 1):
+        S = S0.clone()
+        ops.gemm_desc(A=S.data_ptr(), A2=Yin.data_ptr(), W=g2.w.data_ptr(), out=S.data_ptr() + 2 * P * ld, M=T, N=C, K=64, batch=B, taps=t2,
+                      a_rows=T + 2 * P, a_cols=ld, lda=ld, a_batch_stride=(T + 2 * P) * ld, lda2=2 * Cs, a2_rows=T, a2_cols=2 * Cs, a2_batch_stride=T * 2 * Cs,
+                      ldw=g2.w.shape[1], w_cols=g2.w.shape[1], ldo=ld, out_batch_stride=(T + 2 * P) * ld, bias=g2.bias,
+                      flags=ops.OUT_F16_SPLIT | ops.DUAL_LRELU, alpha=g2.alpha, split_off=Cs, dual_off=2 * Cs, resident_w=res)
+        res_states.append(S)
+    assert torch.equal(res_states[0], res_states[1])
+    ref2 = xv[:, P:P + T] @ wval(g2, 0, C).T + got @ wval(g2, 1, C).T + bias.double()
+    S = res_states[1]
+    raw = S[:, P:P + T, :C].double() + S[:, P:P + T, Cs:Cs + C].double()
+    act = S[:, P:P + T, 2 * Cs:2 * Cs + C].double() + S[:, P:P + T, 3 * Cs:3 * Cs + C].double()
+    sc = float(ref2.abs().max())
+    assert float((raw - ref2).abs().max()) / sc < 3e-6
+    assert float((act - torch.nn.functional.leaky_relu(ref2, 0.2)).abs().max()) / sc < 3e-6
+    assert torch.equal(S[:, :P], S0[:, :P]) and torch.equal(S[:, P + T:], S0[:, P + T:])
+    # 7 taps, N = 1, tanh, fp32 output
+    wl = [torch.randn(1, C, device="cuda", generator=g) * 0.05 for _ in range(7)]
+    cl = PackedConv(wl, torch.randn(1, device="cuda", generator=g) * 0.1, fold=fold)
+    t7 = cl.taps64([(P - 3 + j, 2 * Cs, 3 * Cs, 0) for j in range(7)])
+    wavs = []
+    for res in (0, 1):
+        wav = torch.zeros(B, T, 1, dtype=torch.float32, device="cuda")
+        ops.gemm_desc(A=S0.data_ptr(), W=cl.w.data_ptr(), out=wav.data_ptr(), M=T, N=1, K=64, batch=B, taps=t7, a_rows=T + 2 * P, a_cols=ld, lda=ld,
+                      a_batch_stride=(T + 2 * P) * ld, ldw=cl.w.shape[1], w_cols=cl.w.shape[1], ldo=1, out_batch_stride=T, bias=cl.bias, flags=ops.TANH,
+                      alpha=cl.alpha, resident_w=res)
+        wavs.append(wav)
+    assert torch.equal(wavs[0], wavs[1])
+    ref7 = torch.tanh(sum(xv[:, P - 3 + j:P - 3 + j + T] @ wval(cl, j, C).T for j in range(7)) + cl.bias.double())
+    assert float((wavs[1].double() - ref7).abs().max()) < 1e-5  # absolute, after tanh: pre-activations reach ~3 over 7 x C products

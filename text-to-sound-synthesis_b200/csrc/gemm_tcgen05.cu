@@ -46,6 +46,8 @@ struct GemmParams {
   int tap_acol[MAX_TAPS];
   int tap_wcol[MAX_TAPS];  // W column offset per tap (default tap * Kc)
   unsigned tap_a2_mask;    // bit i set: tap i reads the SECOND A tensor map (a fused GEMM over two activation buffers)
+  unsigned tap_share_mask; // resident-W kernel: bit i set: tap i multiplies the A box tap i-1 staged (same shift / column / operand)
+  int n_pad;               // resident-W kernel: rows of one W box = the MMA's N (N rounded up to 16)
   long long split_off;     // DSB_GEMM_OUT_F16_SPLIT: offset of the lo half inside an output row
   long long dual_off;      // DSB_GEMM_DUAL_LRELU: offset of the LeakyReLU(0.2) copy (hi at +dual_off, lo at +dual_off+split_off)
   int ocg, ocg_stride;     // output column groups: logical column n lives at (n / ocg) * ocg_stride + n % ocg (0 = plain)
@@ -769,6 +771,149 @@ gemm_f16x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   }
 }
 
+// ------------------------------------------------------------------------------------------ resident-W narrow-channel kernel
+// MelGAN's last stages are convs over 32 / 64 channels and millions of time rows (reference vocoder/modules.py:104-126): the generic kernel
+// re-streams every tap's W box and a 64-column A box per (tap, pass) for each 128-row tile -- 288 KB of L2 -> smem traffic per tile of
+// 16 KB of state, and measures L2-bound (7.2 TB/s, 0.12 of the HBM roofline).  Here each tap is one 64-deep k-block; ALL taps' W boxes
+// (num_taps x n_pad rows x 128 B, <= 96 KB) are loaded once per CTA and stay in shared memory, and consecutive taps that read the same A box
+// (the hi*hi / hi*lo passes of one spatial tap, or the folded [hi | lo] . [Wh | Wh], [hi | lo] . [Wl | 0] pair of a 32-channel row) share one
+// staged copy.  MMA N = n_pad (16..128), accumulators 2 x 128 TMEM columns, epilogue shared with the generic kernel.
+struct ResidentSmem {
+  static constexpr int A_BYTES = BLOCK_M * ROW_BYTES;
+  static constexpr int STAGES = 6;
+  static constexpr int W_MAX = 96 * 1024;
+  static constexpr int FIXED = STAGES * A_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 8 * 32 * 32 * 4 /*epilogue transpose tiles*/;
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+conv_resident_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ CUtensorMap tmap_b,
+                     const __grid_constant__ GemmParams p) {
+  using S = ResidentSmem;
+  constexpr int STAGES = S::STAGES;
+  constexpr uint32_t ACC_COLS = 128, TMEM_COLS = 2 * ACC_COLS;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int wbox = p.n_pad * ROW_BYTES;
+  uint8_t* w_smem = smem + STAGES * S::A_BYTES;
+  uint8_t* tail = w_smem + p.num_taps * wbox;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* w_bar = tmem_empty + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_bar + 1);
+  float* epi_smem = reinterpret_cast<float*>(tail + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.tiles_m * p.batch;
+  // N <= 32 is a single 32-column chunk: the two epilogue warps of a TMEM lane quadrant then alternate TILES instead of chunks
+  const bool alt_tiles = p.N <= 32;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_a2);
+    prefetch_tmap(&tmap_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], alt_tiles ? 4 : 8);
+    }
+    mbar_init(w_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_bar, static_cast<uint32_t>(p.num_taps * wbox));
+      for (int t = 0; t < p.num_taps; ++t) tma_load_3d(&tmap_b, w_bar, w_smem + t * wbox, p.tap_wcol[t], 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile % p.tiles_m;
+        const int b = tile / p.tiles_m;
+        for (int t = 0; t < p.num_taps; ++t) {
+          if ((p.tap_share_mask >> t) & 1u) continue;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], S::A_BYTES);
+          tma_load_3d(((p.tap_a2_mask >> t) & 1u) ? &tmap_a2 : &tmap_a, &full_bar[stage], smem + stage * S::A_BYTES, p.tap_acol[t],
+                      m_blk * BLOCK_M + p.tap_shift[t], b);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(KIND, BLOCK_M, p.n_pad);
+      const uint32_t w_addr = smem_u32(w_smem);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      mbar_wait(w_bar, 0);
+      tc_fence_after();
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * ACC_COLS;
+        for (int t = 0; t < p.num_taps; ++t) {
+          if (!((p.tap_share_mask >> t) & 1u)) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+          }
+          const uint64_t da = make_sw128_kmajor_desc(smem_u32(smem + stage * S::A_BYTES));
+          const uint64_t db = make_sw128_kmajor_desc(w_addr + t * wbox);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma<false>(d_tmem, da + 2 * k, db + 2 * k, idesc, (t | k) != 0 ? 1u : 0u);
+          if (t + 1 == p.num_taps || !((p.tap_share_mask >> (t + 1)) & 1u)) {
+            umma_commit(&empty_bar[stage]);  // this A box has no further reader
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+        umma_commit(&tmem_full[as]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    float* sw = epi_smem + (warp - 2) * (32 * 32);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      if (alt_tiles && as != half) continue;
+      const int m_blk = tile % p.tiles_m;
+      const int b = tile / p.tiles_m;
+      const uint32_t aphase = (it >> 1) & 1;
+      epilogue_tile<128>(p, sw, tmem_base + as * ACC_COLS, &tmem_full[as], aphase, m_blk * BLOCK_M + q * 32, 0, b, q, alt_tiles ? 0 : half, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -920,8 +1065,39 @@ extern "C" int dsb_gemm_ex(const dsb_gemm_desc* d, void* stream) {
   DSB_REQUIRE(!any_mn || (kind != DSB_DTYPE_TF32 && d->num_taps == 1 && d->tap_shift[0] == 0 && d->tap_acol[0] == 0),
               "dsb_gemm_ex: MN-major operands need a 2-byte dtype and a single unshifted tap");
 
-  // tile-N choice: fewest waves, then the wider tile (less A re-read)
   const int sms = sm_count();
+  static const bool resident_ok = [] { const char* e = getenv("DSB_CONV_RESIDENT"); return !(e && e[0] == '0'); }();  // A/B switch
+  if (d->resident_w && resident_ok) {
+    DSB_REQUIRE(kind != DSB_DTYPE_TF32 && !any_mn && !p.b_batched && d->K == 64 && d->N <= 128 && d->use_tap_wcol,
+                "dsb_gemm_ex: resident_w needs a 2-byte dtype, K-major operands, K == 64 per tap, N <= 128, explicit tap_wcol and an unbatched W");
+    p.n_pad = (d->N + 15) / 16 * 16;
+    const int w_bytes = d->num_taps * p.n_pad * ROW_BYTES;
+    DSB_REQUIRE(w_bytes <= ResidentSmem::W_MAX, "dsb_gemm_ex: resident_w: %d taps x %d rows do not fit the %d KB weight area", d->num_taps, p.n_pad, ResidentSmem::W_MAX >> 10);
+    p.tap_share_mask = 0;
+    for (int i = 1; i < d->num_taps; ++i)
+      if (p.tap_shift[i] == p.tap_shift[i - 1] && p.tap_acol[i] == p.tap_acol[i - 1] && (((p.tap_a2_mask >> i) ^ (p.tap_a2_mask >> (i - 1))) & 1u) == 0)
+        p.tap_share_mask |= 1u << i;
+    p.tiles_n = 1;
+    CUtensorMap ma, mb;
+    if (make_operand_map(&ma, d->A, kind, d->a_cols > 0 ? d->a_cols : d->K, d->a_rows > 0 ? d->a_rows : d->M, d->batch, d->lda, d->a_batch_stride, BLOCK_M)) return 3;
+    if (make_operand_map(&mb, d->W, kind, d->w_cols > 0 ? d->w_cols : (long long)d->K * d->num_taps, d->N, 1, d->ldw, 0, p.n_pad)) return 3;
+    CUtensorMap ma2 = ma;
+    if (p.tap_a2_mask &&
+        make_operand_map(&ma2, d->A2, kind, d->a2_cols > 0 ? d->a2_cols : d->K, d->a2_rows > 0 ? d->a2_rows : d->M, d->batch, d->lda2, d->a2_batch_stride, BLOCK_M))
+      return 3;
+    const int smem_bytes = ResidentSmem::FIXED + w_bytes;
+    auto kern = kind == DSB_DTYPE_BF16 ? conv_resident_kernel<DSB_DTYPE_BF16> : conv_resident_kernel<DSB_DTYPE_F16>;
+    static bool attr_done[2] = {false, false};
+    if (!attr_done[kind == DSB_DTYPE_BF16]) {
+      DSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ResidentSmem::FIXED + ResidentSmem::W_MAX));
+      attr_done[kind == DSB_DTYPE_BF16] = true;
+    }
+    const int tiles = p.tiles_m * p.batch;
+    const int cap = d->max_ctas > 0 ? d->max_ctas : sms;
+    DSB_CHECK_CUDA(launch_pdl(kern, dim3(tiles < cap ? tiles : cap), dim3(GEMM_THREADS), smem_bytes, reinterpret_cast<cudaStream_t>(stream), ma, ma2, mb, p));
+    return 0;
+  }
+  // tile-N choice: fewest waves, then the wider tile (less A re-read)
   int block_n = d->block_n;
   if (block_n == 0) {
     static const int forced = [] { const char* e = getenv("DSB_GEMM_BLOCK_N"); return e ? atoi(e) : 0; }();  // A/B switch for tuning runs

@@ -89,14 +89,14 @@ class VocoderEngine:
                 rb = mods[i]
                 wd, w1, ws = _fold(rb.block[2]), _fold(rb.block[4]), _fold(rb.shortcut)
                 # g2 (shortcut | 1x1) is packed during calibration: its 1x1 half absorbs the ratio of the two operands' activation scales
-                st["res"].append(dict(d=rb.dilation, g1=_PackedConv([wd[:, :, j] for j in range(3)], rb.block[2].bias), g2=None,
+                st["res"].append(dict(d=rb.dilation, g1=_PackedConv([wd[:, :, j] for j in range(3)], rb.block[2].bias, fold=_c8(cout) == 32), g2=None,
                                       ws=ws[:, :, 0].contiguous(), w1=w1[:, :, 0].contiguous(),
                                       b2=(rb.shortcut.bias.detach() + rb.block[4].bias.detach()).float()))
                 i += 1
             self.stages.append(st)
         last = mods[i + 2]
         wl = _fold(last)  # (1, ngf, 7)
-        self.last = _PackedConv([wl[:, :, j] for j in range(wl.shape[2])], last.bias)
+        self.last = _PackedConv([wl[:, :, j] for j in range(wl.shape[2])], last.bias, fold=_c8(wl.shape[1]) == 32)
         self.c0 = w0.shape[0]
         self._graphs.clear()
         self._bufs.clear()
@@ -144,8 +144,8 @@ class VocoderEngine:
         if calibrate:
             self._amax.zero_()
             for cv, kw in calls:
-                ops.gemm_desc(**dict(kw, flags=kw["flags"] | ops.NO_STORE), W=cv.w.data_ptr(), ldw=cv.w.shape[1], w_cols=cv.w.shape[1], K=cv.Kp,
-                              alpha=cv.alpha / sig_in, bias=cv.bias, amax_out=self._amax)
+                ops.gemm_desc(**dict(kw, flags=kw["flags"] | ops.NO_STORE), W=cv.w.data_ptr(), ldw=cv.w.shape[1], w_cols=cv.w.shape[1],
+                              K=64 if kw.get("resident_w") else cv.Kp, alpha=cv.alpha / sig_in, bias=cv.bias, amax_out=self._amax)
             m = float(self._amax.item())
             if not (m > 0.0 and math.isfinite(m)):
                 raise RuntimeError(f"MelGAN calibration: launch site {key} produced amax = {m}")
@@ -153,8 +153,17 @@ class VocoderEngine:
             self.bias_s[key] = [(cv.bias * self.sig[key]).contiguous() for cv, _ in calls]
         so = self.sig[key]
         for (cv, kw), bs in zip(calls, self.bias_s[key]):
-            ops.gemm_desc(**kw, W=cv.w.data_ptr(), ldw=cv.w.shape[1], w_cols=cv.w.shape[1], K=cv.Kp, alpha=cv.alpha * so / sig_in, bias=bs)
+            ops.gemm_desc(**kw, W=cv.w.data_ptr(), ldw=cv.w.shape[1], w_cols=cv.w.shape[1], K=64 if kw.get("resident_w") else cv.Kp,
+                          alpha=cv.alpha * so / sig_in, bias=bs)
         return so
+
+    @staticmethod
+    def _taps(cv, spatial):
+        """(tap list, resident_w): narrow layers (N <= 128, all W boxes <= 96 KB) run on dsb_gemm_ex's resident-W kernel, whose taps are 64-deep."""
+        t64 = cv.taps64(spatial)
+        if cv.resident_ok(len(t64)):
+            return dict(taps=t64, resident_w=1)
+        return dict(taps=cv.taps(spatial), resident_w=0)
 
     def _forward(self, mel: torch.Tensor, calibrate: bool = False) -> torch.Tensor:
         B, Cm, T = mel.shape
@@ -183,7 +192,7 @@ class VocoderEngine:
                 ops.edge_pad_f16(Sin, Tin, P, 1, 2 * Ci, 2 * Ci, reflect=False)
                 n += 1
             sig = self._scaled(("convT", si), sig, calibrate, [(cv, dict(
-                A=Sin.data_ptr(), out=S.data_ptr() + 2 * (P * ld + col0), M=Tin, N=cv.N, batch=B, taps=cv.taps([(sh, 2 * Ci, 3 * Ci, 0) for sh in shifts]),
+                A=Sin.data_ptr(), out=S.data_ptr() + 2 * (P * ld + col0), M=Tin, N=cv.N, batch=B, **self._taps(cv, [(sh, 2 * Ci, 3 * Ci, 0) for sh in shifts]),
                 a_rows=Tin + 2 * P, a_cols=ldin, lda=ldin, a_batch_stride=(Tin + 2 * P) * ldin, ldo=r * ld, out_batch_stride=(T + 2 * P) * ld,
                 flags=SPLIT | DUAL, split_off=Co, dual_off=2 * Co, out_col_group=Cout, out_col_group_stride=ld))
                 for cv, shifts, col0 in ((st["ca"], (P - 1, P), 0), (st["cb"], (P, P + 1), half * ld))])
@@ -192,14 +201,14 @@ class VocoderEngine:
                 d, g1 = rb["d"], rb["g1"]
                 ops.edge_pad_f16(S, T, P, d, 2 * Co, 2 * Co, reflect=True)
                 sig_y = self._scaled(("g1", si, ri), sig, calibrate, [(g1, dict(
-                    A=S.data_ptr(), out=Y.data_ptr(), M=T, N=Cout, batch=B, taps=g1.taps([(P + (j - 1) * d, 2 * Co, 3 * Co, 0) for j in range(3)]),
+                    A=S.data_ptr(), out=Y.data_ptr(), M=T, N=Cout, batch=B, **self._taps(g1, [(P + (j - 1) * d, 2 * Co, 3 * Co, 0) for j in range(3)]),
                     a_rows=T + 2 * P, a_cols=ld, lda=ld, a_batch_stride=(T + 2 * P) * ld, ldo=2 * Co, out_batch_stride=T * 2 * Co,
                     flags=SPLIT | LRELU, split_off=Co))])
                 if calibrate:  # x is stored at sigma, y at sigma_y: the 1x1 half of the fused weight absorbs sigma / sigma_y (a power of two)
-                    rb["g2"] = _PackedConv([rb["ws"], rb["w1"] * (sig / sig_y)], rb["b2"])
+                    rb["g2"] = _PackedConv([rb["ws"], rb["w1"] * (sig / sig_y)], rb["b2"], fold=Co == 32)
                 g2 = rb["g2"]
                 sig = self._scaled(("g2", si, ri), sig, calibrate, [(g2, dict(
-                    A=S.data_ptr(), A2=Y.data_ptr(), out=S.data_ptr() + 2 * (P * ld), M=T, N=Cout, batch=B, taps=g2.taps([(P, 0, Co, 0), (0, 0, Co, 1)]),
+                    A=S.data_ptr(), A2=Y.data_ptr(), out=S.data_ptr() + 2 * (P * ld), M=T, N=Cout, batch=B, **self._taps(g2, [(P, 0, Co, 0), (0, 0, Co, 1)]),
                     a_rows=T + 2 * P, a_cols=ld, lda=ld, a_batch_stride=(T + 2 * P) * ld, lda2=2 * Co, a2_rows=T, a2_cols=2 * Co,
                     a2_batch_stride=T * 2 * Co, ldo=ld, out_batch_stride=(T + 2 * P) * ld, flags=SPLIT | DUAL, split_off=Co, dual_off=2 * Co,
                     # in place: ONE N tile must cover all Cout columns (a second N tile would re-read rows the first one overwrote)
@@ -210,8 +219,9 @@ class VocoderEngine:
         cv = self.last
         ops.edge_pad_f16(S, T, P, 3, 2 * C, 2 * C, reflect=True)
         wav = torch.empty(B, T, 1, dtype=torch.float32, device=mel.device)
-        ops.gemm_desc(A=S.data_ptr(), W=cv.w.data_ptr(), out=wav.data_ptr(), M=T, N=1, K=cv.Kp, batch=B,
-                      taps=cv.taps([(P - 3 + j, 2 * C, 3 * C, 0) for j in range(7)]), a_rows=T + 2 * P, a_cols=4 * C, lda=4 * C, a_batch_stride=(T + 2 * P) * 4 * C,
+        tp = self._taps(cv, [(P - 3 + j, 2 * C, 3 * C, 0) for j in range(7)])
+        ops.gemm_desc(A=S.data_ptr(), W=cv.w.data_ptr(), out=wav.data_ptr(), M=T, N=1, K=64 if tp["resident_w"] else cv.Kp, batch=B, **tp,
+                      a_rows=T + 2 * P, a_cols=4 * C, lda=4 * C, a_batch_stride=(T + 2 * P) * 4 * C,
                       ldw=cv.w.shape[1], w_cols=cv.w.shape[1], ldo=1, out_batch_stride=T, bias=cv.bias, flags=TANH, alpha=cv.alpha / sig)
         self.launches = n + 2
         return wav.view(B, 1, T)
