@@ -275,6 +275,12 @@ int dsb_lrelu_pad(const float* in, float* out, int B, int T, int C, int pad, flo
 int dsb_mel_pack_f16(const float* mel, void* out_f16, int B, int Cm, int T, int pad, int Kp, void* stream);
 int dsb_edge_pad_f16(void* state_f16, long long ld, long long batch_stride, int B, int T, int P, int d, int col0, int ncols, int reflect,
                      void* stream);
+/* MelGAN output layer on the FMA pipe (reference vocoder/modules.py:121-126: LeakyReLU -> ReflectionPad1d(3) -> Conv1d(ngf, 1, kernel 7) -> tanh):
+   out[b, t] = tanh(scale * sum_{j < kt, c < cs} x[b, row0 + t + j, c] * w[j, c] + bias[0]),  x = hi + lo of the fp16 pair stored at columns
+   [col0, col0 + cs) and [col0 + cs, col0 + 2 cs) of state rows (ld halves per row); the pad rows already hold the reflected samples
+   (dsb_edge_pad_f16).  w (kt, cs) fp32, out (B, T) fp32.  Built for cs == 32, kt == 7; other shapes go through dsb_gemm_ex. */
+int dsb_conv_out_pair(const void* state, long long ld, long long batch_stride, int B, int T, int row0, int col0, int cs, int kt, const float* w,
+                      const float* bias, float scale, float* out, void* stream);
 
 
 /* ---------------------------------------------------------------------------------------------------------------

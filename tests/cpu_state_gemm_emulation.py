@@ -52,6 +52,19 @@ def edge_pad_f16(state, T, P, d, col0, ncols, reflect=True):
         state[:, P + T - 1 + j, col0:col0 + ncols] = state[:, P + T - 1 - j, col0:col0 + ncols] if reflect else 0
 
 
+def conv_out_pair(state, T, row0, col0, w, bias, scale, out=None):
+    """dsb_conv_out_pair's contract: tanh(scale * sum_j x[row0 + t + j] . w[j] + bias), x = hi + lo of the pair columns."""
+    B = state.shape[0]
+    kt, cs = w.shape
+    x = state[:, :, col0:col0 + cs].double() + state[:, :, col0 + cs:col0 + 2 * cs].double()
+    acc = sum(x[:, row0 + j:row0 + j + T] @ w[j].double() for j in range(kt))
+    y = torch.tanh(acc * scale + bias.double()[0]).float()
+    if out is None:
+        return y
+    out.view(B, T).copy_(y)
+    return out
+
+
 def gemm_desc(*, A, W, out, M, N, K, taps, lda, ldw, ldo, dtype=F16, batch=1, a_rows=0, a_cols=0, a_batch_stride=0, w_cols=0, out_batch_stride=0,
               bias=None, flags=0, alpha=1.0, split_off=0, dual_off=0, out_col_group=0, out_col_group_stride=0, A2=None, lda2=0, a2_rows=0, a2_cols=0,
               a2_batch_stride=0, block_n=0, cta_pair=0, residual=None, ld_res=0, geo=None, amax_out=None, resident_w=0):

@@ -15,7 +15,7 @@ def emulated_ops(monkeypatch):
     import _pkg
     _pkg.load()
     from diffsound_b200 import ops, packing, vocoder_engine
-    for name in ("gemm_desc", "mel_pack_f16", "edge_pad_f16", "split_f16"):
+    for name in ("gemm_desc", "mel_pack_f16", "edge_pad_f16", "split_f16", "conv_out_pair"):
         monkeypatch.setattr(ops, name, getattr(E, name))
     E._LIVE.clear()
     real_zeros, real_empty = torch.zeros, torch.empty

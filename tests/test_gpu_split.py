@@ -211,7 +211,7 @@ def test_resident_w_conv_kernel_matches_generic_and_fp64(G, C, T, B):
         Y = torch.zeros(B, T, 2 * Cs, dtype=torch.float16, device="cuda")
         ops.gemm_desc(A=S0.data_ptr(), W=g1.w.data_ptr(), out=Y.data_ptr(), M=T, N=C, K=64, batch=B, taps=t64, a_rows=T + 2 * P, a_cols=ld, lda=ld,
                       a_batch_stride=(T + 2 * P) * ld, ldw=g1.w.shape[1], w_cols=g1.w.shape[1], ldo=2 * Cs, out_batch_stride=T * 2 * Cs, bias=g1.bias,
-                      flags=ops.OUT_F16_SPLIT | ops.LRELU, alpha=g1.alpha, split_off=Cs, resident_w=res)
+                      flags=ops.OUT_F16_SPLIT | ops.LRELU, alpha=g1.alpha, split_off=Cs, resident_w=res, block_n=0 if res else 128)  # block_n: the generic kernel, not the fused pair form
         outs.append(Y)
     assert torch.equal(outs[0], outs[1])
     ref = sum(xv[:, P + (j - 1) * d:P + (j - 1) * d + T] @ wval(g1, j, C).T for j in range(3)) + bias.double()
@@ -249,8 +249,30 @@ def test_resident_w_conv_kernel_matches_generic_and_fp64(G, C, T, B):
         wav = torch.zeros(B, T, 1, dtype=torch.float32, device="cuda")
         ops.gemm_desc(A=S0.data_ptr(), W=cl.w.data_ptr(), out=wav.data_ptr(), M=T, N=1, K=64, batch=B, taps=t7, a_rows=T + 2 * P, a_cols=ld, lda=ld,
                       a_batch_stride=(T + 2 * P) * ld, ldw=cl.w.shape[1], w_cols=cl.w.shape[1], ldo=1, out_batch_stride=T, bias=cl.bias, flags=ops.TANH,
-                      alpha=cl.alpha, resident_w=res)
+                      alpha=cl.alpha, resident_w=res, block_n=0 if res else 128)
         wavs.append(wav)
     assert torch.equal(wavs[0], wavs[1])
     ref7 = torch.tanh(sum(xv[:, P - 3 + j:P - 3 + j + T] @ wval(cl, j, C).T for j in range(7)) + cl.bias.double())
     assert float((wavs[1].double() - ref7).abs().max()) < 1e-5  # absolute, after tanh: pre-activations reach ~3 over 7 x C products
+
+
+@pytest.mark.parametrize("B,T", [(2, 5000), (1, 515), (3, 217088 // 8)])
+def test_conv_out_pair_matches_fp64(G, B, T):
+    """dsb_conv_out_pair: MelGAN's Conv1d(32 -> 1, k=7) + tanh on the FMA pipe, off the activated (hi | lo) pair columns of a state buffer
+    (reference vocoder/modules.py:121-126), vs fp64; also against the tensor-core form of the same layer (dsb_gemm_ex, N = 1)."""
+    ops = G.ops
+    P, C = 9, 32
+    g = torch.Generator(device="cuda").manual_seed(T)
+    x = torch.randn(B, T + 2 * P, C, device="cuda", generator=g) * 40.0
+    S = torch.zeros(B, T + 2 * P, 4 * C, dtype=torch.float16, device="cuda")
+    pr = ops.split_f16(x.view(-1, C)).view(B, T + 2 * P, 2 * C)
+    S[..., 2 * C:] = pr
+    S[..., :2 * C] = 7.0  # raw columns: must not be read
+    xv = pr[..., :C].double() + pr[..., C:].double()
+    w = torch.randn(7, C, device="cuda", generator=g) * 0.01
+    bias = torch.randn(1, device="cuda", generator=g) * 0.1
+    scale = 2.0 ** -3
+    out = ops.conv_out_pair(S, T, P - 3, 2 * C, w, bias, scale)
+    ref = torch.tanh(sum(xv[:, P - 3 + j:P - 3 + j + T] @ w[j].double() for j in range(7)) * scale + bias.double())
+    assert out.shape == (B, T)
+    assert float((out.double() - ref).abs().max()) < 2e-6

@@ -59,6 +59,7 @@ SIGNATURES = {
     "dsb_attention_split_timing": [c_i, c_vp],
     "dsb_mel_pack_f16": [c_vp, c_vp] + [c_i] * 5 + [c_vp],
     "dsb_edge_pad_f16": [c_vp, c_ll, c_ll] + [c_i] * 7 + [c_vp],
+    "dsb_conv_out_pair": [c_vp, c_ll, c_ll] + [c_i] * 6 + [c_vp, c_vp, c_f, c_vp, c_vp],
     "dsb_attention_f16": [c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_i, c_i, c_i, c_i, c_f, c_i, c_vp],
     "dsb_attention_tc2": [c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_i, c_i, c_i, c_i, c_f, c_vp],
     "dsb_attention_tc": [c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_vp, c_ll, c_i, c_i, c_i, c_i, c_f, c_vp],

@@ -30,7 +30,7 @@ int sm_count();
 // 3-D TMA map (K, rows, batch) over a K-contiguous matrix; box = (128 bytes of K, box_rows, 1); SWIZZLE_128B; OOB reads give zeros.
 // kind: DSB_DTYPE_TF32 (fp32 elements) / BF16 / F16.  Returns non-zero and sets the error string on failure.  (gemm_tcgen05.cu)
 int make_operand_map(CUtensorMap* map, const void* ptr, int kind, long long kdim, long long rows, long long batch, long long ld_elems,
-                     long long bstride_elems, int box_rows);
+                     long long bstride_elems, int box_rows, int l2_promo_128 = 0);
 bool pdl_enabled();  // programmatic dependent launch (env DSB_PDL=0 disables)
 
 // Launch with the programmatic-stream-serialization attribute: the grid may be scheduled while its predecessor drains; the

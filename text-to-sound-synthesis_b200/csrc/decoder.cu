@@ -90,16 +90,47 @@ groupnorm_stats_kernel(const float* __restrict__ x, double* __restrict__ stats, 
   const int rs = threadIdx.x / c4n;
   if (rs < tpr) {
     float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int r = r0 + rs; r < r1; r += tpr) {
+    int r = r0 + rs;
+    for (; r + 3 * tpr < r1; r += 4 * tpr) {  // four independent 16-byte loads in flight
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(xb + (long long)(r + u * tpr) * C + c4 * 4);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        s[0] += v[u].x; s[1] += v[u].y; s[2] += v[u].z; s[3] += v[u].w;
+        q[0] += v[u].x * v[u].x; q[1] += v[u].y * v[u].y; q[2] += v[u].z * v[u].z; q[3] += v[u].w * v[u].w;
+      }
+    }
+    for (; r < r1; r += tpr) {
       const float4 v = *reinterpret_cast<const float4*>(xb + (long long)r * C + c4 * 4);
       s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
       q[0] += v.x * v.x; q[1] += v.y * v.y; q[2] += v.z * v.z; q[3] += v.w * v.w;
     }
+    if (cg % 4 == 0 && blockDim.x == 256 && 256 % c4n == 0) {
+      // a thread's four channels share one group: stage one (sum, sumsq) pair per thread, then ONE thread per group adds its members in a fixed
+      // order (no contended shared-memory fp64 atomics: they are CAS loops and dominated the small low-resolution launches)
+      __shared__ double part[256][2];
+      part[threadIdx.x][0] = (double)s[0] + (double)s[1] + (double)s[2] + (double)s[3];
+      part[threadIdx.x][1] = (double)q[0] + (double)q[1] + (double)q[2] + (double)q[3];
+      __syncthreads();
+      if (threadIdx.x < groups) {
+        const int g = threadIdx.x, per = cg / 4;
+        double a = 0.0, c = 0.0;
+        for (int rr = 0; rr < tpr; ++rr)
+          for (int k = 0; k < per; ++k) {
+            a += part[rr * c4n + g * per + k][0];
+            c += part[rr * c4n + g * per + k][1];
+          }
+        sacc[g * 2] = a;
+        sacc[g * 2 + 1] = c;
+      }
+    } else {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int g = (c4 * 4 + j) / cg;
-      atomicAdd(&sacc[g * 2], (double)s[j]);
-      atomicAdd(&sacc[g * 2 + 1], (double)q[j]);
+      for (int j = 0; j < 4; ++j) {
+        const int g = (c4 * 4 + j) / cg;
+        atomicAdd(&sacc[g * 2], (double)s[j]);
+        atomicAdd(&sacc[g * 2 + 1], (double)q[j]);
+      }
     }
   }
   __syncthreads();
@@ -184,6 +215,80 @@ __global__ void groupnorm_apply_kernel(const float* __restrict__ x, const double
       continue;
     }
     *reinterpret_cast<float4*>(out + orow * C + c4 * 4) = r;
+  }
+}
+
+// Padded-image form of the same op, one CTA per (image, padded row): with 256 % (C/4) == 0 a thread keeps ONE float4 channel slot for the whole
+// row, so its mean / rstd / gamma / beta are loop invariants and the element loop has no integer division at all (the flat-index kernel above
+// spends ~5 64-bit div/mod per 16 bytes and measured 2 TB/s on the 80 x 848 level); four independent 16-byte loads in flight per thread.
+__global__ void __launch_bounds__(256) groupnorm_apply_rows_kernel(const float* __restrict__ x, const double* __restrict__ stats,
+                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                   float* __restrict__ out, int H, int W, int C, int groups, float eps, int flags) {
+  const int Hp = H + 2, Wp = W + 2, c4n = C / 4;
+  const int b = blockIdx.x / Hp, yp = blockIdx.x - b * Hp;
+  const int c4 = threadIdx.x % c4n, x0 = threadIdx.x / c4n, xstep = 256 / c4n;
+  const long long rowbase = ((long long)b * Hp + yp) * Wp;
+  const bool row_inside = yp >= 1 && yp <= H;
+  const int cg = C / groups;
+  float meanf[4], rstd[4], ga[4], be[4];
+  if (row_inside) {
+    const double cnt = (double)H * W * cg;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c4 * 4 + j;
+      const int g = c / cg;
+      if (j > 0 && g == (c - 1) / cg) {
+        meanf[j] = meanf[j - 1];
+        rstd[j] = rstd[j - 1];
+      } else {
+        const double mean = stats[((long long)b * groups + g) * 2] / cnt;
+        double var = stats[((long long)b * groups + g) * 2 + 1] / cnt - mean * mean;
+        var = var < 0.0 ? 0.0 : var;
+        meanf[j] = (float)mean;
+        rstd[j] = (float)(1.0 / sqrt(var + (double)eps));
+      }
+      ga[j] = __ldg(gamma + c);
+      be[j] = __ldg(beta + c);
+    }
+  }
+  constexpr int U = 4;
+  for (int xb = x0; xb < Wp; xb += U * xstep) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int xx = xb + u * xstep;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row_inside && xx >= 1 && xx <= W) v[u] = *reinterpret_cast<const float4*>(x + (rowbase + xx) * C + c4 * 4);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int xx = xb + u * xstep;
+      if (xx >= Wp) break;
+      float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row_inside && xx >= 1 && xx <= W) {
+        const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float t = (vv[j] - meanf[j]) * rstd[j] * ga[j] + be[j];
+          if (flags & DSB_GN_SWISH) t = __fdividef(t, 1.0f + __expf(-t));
+          if (flags & DSB_GEMM_ROUND_TF32) t = round_tf32(t);
+          o[j] = t;
+        }
+        r = make_float4(o[0], o[1], o[2], o[3]);
+      }
+      const long long orow = rowbase + xx;
+      if (flags & DSB_SPLIT_OUT_F16) {
+        store_pair_f16(reinterpret_cast<__half*>(out) + orow * 2 * C + c4 * 4, C, r);
+      } else if (flags & DSB_SPLIT_OUT) {
+        const float4 hi = make_float4(round_tf32(r.x), round_tf32(r.y), round_tf32(r.z), round_tf32(r.w));
+        *reinterpret_cast<float4*>(out + orow * 2 * C + c4 * 4) = hi;
+        *reinterpret_cast<float4*>(out + orow * 2 * C + C + c4 * 4) =
+            make_float4(round_tf32(r.x - hi.x), round_tf32(r.y - hi.y), round_tf32(r.z - hi.z), round_tf32(r.w - hi.w));
+      } else {
+        *reinterpret_cast<float4*>(out + orow * C + c4 * 4) = r;
+      }
+    }
   }
 }
 
@@ -328,7 +433,9 @@ extern "C" int dsb_groupnorm_stats(const float* x, double* stats, int B, int P, 
   DSB_REQUIRE(C % 4 == 0 && C % groups == 0 && C / 4 <= 256, "dsb_groupnorm_stats: unsupported channel count %d", C);
   cudaStream_t st = (cudaStream_t)stream;
   DSB_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * B * groups, st));
-  const int rows_per_block = 256;
+  // enough CTAs to fill the machine on the low-resolution levels too (P = 385 padded pixels at 5 x 53)
+  long long rpb = ((long long)P * B) / ((long long)sm_count() * 4);
+  const int rows_per_block = rpb < 16 ? 16 : (rpb > 256 ? 256 : (int)rpb);
   dim3 grid((P + rows_per_block - 1) / rows_per_block, B);
   groupnorm_stats_kernel<<<grid, 256, sizeof(double) * 2 * groups, st>>>(x, stats, P, C, groups, rows_per_block);
   DSB_CHECK_CUDA(cudaGetLastError());
@@ -340,6 +447,11 @@ extern "C" int dsb_groupnorm_apply(const float* x, const double* stats, const fl
   DSB_REQUIRE(!(flags & DSB_SPLIT_OUT) || C % 32 == 0, "dsb_groupnorm_apply: split output needs C %% 32 == 0");
   DSB_REQUIRE(!(flags & DSB_GN_COMPACT) || Lp >= H * W, "dsb_groupnorm_apply: Lp too small");
   const long long total = ((flags & DSB_GN_COMPACT) ? (long long)B * Lp : (long long)B * (H + 2) * (W + 2)) * (C / 4);
+  if (!(flags & DSB_GN_COMPACT) && C / 4 <= 256 && 256 % (C / 4) == 0) {
+    groupnorm_apply_rows_kernel<<<B * (H + 2), 256, 0, (cudaStream_t)stream>>>(x, stats, gamma, beta, out, H, W, C, groups, eps, flags);
+    DSB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   const size_t gn_smem = B * groups <= 2048 ? sizeof(float) * 2 * B * groups : 0;
   groupnorm_apply_kernel<<<ew_grid(total), 256, gn_smem, (cudaStream_t)stream>>>(x, stats, gamma, beta, out, B, H, W, C, groups, eps, flags, Lp);
   DSB_CHECK_CUDA(cudaGetLastError());

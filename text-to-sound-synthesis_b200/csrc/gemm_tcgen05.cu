@@ -48,6 +48,10 @@ struct GemmParams {
   unsigned tap_a2_mask;    // bit i set: tap i reads the SECOND A tensor map (a fused GEMM over two activation buffers)
   unsigned tap_share_mask; // resident-W kernel: bit i set: tap i multiplies the A box tap i-1 staged (same shift / column / operand)
   int n_pad;               // resident-W kernel: rows of one W box = the MMA's N (N rounded up to 16)
+  int a_stages;            // resident-W kernel: depth of the A-box ring (whatever shared memory the resident weights leave, <= 12)
+  // fused split-fp16 pair kernel: f3_nsp spatial taps j, each with row shift tap_shift[j], hi-half columns tap_acol[j] (A) / tap_wcol[j] (W);
+  // the lo halves sit lo_a / lo_w columns further right
+  int f3_nsp, lo_a, lo_w;
   long long split_off;     // DSB_GEMM_OUT_F16_SPLIT: offset of the lo half inside an output row
   long long dual_off;      // DSB_GEMM_DUAL_LRELU: offset of the LeakyReLU(0.2) copy (hi at +dual_off, lo at +dual_off+split_off)
   int ocg, ocg_stride;     // output column groups: logical column n lives at (n / ocg) * ocg_stride + n % ocg (0 = plain)
@@ -662,7 +666,8 @@ gemm_f16x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   const int num_tiles = p.tiles_m * p.tiles_n * p.batch;  // tiles_m counts 256-row pair tiles
   const int num_kb = p.kb_per_tap;                        // k-blocks of the ORIGINAL reduction length K
   const int pair_id = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
-  const int lo_a = p.tap_acol[0], lo_w = p.tap_wcol[0];   // column of the lo halves (= K)
+  const int lo_a = p.lo_a, lo_w = p.lo_w;                 // column distance from a hi half to its lo half
+  const int nsp = p.f3_nsp;                               // spatial taps (1 = a Linear layer; 9 / 3 / 2 = conv taps over padded rows)
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -699,17 +704,20 @@ gemm_f16x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         const int b = tile / (p.tiles_m * p.tiles_n);
         const int row0 = m_blk * (2 * BLOCK_M) + (int)rank * BLOCK_M;
         const int nrow0 = n_blk * BLOCK_N + (int)rank * (BLOCK_N / 2);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          const int c0 = kb * 64;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
-          const uint32_t bar = map_to_cta(smem_u32(&full_bar[stage]), 0);
-          uint8_t* sa = smem + stage * S::STAGE_BYTES;
-          tma_load_3d_2sm(&tmap_a, bar, sa, c0, row0, b);
-          tma_load_3d_2sm(&tmap_a, bar, sa + S::TILE_A, lo_a + c0, row0, b);
-          tma_load_3d_2sm(&tmap_b, bar, sa + 2 * S::TILE_A, c0, nrow0, 0);
-          tma_load_3d_2sm(&tmap_b, bar, sa + 2 * S::TILE_A + S::TILE_B, lo_w + c0, nrow0, 0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        for (int j = 0; j < nsp; ++j) {
+          const int arow = row0 + p.tap_shift[j], acol = p.tap_acol[j], wcol = p.tap_wcol[j];
+          for (int kb = 0; kb < num_kb; ++kb) {
+            const int c0 = kb * 64;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);
+            const uint32_t bar = map_to_cta(smem_u32(&full_bar[stage]), 0);
+            uint8_t* sa = smem + stage * S::STAGE_BYTES;
+            tma_load_3d_2sm(&tmap_a, bar, sa, acol + c0, arow, b);
+            tma_load_3d_2sm(&tmap_a, bar, sa + S::TILE_A, acol + lo_a + c0, arow, b);
+            tma_load_3d_2sm(&tmap_b, bar, sa + 2 * S::TILE_A, wcol + c0, nrow0, 0);
+            tma_load_3d_2sm(&tmap_b, bar, sa + 2 * S::TILE_A + S::TILE_B, wcol + lo_w + c0, nrow0, 0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
@@ -725,7 +733,8 @@ gemm_f16x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int num_kbt = num_kb * nsp;
+        for (int kb = 0; kb < num_kbt; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
@@ -780,9 +789,12 @@ gemm_f16x3_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 // staged copy.  MMA N = n_pad (16..128), accumulators 2 x 128 TMEM columns, epilogue shared with the generic kernel.
 struct ResidentSmem {
   static constexpr int A_BYTES = BLOCK_M * ROW_BYTES;
-  static constexpr int STAGES = 6;
+  static constexpr int MAX_STAGES = 12;
   static constexpr int W_MAX = 96 * 1024;
-  static constexpr int FIXED = STAGES * A_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 8 * 32 * 32 * 4 /*epilogue transpose tiles*/;
+  static constexpr int BAR_BYTES = 512;
+  static constexpr int EPI_BYTES = 8 * 32 * 32 * 4;
+  static constexpr int BUDGET = 227 * 1024 - 1024 /*static smem of the epilogue*/;
+  static constexpr int FIXED = 1024 /*align slack*/ + BAR_BYTES + EPI_BYTES;
 };
 
 template <int KIND>
@@ -790,20 +802,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 conv_resident_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2, const __grid_constant__ CUtensorMap tmap_b,
                      const __grid_constant__ GemmParams p) {
   using S = ResidentSmem;
-  constexpr int STAGES = S::STAGES;
-  constexpr uint32_t ACC_COLS = 128, TMEM_COLS = 2 * ACC_COLS;
+  // 4 accumulator stages: the MMA issuer runs up to three tiles ahead of the epilogue, so staged A boxes are consumed (and their ring slots
+  // re-armed) as they land instead of waiting for an epilogue -- the launch is a stream of 16 KB boxes with a few microseconds of latency each
+  constexpr uint32_t ACC_COLS = 128, ACC_STAGES = 4, TMEM_COLS = ACC_COLS * ACC_STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int STAGES = p.a_stages;
   const int wbox = p.n_pad * ROW_BYTES;
   uint8_t* w_smem = smem + STAGES * S::A_BYTES;
   uint8_t* tail = w_smem + p.num_taps * wbox;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* w_bar = tmem_empty + 2;
+  uint64_t* empty_bar = full_bar + S::MAX_STAGES;
+  uint64_t* tmem_full = empty_bar + S::MAX_STAGES;
+  uint64_t* tmem_empty = tmem_full + ACC_STAGES;
+  uint64_t* w_bar = tmem_empty + ACC_STAGES;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_bar + 1);
-  float* epi_smem = reinterpret_cast<float*>(tail + 256);
+  float* epi_smem = reinterpret_cast<float*>(tail + S::BAR_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -819,7 +833,7 @@ conv_resident_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < (int)ACC_STAGES; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], alt_tiles ? 4 : 8);
     }
@@ -866,8 +880,8 @@ conv_resident_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       mbar_wait(w_bar, 0);
       tc_fence_after();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
+        const int as = it & (ACC_STAGES - 1);
+        const uint32_t aphase = (it / ACC_STAGES) & 1;
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * ACC_COLS;
@@ -894,11 +908,11 @@ conv_resident_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     float* sw = epi_smem + (warp - 2) * (32 * 32);
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int as = it & 1;
-      if (alt_tiles && as != half) continue;
+      if (alt_tiles && (it & 1) != half) continue;
+      const int as = it & (ACC_STAGES - 1);
       const int m_blk = tile % p.tiles_m;
       const int b = tile / p.tiles_m;
-      const uint32_t aphase = (it >> 1) & 1;
+      const uint32_t aphase = (it / ACC_STAGES) & 1;
       epilogue_tile<128>(p, sw, tmem_base + as * ACC_COLS, &tmem_full[as], aphase, m_blk * BLOCK_M + q * 32, 0, b, q, alt_tiles ? 0 : half, lane);
       tc_fence_before();
       __syncwarp();
@@ -932,7 +946,7 @@ static PFN_encodeTiled get_encode() {
 
 // 3-D map (K, rows, batch) over a K-contiguous matrix; box = (128 bytes of K, box_rows, 1); SWIZZLE_128B; OOB -> 0
 int make_operand_map(CUtensorMap* map, const void* ptr, int kind, long long kdim, long long rows, long long batch,
-                            long long ld_elems, long long bstride_elems, int box_rows) {
+                            long long ld_elems, long long bstride_elems, int box_rows, int l2_promo_128) {
   PFN_encodeTiled enc = get_encode();
   DSB_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   const int es = kind == DSB_DTYPE_TF32 ? 4 : 2;
@@ -944,8 +958,9 @@ int make_operand_map(CUtensorMap* map, const void* ptr, int kind, long long kdim
   cuuint32_t box[3] = {(cuuint32_t)(ROW_BYTES / es), (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(map, kind == DSB_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : (kind == DSB_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32), 3, const_cast<void*>(ptr), gdim, gstr,
-                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   // state rows [raw pair | activated pair] are read one 128-byte half at a time: a 256-byte promotion would fetch the other half too
+                   l2_promo_128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DSB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): k=%lld rows=%lld batch=%lld ld=%lld", (int)r, kdim, rows, batch, ld_elems);
   return 0;
 }
@@ -1079,17 +1094,24 @@ extern "C" int dsb_gemm_ex(const dsb_gemm_desc* d, void* stream) {
         p.tap_share_mask |= 1u << i;
     p.tiles_n = 1;
     CUtensorMap ma, mb;
-    if (make_operand_map(&ma, d->A, kind, d->a_cols > 0 ? d->a_cols : d->K, d->a_rows > 0 ? d->a_rows : d->M, d->batch, d->lda, d->a_batch_stride, BLOCK_M)) return 3;
+    static const int promo128 = [] { const char* e = getenv("DSB_CONV_RESIDENT_PROMO256"); return (e && e[0] == '1') ? 0 : 1; }();  // A/B switch
+    if (make_operand_map(&ma, d->A, kind, d->a_cols > 0 ? d->a_cols : d->K, d->a_rows > 0 ? d->a_rows : d->M, d->batch, d->lda, d->a_batch_stride, BLOCK_M, promo128)) return 3;
     if (make_operand_map(&mb, d->W, kind, d->w_cols > 0 ? d->w_cols : (long long)d->K * d->num_taps, d->N, 1, d->ldw, 0, p.n_pad)) return 3;
     CUtensorMap ma2 = ma;
     if (p.tap_a2_mask &&
-        make_operand_map(&ma2, d->A2, kind, d->a2_cols > 0 ? d->a2_cols : d->K, d->a2_rows > 0 ? d->a2_rows : d->M, d->batch, d->lda2, d->a2_batch_stride, BLOCK_M))
+        make_operand_map(&ma2, d->A2, kind, d->a2_cols > 0 ? d->a2_cols : d->K, d->a2_rows > 0 ? d->a2_rows : d->M, d->batch, d->lda2, d->a2_batch_stride, BLOCK_M, promo128))
       return 3;
-    const int smem_bytes = ResidentSmem::FIXED + w_bytes;
+    p.a_stages = (ResidentSmem::BUDGET - ResidentSmem::FIXED - w_bytes) / ResidentSmem::A_BYTES;
+    if (p.a_stages > ResidentSmem::MAX_STAGES) p.a_stages = ResidentSmem::MAX_STAGES;
+    {
+      static const int forced = [] { const char* e = getenv("DSB_CONV_RESIDENT_STAGES"); return e ? atoi(e) : 0; }();  // tuning runs
+      if (forced >= 2 && forced < p.a_stages) p.a_stages = forced;
+    }
+    const int smem_bytes = ResidentSmem::FIXED + w_bytes + p.a_stages * ResidentSmem::A_BYTES;
     auto kern = kind == DSB_DTYPE_BF16 ? conv_resident_kernel<DSB_DTYPE_BF16> : conv_resident_kernel<DSB_DTYPE_F16>;
     static bool attr_done[2] = {false, false};
     if (!attr_done[kind == DSB_DTYPE_BF16]) {
-      DSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ResidentSmem::FIXED + ResidentSmem::W_MAX));
+      DSB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ResidentSmem::BUDGET));
       attr_done[kind == DSB_DTYPE_BF16] = true;
     }
     const int tiles = p.tiles_m * p.batch;
@@ -1119,18 +1141,32 @@ extern "C" int dsb_gemm_ex(const dsb_gemm_desc* d, void* stream) {
   DSB_REQUIRE(!(any_mn && d->cta_pair > 0), "dsb_gemm_ex: the cta_group::2 kernel takes K-major operands only");
   const bool use_pair = !any_mn && (d->cta_pair > 0 || (d->cta_pair == 0 && d->block_n == 0 && block_n == 256 && d->M > BLOCK_M &&
                                                         (long long)d->K * d->num_taps >= 2048 && pair_default()));
-  // split-fp16 tap list (lo*hi, hi*lo, hi*hi of one unshifted operand pair): run the three passes off ONE staged copy of the four tiles
+  // split-fp16 tap list -- per spatial tap j the triple (shift_j, A lo, W hi), (shift_j, A hi, W lo), (shift_j, A hi, W hi) with constant hi -> lo column
+  // distances: run the three passes off ONE staged copy of the four tiles (Linear layers: one unshifted triple; convs: 9 / 3 / 2 shifted triples)
   static const bool fuse_ok = [] { const char* e = getenv("DSB_GEMM_F16X3_FUSED"); return !(e && e[0] == '0'); }();
-  const bool fused3 = use_pair && fuse_ok && kind == DSB_DTYPE_F16 && d->num_taps == 3 && !p.tap_a2_mask && d->batch == 1 && !p.b_batched &&
-                      p.tap_shift[0] == 0 && p.tap_shift[1] == 0 && p.tap_shift[2] == 0 && p.tap_acol[0] == d->K && p.tap_acol[1] == 0 && p.tap_acol[2] == 0 &&
-                      p.tap_wcol[0] == 0 && p.tap_wcol[1] == d->K && p.tap_wcol[2] == 0 && d->K % 64 == 0;
+  static const bool fuse_conv_ok = [] { const char* e = getenv("DSB_GEMM_F16X3_FUSED_CONV"); return !(e && e[0] == '0'); }();  // A/B switch
+  bool f3_pattern = fuse_ok && kind == DSB_DTYPE_F16 && d->num_taps % 3 == 0 && !p.tap_a2_mask && !p.b_batched && !any_mn && d->K % 64 == 0 && d->M > BLOCK_M;
+  int f3_lo_a = 0, f3_lo_w = 0;
+  if (f3_pattern) {
+    f3_lo_a = p.tap_acol[0] - p.tap_acol[1];
+    f3_lo_w = p.tap_wcol[1] - p.tap_wcol[0];
+    for (int j = 0; j < d->num_taps && f3_pattern; j += 3)
+      f3_pattern = p.tap_shift[j] == p.tap_shift[j + 1] && p.tap_shift[j] == p.tap_shift[j + 2] && p.tap_acol[j + 1] == p.tap_acol[j + 2] &&
+                   p.tap_acol[j] - p.tap_acol[j + 1] == f3_lo_a && p.tap_wcol[j] == p.tap_wcol[j + 2] && p.tap_wcol[j + 1] - p.tap_wcol[j] == f3_lo_w;
+    f3_pattern = f3_pattern && f3_lo_a > 0 && f3_lo_w > 0;
+  }
+  const bool f3_linear = f3_pattern && d->num_taps == 3 && p.tap_shift[0] == 0 && d->batch == 1;  // the denoiser's Linear layers (any N)
+  // conv form: whenever the caller left tile shape and pairing to the library
+  const bool f3_conv = f3_pattern && !f3_linear && fuse_conv_ok && d->block_n == 0 && d->cta_pair == 0;
+  const bool fused3 = f3_pattern && ((use_pair && f3_linear) || f3_conv);
   bool fused_n128 = false;
-  if (use_pair) {
+  const bool pair_tiles = use_pair || fused3;
+  if (pair_tiles) {
     block_n = 256;
     p.tiles_m = (d->M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
     // fewer 256-wide tiles than CTA pairs: halve the tile width so that every pair runs two tiles and overlaps an epilogue with a mainloop
     static const bool n128_ok = [] { const char* e = getenv("DSB_GEMM_F16X3_N128"); return e && e[0] == '1'; }();  // opt-in: measured SLOWER at B=16 (proj 25.2 -> 26.4 us, MLP2 76.4 -> 93.9 us): the narrower tile is shared-memory bound
-    if (fused3 && n128_ok && d->N >= 256 && (long long)p.tiles_m * ((d->N + 255) / 256) <= (d->max_ctas > 0 ? d->max_ctas : sms) / 2) {
+    if (fused3 && ((n128_ok && d->N >= 256 && (long long)p.tiles_m * ((d->N + 255) / 256) <= (d->max_ctas > 0 ? d->max_ctas : sms) / 2) || d->N <= 128)) {
       fused_n128 = true;
       block_n = 128;
     }
@@ -1145,8 +1181,7 @@ extern "C" int dsb_gemm_ex(const dsb_gemm_desc* d, void* stream) {
   if (p.b_mn) {
     if (make_operand_map_mn(&mb, d->W, kind, d->N, d->K, p.b_batched ? d->batch : 1, d->ldw, d->w_batch_stride)) return 3;
   } else if (make_operand_map(&mb, d->W, kind, d->w_cols > 0 ? d->w_cols : (long long)d->K * d->num_taps, d->N, p.b_batched ? d->batch : 1, d->ldw,
-                              d->w_batch_stride, use_pair ? block_n / 2 : block_n)) return 3;
-  (void)fused_n128;
+                              d->w_batch_stride, pair_tiles ? block_n / 2 : block_n)) return 3;
   CUtensorMap ma2 = ma;
   if (p.tap_a2_mask) {
     DSB_REQUIRE(!any_mn, "dsb_gemm_ex: a second A operand is K-major only");
@@ -1155,11 +1190,17 @@ extern "C" int dsb_gemm_ex(const dsb_gemm_desc* d, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int max_ctas = d->max_ctas > 0 ? d->max_ctas : sms;
   if (fused3) {
-    p.tap_wcol[0] = (int)d->K;  // the fused kernel reads the lo-half columns from tap_acol[0] / tap_wcol[0]
-    const int tiles = p.tiles_m * p.tiles_n;
+    p.f3_nsp = d->num_taps / 3;
+    p.lo_a = f3_lo_a;
+    p.lo_w = f3_lo_w;
+    for (int j = 0; j < p.f3_nsp; ++j) {  // triple j -> spatial tap j: (row shift, hi-half column of A, hi-half column of W)
+      const int sh = p.tap_shift[3 * j], ac = p.tap_acol[3 * j + 1], wc = p.tap_wcol[3 * j];
+      p.tap_shift[j] = sh; p.tap_acol[j] = ac; p.tap_wcol[j] = wc;
+    }
+    const long long tiles = (long long)p.tiles_m * p.tiles_n * p.batch;
     int pairs = max_ctas / 2;
     if (pairs < 1) pairs = 1;
-    if (tiles < pairs) pairs = tiles;
+    if (tiles < pairs) pairs = (int)tiles;
     static bool attr_done[2] = {false, false};
     if (fused_n128) {
       if (!attr_done[0]) { DSB_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16x3_pair_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairSplitSmem<128>::TOTAL)); attr_done[0] = true; }

@@ -243,6 +243,17 @@ def edge_pad_f16(state, T, P, d, col0, ncols, reflect=True):
     _lib.check(_lib.lib().dsb_edge_pad_f16(state.data_ptr(), ld, Tp * ld, B, T, P, d, col0, ncols, 1 if reflect else 0, _stream()), "dsb_edge_pad_f16")
 
 
+def conv_out_pair(state, T, row0, col0, w, bias, scale, out=None):
+    """state (B, rows, ld) fp16 with the activated (hi | lo) pair at columns [col0, col0 + 2 cs); w (kt, cs) fp32 -> tanh(scale * conv + bias) (B, T) fp32."""
+    _need_cuda(state, w, bias)
+    B, rows, ld = state.shape
+    kt, cs = w.shape
+    out = torch.empty(B, T, dtype=torch.float32, device=state.device) if out is None else out
+    _lib.check(_lib.lib().dsb_conv_out_pair(state.data_ptr(), ld, rows * ld, B, T, row0, col0, cs, kt, w.data_ptr(), _ptr(bias), float(scale), out.data_ptr(),
+                                            _stream()), "dsb_conv_out_pair")
+    return out
+
+
 def gemm_f32(a, w, bias=None, residual=None, out=None, *, gelu=False, round_out=False):
     """Exact fp32 FFMA GEMM (set-up tables, fp32-exact mode)."""
     _need_cuda(a, w, bias, residual, out)

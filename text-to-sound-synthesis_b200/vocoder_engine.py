@@ -97,6 +97,11 @@ class VocoderEngine:
         last = mods[i + 2]
         wl = _fold(last)  # (1, ngf, 7)
         self.last = _PackedConv([wl[:, :, j] for j in range(wl.shape[2])], last.bias, fold=_c8(wl.shape[1]) == 32)
+        # 32-channel rows, 7 taps (the shipped generator): the output conv runs on the FMA pipe straight off the state buffer (dsb_conv_out_pair)
+        self.last_w = None
+        if _c8(wl.shape[1]) == 32 and wl.shape[2] == 7 and wl.shape[0] == 1:
+            self.last_w = torch.zeros(7, 32, dtype=torch.float32, device=dev)
+            self.last_w[:, :wl.shape[1]] = wl[0].t()
         self.c0 = w0.shape[0]
         self._graphs.clear()
         self._bufs.clear()
@@ -219,6 +224,10 @@ class VocoderEngine:
         cv = self.last
         ops.edge_pad_f16(S, T, P, 3, 2 * C, 2 * C, reflect=True)
         wav = torch.empty(B, T, 1, dtype=torch.float32, device=mel.device)
+        if self.last_w is not None:
+            ops.conv_out_pair(S, T, P - 3, 2 * C, self.last_w, cv.bias, 1.0 / sig, out=wav)
+            self.launches = n + 2
+            return wav.view(B, 1, T)
         tp = self._taps(cv, [(P - 3 + j, 2 * C, 3 * C, 0) for j in range(7)])
         ops.gemm_desc(A=S.data_ptr(), W=cv.w.data_ptr(), out=wav.data_ptr(), M=T, N=1, K=64 if tp["resident_w"] else cv.Kp, batch=B, **tp,
                       a_rows=T + 2 * P, a_cols=4 * C, lda=4 * C, a_batch_stride=(T + 2 * P) * 4 * C,
