@@ -240,7 +240,7 @@ def gemm_roofline(eng, B, peaks, peaks_src, traffic):
     peak = peak_bf16 / 2.0 if eng.precision == "tf32" else peak_bf16
     passes = 3 if split else 1
     tr = traffic.get(f"gemm_{eng.precision}_B{B}")
-    return {"bound": "tensor", "kernel": f"gemm_tcgen05{'_pair' if split else ''}_kernel<f16> ({eng.precision})", "achieved": round(achieved, 1), "peak": round(peak, 1),
+    return {"bound": "tensor", "kernel": ("gemm_f16x3_pair_kernel<256> (fused split-fp16, tcgen05 cta_group::2)" if split else f"gemm_tcgen05_kernel<f16> ({eng.precision})"), "achieved": round(achieved, 1), "peak": round(peak, 1),
             "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
             "tensor_pipe": {"mma_passes_per_product": passes, "executed_tflops": round(achieved * passes, 1), "frac_of_peak": round(achieved * passes / peak, 4),
                             "note": "f16x3 = lo*hi + hi*lo + hi*hi fp16 passes per fp32-equivalent product; executed = algorithmic x passes"},
