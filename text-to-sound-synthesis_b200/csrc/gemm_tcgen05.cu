@@ -1131,7 +1131,11 @@ extern "C" int dsb_gemm_ex(const dsb_gemm_desc* d, void* stream) {
       const long long t256 = (long long)p.tiles_m * ((d->N + 255) / 256) * d->batch;
       const long long t128 = (long long)p.tiles_m * ((d->N + 127) / 128) * d->batch;
       const long long cost256 = ((t256 + sms - 1) / sms) * 2, cost128 = ((t128 + sms - 1) / sms);
-      block_n = cost128 < cost256 ? 128 : 256;
+      // where the 256-wide choice leads to the CTA-pair / fused split-fp16 kernels, 128-wide tiles only when they save at least a fifth of the
+      // waves: the pair tile has twice the arithmetic intensity per staged byte.  (A bare "fewer waves" rule picked the 1-CTA 128-wide kernel for 29 vs 30 waves
+      // at M = 67 840 and ran the N = 1024 / 4096 layers of a 256-clip batch at half the fused kernel's rate: tools/batch_scaling.py.)
+      const bool pair_possible = !any_mn && d->cta_pair >= 0 && d->M > BLOCK_M && (long long)d->K * d->num_taps >= 2048 && pair_default();
+      block_n = (pair_possible ? cost128 * 5 < cost256 * 4 : cost128 < cost256) ? 128 : 256;
     }
   }
   DSB_REQUIRE(block_n == 128 || block_n == 256, "dsb_gemm_ex: block_n must be 0, 128 or 256");
