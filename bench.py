@@ -421,7 +421,7 @@ def run_gpu_arm(args):
                 "config": {"workload": workload_name(B, K, args.layers),
                            "arithmetic": {"f16x3": "denoiser GEMM / attention operands are fp16 (hi | lo) pairs (22 significand bits), three tcgen05 kind::f16 passes per product, "
                                                    "fp32 TMEM accumulation = fp32-class logits (the reference's nn.Linear is fp32); residual stream / LayerNorm / softmax fp32; "
-                                                   "log_softmax fp64; decoder / vocoder convs split-TF32 (3-pass)",
+                                                   "log_softmax fp64; decoder / vocoder convs split-fp16 pairs (3 passes, fp32 accumulation), the decoder AttnBlocks split-TF32",
                                           "f16": "denoiser operands single-pass fp16; decoder / vocoder split-TF32", "tf32": "tf32", "fp32": "FFMA"}[args.precision],
                            "global_batch": B * world, "parallelism": f"dp{world} (independent captions per rank, all_gather of waveforms)",
                            "l2_policy": "working set per diffusion step (3.1 GB of (hi | lo) fp16 weights) exceeds the 126 MB L2; no explicit flush"},
