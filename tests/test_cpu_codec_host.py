@@ -92,3 +92,41 @@ def test_melgan_engine_host_logic_shipped_checkpoint(emulated_ops):
     err = rel_err(wav, ref)
     print("melgan shipped weights, 12 frames (emulated kernels) rel err", err, "max |wav|", float(ref.abs().max()))
     assert err < 1e-3
+
+
+@pytest.mark.parametrize("C,fold", [(32, True), (28, True), (20, False), (64, False), (128, False)])
+def test_packed_conv_tap_forms_compute_the_same_conv(emulated_ops, C, fold):
+    """packing.PackedConv: the 3-pass tap list (taps), its 64-deep form for the resident-W kernel (taps64, A boxes shared between adjacent taps) and
+    the folded [Wh | Wh], [Wl | 0] packing of 32-channel rows must all describe the SAME dilated 3-tap conv (reference vocoder/modules.py:77-81) --
+    checked through the emulated dsb_gemm_ex contract against a direct fp64 convolution of the pair values."""
+    from diffsound_b200 import packing
+    P, d, T, B = 9, 3, 70, 2
+    Cs = (C + 7) // 8 * 8
+    ld = 4 * Cs
+    g = torch.Generator().manual_seed(C)
+    x = torch.randn(B, T + 2 * P, C, generator=g)
+    S = E.track(torch.zeros(B, T + 2 * P, ld, dtype=torch.float16))
+    pr = E.split_f16(x.view(-1, C)).view(B, T + 2 * P, 2 * C)
+    S[..., 2 * Cs:2 * Cs + C], S[..., 3 * Cs:3 * Cs + C] = pr[..., :C], pr[..., C:]
+    xv = pr[..., :C].double() + pr[..., C:].double()
+    ws = [torch.randn(C, C, generator=g) * 0.1 for _ in range(3)]
+    bias = torch.randn(C, generator=g)
+    spatial = [(P + (j - 1) * d, 2 * Cs, 3 * Cs, 0) for j in range(3)]
+    outs = []
+    for use_fold, form in ((False, "taps"), (False, "taps64"), (fold, "taps64")):
+        cv = packing.PackedConv(ws, bias, fold=use_fold)
+        tp = getattr(cv, form)(spatial)
+        K = 64 if form == "taps64" else cv.Kp
+        if form == "taps64":
+            assert cv.resident_ok(len(tp)) == (len(tp) * ((C + 15) // 16 * 16) * 128 <= 96 * 1024 and C <= 128)
+            shared = sum(1 for a, b in zip(tp, tp[1:]) if a[0] == b[0] and a[1] == b[1] and a[3] == b[3])
+            assert shared == len(tp) // (2 if use_fold else 3)  # one shared A box per (spatial tap, 64-column slice)
+        Y = E.track(torch.zeros(B, T, 2 * Cs, dtype=torch.float16))
+        E.gemm_desc(A=S.data_ptr(), W=cv.w.data_ptr(), out=Y.data_ptr(), M=T, N=C, K=K, batch=B, taps=tp, a_rows=T + 2 * P, a_cols=ld, lda=ld,
+                    a_batch_stride=(T + 2 * P) * ld, ldw=cv.w.shape[1], w_cols=cv.w.shape[1], ldo=2 * Cs, out_batch_stride=T * 2 * Cs, bias=cv.bias,
+                    flags=E.OUT_F16_SPLIT, alpha=cv.alpha, split_off=Cs, resident_w=int(form == "taps64" and cv.resident_ok(len(tp))))
+        outs.append(Y[..., :C].double() + Y[..., Cs:Cs + C].double())
+        wv = [(cv.w[:, j * 2 * cv.Kp:j * 2 * cv.Kp + C].double() + cv.w[:, j * 2 * cv.Kp + cv.Kp:j * 2 * cv.Kp + cv.Kp + C].double()) * cv.alpha for j in range(3)]
+    ref = sum(xv[:, P + (j - 1) * d:P + (j - 1) * d + T] @ wv[j].T for j in range(3)) + bias.double()
+    for o in outs:
+        assert float((o - ref).abs().max()) / float(ref.abs().max()) < 2e-6
